@@ -1,0 +1,152 @@
+/*
+ * pyratslam_b200.h -- C ABI of the B200-native pose-cell / view-template hot path.
+ *
+ * This is the drop-in boundary.  The reference (bjkomer/pyratslam) has no FFI of
+ * its own: its operator layer is the Python class `Convolution`
+ * (ratslam/convolution.py:10-697, OpenCL via pyopencl), driven by
+ * `PoseCellNetwork` (ratslam/posecell_network.py:22-353), and the numpy loop in
+ * `ViewTemplates.match` (ratslam/view_templates.py:63-75).  Each entry point below
+ * names the reference code it replaces.  Plain pointers and sizes only; `stream`
+ * is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *
+ * Every function returns 0 on success or a negative PRS_E_* code;
+ * `prs_last_error()` gives the message of the last failure on the calling thread.
+ * There is no CPU fallback: without a CUDA device every compute entry fails.
+ *
+ * Pose-cell state layout in HBM ("theta-major"):  state[b][th][x][y], y fastest,
+ * element type float (dtype 0) or double (dtype 1).  The reference's numpy layout
+ * is [x][y][th]; `prs_pc_import_xyt` / `prs_pc_export_xyt` convert.
+ */
+#ifndef PYRATSLAM_B200_H
+#define PYRATSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PRS_API __attribute__((visibility("default")))
+#else
+#define PRS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRS_OK 0
+#define PRS_E_INVALID (-1) /* bad argument (shape, dtype, null pointer) */
+#define PRS_E_CUDA (-2)    /* CUDA runtime error, see prs_last_error() */
+#define PRS_E_NODEVICE (-3)
+
+#define PRS_F32 0
+#define PRS_F64 1
+
+/* per-network error bits written by the step kernels into `err[b]` */
+#define PRS_ERR_LUT_KEY 1 /* fractional x offset exactly +0.5: the reference raises KeyError
+                             (posecell_network.py:249) */
+#define PRS_ERR_RADIUS 2  /* 3+ceil|vtrans/0.2| > min(X,Y): the reference convolves unwritten
+                             memory (convolution.py:661-675) */
+#define PRS_ERR_THETA 4   /* |floor(vrot/(2pi/Th)+.5)| beyond the filter table */
+
+#define PRS_OG_RANGE 8    /* theta-origin filters are tabulated for og in [-8, 8] */
+
+#define PRS_VT_MODE_REF 0      /* 15 windowed row offsets, view_templates.py:16-28 */
+#define PRS_VT_MODE_CIRCULAR 1 /* all 32 cyclic row shifts (extension; BASELINE config 5) */
+
+PRS_API const char* prs_last_error(void);
+PRS_API int prs_version(void);
+/* number of CUDA devices visible, or a negative error code */
+PRS_API int prs_device_count(void);
+
+/* ------------------------------------------------------------------ pose cells */
+
+/* Host-side tables, all float64, computed by the caller exactly as the reference
+ * computes them (numpy/scipy on the host) so that no device libm result can change
+ * a filter.  Copied to the device by prs_pc_create. */
+typedef struct prs_pc_config {
+  int X, Y, Th;          /* PoseCellNetwork(shape), posecell_network.py:24-26 */
+  int B;                 /* number of independent networks (1 for the drop-in class) */
+  int dtype;             /* PRS_F32 or PRS_F64 */
+  double vtrans_scale;   /* pc_vtrans_scale = 0.2, posecell_network.py:35 */
+  double vrot_scale;     /* pc_vrot_scale = 2*pi/Th, posecell_network.py:36 */
+  const double* ge;      /* [7]  exp(-d^2/(2 sigma_e^2)) : kernel_3d == aE ge(x)ge(x)ge - aI gi(x)gi(x)gi */
+  const double* gi;      /* [7]  exp(-d^2/(2 sigma_i^2))   (posecell_network.py:97-113) */
+  double aE, aI;         /* amplitudes including the 1/|sum| normalisation */
+  const double* f2d;     /* [2][7][7] LUT filters F0 (origin 0,0) and F-1 (origin -1,-1),
+                            posecell_network.py:50-59,210-222 */
+  const double* f1d;     /* [2*PRS_OG_RANGE+1][7] theta filters for og=-8..8, posecell_network.py:224-235 */
+  const double* cos_th;  /* [Th] cos((k-mid)*vrot_scale), posecell_network.py:260-261 */
+  const double* sin_th;  /* [Th] sin((k-mid)*vrot_scale) */
+} prs_pc_config;
+
+typedef struct prs_pc_plan* prs_pc_handle;
+
+/* replaces Convolution.__init__/set_params/set_text/build_program (convolution.py:11-35,37-91,94-398) */
+PRS_API int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out);
+PRS_API int prs_pc_destroy(prs_pc_handle h);
+/* bytes of one full state tensor [B][Th][X][Y] */
+PRS_API size_t prs_pc_state_bytes(prs_pc_handle h);
+/* which kernel family a step uses: 0 = generic multi-kernel path, 1 = fused SMEM-resident kernel */
+PRS_API int prs_pc_path(prs_pc_handle h);
+/* force the generic path (1) or let the plan choose (0); for tests and profiling */
+PRS_API int prs_pc_force_generic(prs_pc_handle h, int on);
+
+/* One PoseCellNetwork.update() for all B networks (posecell_network.py:326-353):
+ *   state  : device, [B][Th][X][Y] of the plan's dtype, updated in place
+ *   odom   : device, double [B][2] = (vtrans, vrot) as passed to update()
+ *   gi     : device, [B] of the plan's dtype, global inhibition (posecell_network.py:34)
+ *   argmax : device, int64 [B]  flat index x*Y*Th + y*Th + th of the first maximum
+ *            (numpy.argmax order, posecell_network.py:317-319)
+ *   total  : device, [B] of the plan's dtype, the sum before normalisation (posecell_network.py:343)
+ *   err    : device, int32 [B], PRS_ERR_* bits (0 = fine)
+ */
+PRS_API int prs_pc_step(prs_pc_handle h, void* state, const double* odom, const void* gi, long long* argmax,
+                void* total, int* err, void* stream);
+/* T consecutive updates with odometry odom[T][B][2]; argmax[T][B], total[T][B]; err[B] is OR-ed */
+PRS_API int prs_pc_run(prs_pc_handle h, void* state, const double* odom, int T, const void* gi,
+               long long* argmax, void* total, int* err, void* stream);
+/* Same as prs_pc_step with HOST odometry/results: H2D copy, step, D2H copy, stream sync.
+ * odom_host/argmax_host/err_host should be pinned for the copies to be asynchronous. */
+PRS_API int prs_pc_step_host(prs_pc_handle h, void* state, const double* odom_host, const void* gi,
+                     long long* argmax_host, int* err_host, void* stream);
+
+/* PoseCellNetwork.path_integration() alone (posecell_network.py:252-314): per-plane shifted 7x7
+ * correlate + clamp, theta correlate + clamp; no attractor dynamics, no normalisation. */
+PRS_API int prs_pc_path_integration(prs_pc_handle h, void* state, const double* odom, int* err, void* stream);
+
+/* posecells[loc] += energy for network b (posecell_network.py:322-324) */
+PRS_API int prs_pc_inject(prs_pc_handle h, void* state, int b, int x, int y, int th, double energy, void* stream);
+/* arg-max without an update (get_pc_max, posecell_network.py:317-319) */
+PRS_API int prs_pc_argmax(prs_pc_handle h, const void* state, long long* argmax, void* stream);
+/* layout conversion between the reference's [B][x][y][th] and theta-major [B][th][x][y] (device to device) */
+PRS_API int prs_pc_import_xyt(prs_pc_handle h, void* state, const void* xyt, void* stream);
+PRS_API int prs_pc_export_xyt(prs_pc_handle h, const void* state, void* xyt, void* stream);
+
+/* --------------------------------------------------------------- view templates */
+
+/* Sub-sample a camera frame into a template: rows/cols strictly inside (lo, hi) with
+ * (idx-lo) % step != 0 -- the boolean mask of view_templates.py:48-57 applied as in :64.
+ * frame: device uint8 [im_rows][im_cols]; out: device uint8 [n_rows][n_cols]. */
+PRS_API int prs_vt_extract_u8(const uint8_t* frame, int im_rows, int im_cols, int row_lo, int row_hi, int row_step,
+                      int col_lo, int col_hi, int col_step, uint8_t* out, int n_rows, int n_cols, void* stream);
+
+/* Sweep a library of n 32x32 templates against one query (ViewTemplates.match line 65 and
+ * ViewTemplate.match, view_templates.py:16-28,65):
+ *   key_out : device uint64, receives (min_score << 32) | (base_index + argmin), ties -> lowest
+ *             index (numpy.argmin, view_templates.py:73).  n == 0 leaves key_out = UINT64_MAX.
+ *   scores  : optional device uint32 [n] (u8) / float [n] (f32): per-template min score, or NULL.
+ * u8: score = sum((a - b) mod 256) exactly as numpy uint8 arithmetic gives it.
+ * f32: score = sum |a - b| in float32; the key holds the IEEE bits of the score. */
+PRS_API int prs_vt_sweep_u8(const uint8_t* lib, long long n, const uint8_t* query, int mode, long long base_index,
+                    unsigned long long* key_out, uint32_t* scores, void* stream);
+PRS_API int prs_vt_sweep_f32(const float* lib, long long n, const float* query, int mode, long long base_index,
+                     unsigned long long* key_out, float* scores, void* stream);
+/* HOST query in, HOST key out: H2D copy of the 1 KiB query, sweep, D2H of the 8-byte key, sync.
+ * lib stays resident on the device; scratch is a device buffer of >= 1024+8 bytes. */
+PRS_API int prs_vt_match_host_u8(const uint8_t* lib, long long n, const uint8_t* query_host, int mode,
+                         long long base_index, unsigned long long* key_host, void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYRATSLAM_B200_H */

@@ -1,0 +1,106 @@
+"""ctypes binding of libpyratslam_b200.so (the C ABI in include/pyratslam_b200.h).
+
+There is no CPU fallback: if the shared library has not been built, or no CUDA
+device is present when a compute entry is called, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_longlong, c_size_t, c_uint64, c_void_p
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "_lib", "libpyratslam_b200.so")
+
+PRS_F32, PRS_F64 = 0, 1
+ERR_LUT_KEY, ERR_RADIUS, ERR_THETA = 1, 2, 4
+OG_RANGE = 8
+VT_MODE_REF, VT_MODE_CIRCULAR = 0, 1
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+class PcConfig(Structure):
+    _fields_ = [
+        ("X", c_int), ("Y", c_int), ("Th", c_int), ("B", c_int), ("dtype", c_int),
+        ("vtrans_scale", c_double), ("vrot_scale", c_double),
+        ("ge", POINTER(c_double)), ("gi", POINTER(c_double)),
+        ("aE", c_double), ("aI", c_double),
+        ("f2d", POINTER(c_double)), ("f1d", POINTER(c_double)),
+        ("cos_th", POINTER(c_double)), ("sin_th", POINTER(c_double)),
+    ]
+
+
+_SIGNATURES = {
+    "prs_last_error": (c_char_p, []),
+    "prs_version": (c_int, []),
+    "prs_device_count": (c_int, []),
+    "prs_pc_create": (c_int, [POINTER(PcConfig), POINTER(c_void_p)]),
+    "prs_pc_destroy": (c_int, [c_void_p]),
+    "prs_pc_state_bytes": (c_size_t, [c_void_p]),
+    "prs_pc_path": (c_int, [c_void_p]),
+    "prs_pc_force_generic": (c_int, [c_void_p, c_int]),
+    "prs_pc_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "prs_pc_run": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "prs_pc_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "prs_pc_path_integration": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "prs_pc_inject": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p]),
+    "prs_pc_argmax": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "prs_pc_import_xyt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "prs_pc_export_xyt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "prs_vt_extract_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_int, c_int, c_void_p]),
+    "prs_vt_sweep_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
+    "prs_vt_sweep_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
+    "prs_vt_match_host_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (loads on first use)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                "%s is missing: build it with `python -m pyratslam_b200.build` (needs nvcc). "
+                "pyratslam_b200 has no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().prs_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError("%s: %s" % (what, msg) if what else msg)
+        raise NativeError("%s failed (%d): %s" % (what, rc, msg))
+
+
+def stream_ptr():
+    """The current torch CUDA stream as a void* for the C ABI."""
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise NativeError("pyratslam_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    lib()

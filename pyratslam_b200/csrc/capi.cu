@@ -1,0 +1,214 @@
+// C ABI glue: error reporting, plan life-cycle and the dispatch between the generic
+// multi-kernel path and the fused SMEM-resident kernel.  See include/pyratslam_b200.h.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void prs_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* prs_last_error(void) { return g_err; }
+extern "C" int prs_version(void) { return 100; }
+
+extern "C" int prs_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    prs_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return PRS_E_NODEVICE;
+  }
+  return n;
+}
+
+template <typename T>
+static void fill_tables(PcTables<T>& t, const prs_pc_config* c) {
+  for (int i = 0; i < 7; ++i) {
+    t.ge[i] = (T)c->ge[i];
+    t.gi[i] = (T)c->gi[i];
+    t.gex[i] = (T)(c->aE * c->ge[i]);
+    t.gix[i] = (T)(c->aI * c->gi[i]);
+  }
+  for (int f = 0; f < 2; ++f)
+    for (int i = 0; i < 49; ++i) t.f2d[f][i] = (T)c->f2d[f * 49 + i];
+  for (int o = 0; o < PRS_NOG; ++o)
+    for (int i = 0; i < 7; ++i) t.f1d[o][i] = (T)c->f1d[o * 7 + i];
+}
+
+static void free_plan(prs_pc_plan* p) {
+  void* ptrs[] = {p->cos_th, p->sin_th, p->s1,       p->s2,        p->s3,     p->s4,       p->shift, p->fsel,
+                  p->ogi,    p->part_val, p->part_idx, p->inv_total, p->d_odom, p->d_argmax, p->d_err, p->d_total,
+                  p->tab_dev};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  delete p;
+}
+
+extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
+  PRS_REQUIRE(cfg && out, "prs_pc_create: null argument");
+  PRS_REQUIRE(cfg->X >= 3 && cfg->Y >= 3 && cfg->Th >= 3,
+              "prs_pc_create: every grid dimension must be >= 3 (7-tap periodic filters), got %dx%dx%d", cfg->X,
+              cfg->Y, cfg->Th);
+  PRS_REQUIRE(cfg->B >= 1 && cfg->B <= 65535, "prs_pc_create: B must be in [1, 65535], got %d", cfg->B);
+  PRS_REQUIRE(cfg->Th <= 65535, "prs_pc_create: Th must be <= 65535");
+  PRS_REQUIRE((long long)cfg->X * cfg->Y * cfg->Th < (1LL << 31), "prs_pc_create: grid too large");
+  PRS_REQUIRE(cfg->dtype == PRS_F32 || cfg->dtype == PRS_F64, "prs_pc_create: dtype must be PRS_F32 or PRS_F64");
+  PRS_REQUIRE(cfg->ge && cfg->gi && cfg->f2d && cfg->f1d && cfg->cos_th && cfg->sin_th, "prs_pc_create: null table");
+  PRS_REQUIRE(cfg->vtrans_scale > 0 && cfg->vrot_scale > 0, "prs_pc_create: scales must be positive");
+  int ndev = prs_device_count();
+  if (ndev <= 0) {
+    prs_set_error("prs_pc_create: no CUDA device (this library has no CPU path)");
+    return PRS_E_NODEVICE;
+  }
+  prs_pc_plan* p = new (std::nothrow) prs_pc_plan();
+  PRS_REQUIRE(p, "prs_pc_create: out of host memory");
+  memset(p, 0, sizeof(*p));
+  p->X = cfg->X;
+  p->Y = cfg->Y;
+  p->Th = cfg->Th;
+  p->B = cfg->B;
+  p->dtype = cfg->dtype;
+  p->N = (long long)cfg->X * cfg->Y * cfg->Th;
+  p->vtrans_scale = cfg->vtrans_scale;
+  p->vrot_scale = cfg->vrot_scale;
+  fill_tables(p->tf, cfg);
+  fill_tables(p->td, cfg);
+  const size_t es = cfg->dtype == PRS_F32 ? 4 : 8;
+  const size_t sbytes = (size_t)p->B * p->N * es;
+  p->nblk_plane = (p->X * p->Y + 255) / 256;
+  const size_t np = (size_t)p->B * p->Th * p->nblk_plane;
+#define ALLOC(ptr, bytes)                                                        \
+  do {                                                                           \
+    cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                        \
+    if (e_ != cudaSuccess) {                                                     \
+      prs_set_error("prs_pc_create: cudaMalloc(%zu): %s", (size_t)(bytes), cudaGetErrorString(e_)); \
+      free_plan(p);                                                              \
+      return PRS_E_CUDA;                                                         \
+    }                                                                            \
+  } while (0)
+  ALLOC(p->cos_th, p->Th * sizeof(double));
+  ALLOC(p->sin_th, p->Th * sizeof(double));
+  ALLOC(p->shift, (size_t)p->B * p->Th * 2 * sizeof(int));
+  ALLOC(p->fsel, (size_t)p->B * p->Th);
+  ALLOC(p->ogi, (size_t)p->B * sizeof(int));
+  ALLOC(p->part_val, np * es);
+  ALLOC(p->part_idx, np * sizeof(long long));
+  ALLOC(p->inv_total, (size_t)p->B * es);
+  ALLOC(p->d_odom, (size_t)p->B * 2 * sizeof(double));
+  ALLOC(p->d_argmax, (size_t)p->B * sizeof(long long));
+  ALLOC(p->d_err, (size_t)p->B * sizeof(int));
+  ALLOC(p->d_total, (size_t)p->B * es);
+  ALLOC(p->tab_dev, sizeof(PcTables<float>));
+  p->resident_ok = prs_pc_resident_supported(p);
+  // The generic path's four scratch tensors are only allocated when that path can be taken
+  // for this plan; prs_pc_force_generic allocates them lazily otherwise.
+  if (!p->resident_ok) {
+    ALLOC(p->s1, sbytes);
+    ALLOC(p->s2, sbytes);
+    ALLOC(p->s3, sbytes);
+    ALLOC(p->s4, sbytes);
+  }
+#undef ALLOC
+  cudaError_t e = cudaMemcpy(p->cos_th, cfg->cos_th, p->Th * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(p->sin_th, cfg->sin_th, p->Th * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(p->tab_dev, &p->tf, sizeof(PcTables<float>), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    prs_set_error("prs_pc_create: table upload: %s", cudaGetErrorString(e));
+    free_plan(p);
+    return PRS_E_CUDA;
+  }
+  *out = p;
+  return PRS_OK;
+}
+
+extern "C" int prs_pc_destroy(prs_pc_handle h) {
+  if (h) free_plan(h);
+  return PRS_OK;
+}
+
+extern "C" size_t prs_pc_state_bytes(prs_pc_handle h) {
+  return h ? (size_t)h->B * h->N * (h->dtype == PRS_F32 ? 4 : 8) : 0;
+}
+
+static int ensure_scratch(prs_pc_handle h) {
+  if (!h->s1) {
+    const size_t sbytes = prs_pc_state_bytes(h);
+    void** slots[] = {&h->s1, &h->s2, &h->s3, &h->s4};
+    for (void** s : slots) PRS_CUDA(cudaMalloc(s, sbytes));
+  }
+  return PRS_OK;
+}
+
+extern "C" int prs_pc_path(prs_pc_handle h) { return (h && h->resident_ok && !h->force_generic) ? 1 : 0; }
+
+extern "C" int prs_pc_force_generic(prs_pc_handle h, int on) {
+  PRS_REQUIRE(h, "prs_pc_force_generic: null handle");
+  if (on) {
+    int rc = ensure_scratch(h);
+    if (rc != PRS_OK) return rc;
+  }
+  h->force_generic = on ? 1 : 0;
+  return PRS_OK;
+}
+
+static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T, const void* gi, long long* argmax,
+                         void* total, int* err, cudaStream_t st) {
+  const size_t es = h->dtype == PRS_F32 ? 4 : 8;
+  if (prs_pc_path(h) == 1) return prs_pc_resident_step(h, state, odom, T, gi, argmax, total, err, st);
+  for (int t = 0; t < T; ++t) {
+    int rc = prs_pc_generic_step(h, state, odom + (size_t)t * h->B * 2, gi, argmax + (size_t)t * h->B,
+                                 (char*)total + (size_t)t * h->B * es, err, st);
+    if (rc != PRS_OK) return rc;
+  }
+  return PRS_OK;
+}
+
+extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, const void* gi, long long* argmax,
+                           void* total, int* err, void* stream) {
+  PRS_REQUIRE(h && state && odom && gi && argmax && total && err, "prs_pc_step: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
+  return step_dispatch(h, state, odom, 1, gi, argmax, total, err, st);
+}
+
+extern "C" int prs_pc_path_integration(prs_pc_handle h, void* state, const double* odom, int* err, void* stream) {
+  PRS_REQUIRE(h && state && odom && err, "prs_pc_path_integration: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_scratch(h);
+  if (rc != PRS_OK) return rc;
+  PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
+  return prs_pc_generic_path_integration(h, state, odom, err, st);
+}
+
+extern "C" int prs_pc_run(prs_pc_handle h, void* state, const double* odom, int T, const void* gi, long long* argmax,
+                          void* total, int* err, void* stream) {
+  PRS_REQUIRE(h && state && odom && gi && argmax && total && err, "prs_pc_run: null argument");
+  PRS_REQUIRE(T >= 0, "prs_pc_run: negative step count");
+  cudaStream_t st = (cudaStream_t)stream;
+  PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
+  if (T == 0) return PRS_OK;
+  return step_dispatch(h, state, odom, T, gi, argmax, total, err, st);
+}
+
+extern "C" int prs_pc_step_host(prs_pc_handle h, void* state, const double* odom_host, const void* gi,
+                                long long* argmax_host, int* err_host, void* stream) {
+  PRS_REQUIRE(h && state && odom_host && gi && argmax_host && err_host, "prs_pc_step_host: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PRS_CUDA(cudaMemcpyAsync(h->d_odom, odom_host, (size_t)h->B * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = prs_pc_step(h, state, h->d_odom, gi, h->d_argmax, h->d_total, h->d_err, st);
+  if (rc != PRS_OK) return rc;
+  PRS_CUDA(cudaMemcpyAsync(argmax_host, h->d_argmax, (size_t)h->B * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  PRS_CUDA(cudaMemcpyAsync(err_host, h->d_err, (size_t)h->B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  PRS_CUDA(cudaStreamSynchronize(st));
+  return PRS_OK;
+}

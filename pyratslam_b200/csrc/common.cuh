@@ -1,0 +1,83 @@
+// Shared declarations for the pyratslam_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pyratslam_b200.h"
+
+void prs_set_error(const char* fmt, ...);
+
+#define PRS_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      prs_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));        \
+      return PRS_E_CUDA;                                                                       \
+    }                                                                                          \
+  } while (0)
+
+#define PRS_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      prs_set_error(__VA_ARGS__);   \
+      return PRS_E_INVALID;         \
+    }                               \
+  } while (0)
+
+#define PRS_NOG (2 * PRS_OG_RANGE + 1)
+
+// Filter tables in the arithmetic type of the plan.  Passed to kernels by value
+// (kernel parameter space = constant bank, 1960 bytes for double).
+template <typename T>
+struct PcTables {
+  T ge[7], gi[7];    // theta and y passes of the separable E / I Gaussians
+  T gex[7], gix[7];  // x pass with the amplitudes aE, aI folded in
+  T f2d[2][49];      // F0 and F-1 of the path-integration LUT, [a*7+b]
+  T f1d[PRS_NOG][7]; // theta filters for og = -PRS_OG_RANGE..PRS_OG_RANGE
+};
+
+struct prs_pc_plan {
+  int X, Y, Th, B, dtype;
+  long long N;  // cells per network
+  double vtrans_scale, vrot_scale;
+  PcTables<float> tf;
+  PcTables<double> td;
+  double* cos_th;  // device [Th]
+  double* sin_th;
+  // generic path scratch, each [B][N] of dtype
+  void *s1, *s2, *s3, *s4;
+  int* shift;           // [B][Th][2] integer origins (ox, oy)
+  unsigned char* fsel;  // [B][Th] 0 = F0, 1 = F-1
+  int* ogi;             // [B] index into f1d
+  int nblk_plane;       // blocks per theta plane in the generic kernels
+  void* part_val;       // [B][Th*nblk_plane] partial sums, later partial maxima
+  long long* part_idx;  // [B][Th*nblk_plane]
+  void* inv_total;      // [B]
+  // staging for the *_host entry points
+  double* d_odom;
+  long long* d_argmax;
+  int* d_err;
+  void* d_total;
+  int force_generic;
+  int resident_ok;      // the fused SMEM-resident kernel supports this shape/dtype
+  void* tab_dev;        // device copy of PcTables<float> for the resident kernel
+};
+
+// launchers implemented per translation unit
+int prs_pc_generic_step(prs_pc_plan* p, void* state, const double* odom, const void* gi, long long* argmax,
+                        void* total, int* err, cudaStream_t st);
+int prs_pc_generic_path_integration(prs_pc_plan* p, void* state, const double* odom, int* err, cudaStream_t st);
+int prs_pc_generic_argmax(prs_pc_plan* p, const void* state, long long* argmax, cudaStream_t st);
+int prs_pc_resident_supported(const prs_pc_plan* p);
+int prs_pc_resident_step(prs_pc_plan* p, void* state, const double* odom, int T, const void* gi, long long* argmax,
+                         void* total, int* err, cudaStream_t st);
+
+// ---- small device helpers -------------------------------------------------
+__device__ __forceinline__ int wrap1(int v, int n) {  // valid for -n <= v < 2n
+  v = v < 0 ? v + n : v;
+  return v >= n ? v - n : v;
+}
+__device__ __forceinline__ int modp(int v, int n) {  // any v
+  int r = v % n;
+  return r < 0 ? r + n : r;
+}

@@ -1,0 +1,420 @@
+// Generic pose-cell update: any grid shape, float or double, any batch.
+//
+// One PoseCellNetwork.update() (ratslam/posecell_network.py:326-353) as a short
+// sequence of kernels over the theta-major state [B][Th][X][Y] kept in HBM/L2:
+//
+//   k_plan         odometry -> integer origins, LUT filter choice, theta origin   (:252-267,249,304)
+//   k_dog_theta    E,I = ge*P, gi*P along theta   \  the 7x7x7 DoG correlate of :336 (convolution.py
+//   k_dog_y        E,I along y                     > :228-246) as separable E - I: kernel_3d ==
+//   k_dog_x_inhib  A = max(aE*E - aI*I - gi, 0)   /  aE ge(x)ge(x)ge - aI gi(x)gi(x)gi; inhibition :339-340,
+//                  + per-block partial sums                                        sum for :343
+//   k_sum_final    total, 1/total                                                  (:343-345)
+//   k_shift2d      per-plane shifted 7x7 correlate, * 1/total, clamp               (:273-274,300; convolution.py:320-340)
+//   k_theta_final  7-tap theta correlate, clamp, per-block arg-max                 (:304-314; convolution.py:344-359)
+//   k_argmax_final first maximum in the reference's C order [x][y][th]             (:317-319)
+//
+// The normalisation is applied after the 2-D stage instead of before it: every
+// operation in between is linear or a clamp at zero, so only rounding differs.
+// This path is the strict-parity (float64) implementation and the one used for
+// shapes the fused SMEM-resident kernel (posecell_resident.cu) does not cover.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T>
+__device__ __forceinline__ T fma_t(T a, T b, T c);
+template <>
+__device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <>
+__device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+
+// ---------------------------------------------------------------------------
+// Decisions of one path-integration step, bit-for-bit the float64 arithmetic numpy does on the host
+// (explicit _rn intrinsics keep the compiler from contracting mul+sub into an FMA).
+__global__ void k_plan(const double* __restrict__ odom, const double* __restrict__ cos_th,
+                       const double* __restrict__ sin_th, int B, int Th, int minXY, double vtrans_scale,
+                       double vrot_scale, int* __restrict__ shift, unsigned char* __restrict__ fsel,
+                       int* __restrict__ ogi, int* __restrict__ err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Th) return;
+  int b = i / Th, k = i - b * Th;
+  double vt = __ddiv_rn(odom[2 * b], vtrans_scale);
+  double ex = __dmul_rn(vt, cos_th[k]);
+  double ey = __dmul_rn(vt, sin_th[k]);
+  double oxd = rint(ex), oyd = rint(ey);  // numpy.around: half to even
+  double dx = __dsub_rn(ex, oxd);
+  int key = (int)__dmul_rn(dx, 10.0);  // int(): truncation toward zero
+  shift[2 * i] = (int)oxd;
+  shift[2 * i + 1] = (int)oyd;
+  fsel[i] = key < 0 ? 1 : 0;
+  int e = 0;
+  if (key >= 5) e |= PRS_ERR_LUT_KEY;
+  if (k == 0) {
+    double radius = ceil(fabs(vt));
+    if (!(3.0 + radius <= (double)minXY)) e |= PRS_ERR_RADIUS;
+    double vr = __ddiv_rn(odom[2 * b + 1], vrot_scale);
+    double og = floor(__dadd_rn(vr, 0.5));
+    if (!(fabs(og) <= 64.0)) e |= PRS_ERR_THETA;
+    int ogc = og < -(double)PRS_OG_RANGE ? -PRS_OG_RANGE : (og > (double)PRS_OG_RANGE ? PRS_OG_RANGE : (int)og);
+    ogi[b] = ogc + PRS_OG_RANGE;
+  }
+  if (e) atomicOr(&err[b], e);  // err[] is zeroed by the caller (prs_pc_step) and OR-ed across steps (prs_pc_run)
+}
+
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_dog_theta(const T* __restrict__ P, T* __restrict__ E, T* __restrict__ I,
+                                                        int XY, int Th, PcTables<T> tab) {
+  int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= XY) return;
+  int k = blockIdx.y;
+  size_t base = (size_t)blockIdx.z * Th * XY;
+  T e = 0, i = 0;
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    int kk = wrap1(k + t - 3, Th);
+    T v = P[base + (size_t)kk * XY + p];
+    e = fma_t(tab.ge[t], v, e);
+    i = fma_t(tab.gi[t], v, i);
+  }
+  size_t o = base + (size_t)k * XY + p;
+  E[o] = e;
+  I[o] = i;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_dog_y(const T* __restrict__ Ei, const T* __restrict__ Ii, T* __restrict__ E,
+                                                    T* __restrict__ I, int X, int Y, int Th, PcTables<T> tab) {
+  int XY = X * Y;
+  int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= XY) return;
+  int x = p / Y, y = p - x * Y;
+  size_t row = ((size_t)blockIdx.z * Th + blockIdx.y) * XY + (size_t)x * Y;
+  T e = 0, i = 0;
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    int yy = wrap1(y + t - 3, Y);
+    e = fma_t(tab.ge[t], Ei[row + yy], e);
+    i = fma_t(tab.gi[t], Ii[row + yy], i);
+  }
+  E[row + y] = e;
+  I[row + y] = i;
+}
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = l < (kThreads / 32) ? sm[l] : T(0);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v;  // valid in thread 0
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    k_dog_x_inhib(const T* __restrict__ Ei, const T* __restrict__ Ii, T* __restrict__ A, const T* __restrict__ gi, int X,
+                  int Y, int Th, PcTables<T> tab, T* __restrict__ part) {
+  __shared__ T sm[kThreads / 32];
+  int XY = X * Y;
+  int p = blockIdx.x * kThreads + threadIdx.x;
+  T a = 0;
+  if (p < XY) {
+    int x = p / Y, y = p - x * Y;
+    size_t plane = ((size_t)blockIdx.z * Th + blockIdx.y) * XY;
+    T e = 0, i = 0;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      int xx = wrap1(x + t - 3, X);
+      e = fma_t(tab.gex[t], Ei[plane + (size_t)xx * Y + y], e);
+      i = fma_t(tab.gix[t], Ii[plane + (size_t)xx * Y + y], i);
+    }
+    a = e - i;
+    T g = gi[blockIdx.z];
+    a = (a < g) ? T(0) : a - g;  // posecell_network.py:339-340
+    A[plane + p] = a;
+  }
+  T s = block_sum(a, sm);
+  if (threadIdx.x == 0) part[((size_t)blockIdx.z * Th + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_sum_final(const T* __restrict__ part, int np, T* __restrict__ total,
+                                                        T* __restrict__ inv_total) {
+  __shared__ T sm[kThreads / 32];
+  const T* p = part + (size_t)blockIdx.x * np;
+  T s = 0;
+  for (int i = threadIdx.x; i < np; i += kThreads) s += p[i];
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) {
+    total[blockIdx.x] = s;
+    inv_total[blockIdx.x] = (s != T(0)) ? T(1) / s : T(1);  // posecell_network.py:344-345
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    k_shift2d(const T* __restrict__ A, T* __restrict__ Bp, const int* __restrict__ shift,
+              const unsigned char* __restrict__ fsel, const T* __restrict__ inv_total, int X, int Y, int Th,
+              PcTables<T> tab) {
+  int XY = X * Y;
+  int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= XY) return;
+  int x = p / Y, y = p - x * Y;
+  int bk = blockIdx.z * Th + blockIdx.y;
+  size_t plane = (size_t)bk * XY;
+  int ox = shift[2 * bk], oy = shift[2 * bk + 1];
+  const T* F = tab.f2d[fsel[bk]];
+  int xs[7], ys[7];
+  int sx = modp(x + ox - 3, X), sy = modp(y + oy - 3, Y);
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    xs[t] = (sx + t) % X;
+    ys[t] = (sy + t) % Y;
+  }
+  T acc = 0;
+#pragma unroll
+  for (int a = 0; a < 7; ++a) {
+    const T* row = A + plane + (size_t)xs[a] * Y;
+#pragma unroll
+    for (int b = 0; b < 7; ++b) acc = fma_t(F[a * 7 + b], row[ys[b]], acc);
+  }
+  acc *= inv_total[blockIdx.z];
+  Bp[plane + p] = (acc < T(0)) ? T(0) : acc;  // posecell_network.py:300
+}
+
+template <typename T>
+__device__ __forceinline__ void amax_combine(T& v, long long& i, T v2, long long i2) {
+  if (v2 > v || (v2 == v && i2 < i)) {
+    v = v2;
+    i = i2;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void block_argmax(T& v, long long& idx, T* smv, long long* smi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    T v2 = __shfl_down_sync(0xffffffffu, v, o);
+    long long i2 = __shfl_down_sync(0xffffffffu, idx, o);
+    amax_combine(v, idx, v2, i2);
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    smv[w] = v;
+    smi[w] = idx;
+  }
+  __syncthreads();
+  if (w == 0) {
+    if (l < kThreads / 32) {
+      v = smv[l];
+      idx = smi[l];
+    } else {
+      v = -INFINITY;
+      idx = 0x7fffffffffffffffLL;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      T v2 = __shfl_down_sync(0xffffffffu, v, o);
+      long long i2 = __shfl_down_sync(0xffffffffu, idx, o);
+      amax_combine(v, idx, v2, i2);
+    }
+  }
+}
+
+// FINAL == true : theta correlate + clamp + store + partial arg-max (update step)
+// FINAL == false: partial arg-max of an existing state (get_pc_max without update)
+template <typename T, bool FINAL>
+__global__ void __launch_bounds__(kThreads)
+    k_theta_final(const T* __restrict__ Bp, T* __restrict__ S, const int* __restrict__ ogi, int X, int Y, int Th,
+                  PcTables<T> tab, T* __restrict__ part_val, long long* __restrict__ part_idx) {
+  __shared__ T smv[kThreads / 32];
+  __shared__ long long smi[kThreads / 32];
+  int XY = X * Y;
+  int p = blockIdx.x * kThreads + threadIdx.x;
+  int k = blockIdx.y;
+  size_t base = (size_t)blockIdx.z * Th * XY;
+  T c = -INFINITY;
+  long long idx = 0x7fffffffffffffffLL;
+  if (p < XY) {
+    if (FINAL) {
+      const T* f = tab.f1d[ogi[blockIdx.z]];
+      c = 0;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) c = fma_t(f[t], Bp[base + (size_t)wrap1(k + t - 3, Th) * XY + p], c);
+      c = (c < T(0)) ? T(0) : c;  // posecell_network.py:314
+      S[base + (size_t)k * XY + p] = c;
+    } else {
+      c = Bp[base + (size_t)k * XY + p];
+    }
+    idx = (long long)p * Th + k;  // reference flat index (x*Y + y)*Th + th
+  }
+  block_argmax(c, idx, smv, smi);
+  if (threadIdx.x == 0) {
+    size_t o = ((size_t)blockIdx.z * Th + blockIdx.y) * gridDim.x + blockIdx.x;
+    part_val[o] = c;
+    part_idx[o] = idx;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_argmax_final(const T* __restrict__ part_val,
+                                                           const long long* __restrict__ part_idx, int np,
+                                                           long long* __restrict__ argmax) {
+  __shared__ T smv[kThreads / 32];
+  __shared__ long long smi[kThreads / 32];
+  const T* pv = part_val + (size_t)blockIdx.x * np;
+  const long long* pi = part_idx + (size_t)blockIdx.x * np;
+  T v = -INFINITY;
+  long long idx = 0x7fffffffffffffffLL;
+  for (int i = threadIdx.x; i < np; i += kThreads) amax_combine(v, idx, pv[i], pi[i]);
+  block_argmax(v, idx, smv, smi);
+  if (threadIdx.x == 0) argmax[blockIdx.x] = idx;
+}
+
+template <typename T>
+__global__ void k_fill(T* p, int n, T v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+template <typename T>
+__global__ void k_inject(T* state, size_t off, T energy) {
+  state[off] += energy;
+}
+
+// xyt[b][x][y][th]  <->  state[b][th][x][y]
+template <typename T, bool IMPORT>
+__global__ void __launch_bounds__(kThreads) k_transpose(T* __restrict__ state, T* __restrict__ xyt, int XY, int Th) {
+  int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= XY) return;
+  size_t base = (size_t)blockIdx.z * Th * XY;
+  int k = blockIdx.y;
+  if (IMPORT)
+    state[base + (size_t)k * XY + p] = xyt[base + (size_t)p * Th + k];
+  else
+    xyt[base + (size_t)p * Th + k] = state[base + (size_t)k * XY + p];
+}
+
+template <typename T>
+int generic_step_t(prs_pc_plan* p, const PcTables<T>& tab, T* state, const double* odom, const T* gi, long long* argmax,
+                   T* total, int* err, cudaStream_t st) {
+  const int X = p->X, Y = p->Y, Th = p->Th, B = p->B, XY = X * Y;
+  dim3 grid(p->nblk_plane, Th, B);
+  const int np = Th * p->nblk_plane;
+  T *s1 = (T*)p->s1, *s2 = (T*)p->s2, *s3 = (T*)p->s3, *s4 = (T*)p->s4;
+  int nbt = B * Th;
+  k_plan<<<(nbt + 127) / 128, 128, 0, st>>>(odom, p->cos_th, p->sin_th, B, Th, X < Y ? X : Y, p->vtrans_scale,
+                                            p->vrot_scale, p->shift, p->fsel, p->ogi, err);
+  k_dog_theta<T><<<grid, kThreads, 0, st>>>(state, s1, s2, XY, Th, tab);
+  k_dog_y<T><<<grid, kThreads, 0, st>>>(s1, s2, s3, s4, X, Y, Th, tab);
+  k_dog_x_inhib<T><<<grid, kThreads, 0, st>>>(s3, s4, s1, gi, X, Y, Th, tab, (T*)p->part_val);
+  k_sum_final<T><<<B, kThreads, 0, st>>>((const T*)p->part_val, np, total, (T*)p->inv_total);
+  k_shift2d<T><<<grid, kThreads, 0, st>>>(s1, s2, p->shift, p->fsel, (const T*)p->inv_total, X, Y, Th, tab);
+  k_theta_final<T, true><<<grid, kThreads, 0, st>>>(s2, state, p->ogi, X, Y, Th, tab, (T*)p->part_val, p->part_idx);
+  k_argmax_final<T><<<B, kThreads, 0, st>>>((const T*)p->part_val, p->part_idx, np, argmax);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+template <typename T>
+int generic_path_integration_t(prs_pc_plan* p, const PcTables<T>& tab, T* state, const double* odom, int* err,
+                               cudaStream_t st) {
+  const int X = p->X, Y = p->Y, Th = p->Th, B = p->B;
+  dim3 grid(p->nblk_plane, Th, B);
+  int nbt = B * Th;
+  k_plan<<<(nbt + 127) / 128, 128, 0, st>>>(odom, p->cos_th, p->sin_th, B, Th, X < Y ? X : Y, p->vtrans_scale,
+                                            p->vrot_scale, p->shift, p->fsel, p->ogi, err);
+  k_fill<T><<<(B + 127) / 128, 128, 0, st>>>((T*)p->inv_total, B, T(1));
+  k_shift2d<T><<<grid, kThreads, 0, st>>>(state, (T*)p->s2, p->shift, p->fsel, (const T*)p->inv_total, X, Y, Th, tab);
+  k_theta_final<T, true><<<grid, kThreads, 0, st>>>((const T*)p->s2, state, p->ogi, X, Y, Th, tab, (T*)p->part_val,
+                                                    p->part_idx);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+}  // namespace
+
+int prs_pc_generic_path_integration(prs_pc_plan* p, void* state, const double* odom, int* err, cudaStream_t st) {
+  if (p->dtype == PRS_F32) return generic_path_integration_t<float>(p, p->tf, (float*)state, odom, err, st);
+  return generic_path_integration_t<double>(p, p->td, (double*)state, odom, err, st);
+}
+
+int prs_pc_generic_step(prs_pc_plan* p, void* state, const double* odom, const void* gi, long long* argmax, void* total,
+                        int* err, cudaStream_t st) {
+  if (p->dtype == PRS_F32)
+    return generic_step_t<float>(p, p->tf, (float*)state, odom, (const float*)gi, argmax, (float*)total, err, st);
+  return generic_step_t<double>(p, p->td, (double*)state, odom, (const double*)gi, argmax, (double*)total, err, st);
+}
+
+int prs_pc_generic_argmax(prs_pc_plan* p, const void* state, long long* argmax, cudaStream_t st) {
+  dim3 grid(p->nblk_plane, p->Th, p->B);
+  const int np = p->Th * p->nblk_plane;
+  if (p->dtype == PRS_F32) {
+    k_theta_final<float, false><<<grid, kThreads, 0, st>>>((const float*)state, nullptr, nullptr, p->X, p->Y, p->Th, p->tf,
+                                                           (float*)p->part_val, p->part_idx);
+    k_argmax_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, p->part_idx, np, argmax);
+  } else {
+    k_theta_final<double, false><<<grid, kThreads, 0, st>>>((const double*)state, nullptr, nullptr, p->X, p->Y, p->Th,
+                                                            p->td, (double*)p->part_val, p->part_idx);
+    k_argmax_final<double><<<p->B, kThreads, 0, st>>>((const double*)p->part_val, p->part_idx, np, argmax);
+  }
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+// ---------------------------------------------------------------------------- C ABI (shape-independent parts)
+extern "C" int prs_pc_inject(prs_pc_handle h, void* state, int b, int x, int y, int th, double energy, void* stream) {
+  PRS_REQUIRE(h && state, "prs_pc_inject: null argument");
+  PRS_REQUIRE(b >= 0 && b < h->B && x >= 0 && x < h->X && y >= 0 && y < h->Y && th >= 0 && th < h->Th,
+              "prs_pc_inject: location (%d,%d,%d) of network %d is outside the %dx%dx%d grid", x, y, th, b, h->X, h->Y,
+              h->Th);
+  size_t off = ((size_t)b * h->Th + th) * h->X * h->Y + (size_t)x * h->Y + y;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->dtype == PRS_F32)
+    k_inject<float><<<1, 1, 0, st>>>((float*)state, off, (float)energy);
+  else
+    k_inject<double><<<1, 1, 0, st>>>((double*)state, off, energy);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+extern "C" int prs_pc_argmax(prs_pc_handle h, const void* state, long long* argmax, void* stream) {
+  PRS_REQUIRE(h && state && argmax, "prs_pc_argmax: null argument");
+  return prs_pc_generic_argmax(h, state, argmax, (cudaStream_t)stream);
+}
+
+static int transpose(prs_pc_handle h, void* state, void* xyt, bool import, cudaStream_t st) {
+  dim3 grid(h->nblk_plane, h->Th, h->B);
+  int XY = h->X * h->Y;
+  if (h->dtype == PRS_F32) {
+    if (import)
+      k_transpose<float, true><<<grid, kThreads, 0, st>>>((float*)state, (float*)xyt, XY, h->Th);
+    else
+      k_transpose<float, false><<<grid, kThreads, 0, st>>>((float*)state, (float*)xyt, XY, h->Th);
+  } else {
+    if (import)
+      k_transpose<double, true><<<grid, kThreads, 0, st>>>((double*)state, (double*)xyt, XY, h->Th);
+    else
+      k_transpose<double, false><<<grid, kThreads, 0, st>>>((double*)state, (double*)xyt, XY, h->Th);
+  }
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+extern "C" int prs_pc_import_xyt(prs_pc_handle h, void* state, const void* xyt, void* stream) {
+  PRS_REQUIRE(h && state && xyt, "prs_pc_import_xyt: null argument");
+  return transpose(h, state, const_cast<void*>(xyt), true, (cudaStream_t)stream);
+}
+
+extern "C" int prs_pc_export_xyt(prs_pc_handle h, const void* state, void* xyt, void* stream) {
+  PRS_REQUIRE(h && state && xyt, "prs_pc_export_xyt: null argument");
+  return transpose(h, const_cast<void*>(state), xyt, false, (cudaStream_t)stream);
+}

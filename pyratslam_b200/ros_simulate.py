@@ -1,0 +1,101 @@
+"""Offline replay of the ROS node's update loop (``ratslam/ros_simulate.py``) on the GPU path.
+
+ROS itself (rospy, cv_bridge, rosbag) is transport and out of scope; what is kept is what the node
+computes per message (``ros_simulate.py:52-57,67-70,98-105,125-137,152-166``):
+
+* odometry twist ``(linear.x, angular.z)``: dropped unless one component exceeds 0.001 in magnitude,
+  else ``vtrans = linear.x / 10``, ``vrot = angular.z / 10`` -> ``PoseCellNetwork.update`` ->
+  ``ExperienceMap.update`` with the arg-max cell;
+* camera frame (mono8, 256x256): ``ViewTemplates.match`` with the current arg-max cell -> template index.
+
+The live node interleaves these on two threads; the replay fixes the order per time step as
+odometry first, then the frame (the same order the oracle's ``replay_run`` uses).
+"""
+from __future__ import annotations
+
+import math
+from collections import deque
+
+import numpy as np
+
+from .experience_map import ExperienceMap
+from .posecell_network import PoseCellNetwork
+from .view_templates import ViewTemplates
+
+POSE_SIZE = (21, 21, 36)
+IM_SIZE = (256, 256)
+X_RANGE = (32, 96)
+Y_RANGE = (32, 96)
+X_STEP = 2
+Y_STEP = 2
+MATCH_THRESHOLD = 45000
+ODOM_FREQ = 10
+
+
+class RatslamRos(object):
+    """The node's state and callbacks, fed from arrays instead of ROS topics."""
+
+    def __init__(self, pose_size=POSE_SIZE, match_threshold=MATCH_THRESHOLD, **pcn_kwargs):
+        self.im_count = 0
+        self.pcn = PoseCellNetwork(shape=pose_size, **pcn_kwargs)
+        self.pc_count = 0
+        self.twist_data = deque()
+        self.odom_freq = ODOM_FREQ
+        midpoint = (math.floor(pose_size[0] / 2), math.floor(pose_size[1] / 2), math.floor(pose_size[2] / 2))
+        self.pcn.inject(1, midpoint)
+        self.vts = ViewTemplates(x_range=X_RANGE, y_range=Y_RANGE, x_step=X_STEP, y_step=Y_STEP,
+                                 im_x=IM_SIZE[0], im_y=IM_SIZE[1], match_threshold=match_threshold)
+        self.vt_count = 0
+        self.em = ExperienceMap()
+        self.em_count = 0
+        self.published_index = []
+        self.published_pose = []
+
+    # ros_simulate.py:98-105 (image already decoded to a uint8 array)
+    def vis_callback(self, im):
+        pc_max = self.pcn.get_pc_max()
+        n0 = len(self.vts.templates)
+        tm = self.vts.match(input=im, pc_x=pc_max[0], pc_y=pc_max[1], pc_th=pc_max[2])
+        index = tm.get_index()
+        self.published_index.append(index)
+        return index, len(self.vts.templates) > n0
+
+    # ros_simulate.py:125-129 (twist as a (linear.x, angular.z) pair)
+    def odom_callback(self, twist):
+        if abs(twist[0]) > 0.001 or abs(twist[1]) > 0.001:
+            self.twist_data.append(twist)
+
+    # ros_simulate.py:134-146
+    def update_posecells(self, vtrans, vrot):
+        pc_max = self.pcn.update((vtrans, vrot))
+        self.em.update(vtrans, vrot, pc_max)
+        self.published_pose.append(self.em.get_current_point())
+
+    # ros_simulate.py:152-166, one pass of the loop body
+    def spin_once(self):
+        if self.twist_data:
+            twist = self.twist_data.popleft()
+            self.update_posecells(twist[0] / self.odom_freq, twist[1] / self.odom_freq)
+            return True
+        return False
+
+
+def replay(frames, odom, **kwargs):
+    """Run the loop over ``frames[T,256,256]`` (uint8) and ``odom[T,2]``; returns per-frame records."""
+    node = RatslamRos(**kwargs)
+    T = len(frames)
+    rec = {"template": np.zeros(T, np.int64), "created": np.zeros(T, np.bool_),
+           "argmax": np.zeros((T, 3), np.int64), "n_exp": np.zeros(T, np.int64), "em_xy": np.zeros((T, 2))}
+    for t in range(T):
+        node.odom_callback((float(odom[t, 0]), float(odom[t, 1])))
+        node.spin_once()
+        rec["argmax"][t] = node.pcn.get_pc_max()
+        idx, created = node.vis_callback(frames[t])
+        rec["template"][t] = idx
+        rec["created"][t] = created
+        rec["n_exp"][t] = len(node.em.experiences)
+        if node.em.current_exp is not None:
+            rec["em_xy"][t] = node.em.get_current_point()
+    rec["n_templates"] = len(node.vts.templates)
+    rec["node"] = node
+    return rec

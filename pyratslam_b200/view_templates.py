@@ -1,0 +1,345 @@
+"""View templates on the B200: the reference's class surface over the CUDA sweep kernel.
+
+``ViewTemplates`` / ``ViewTemplate`` keep the names, arguments and decisions of
+``ratslam/view_templates.py`` -- ``ViewTemplates.match(input, pc_x, pc_y, pc_th)``
+returns the best stored template or creates one (strict ``>`` threshold test,
+first minimum wins) -- while the library lives in HBM as one ``[capacity, 32,
+32]`` tensor and every match is a single streaming sweep
+(``csrc/view_templates.cu``) instead of a Python loop over templates.
+
+``ShardedViewTemplates`` splits a very large library by contiguous template
+ranges over the ranks of a ``torch.distributed`` group; the only exchange is one
+8-byte MIN all-reduce of the packed ``(score << 32 | index)`` key per query.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .sharding import decide, reduce_packed_key, unpack_key
+
+_KEY_NONE = (1 << 64) - 1
+
+
+class ViewTemplate:
+    """One stored view, tied to the pose cell that was most active when it was created
+    (``view_templates.py:4-37``)."""
+
+    max_offset = 8
+
+    def __init__(self, pc_x, pc_y, pc_th, index, template=None, _owner=None):
+        self.pc_x, self.pc_y, self.pc_th = pc_x, pc_y, pc_th
+        self.index = index
+        self._template = template
+        self._owner = _owner
+        self.max_offset = 8
+
+    @property
+    def template(self):
+        if self._template is None and self._owner is not None:
+            self._template = self._owner._fetch_template(self.index)
+        return self._template
+
+    def match(self, new_template):
+        """Score of ``new_template`` against this one (``view_templates.py:16-28``), computed on the device."""
+        nat.require_cuda()
+        a = np.ascontiguousarray(self.template)
+        b = np.ascontiguousarray(new_template)
+        if a.shape != (32, 32) or b.shape != (32, 32):
+            raise NotImplementedError("the CUDA matcher handles 32x32 templates (the reference configuration)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        key = torch.empty(1, dtype=torch.int64, device=dev)
+        if a.dtype == np.uint8 and b.dtype == np.uint8:
+            ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+            nat.check(nat.lib().prs_vt_sweep_u8(ta.data_ptr(), 1, tb.data_ptr(), nat.VT_MODE_REF, 0, key.data_ptr(),
+                                                None, nat.stream_ptr()), "prs_vt_sweep_u8")
+            return np.uint64(int(key.item()) >> 32)
+        ta = torch.from_numpy(a.astype(np.float32)).to(dev)
+        tb = torch.from_numpy(b.astype(np.float32)).to(dev)
+        nat.check(nat.lib().prs_vt_sweep_f32(ta.data_ptr(), 1, tb.data_ptr(), nat.VT_MODE_REF, 0, key.data_ptr(),
+                                             None, nat.stream_ptr()), "prs_vt_sweep_f32")
+        return np.array([int(key.item()) >> 32], dtype=np.uint32).view(np.float32)[0]
+
+    def location(self):
+        return (self.pc_x, self.pc_y, self.pc_th)
+
+    def get_index(self):
+        return self.index
+
+
+class _TemplateList:
+    """``ViewTemplates.templates``: behaves like the reference's Python list of ``ViewTemplate`` objects,
+    but the objects are made on demand so that a 10^6-entry library is not 10^6 Python objects."""
+
+    def __init__(self, owner):
+        self._o = owner
+        self._cache = {}
+
+    def __len__(self):
+        return self._o._n
+
+    def __getitem__(self, i):
+        n = self._o._n
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(n))]
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError("list index out of range")
+        t = self._cache.get(i)
+        if t is None:
+            x, y, th = self._o._loc[i]
+            t = ViewTemplate(self._o._loc_cast(x), self._o._loc_cast(y), self._o._loc_cast(th), i, None, self._o)
+            self._cache[i] = t
+        return t
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class ViewTemplates:
+    """Drop-in for ``ratslam/view_templates.py:ViewTemplates`` with a device-resident library."""
+
+    def __init__(self, x_range, y_range, x_step, y_step, im_x, im_y, match_threshold, mode="ref", capacity=1024,
+                 device=None):
+        nat.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.x_range, self.y_range = tuple(x_range), tuple(y_range)
+        self.x_step, self.y_step = int(x_step), int(y_step)
+        self.im_x, self.im_y = int(im_x), int(im_y)
+        # view_templates.py:44 with Python-2 integer division
+        self.shape = ((x_range[1] - x_range[0]) // x_step, (y_range[1] - y_range[0]) // y_step)
+        self.match_threshold = match_threshold
+        self.mode = {"ref": nat.VT_MODE_REF, "circular": nat.VT_MODE_CIRCULAR}[mode]
+        # rows are selected by y_range (base / im_x is the row index), columns by x_range
+        cnt = lambda lo, hi, st: (hi - lo - 1) - (hi - lo - 1) // st  # noqa: E731
+        self._n_rows = cnt(y_range[0], y_range[1], y_step)
+        self._n_cols = cnt(x_range[0], x_range[1], x_step)
+        if self._n_rows * self._n_cols != self.shape[0] * self.shape[1]:
+            raise ValueError("cannot reshape array of size %d into shape %r"
+                             % (self._n_rows * self._n_cols, self.shape))
+        if self.shape != (32, 32):
+            raise NotImplementedError("the CUDA matcher handles 32x32 templates (the reference configuration), "
+                                      "got %r" % (self.shape,))
+        self._mask = None
+        self._n = 0
+        self._dtype = None           # torch dtype of the library, fixed by the first frame
+        self._lib = None             # [capacity, 32, 32]
+        self._capacity = int(capacity)
+        self._loc = np.zeros((self._capacity, 3), dtype=np.float64)
+        self._loc_is_int = True
+        self.templates = _TemplateList(self)
+        self._key = torch.empty(1, dtype=torch.int64, device=self.device)
+        self._key_pin = torch.empty(1, dtype=torch.int64).pin_memory()
+        self._frame_dev = torch.empty((self.im_x, self.im_y), dtype=torch.uint8, device=self.device)
+        self._tpl_u8 = torch.empty((32, 32), dtype=torch.uint8, device=self.device)
+        self._frame_pin = torch.empty((self.im_x, self.im_y), dtype=torch.uint8).pin_memory()
+        self.last_score = None       # best score of the most recent match() (None when the library was empty)
+
+    # ------------------------------------------------------------------ reference attributes
+    @property
+    def mask(self):
+        """The boolean sub-sampling mask of view_templates.py:48-57 (built lazily; the device path does not need it)."""
+        if self._mask is None:
+            base = np.arange(self.im_x * self.im_y)
+            row, col = base // self.im_x, base % self.im_x
+            m = ((row > self.y_range[0]) & (row < self.y_range[1]) & (col > self.x_range[0]) & (col < self.x_range[1])
+                 & ((row - self.y_range[0]) % self.y_step != 0) & ((col - self.x_range[0]) % self.x_step != 0))
+            self._mask = m.reshape((self.im_x, self.im_y))
+        return self._mask
+
+    def __len__(self):
+        return self._n
+
+    def _loc_cast(self, v):
+        return int(v) if self._loc_is_int else float(v)
+
+    def _fetch_template(self, i):
+        return self._lib[i].cpu().numpy()
+
+    # ------------------------------------------------------------------ library management
+    def _ensure_lib(self, torch_dtype):
+        if self._lib is None:
+            self._dtype = torch_dtype
+            self._lib = torch.empty((self._capacity, 32, 32), dtype=torch_dtype, device=self.device)
+        elif self._dtype != torch_dtype:
+            raise TypeError("library holds %s templates, got a %s frame" % (self._dtype, torch_dtype))
+
+    def _grow(self, need):
+        if need <= self._capacity:
+            return
+        cap = max(need, self._capacity * 2)
+        new = torch.empty((cap, 32, 32), dtype=self._dtype, device=self.device)
+        new[: self._n].copy_(self._lib[: self._n])
+        self._lib = new
+        loc = np.zeros((cap, 3), dtype=np.float64)
+        loc[: self._n] = self._loc[: self._n]
+        self._loc = loc
+        self._capacity = cap
+
+    def load_library(self, templates, locations=None):
+        """Bulk-load ``templates[n, 32, 32]`` (uint8 or float32; numpy or torch) as templates 0..n-1."""
+        t = templates if isinstance(templates, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(templates))
+        if t.dtype not in (torch.uint8, torch.float32):
+            raise TypeError("templates must be uint8 or float32")
+        n = t.shape[0]
+        self._dtype = t.dtype
+        self._lib = t.to(self.device).contiguous()
+        self._capacity = n
+        self._n = n
+        self._loc = np.zeros((n, 3), dtype=np.float64) if locations is None else np.asarray(locations, np.float64)
+        self.templates = _TemplateList(self)
+
+    def _append(self, tpl_dev, pc_x, pc_y, pc_th):
+        self._grow(self._n + 1)
+        self._lib[self._n].copy_(tpl_dev)
+        self._loc[self._n] = (pc_x, pc_y, pc_th)
+        if not all(float(v).is_integer() for v in (pc_x, pc_y, pc_th)):
+            self._loc_is_int = False
+        self._n += 1
+        return self.templates[self._n - 1]
+
+    # ------------------------------------------------------------------ matching
+    def _subsample(self, input):
+        """Frame -> device template ``[32, 32]`` in the library dtype (view_templates.py:64)."""
+        if isinstance(input, torch.Tensor):
+            fr = input
+        else:
+            fr = np.asarray(input)
+        if tuple(fr.shape) != (self.im_x, self.im_y):
+            raise IndexError("boolean index did not match indexed array: frame %r, mask %r"
+                             % (tuple(fr.shape), (self.im_x, self.im_y)))
+        is_u8 = (fr.dtype == torch.uint8) if isinstance(fr, torch.Tensor) else (fr.dtype == np.uint8)
+        if is_u8:
+            if isinstance(fr, torch.Tensor):
+                self._frame_dev.copy_(fr, non_blocking=True)
+            else:
+                self._frame_pin.numpy()[...] = fr
+                self._frame_dev.copy_(self._frame_pin, non_blocking=True)
+            nat.check(nat.lib().prs_vt_extract_u8(
+                self._frame_dev.data_ptr(), self.im_x, self.im_y, self.y_range[0], self.y_range[1], self.y_step,
+                self.x_range[0], self.x_range[1], self.x_step, self._tpl_u8.data_ptr(), self._n_rows, self._n_cols,
+                nat.stream_ptr()), "prs_vt_extract_u8")
+            return self._tpl_u8, torch.uint8
+        # float frames: ordinary SAD in float32
+        t = fr if isinstance(fr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(fr))
+        t = t.to(self.device, torch.float32)
+        r0, c0 = self.y_range[0] + 1, self.x_range[0] + 1
+        if self.x_step != 2 or self.y_step != 2:
+            m = torch.from_numpy(self.mask).to(self.device)
+            return t[m].reshape(32, 32).contiguous(), torch.float32
+        return t[r0: self.y_range[1]: 2, c0: self.x_range[1]: 2].contiguous(), torch.float32
+
+    def _sweep(self, tpl, torch_dtype, key_dev):
+        fn = nat.lib().prs_vt_sweep_u8 if torch_dtype == torch.uint8 else nat.lib().prs_vt_sweep_f32
+        lib_ptr = self._lib.data_ptr() if self._n else None
+        nat.check(fn(lib_ptr, self._n, tpl.data_ptr(), self.mode, 0, key_dev.data_ptr(), None, nat.stream_ptr()),
+                  "prs_vt_sweep")
+
+    def _decode(self, key, torch_dtype):
+        """``(score, index)`` from the packed key, or ``(None, -1)`` when nothing was compared."""
+        key &= _KEY_NONE
+        if key == _KEY_NONE:
+            return None, -1
+        hi, idx = key >> 32, key & 0xFFFFFFFF
+        if torch_dtype == torch.uint8:
+            return int(hi), int(idx)
+        return float(np.array([hi], dtype=np.uint32).view(np.float32)[0]), int(idx)
+
+    def scores(self, input):
+        """Per-template scores of a frame against the whole library (numpy array); for inspection and tests."""
+        with torch.cuda.device(self.device):
+            tpl, td = self._subsample(input)
+            self._ensure_lib(td)
+            out = torch.empty(self._n, dtype=torch.int32 if td == torch.uint8 else torch.float32, device=self.device)
+            fn = nat.lib().prs_vt_sweep_u8 if td == torch.uint8 else nat.lib().prs_vt_sweep_f32
+            nat.check(fn(self._lib.data_ptr(), self._n, tpl.data_ptr(), self.mode, 0, self._key.data_ptr(),
+                         out.data_ptr(), nat.stream_ptr()), "prs_vt_sweep")
+            res = out.cpu().numpy()
+            return res.view(np.uint32).astype(np.int64) if td == torch.uint8 else res
+
+    def match(self, input, pc_x, pc_y, pc_th):
+        """Best stored template for this frame, or a newly created one (``view_templates.py:63-75``)."""
+        with torch.cuda.device(self.device):
+            tpl, td = self._subsample(input)
+            self._ensure_lib(td)
+            self._sweep(tpl, td, self._key)
+            self._key_pin.copy_(self._key, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            score, idx = self._decode(int(self._key_pin[0]), td)
+            self.last_score = score
+            if score is None or score > self.match_threshold:
+                return self._append(tpl, pc_x, pc_y, pc_th)
+            return self.templates[idx]
+
+    # north_star spelling: force creation of a template from a frame
+    def create(self, input, pc_x, pc_y, pc_th):
+        with torch.cuda.device(self.device):
+            tpl, td = self._subsample(input)
+            self._ensure_lib(td)
+            return self._append(tpl, pc_x, pc_y, pc_th)
+
+
+class ShardedViewTemplates:
+    """A template library split by contiguous index ranges over the ranks of a process group.
+
+    Rank r holds templates ``[base_r, base_r + n_r)``.  ``match_key`` sweeps the local shard and MIN-reduces the
+    packed key over the group (NCCL on GPUs), which yields the global minimum score and, among equal scores, the
+    lowest global index -- ``numpy.argmin`` semantics (``view_templates.py:73``).  New templates are appended
+    to the last rank's shard so global indices stay contiguous.
+    """
+
+    def __init__(self, local_templates, base_index, match_threshold, mode="ref", group=None, device=None):
+        import torch.distributed as dist
+        nat.require_cuda()
+        self._dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        t = local_templates if isinstance(local_templates, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(local_templates))
+        if t.dtype not in (torch.uint8, torch.float32):
+            raise TypeError("templates must be uint8 or float32")
+        self._lib = t.to(self.device).contiguous()
+        self._n = int(t.shape[0])
+        self._dtype = t.dtype
+        self.base_index = int(base_index)
+        self.match_threshold = match_threshold
+        self.mode = {"ref": nat.VT_MODE_REF, "circular": nat.VT_MODE_CIRCULAR}[mode]
+        self._key = torch.empty(1, dtype=torch.int64, device=self.device)
+        counts = torch.tensor([self._n], dtype=torch.int64, device=self.device)
+        allc = [torch.zeros_like(counts) for _ in range(self.world)]
+        dist.all_gather(allc, counts, group=group)
+        self.n_total = int(sum(int(c.item()) for c in allc))
+
+    def local_sweep(self, query_dev):
+        """Launch the local sweep; the packed key is left in ``self._key`` on the device."""
+        fn = nat.lib().prs_vt_sweep_u8 if self._dtype == torch.uint8 else nat.lib().prs_vt_sweep_f32
+        lib_ptr = self._lib.data_ptr() if self._n else None
+        nat.check(fn(lib_ptr, self._n, query_dev.data_ptr(), self.mode, self.base_index, self._key.data_ptr(), None,
+                     nat.stream_ptr()), "prs_vt_sweep")
+        return self._key
+
+    def match_key(self, query_dev):
+        """Global ``(score, index)`` of the best match over all shards; identical on every rank."""
+        with torch.cuda.device(self.device):
+            key = reduce_packed_key(self.local_sweep(query_dev), self.group)
+            k = int(key.item())
+        return unpack_key(k, is_float=self._dtype != torch.uint8)
+
+    def match(self, query_dev):
+        """``(index, created)`` with the reference's create-or-match rule applied identically on every rank."""
+        score, idx = self.match_key(query_dev)
+        index, created = decide(score, idx, self.n_total, self.match_threshold)
+        if created:
+            if self.rank == self.world - 1:
+                grown = torch.empty((self._n + 1, 32, 32), dtype=self._dtype, device=self.device)
+                grown[: self._n].copy_(self._lib)
+                grown[self._n].copy_(query_dev.reshape(32, 32))
+                self._lib, self._n = grown, self._n + 1
+            self.n_total += 1
+        return index, created

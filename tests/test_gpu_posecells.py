@@ -1,0 +1,195 @@
+"""GPU parity of the pose-cell path against the oracle and the reference-generated fixtures.
+
+Every call goes through the C ABI (ctypes -> libpyratslam_b200.so).  Bars:
+arg-max cell bit-exact at every step; activities  max|gpu - ref| / max|ref|  <= 1e-5 in float32 and
+<= 1e-12 in float64.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import drivers as odrv
+from oracle import posecells as opc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.float32: 1e-5, np.float64: 1e-12}
+PATHS = ["auto", "generic"]
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _make(shape, dtype, path, **kw):
+    from pyratslam_b200 import PoseCellNetwork
+    net = PoseCellNetwork(shape, dtype=dtype, **kw)
+    if path == "generic":
+        net._ens.force_generic(True)
+    return net
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name,shape,inject", [
+    ("simulate_50x50x10.npz", (50, 50, 10), None),
+    ("ros_21x21x36.npz", (21, 21, 36), None),
+    ("ros_21x21x36_dies.npz", (21, 21, 36), None),
+    ("odd_9x8x7.npz", (9, 8, 7), (4, 3, 2)),
+    ("odd_17x23x11.npz", (17, 23, 11), (16, 0, 10)),
+])
+def test_golden_trajectories(golden, name, shape, inject, dtype, path):
+    g = golden(name)
+    net = _make(shape, dtype, path)
+    net.inject(1, tuple(s // 2 for s in shape) if inject is None else inject)
+    worst = 0.0
+    for s, v in enumerate(g["odom"]):
+        got = net.update(v)
+        assert tuple(got) == tuple(g["argmax"][s]), (name, s, got, g["argmax"][s])
+        key = "state_%03d" % s
+        if key in g.files:
+            ref = g[key]
+            if ref.max() == 0:
+                assert net.posecells.max() == 0
+            else:
+                worst = max(worst, _rel(net.posecells, ref))
+    assert worst <= RTOL[dtype], worst
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_simulate_driver(golden, dtype):
+    from pyratslam_b200 import simulate
+    trace = simulate.main(steps=40, verbose=False, dtype=dtype)
+    assert [tuple(t) for t in trace] == [tuple(t) for t in golden("simulate_50x50x10.npz")["argmax"].tolist()]
+
+
+def test_keyerror_and_radius(golden):
+    for v, expect in golden("keyerror.npz")["cases"]:
+        net = _make((21, 21, 36), np.float32, "auto")
+        net.inject(1, (10, 10, 18))
+        if expect:
+            before = net.posecells
+            with pytest.raises(KeyError):
+                net.update((v, 0.0))
+            assert np.array_equal(net.posecells, before)   # raised before the device state was touched
+        else:
+            net.update((v, 0.0))
+    net = _make((9, 8, 7), np.float32, "auto")
+    net.inject(1, (4, 3, 2))
+    with pytest.raises(ValueError):
+        net.update((1.3, 0.0))     # 6.5 cells: 3 + 7 > 8
+
+
+def test_device_error_flags_for_ensembles():
+    from pyratslam_b200 import PoseCellEnsemble
+    ens = PoseCellEnsemble((21, 21, 36), 3)
+    ens.inject(1, (10, 10, 18))
+    with pytest.raises(KeyError):
+        ens.update(np.array([[0.03, 0.0], [0.1, 0.0], [0.02, 0.0]]))     # network 1 hits the LUT hole
+    with pytest.raises(ValueError):
+        ens.update(np.array([[0.03, 0.0], [0.02, 0.0], [4.0, 0.0]]))     # 20 cells > 21 - 3
+
+
+def test_inject_argmax_ties_and_roundtrip():
+    net = _make((9, 8, 7), np.float32, "auto")
+    assert net.get_pc_max() == (0, 0, 0)                 # all-zero grid -> first cell
+    rng = np.random.default_rng(0)
+    st = rng.uniform(0, 1, (9, 8, 7))
+    st[5, 2, 3] = 2.0
+    st[2, 7, 6] = 2.0                                    # equal maxima: the lower flat index wins
+    net.posecells = st
+    assert np.allclose(net.posecells, st.astype(np.float32))
+    assert net.get_pc_max() == (2, 7, 6)
+    net.inject(0.5, (5, 2, 3))
+    assert net.get_pc_max() == (5, 2, 3)
+    net.inject(1.0, (-1, -1, -1))                        # numpy-style negative indices
+    assert net.posecells[8, 7, 6] == pytest.approx(st[8, 7, 6] + 1.0, rel=1e-6)
+    with pytest.raises(IndexError):
+        net.inject(1.0, (9, 0, 0))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_path_integration_alone(dtype):
+    shape = (17, 23, 11)
+    ref = opc.PoseCellNetwork(shape)
+    rng = np.random.default_rng(3)
+    st = rng.uniform(0, 1, shape)
+    ref.posecells = st.copy()
+    net = _make(shape, dtype, "auto")
+    net.posecells = st
+    for v in [(0.37, 0.21), (-0.8, -0.4)]:
+        ref.path_integration(*v)
+        net.path_integration(*v)
+    assert _rel(net.posecells, ref.posecells) <= (2e-6 if dtype == np.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("path", PATHS)
+def test_ensemble_against_oracle(dtype, path):
+    from pyratslam_b200 import PoseCellEnsemble
+    shape, B, T = (21, 21, 36), 12, 25
+    rng = np.random.default_rng(3)
+    gis = np.linspace(0.05, 0.25, B)
+    odom = np.stack([rng.uniform(0, 0.3, (T, B)), rng.uniform(-0.1, 0.1, (T, B))], axis=-1)
+    ref_amax, ref_states = opc.run_ensemble(shape, gis, odom)
+    ens = PoseCellEnsemble(shape, B, global_inhibition=gis, dtype=dtype)
+    if path == "generic":
+        ens.force_generic(True)
+    ens.inject(1.0, tuple(s // 2 for s in shape))
+    # half the steps one at a time through the host entry, the rest as one multi-step run
+    got = [ens.update(odom[t]) for t in range(10)]
+    got = np.concatenate([np.stack(got), ens.run(odom[10:])])
+    assert np.array_equal(got, ref_amax)
+    assert _rel(ens.posecells, ref_states) <= RTOL[dtype]
+
+
+def test_large_grid_one_step_against_oracle():
+    """BASELINE config 3 at full size (256x256x72): two steps against the scipy oracle (a few seconds)."""
+    shape = (256, 256, 72)
+    ref = opc.PoseCellNetwork(shape)
+    net = _make(shape, np.float32, "auto")
+    for n in (ref, net):
+        n.inject(1.0, (128, 128, 36))
+        n.inject(0.5, (3, 250, 70))      # a second packet across the periodic boundary
+    for v in [(0.21, 0.03), (0.12, -0.04)]:
+        assert tuple(net.update(v)) == tuple(ref.update(v))
+    assert _rel(net.posecells, ref.posecells) <= 1e-5
+
+
+def test_translation_equivariance_large():
+    """Size-independent property: the update commutes with a cyclic shift of the whole grid."""
+    shape = (64, 48, 36)
+    rng = np.random.default_rng(9)
+    st = np.zeros(shape)
+    st[10:14, 20:23, 5:9] = rng.uniform(0.5, 1.0, (4, 3, 4))
+    a = _make(shape, np.float32, "auto")
+    b = _make(shape, np.float32, "auto")
+    a.posecells = st
+    b.posecells = np.roll(st, (17, -9, 30), axis=(0, 1, 2))
+    for v in [(0.2, 0.05), (0.1, -0.05), (0.3, 0.0)]:
+        ma, mb = a.update(v), b.update(v)
+        assert ((ma[0] + 17) % 64, (ma[1] - 9) % 48, (ma[2] + 30) % 36) == tuple(mb)
+    assert _rel(np.roll(a.posecells, (17, -9, 30), axis=(0, 1, 2)), b.posecells) <= 2e-6
+
+
+def test_full_size_ensemble_replicas_and_samples():
+    """BASELINE config 4 at full size: 4096 networks; a sample is checked against the oracle and
+    identical networks must produce identical bits."""
+    from pyratslam_b200 import PoseCellEnsemble
+    shape, B, T = (21, 21, 36), 4096, 6
+    rng = np.random.default_rng(3)
+    gis = np.linspace(0.05, 0.25, B)
+    odom = np.stack([rng.uniform(0, 0.3, (T, B)), rng.uniform(-0.1, 0.1, (T, B))], axis=-1)
+    gis[1000], odom[:, 1000] = gis[7], odom[:, 7]        # network 1000 is a replica of network 7
+    ens = PoseCellEnsemble(shape, B, global_inhibition=gis)
+    ens.inject(1.0, (10, 10, 18))
+    got = ens.run(odom)
+    pick = [0, 7, 1000, 2047, 4095]
+    ref_amax, ref_states = opc.run_ensemble(shape, gis[pick], odom[:, pick])
+    assert np.array_equal(got[:, pick], ref_amax)
+    st = ens.state
+    assert torch.equal(st[7], st[1000])
+    pc = ens.posecells
+    assert _rel(pc[pick], ref_states) <= 1e-5

@@ -1,0 +1,173 @@
+"""GPU parity of the view-template matcher: template ids, create-vs-match decisions and scores are
+bit-exact against the oracle / the reference-generated fixtures (integer arithmetic)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import view_templates as ovt
+from synth import synth_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def _vts(threshold=45000, **kw):
+    from pyratslam_b200 import ViewTemplates
+    return ViewTemplates((32, 96), (32, 96), 2, 2, 256, 256, threshold, **kw)
+
+
+def test_golden_frame_sequence(golden):
+    g = golden("view_templates.npz")
+    vts = _vts()
+    assert vts.shape == tuple(g["shape"]) and int(vts.mask.sum()) == int(g["mask_count"])
+    T = int(g["n_frames"])
+    frames = synth_frames(np.random.default_rng(int(g["frame_seed"])), T)
+    for t in range(T):
+        n0 = len(vts.templates)
+        tm = vts.match(frames[t], t % 21, (2 * t) % 21, t % 36)
+        assert tm.get_index() == g["index"][t], t
+        assert (len(vts.templates) > n0) == bool(g["created"][t]), t
+        assert (vts.last_score if vts.last_score is not None else -1) == g["best_score"][t], t
+        assert len(vts.templates) == g["n_templates"][t]
+    # stored templates are the sub-sampled frames, locations are what match() was given
+    t3 = vts.templates[3]
+    assert np.array_equal(t3.template, frames[3][vts.mask].reshape(32, 32))
+    assert t3.location() == (3, 6, 3) and t3.get_index() == 3
+
+
+def test_score_tables(golden):
+    from pyratslam_b200 import ViewTemplate
+    g = golden("view_templates.npz")
+    lib, qs = g["lib_u8"], g["queries_u8"]
+    vts = _vts()
+    vts.load_library(lib)
+    for qi, q in enumerate(qs):
+        frame = np.zeros((256, 256), np.uint8)
+        rows = np.arange(33, 96, 2)
+        frame[np.ix_(rows, rows)] = q
+        assert vts.scores(frame).tolist() == g["scores_u8"][qi].tolist()
+        assert int(ViewTemplate(0, 0, 0, 0, lib[2]).match(q)) == g["scores_u8"][qi][2]
+    vf = _vts()
+    vf.load_library(lib.astype(np.float32))
+    for qi, q in enumerate(qs):
+        frame = np.zeros((256, 256), np.float32)
+        frame[np.ix_(rows, rows)] = q
+        assert vf.scores(frame).astype(np.float64).tolist() == g["scores_f64"][qi].tolist()
+
+
+def test_threshold_is_strict(golden):
+    g = golden("view_templates.npz")
+    lib, qs = g["lib_u8"], g["queries_u8"]
+    best = int(g["scores_u8"][3].min())
+    rows = np.arange(33, 96, 2)
+    f0 = np.zeros((256, 256), np.uint8)
+    f1 = np.zeros((256, 256), np.uint8)
+    f0[np.ix_(rows, rows)] = lib[int(g["scores_u8"][3].argmin())]
+    f1[np.ix_(rows, rows)] = qs[3]
+    out = []
+    for thr in (best, best - 1):
+        v = _vts(thr)
+        out += [v.match(f0, 0, 0, 0).get_index(), v.match(f1, 0, 0, 0).get_index()]
+    assert out == g["threshold_case"].tolist() == [0, 0, 0, 1]
+
+
+def _sweep(lib_t, q_t, mode, want_scores=True):
+    from pyratslam_b200 import _native as nat
+    n = lib_t.shape[0]
+    key = torch.zeros(1, dtype=torch.int64, device="cuda")
+    if lib_t.dtype == torch.uint8:
+        sc = torch.zeros(max(n, 1), dtype=torch.int32, device="cuda")
+        fn = nat.lib().prs_vt_sweep_u8
+    else:
+        sc = torch.zeros(max(n, 1), dtype=torch.float32, device="cuda")
+        fn = nat.lib().prs_vt_sweep_f32
+    nat.check(fn(lib_t.data_ptr() if n else None, n, q_t.data_ptr(), mode, 0, key.data_ptr(),
+                 sc.data_ptr() if want_scores else None, None))
+    torch.cuda.synchronize()
+    return int(key.item()) & ((1 << 64) - 1), sc[:n].cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", ["ref", "circular"])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 64, 1001])
+def test_ragged_library_sizes_u8(mode, n):
+    rng = np.random.default_rng(100 + n)
+    lib = rng.integers(0, 256, (n, 32, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (32, 32), dtype=np.uint8)
+    if n > 3:
+        lib[n - 1] = lib[2]                    # a tie: the lower index must win
+        q = lib[2].copy()
+    key, sc = _sweep(torch.from_numpy(lib).cuda(), torch.from_numpy(q).cuda(), 0 if mode == "ref" else 1)
+    if n == 0:
+        assert key == (1 << 64) - 1
+        return
+    ref = ovt.library_scores(lib, q, mode=mode)
+    assert sc.view(np.uint32).astype(np.int64).tolist() == ref.astype(np.int64).tolist()
+    assert key == (int(ref.min()) << 32) | int(np.argmin(ref))
+
+
+@pytest.mark.parametrize("mode", ["ref", "circular"])
+def test_float32_library(mode):
+    rng = np.random.default_rng(5)
+    lib = rng.integers(0, 256, (777, 32, 32)).astype(np.float32)      # integer-valued: sums are exact
+    q = np.roll(lib[400], 5 if mode == "ref" else 13, axis=0) + 0.0
+    lib[600] = lib[400]
+    key, sc = _sweep(torch.from_numpy(lib).cuda(), torch.from_numpy(q).cuda(), 0 if mode == "ref" else 1)
+    ref = ovt.library_scores(lib, q, mode=mode)
+    assert np.array_equal(sc, ref)
+    j = int(np.argmin(ref))
+    assert j == 400 and key & 0xFFFFFFFF == 400
+    assert np.array([key >> 32], dtype=np.uint32).view(np.float32)[0] == ref[j]
+    # non-integer data: same selection, scores within float32 summation error
+    libr = rng.uniform(0, 255, (300, 32, 32)).astype(np.float32)
+    qr = (libr[123] + rng.normal(0, 2, (32, 32))).astype(np.float32)
+    key, sc = _sweep(torch.from_numpy(libr).cuda(), torch.from_numpy(qr).cuda(), 0 if mode == "ref" else 1)
+    ref = ovt.library_scores(libr.astype(np.float64), qr.astype(np.float64), mode=mode)
+    assert key & 0xFFFFFFFF == int(np.argmin(ref)) == 123
+    assert np.abs(sc - ref).max() <= 1e-5 * ref.max()
+
+
+def test_extract_matches_mask():
+    rng = np.random.default_rng(1)
+    frame = rng.integers(0, 256, (256, 256), dtype=np.uint8)
+    vts = _vts()
+    tm = vts.match(frame, 1, 2, 3)
+    assert np.array_equal(tm.template, frame[vts.mask].reshape(32, 32))
+    # torch frames already on the device take the same path
+    tm2 = vts.match(torch.from_numpy(frame).cuda(), 1, 2, 3)
+    assert tm2.get_index() == 0 and vts.last_score == 0
+
+
+def test_million_template_library_properties():
+    """BASELINE config 5 at full size (2^20 templates, 1 GiB): a planted darker, row-shifted copy is found;
+    the key equals min/argmin of the per-template scores; a 4096-template slice equals the oracle."""
+    n = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(4)
+    lib = torch.randint(0, 256, (n, 32, 32), dtype=torch.uint8, device="cuda", generator=g)
+    target = 777_777
+    src = lib[target].cpu().numpy()
+    q = np.roll(np.clip(src.astype(np.int16) - 2, 0, 255).astype(np.uint8), -4, axis=0)
+    key, sc = _sweep(lib, torch.from_numpy(q).cuda(), 0)
+    sc = sc.view(np.uint32).astype(np.int64)
+    assert key & 0xFFFFFFFF == target == int(np.argmin(sc)) and key >> 32 == int(sc.min())
+    lo = 500_000
+    ref = ovt.library_scores(lib[lo:lo + 4096].cpu().numpy(), q)
+    assert sc[lo:lo + 4096].tolist() == ref.astype(np.int64).tolist()
+    # circular mode finds any rotation exactly
+    qc = np.roll(src, 19, axis=0)
+    key, _ = _sweep(lib, torch.from_numpy(qc).cuda(), 1, want_scores=False)
+    assert key == target                       # score 0, index target
+
+
+def test_replay_loop_matches_reference_fixture(golden):
+    from pyratslam_b200 import ros_simulate
+    g = golden("replay_ros.npz")
+    T = int(g["n_frames"])
+    frames = synth_frames(np.random.default_rng(int(g["frame_seed"])), T)
+    for dtype in (np.float32, np.float64):
+        rec = ros_simulate.replay(frames, g["odom"], dtype=dtype)
+        assert np.array_equal(rec["template"], g["template"])
+        assert np.array_equal(rec["created"], g["created"])
+        assert np.array_equal(rec["argmax"], g["argmax"])
+        assert np.array_equal(rec["n_exp"], g["n_exp"])
+        assert np.allclose(rec["em_xy"][-1], g["em_xy"][-1], rtol=0, atol=0)
+        fs = rec["node"].pcn.posecells
+        assert np.abs(fs - g["final_state"]).max() / g["final_state"].max() <= (1e-5 if dtype == np.float32 else 1e-12)
