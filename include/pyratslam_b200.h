@@ -114,7 +114,7 @@ PRS_API int prs_pc_step_host(prs_pc_handle h, void* state, const double* odom_ho
  * correlate + clamp, theta correlate + clamp; no attractor dynamics, no normalisation. */
 PRS_API int prs_pc_path_integration(prs_pc_handle h, void* state, const double* odom, int* err, void* stream);
 
-/* posecells[loc] += energy for network b (posecell_network.py:322-324) */
+/* posecells[loc] += energy for network b, or for every network when b < 0 (posecell_network.py:322-324) */
 PRS_API int prs_pc_inject(prs_pc_handle h, void* state, int b, int x, int y, int th, double energy, void* stream);
 /* arg-max without an update (get_pc_max, posecell_network.py:317-319) */
 PRS_API int prs_pc_argmax(prs_pc_handle h, const void* state, long long* argmax, void* stream);

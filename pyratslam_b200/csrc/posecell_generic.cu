@@ -286,8 +286,9 @@ __global__ void k_fill(T* p, int n, T v) {
 }
 
 template <typename T>
-__global__ void k_inject(T* state, size_t off, T energy) {
-  state[off] += energy;
+__global__ void k_inject(T* state, size_t off, size_t stride, int count, T energy) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) state[off + (size_t)i * stride] += energy;
 }
 
 // xyt[b][x][y][th]  <->  state[b][th][x][y]
@@ -373,15 +374,16 @@ int prs_pc_generic_argmax(prs_pc_plan* p, const void* state, long long* argmax, 
 // ---------------------------------------------------------------------------- C ABI (shape-independent parts)
 extern "C" int prs_pc_inject(prs_pc_handle h, void* state, int b, int x, int y, int th, double energy, void* stream) {
   PRS_REQUIRE(h && state, "prs_pc_inject: null argument");
-  PRS_REQUIRE(b >= 0 && b < h->B && x >= 0 && x < h->X && y >= 0 && y < h->Y && th >= 0 && th < h->Th,
+  PRS_REQUIRE(b < h->B && x >= 0 && x < h->X && y >= 0 && y < h->Y && th >= 0 && th < h->Th,
               "prs_pc_inject: location (%d,%d,%d) of network %d is outside the %dx%dx%d grid", x, y, th, b, h->X, h->Y,
               h->Th);
-  size_t off = ((size_t)b * h->Th + th) * h->X * h->Y + (size_t)x * h->Y + y;
+  const int first = b < 0 ? 0 : b, count = b < 0 ? h->B : 1;
+  size_t off = ((size_t)first * h->Th + th) * h->X * h->Y + (size_t)x * h->Y + y;
   cudaStream_t st = (cudaStream_t)stream;
   if (h->dtype == PRS_F32)
-    k_inject<float><<<1, 1, 0, st>>>((float*)state, off, (float)energy);
+    k_inject<float><<<(count + 127) / 128, 128, 0, st>>>((float*)state, off, (size_t)h->N, count, (float)energy);
   else
-    k_inject<double><<<1, 1, 0, st>>>((double*)state, off, energy);
+    k_inject<double><<<(count + 127) / 128, 128, 0, st>>>((double*)state, off, (size_t)h->N, count, energy);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }

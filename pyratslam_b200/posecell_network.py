@@ -140,11 +140,10 @@ class PoseCellEnsemble:
         x, y, th = (v + n if -n <= v < 0 else v for v, n in ((x, X), (y, Y), (th, Th)))  # numpy negative indices
         if not (0 <= x < X and 0 <= y < Y and 0 <= th < Th):
             raise IndexError("index %r is out of bounds for shape %r" % (tuple(loc), self.shape))
-        nets = range(self.n_networks) if network is None else [int(network)]
+        b = -1 if network is None else int(network)
         with torch.cuda.device(self.device):
-            for b in nets:
-                nat.check(nat.lib().prs_pc_inject(self._h, self._state.data_ptr(), b, x, y, th, float(energy),
-                                                  nat.stream_ptr()), "prs_pc_inject")
+            nat.check(nat.lib().prs_pc_inject(self._h, self._state.data_ptr(), b, x, y, th, float(energy),
+                                              nat.stream_ptr()), "prs_pc_inject")
 
     def _unravel(self, flat):
         X, Y, Th = self.shape

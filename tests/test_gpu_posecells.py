@@ -79,7 +79,7 @@ def test_keyerror_and_radius(golden):
     net = _make((9, 8, 7), np.float32, "auto")
     net.inject(1, (4, 3, 2))
     with pytest.raises(ValueError):
-        net.update((1.3, 0.0))     # 6.5 cells: 3 + 7 > 8
+        net.update((1.32, 0.0))    # 6.6 cells: 3 + 7 > 8
 
 
 def test_device_error_flags_for_ensembles():
@@ -159,7 +159,8 @@ def test_large_grid_one_step_against_oracle():
 
 
 def test_translation_equivariance_large():
-    """Size-independent property: the update commutes with a cyclic shift of the whole grid."""
+    """Size-independent property: the update commutes with a cyclic shift of the grid in x and y
+    (not in theta: the heading decides which way a plane moves)."""
     shape = (64, 48, 36)
     rng = np.random.default_rng(9)
     st = np.zeros(shape)
@@ -167,11 +168,11 @@ def test_translation_equivariance_large():
     a = _make(shape, np.float32, "auto")
     b = _make(shape, np.float32, "auto")
     a.posecells = st
-    b.posecells = np.roll(st, (17, -9, 30), axis=(0, 1, 2))
+    b.posecells = np.roll(st, (17, -9), axis=(0, 1))
     for v in [(0.2, 0.05), (0.1, -0.05), (0.3, 0.0)]:
         ma, mb = a.update(v), b.update(v)
-        assert ((ma[0] + 17) % 64, (ma[1] - 9) % 48, (ma[2] + 30) % 36) == tuple(mb)
-    assert _rel(np.roll(a.posecells, (17, -9, 30), axis=(0, 1, 2)), b.posecells) <= 2e-6
+        assert ((ma[0] + 17) % 64, (ma[1] - 9) % 48, ma[2]) == tuple(mb)
+    assert _rel(np.roll(a.posecells, (17, -9), axis=(0, 1)), b.posecells) <= 2e-6
 
 
 def test_full_size_ensemble_replicas_and_samples():
