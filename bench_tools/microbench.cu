@@ -74,6 +74,47 @@ __global__ void __launch_bounds__(256) k_fp(float* out, long long* cycles, float
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// The stage-4 inner loop of the resident pose-cell kernel without any memory traffic:
+// acc[j] += row[(j+q-3) mod 21] * cf[q], 21 outputs x 7 taps, as packed FFMA2 (PACKED) or scalar FFMA.
+template <bool PACKED, int ORDER>
+__global__ void __launch_bounds__(448, 1) k_pattern(float* out, long long* cycles, float seed) {
+  constexpr int Y = 21;
+  float2 acc[Y], row[Y], cf[7];
+#pragma unroll
+  for (int j = 0; j < Y; ++j) {
+    acc[j] = make_float2(0.f, 0.f);
+    row[j] = make_float2(seed + j + threadIdx.x, seed - j);
+  }
+#pragma unroll
+  for (int q = 0; q < 7; ++q) cf[q] = make_float2(1.0f + 1e-6f * q * seed, 1.0f - 1e-6f * q * seed);
+  long long t0 = clock64();
+  for (int it = 0; it < ITERS / 8; ++it) {
+#pragma unroll
+    for (int u = 0; u < (ORDER == 0 ? Y : (ORDER == 1 ? 7 : Y)); ++u) {
+#pragma unroll
+      for (int v = 0; v < (ORDER == 0 ? 7 : (ORDER == 1 ? Y : 7)); ++v) {
+        // ORDER 0: outputs outer, taps inner.  1: taps outer, outputs inner (cf reused).  2: inputs outer (row reused).
+        const int j = ORDER == 0 ? u : (ORDER == 1 ? v : (u - v + 3 + Y) % Y);
+        const int q = ORDER == 0 ? v : (ORDER == 1 ? u : v);
+        if (PACKED) {
+          acc[j] = __ffma2_rn(row[(j + q + Y - 3) % Y], cf[q], acc[j]);
+        } else {
+          acc[j].x = fmaf(row[(j + q + Y - 3) % Y].x, cf[q].x, acc[j].x);
+          acc[j].y = fmaf(row[(j + q + Y - 3) % Y].y, cf[q].y, acc[j].y);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < Y; ++j) row[j].x += 1e-7f * acc[(j + 1) % Y].y;  // keep the rows live and changing
+  }
+  long long t1 = clock64();
+  float s = 0;
+#pragma unroll
+  for (int j = 0; j < Y; ++j) s += acc[j].x + acc[j].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 __global__ void __launch_bounds__(256) k_dfma(double* out, long long* cycles, double seed) {
   double a[8];
 #pragma unroll
@@ -193,6 +234,34 @@ int main() {
   cudaDeviceProp prop;
   CHECK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s, %d SMs, %d kHz\n", prop.name, prop.multiProcessorCount, prop.clockRate);
+  {
+    // one 448-thread CTA per SM, like the resident kernel: FMA/clk/SM from the in-kernel cycle count
+    for (int var = 0; var < 6; ++var) {
+      const int packed = var & 1, order = var >> 1;
+      long long* cyc;
+      CHECK(cudaMalloc(&cyc, 148 * sizeof(long long)));
+      for (int rep = 0; rep < 2; ++rep) {
+        switch (var) {
+          case 0: k_pattern<false, 0><<<148, 448>>>(outf, cyc, 1.0f); break;
+          case 1: k_pattern<true, 0><<<148, 448>>>(outf, cyc, 1.0f); break;
+          case 2: k_pattern<false, 1><<<148, 448>>>(outf, cyc, 1.0f); break;
+          case 3: k_pattern<true, 1><<<148, 448>>>(outf, cyc, 1.0f); break;
+          case 4: k_pattern<false, 2><<<148, 448>>>(outf, cyc, 1.0f); break;
+          default: k_pattern<true, 2><<<148, 448>>>(outf, cyc, 1.0f); break;
+        }
+        CHECK(cudaDeviceSynchronize());
+      }
+      long long h[148];
+      CHECK(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+      double mean = 0;
+      for (int i = 0; i < 148; ++i) mean += (double)h[i];
+      mean /= 148;
+      double fma = 2.0 * 147.0 * (ITERS / 8) * 448.0;
+      printf("stage-4 pattern %-5s order %d, 448 thr/SM: %7.1f FMA/clk/SM (peak 128)\n", packed ? "FFMA2" : "FFMA", order,
+             fma / mean);
+      cudaFree(cyc);
+    }
+  }
   for (int bps : {2, 4, 8}) {
     run("FFMA reg,reg,reg", 16.0 * ITERS, bps, [&](int g, long long* c) { k_fp<0><<<g, 256>>>(outf, c, 1.0f); });
     run("FFMA reg,const,reg", 16.0 * ITERS, bps, [&](int g, long long* c) { k_fp<1><<<g, 256>>>(outf, c, 1.0f); });

@@ -12,8 +12,8 @@
 //   stage[N] float        the next network's state as it lies in HBM, theta-major [th][x][y]   4N bytes
 //   buf2[N]  float2       (E, I) pairs of the separable DoG, [th][x][y]                        8N bytes
 //     after the x pass the same bytes are reused as two plane-pair-interleaved tensors
-//       A2[NP][x][y] float2 = (A'[kp], A'[kp+NP])   inhibited activity, already moved by the integer
-//                                                   (x, y) origin of its plane
+//       A2[NP][x+halo][y] float2 = (A'[kp], A'[kp+NP])  inhibited activity, already moved by the integer
+//                                                   (x, y) origin of its plane, 3 periodic halo rows each side
 //       B2[NP][x][y] float2 = (B[kp],  B[kp+NP])    after the 2-D correlate
 // Stages (a __syncthreads between each):
 //   1 theta pass   thread = one (x,y) line of Th cells in registers, stage -> buf2         11 op / cell
@@ -26,6 +26,8 @@
 // The FMA-heavy stages use the sm_100 packed instruction (fma.rn.f32x2, SASS FFMA2): same FP32 pipe
 // rate as scalar FFMA (measured, bench_tools/microbench.cu) for half the issue slots, which is what
 // lets the shared-memory loads issue alongside.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -35,15 +37,21 @@ struct ResLayout {
   static constexpr int XY = X * Y;
   static constexpr int N = XY * T;
   static constexpr int NP = (T + 1) / 2;
+  // A2 plane: X+6 rows (3 periodic halo rows on each side, so stage 4 never wraps an index).  The plane
+  // stride is padded until PS == X*Y (mod 16): then the float2 slot read by item (kp, x) is
+  // Y*(kp*X + x) + const (mod 16) -- an odd stride across the whole warp, i.e. no bank conflicts.
+  static constexpr int kPSraw = (X + 6) * Y;
+  static constexpr int PS = kPSraw + ((XY % 16) - (kPSraw % 16) + 16) % 16;
+  static constexpr int kPlanInts = 4 * T + 4;                              // int4 (ox, oy, ox*Y+oy, fsel)[T], misc[4]
   static constexpr size_t kStageOff = 0;                                   // float[N]
-  static constexpr size_t kBufOff = ((size_t)4 * N + 15) / 16 * 16;        // float2[max(N, 2*NP*XY)]
-  static constexpr size_t kBufBytes = (size_t)8 * (2 * NP * XY > N ? 2 * NP * XY : N);
+  static constexpr size_t kBufOff = ((size_t)4 * N + 15) / 16 * 16;        // float2[max(N, NP*PS + NP*XY)]
+  static constexpr size_t kBufBytes = (size_t)8 * (NP * PS + NP * XY > N ? NP * PS + NP * XY : N);
   static constexpr size_t kTabOff = (kBufOff + kBufBytes + 15) / 16 * 16;  // PcTables<float>, 1 KiB slot
   static constexpr size_t kPairOff = kTabOff + 1024;                       // float2[4][7][8] paired 2-D coefficients
   static constexpr size_t kCfOff = kPairOff + 4 * 7 * 8 * 8;               // float2[7] (ge,gi), float2[7] (gex,gix)
-  static constexpr size_t kIntOff = kCfOff + 16 * 8;                       // int ox[T], oy[T], fsel[T], misc[4]
-  static constexpr size_t kRedOff = (kIntOff + (3 * T + 4) * 4 + 15) / 16 * 16;  // long long[32], float[32], float[4]
-  static constexpr size_t kBarOff = kRedOff + 32 * 8 + 32 * 4 + 16;        // mbarrier (8 bytes)
+  static constexpr size_t kPlanOff = kCfOff + 16 * 8;                      // two plans (double buffered)
+  static constexpr size_t kRedOff = (kPlanOff + 2 * kPlanInts * 4 + 15) / 16 * 16;  // int[32], float[32], float[4]
+  static constexpr size_t kBarOff = kRedOff + 32 * 4 + 32 * 4 + 16;        // mbarrier (8 bytes)
   static constexpr size_t kBytes = kBarOff + 16;
 };
 static_assert(sizeof(PcTables<float>) <= 1024, "tables must fit their shared-memory slot");
@@ -78,21 +86,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int NT>
-__device__ __forceinline__ float block_sum_bcast(float v, float* red, float* out_slot) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) red[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    float s = l < (NT + 31) / 32 ? red[l] : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (l == 0) *out_slot = s;
+// Decisions of one update for theta plane k, float64 exactly as numpy computes them on the host
+// (posecell_network.py:252-267,249,304).  plan[k] = (ox mod X, oy mod Y, ox*Y + oy, LUT filter).
+template <int X, int Y, int T>
+__device__ __forceinline__ void plan_plane(int k, const double* __restrict__ od, const double* __restrict__ cos_th,
+                                           const double* __restrict__ sin_th, double vtrans_scale, double vrot_scale,
+                                           int* plan, int* err_b) {
+  const double vt = __ddiv_rn(od[0], vtrans_scale);
+  const double ex = __dmul_rn(vt, cos_th[k]);
+  const double ey = __dmul_rn(vt, sin_th[k]);
+  const double oxd = rint(ex), oyd = rint(ey);  // numpy.around: half to even
+  const int key = (int)__dmul_rn(__dsub_rn(ex, oxd), 10.0);
+  const int ox = modp((int)oxd, X), oy = modp((int)oyd, Y);
+  reinterpret_cast<int4*>(plan)[k] = make_int4(ox, oy, ox * Y + oy, key < 0 ? 1 : 0);
+  int e = key >= 5 ? PRS_ERR_LUT_KEY : 0;
+  if (k == 0) {
+    if (!(3.0 + ceil(fabs(vt)) <= (double)(X < Y ? X : Y))) e |= PRS_ERR_RADIUS;
+    const double og = floor(__dadd_rn(__ddiv_rn(od[1], vrot_scale), 0.5));
+    if (!(fabs(og) <= 64.0)) e |= PRS_ERR_THETA;
+    const int ogc = og < -(double)PRS_OG_RANGE ? -PRS_OG_RANGE : (og > (double)PRS_OG_RANGE ? PRS_OG_RANGE : (int)og);
+    plan[4 * T] = ogc + PRS_OG_RANGE;
   }
-  __syncthreads();
-  return *out_slot;
+  if (e) atomicOr(err_b, e);
 }
 
 template <int X, int Y, int T, int NT>
@@ -100,31 +115,32 @@ __global__ void __launch_bounds__(NT, 1)
     k_pc_resident(float* state, const double* __restrict__ odom, int n_steps, const float* __restrict__ gi,
                   long long* __restrict__ argmax, float* __restrict__ total, int* __restrict__ err,
                   const double* __restrict__ cos_th, const double* __restrict__ sin_th, double vtrans_scale,
-                  double vrot_scale, int B, const PcTables<float>* __restrict__ tab_g) {
+                  double vrot_scale, int B, const PcTables<float>* __restrict__ tab_g, int ablate) {
   using L = ResLayout<X, Y, T>;
-  constexpr int XY = L::XY, N = L::N, NP = L::NP;
+  constexpr int XY = L::XY, N = L::N, NP = L::NP, PS = L::PS;
+  constexpr int kPlanT0 = NT - 64;  // the threads that prepare the next update's plan during stage 4
   static_assert(X >= 7 && Y >= 7 && T >= 3, "resident kernel needs X, Y >= 7");
   static_assert((N * 4) % 16 == 0, "bulk copies move multiples of 16 bytes");
+  static_assert(kPlanT0 >= NP * X && T <= 64, "the planning threads must be idle in stage 4");
+  static_assert(NP * X <= NT && NP * Y <= NT && XY <= NT, "one work item per thread in stages 1, 3, 4, 5");
   extern __shared__ __align__(128) unsigned char smem[];
   float* stage = reinterpret_cast<float*>(smem + L::kStageOff);
   float2* buf2 = reinterpret_cast<float2*>(smem + L::kBufOff);
-  float2* A2 = buf2;
-  float2* B2 = buf2 + NP * XY;
+  float2* A2 = buf2;            // [NP][X+6 rows][Y], plane stride PS
+  float2* B2 = buf2 + NP * PS;  // [NP][X][Y]
   const PcTables<float>* tab = reinterpret_cast<const PcTables<float>*>(smem + L::kTabOff);
   float2* s_f2p = reinterpret_cast<float2*>(smem + L::kPairOff);  // [(fs0*2+fs1)*7 + a][8]
   float2* s_cf_ty = reinterpret_cast<float2*>(smem + L::kCfOff);
   float2* s_cf_x = s_cf_ty + 7;
-  int* s_ox = reinterpret_cast<int*>(smem + L::kIntOff);
-  int* s_oy = s_ox + T;
-  int* s_fs = s_oy + T;
-  int* s_misc = s_fs + T;
-  long long* red_i = reinterpret_cast<long long*>(smem + L::kRedOff);
-  float* red_f = reinterpret_cast<float*>(smem + L::kRedOff + 32 * 8);
+  int* s_plan = reinterpret_cast<int*>(smem + L::kPlanOff);
+  int* red_i = reinterpret_cast<int*>(smem + L::kRedOff);
+  float* red_f = reinterpret_cast<float*>(smem + L::kRedOff + 32 * 4);
   float* s_val = red_f + 32;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + L::kBarOff);
   const int tid = threadIdx.x;
+  const int wid = tid >> 5, lane = tid & 31;
 
-  // ---- one-time set-up: tables, coefficient pairs, mbarrier, first prefetch
+  // ---- one-time set-up: tables, coefficient pairs, mbarrier, first prefetch, first plan
   for (int i = tid; i < (int)(sizeof(PcTables<float>) / 4); i += NT)
     reinterpret_cast<float*>(smem + L::kTabOff)[i] = reinterpret_cast<const float*>(tab_g)[i];
   if (tid < 7) {
@@ -144,63 +160,52 @@ __global__ void __launch_bounds__(NT, 1)
       bulk_g2s(stage, state + (size_t)blockIdx.x * N, N * 4, bar);
     }
   }
+  if (tid >= kPlanT0 && tid < kPlanT0 + T && (int)blockIdx.x < B && n_steps > 0)
+    plan_plane<X, Y, T>(tid - kPlanT0, odom + (size_t)blockIdx.x * 2, cos_th, sin_th, vtrans_scale, vrot_scale, s_plan,
+                        err + blockIdx.x);
   __syncthreads();
   uint32_t parity = 0;
+  int slot = 0;
 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     float* gst = state + (size_t)b * N;
     const float g_inh = gi[b];
     for (int step = 0; step < n_steps; ++step) {
-      const double* od = odom + ((size_t)step * B + b) * 2;
-      // ---- decisions of this step, float64 exactly as numpy computes them on the host
-      //      (posecell_network.py:252-267,249,304)
-      if (tid < T) {
-        const double vt = __ddiv_rn(od[0], vtrans_scale);
-        const double ex = __dmul_rn(vt, cos_th[tid]);
-        const double ey = __dmul_rn(vt, sin_th[tid]);
-        const double oxd = rint(ex), oyd = rint(ey);
-        const int key = (int)__dmul_rn(__dsub_rn(ex, oxd), 10.0);
-        s_ox[tid] = modp((int)oxd, X);
-        s_oy[tid] = modp((int)oyd, Y);
-        s_fs[tid] = key < 0 ? 1 : 0;
-        int e = key >= 5 ? PRS_ERR_LUT_KEY : 0;
-        if (tid == 0) {
-          if (!(3.0 + ceil(fabs(vt)) <= (double)(X < Y ? X : Y))) e |= PRS_ERR_RADIUS;
-          const double og = floor(__dadd_rn(__ddiv_rn(od[1], vrot_scale), 0.5));
-          if (!(fabs(og) <= 64.0)) e |= PRS_ERR_THETA;
-          const int ogc = og < -(double)PRS_OG_RANGE ? -PRS_OG_RANGE : (og > (double)PRS_OG_RANGE ? PRS_OG_RANGE : (int)og);
-          s_misc[0] = ogc + PRS_OG_RANGE;
-        }
-        if (e) atomicOr(&err[b], e);
-      }
+      const int* plan = s_plan + slot * L::kPlanInts;
+      const int4* plan4 = reinterpret_cast<const int4*>(plan);
 
-      // ---- 1. theta pass of the separable DoG: stage (or global on later steps) -> (E, I) pairs
+      // ---- 1. theta pass of the separable DoG: stage (or global on later steps) -> (E, I) pairs.
+      //      The pair of plane k is stored at (x - ox_k, y - oy_k): the integer origin the reference adds
+      //      to its read index in the 2-D stage (convolution.py:320-340) is applied here, once, as a
+      //      translation of the whole plane; every later stage is a periodic correlate and commutes with it.
       if (step == 0) {
         mbar_wait(bar, parity);
         parity ^= 1;
       }
-      {
+      if (!(ablate & 1) && tid < XY) {
         const float e0 = tab->ge[3], e1 = tab->ge[2], e2 = tab->ge[1], e3 = tab->ge[0];
         const float i0 = tab->gi[3], i1 = tab->gi[2], i2 = tab->gi[1], i3 = tab->gi[0];
-        for (int p = tid; p < XY; p += NT) {
-          float in[T];
-          if (step == 0) {
+        const int p = tid;
+        const int x = p / Y, y = p - x * Y;
+        float in[T];
+        if (step == 0) {
 #pragma unroll
-            for (int k = 0; k < T; ++k) in[k] = stage[k * XY + p];
-          } else {
+          for (int k = 0; k < T; ++k) in[k] = stage[k * XY + p];
+        } else {
 #pragma unroll
-            for (int k = 0; k < T; ++k) in[k] = gst[k * XY + p];
-          }
+          for (int k = 0; k < T; ++k) in[k] = gst[k * XY + p];
+        }
 #pragma unroll
-          for (int k = 0; k < T; ++k) {
-            const float c = in[k];
-            const float s1 = in[(k + 1) % T] + in[(k + T - 1) % T];
-            const float s2 = in[(k + 2) % T] + in[(k + T - 2) % T];
-            const float s3 = in[(k + 3) % T] + in[(k + T - 3) % T];
-            const float e = fmaf(e0, c, fmaf(e1, s1, fmaf(e2, s2, e3 * s3)));
-            const float i = fmaf(i0, c, fmaf(i1, s1, fmaf(i2, s2, i3 * s3)));
-            buf2[k * XY + p] = make_float2(e, i);
-          }
+        for (int k = 0; k < T; ++k) {
+          const float c = in[k];
+          const float s1 = in[(k + 1) % T] + in[(k + T - 1) % T];
+          const float s2 = in[(k + 2) % T] + in[(k + T - 2) % T];
+          const float s3 = in[(k + 3) % T] + in[(k + T - 3) % T];
+          const float e = fmaf(e0, c, fmaf(e1, s1, fmaf(e2, s2, e3 * s3)));
+          const float i = fmaf(i0, c, fmaf(i1, s1, fmaf(i2, s2, i3 * s3)));
+          const int4 pl = plan4[k];
+          const int dst = k * XY + p - pl.z + (x < pl.x ? XY : 0) + (y < pl.y ? Y : 0);
+          buf2[dst] = make_float2(e, i);
         }
       }
       __syncthreads();
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(NT, 1)
       }
 
       // ---- 2. y pass, in place on each (theta, x) line
-      {
+      if (!(ablate & 2)) {
         float2 cf[7];
 #pragma unroll
         for (int t = 0; t < 7; ++t) cf[t] = s_cf_ty[t];
@@ -241,21 +246,23 @@ __global__ void __launch_bounds__(NT, 1)
       __syncthreads();
 
       // ---- 3. x pass + global inhibition (posecell_network.py:339-340) + sum (:343).
-      //      Lines are enumerated theta-fastest so that a warp's loads stride by one plane (odd stride:
-      //      no bank conflicts).
-      constexpr int IT3 = (T * Y + NT - 1) / NT;
-      float keep[IT3][X];
+      //      A thread takes the same (y) column of BOTH planes of a pair (kp, kp+NP), so that the result is
+      //      written as one float2 per cell.  Items are enumerated plane-fastest: a warp's accesses stride by
+      //      one plane (an odd number of float2 slots), which is free of bank conflicts.
+      float2 keep[X];
       float psum = 0.f;
-      {
+#pragma unroll
+      for (int x = 0; x < X; ++x) keep[x] = make_float2(0.f, 0.f);
+      const int y3 = tid / NP, kp3 = tid - y3 * NP;
+      if (!(ablate & 4) && tid < NP * Y) {
         float2 cf[7];
 #pragma unroll
         for (int t = 0; t < 7; ++t) cf[t] = s_cf_x[t];
 #pragma unroll
-        for (int it = 0; it < IT3; ++it) {
-          const int ln = tid + it * NT;
-          if (ln < T * Y) {
-            const int y = ln / T, k = ln - y * T;
-            const float2* col = buf2 + k * XY + y;
+        for (int h = 0; h < 2; ++h) {
+          const int k = kp3 + h * NP;
+          if (k < T) {
+            const float2* col = buf2 + k * XY + y3;
             float2 in[X];
 #pragma unroll
             for (int x = 0; x < X; ++x) in[x] = col[x * Y];
@@ -266,147 +273,148 @@ __global__ void __launch_bounds__(NT, 1)
               for (int t = 0; t < 7; ++t) acc = ffma2(in[(x + t + X - 3) % X], cf[t], acc);
               float a = acc.x - acc.y;
               a = (a < g_inh) ? 0.f : a - g_inh;
-              keep[it][x] = a;
+              if (h == 0)
+                keep[x].x = a;
+              else
+                keep[x].y = a;
               psum += a;
             }
           }
         }
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      if (lane == 0) red_f[wid] = psum;
       __syncthreads();  // every (E, I) pair has been consumed: the bytes become A2 / B2
-      // Store A moved by the plane's integer origin: A'[x'][y'] = A[(x'+ox) % X][(y'+oy) % Y]
-      // (convolution.py:320-340 adds origin_x[k], origin_y[k] to the read index; here it is subtracted
-      // from the write index once), interleaved with the partner plane k +- NP.
+      if (!(ablate & 8) && tid < NP * Y) {
+        float2* dst = A2 + kp3 * PS + y3;  // row r of the halo layout is grid row r - 3
 #pragma unroll
-      for (int it = 0; it < IT3; ++it) {
-        const int ln = tid + it * NT;
-        if (ln < T * Y) {
-          const int y = ln / T, k = ln - y * T;
-          const int half = k >= NP ? 1 : 0;
-          const int kp = k - half * NP;
-          int ys = y - s_oy[k];
-          ys += ys < 0 ? Y : 0;
-          int xs = X - s_ox[k];  // (0 - ox) mod X, in 1..X
-          xs -= xs >= X ? X : 0;
-          float* dst = reinterpret_cast<float*>(A2 + kp * XY + ys) + half;
-#pragma unroll
-          for (int x = 0; x < X; ++x) {
-            dst[xs * (2 * Y)] = keep[it][x];
-            xs = (xs + 1 == X) ? 0 : xs + 1;
-          }
+        for (int x = 0; x < X; ++x) {
+          dst[(x + 3) * Y] = keep[x];
+          if (x < 3) dst[(x + 3 + X) * Y] = keep[x];
+          if (x >= X - 3) dst[(x + 3 - X) * Y] = keep[x];
         }
       }
-      const float tot = block_sum_bcast<NT>(psum, red_f, s_val);  // contains the barrier that publishes A2
-      const float inv = (tot != 0.f) ? 1.f / tot : 1.f;           // posecell_network.py:344-345
+      if (wid == 0) {
+        float sacc = lane < (NT + 31) / 32 ? red_f[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) s_val[0] = sacc;
+      }
+      __syncthreads();  // publishes A2 and the total
+      const float tot = s_val[0];
+      const float inv = (tot != 0.f) ? 1.f / tot : 1.f;  // posecell_network.py:344-345
 
-      // ---- 4. 7x7 periodic correlate of both planes of a pair at once (posecell_network.py:273-274,300)
-      {
-        for (int item = tid; item < NP * X; item += NT) {
-          const int kp = item / X, x = item - kp * X;
-          const int k1 = (kp + NP < T) ? kp + NP : kp;
-          const float2* ctab = s_f2p + (s_fs[kp] * 2 + s_fs[k1]) * 56;
-          const float2* plane = A2 + kp * XY;
-          float2 acc[Y];
+      // ---- 4. 7x7 periodic correlate of both planes of a pair at once (posecell_network.py:273-274,300);
+      //      meanwhile two otherwise idle warps prepare the plan of the next update.
+      const bool last_step = (step + 1 == n_steps);
+      const int nb = last_step ? b + (int)gridDim.x : b;
+      const int nstep = last_step ? 0 : step + 1;
+      if (tid >= kPlanT0) {
+        if (tid < kPlanT0 + T && nb < B)
+          plan_plane<X, Y, T>(tid - kPlanT0, odom + ((size_t)nstep * B + nb) * 2, cos_th, sin_th, vtrans_scale,
+                              vrot_scale, s_plan + (slot ^ 1) * L::kPlanInts, err + nb);
+      } else if (!(ablate & 16) && tid < NP * X) {
+        const int kp = tid / X, x = tid - kp * X;
+        const int k1 = (kp + NP < T) ? kp + NP : kp;
+        const float2* ctab = s_f2p + (plan4[kp].w * 2 + plan4[k1].w) * 56;
+        const float2* rows = A2 + kp * PS + x * Y;  // halo layout: tap row a of output row x is row x + a
+        float2 acc[Y];
 #pragma unroll
-          for (int j = 0; j < Y; ++j) acc[j] = make_float2(0.f, 0.f);
+        for (int j = 0; j < Y; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int a = 0; a < 7; ++a) {
-            int xr = x + a - 3;
-            xr += xr < 0 ? X : 0;
-            xr -= xr >= X ? X : 0;
-            const float2* r = plane + xr * Y;
-            float2 row[Y];
+        for (int a = 0; a < 7; ++a) {
+          float2 row[Y];
 #pragma unroll
-            for (int j = 0; j < Y; ++j) row[j] = r[j];
-            const float4* cp = reinterpret_cast<const float4*>(ctab + a * 8);
-            const float4 c01 = cp[0], c23 = cp[1], c45 = cp[2], c6x = cp[3];
-            const float2 cf[7] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y),
-                                  make_float2(c23.z, c23.w), make_float2(c45.x, c45.y), make_float2(c45.z, c45.w),
-                                  make_float2(c6x.x, c6x.y)};
-#pragma unroll
-            for (int j = 0; j < Y; ++j) {
-#pragma unroll
-              for (int q = 0; q < 7; ++q) acc[j] = ffma2(row[(j + q + Y - 3) % Y], cf[q], acc[j]);
-            }
-          }
-          float2* o = B2 + kp * XY + x * Y;
+          for (int j = 0; j < Y; ++j) row[j] = rows[a * Y + j];
+          const float4* cp = reinterpret_cast<const float4*>(ctab + a * 8);
+          const float4 c01 = cp[0], c23 = cp[1], c45 = cp[2], c6x = cp[3];
+          const float2 cf[7] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y),
+                                make_float2(c23.z, c23.w), make_float2(c45.x, c45.y), make_float2(c45.z, c45.w),
+                                make_float2(c6x.x, c6x.y)};
 #pragma unroll
           for (int j = 0; j < Y; ++j) {
-            const float v0 = acc[j].x * inv, v1 = acc[j].y * inv;
-            o[j] = make_float2((v0 < 0.f) ? 0.f : v0, (v1 < 0.f) ? 0.f : v1);  // posecell_network.py:300
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc[j] = ffma2(row[(j + q + Y - 3) % Y], cf[q], acc[j]);
           }
+        }
+        float2* o = B2 + kp * XY + x * Y;
+#pragma unroll
+        for (int j = 0; j < Y; ++j) {
+          const float v0 = acc[j].x * inv, v1 = acc[j].y * inv;
+          o[j] = make_float2((v0 < 0.f) ? 0.f : v0, (v1 < 0.f) ? 0.f : v1);  // posecell_network.py:300
         }
       }
       __syncthreads();
 
       // ---- 5. theta pass (convolution.py:344-359), clamp, arg-max, registers -> global
       float best = -INFINITY;
-      long long bidx = 0x7fffffffffffffffLL;
-      {
+      int bidx = 0x7fffffff;
+      if (!(ablate & 32) && tid < XY) {
+        const int p = tid;
         float fc[7];
-        const float* f1 = tab->f1d[s_misc[0]];
+        const float* f1 = tab->f1d[plan[4 * T]];
 #pragma unroll
         for (int t = 0; t < 7; ++t) fc[t] = f1[t];
-        for (int p = tid; p < XY; p += NT) {
-          float2 pin[NP];
+        float2 pin[NP];
 #pragma unroll
-          for (int kk = 0; kk < NP; ++kk) pin[kk] = B2[kk * XY + p];
-          if constexpr (T % 2 == 0) {
-            // planes kk and kk+NP advance together; a tap that leaves [0, NP) lands in the partner half
-            float2 cf2[7];
+        for (int kk = 0; kk < NP; ++kk) pin[kk] = B2[kk * XY + p];
+        if constexpr (T % 2 == 0) {
+          // planes kk and kk+NP advance together; a tap that leaves [0, NP) lands in the partner half
+          float2 cf2[7];
 #pragma unroll
-            for (int t = 0; t < 7; ++t) cf2[t] = make_float2(fc[t], fc[t]);
-            float2 out[NP];
+          for (int t = 0; t < 7; ++t) cf2[t] = make_float2(fc[t], fc[t]);
+          float2 out[NP];
 #pragma unroll
-            for (int kk = 0; kk < NP; ++kk) {
-              float2 acc = make_float2(0.f, 0.f);
+          for (int kk = 0; kk < NP; ++kk) {
+            float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-              for (int t = 0; t < 7; ++t) {
-                const int m = kk + t - 3;
-                float2 v;
-                if (m < 0)
-                  v = make_float2(pin[m + NP].y, pin[m + NP].x);
-                else if (m >= NP)
-                  v = make_float2(pin[m - NP].y, pin[m - NP].x);
-                else
-                  v = pin[m];
-                acc = ffma2(v, cf2[t], acc);
-              }
-              out[kk] = make_float2(acc.x < 0.f ? 0.f : acc.x, acc.y < 0.f ? 0.f : acc.y);  // posecell_network.py:314
+            for (int t = 0; t < 7; ++t) {
+              const int m = kk + t - 3;
+              float2 v;
+              if (m < 0)
+                v = make_float2(pin[m + NP].y, pin[m + NP].x);
+              else if (m >= NP)
+                v = make_float2(pin[m - NP].y, pin[m - NP].x);
+              else
+                v = pin[m];
+              acc = ffma2(v, cf2[t], acc);
             }
+            out[kk] = make_float2(acc.x < 0.f ? 0.f : acc.x, acc.y < 0.f ? 0.f : acc.y);  // posecell_network.py:314
+          }
 #pragma unroll
-            for (int kk = 0; kk < NP; ++kk) {
-              gst[kk * XY + p] = out[kk].x;
-              if (out[kk].x > best) {  // k ascending within p, p ascending: strict '>' keeps the lowest flat index
-                best = out[kk].x;
-                bidx = (long long)p * T + kk;
-              }
+          for (int kk = 0; kk < NP; ++kk) {
+            gst[kk * XY + p] = out[kk].x;
+            if (out[kk].x > best) {  // theta ascending: strict '>' keeps the lowest flat index of this line
+              best = out[kk].x;
+              bidx = p * T + kk;
             }
+          }
 #pragma unroll
-            for (int kk = 0; kk < NP; ++kk) {
-              gst[(kk + NP) * XY + p] = out[kk].y;
-              if (out[kk].y > best) {
-                best = out[kk].y;
-                bidx = (long long)p * T + kk + NP;
-              }
+          for (int kk = 0; kk < NP; ++kk) {
+            gst[(kk + NP) * XY + p] = out[kk].y;
+            if (out[kk].y > best) {
+              best = out[kk].y;
+              bidx = p * T + kk + NP;
             }
-          } else {
-            float in[T];
+          }
+        } else {
+          float in[T];
 #pragma unroll
-            for (int kk = 0; kk < NP; ++kk) {
-              in[kk] = pin[kk].x;
-              if (kk + NP < T) in[kk + NP] = pin[kk].y;
-            }
+          for (int kk = 0; kk < NP; ++kk) {
+            in[kk] = pin[kk].x;
+            if (kk + NP < T) in[kk + NP] = pin[kk].y;
+          }
 #pragma unroll
-            for (int k = 0; k < T; ++k) {
-              float c = 0.f;
+          for (int k = 0; k < T; ++k) {
+            float c = 0.f;
 #pragma unroll
-              for (int t = 0; t < 7; ++t) c = fmaf(fc[t], in[(k + t + T - 3) % T], c);
-              c = (c < 0.f) ? 0.f : c;
-              gst[k * XY + p] = c;
-              if (c > best) {
-                best = c;
-                bidx = (long long)p * T + k;
-              }
+            for (int t = 0; t < 7; ++t) c = fmaf(fc[t], in[(k + t + T - 3) % T], c);
+            c = (c < 0.f) ? 0.f : c;
+            gst[k * XY + p] = c;
+            if (c > best) {
+              best = c;
+              bidx = p * T + k;
             }
           }
         }
@@ -415,38 +423,35 @@ __global__ void __launch_bounds__(NT, 1)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const float v2 = __shfl_xor_sync(0xffffffffu, best, o);
-        const long long i2 = __shfl_xor_sync(0xffffffffu, bidx, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bidx, o);
         if (v2 > best || (v2 == best && i2 < bidx)) {
           best = v2;
           bidx = i2;
         }
       }
-      {
-        const int w = tid >> 5, l = tid & 31;
-        if (l == 0) {
-          red_f[w] = best;
-          red_i[w] = bidx;
-        }
-        __syncthreads();
-        if (w == 0) {
-          float v = l < (NT + 31) / 32 ? red_f[l] : -INFINITY;
-          long long ix = l < (NT + 31) / 32 ? red_i[l] : 0x7fffffffffffffffLL;
+      if (lane == 0) {
+        red_f[wid] = best;
+        red_i[wid] = bidx;
+      }
+      __syncthreads();  // the state in global memory and every SMEM slot are consistent for the next update
+      if (wid == 0) {
+        float v = lane < (NT + 31) / 32 ? red_f[lane] : -INFINITY;
+        int ix = lane < (NT + 31) / 32 ? red_i[lane] : 0x7fffffff;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
-            const long long i2 = __shfl_xor_sync(0xffffffffu, ix, o);
-            if (v2 > v || (v2 == v && i2 < ix)) {
-              v = v2;
-              ix = i2;
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+          const int i2 = __shfl_xor_sync(0xffffffffu, ix, o);
+          if (v2 > v || (v2 == v && i2 < ix)) {
+            v = v2;
+            ix = i2;
           }
-          if (l == 0) {
-            argmax[(size_t)step * B + b] = ix;
-            total[(size_t)step * B + b] = tot;
-          }
+        }
+        if (lane == 0) {
+          argmax[(size_t)step * B + b] = (long long)ix;
+          total[(size_t)step * B + b] = tot;
         }
       }
-      __syncthreads();  // state in global and every SMEM slot are consistent before the next step / network
+      slot ^= 1;
     }
   }
 }
@@ -465,8 +470,13 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
   PRS_CUDA(cudaGetDevice(&dev));
   PRS_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p->B < nsm ? p->B : nsm;
+  // PRS_RESIDENT_ABLATE (profiling only): bit i skips stage i+1 to attribute time; results are then meaningless
+  static int ablate = [] {
+    const char* e = getenv("PRS_RESIDENT_ABLATE");
+    return e ? atoi(e) : 0;
+  }();
   kern<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale,
-                                    p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev);
+                                    p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
@@ -481,8 +491,16 @@ int prs_pc_resident_supported(const prs_pc_plan* p) {
 
 int prs_pc_resident_step(prs_pc_plan* p, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st) {
-  if (p->X == 21 && p->Y == 21 && p->Th == 36)
+  if (p->X == 21 && p->Y == 21 && p->Th == 36) {
+    // PRS_RESIDENT_NT selects the CTA size (tuning knob; the default is the measured best)
+    static int nt = [] {
+      const char* e = getenv("PRS_RESIDENT_NT");
+      return e ? atoi(e) : 448;
+    }();
+    if (nt == 512)
+      return launch<21, 21, 36, 512>(p, (float*)state, odom, T, (const float*)gi, argmax, (float*)total, err, st);
     return launch<21, 21, 36, 448>(p, (float*)state, odom, T, (const float*)gi, argmax, (float*)total, err, st);
+  }
   prs_set_error("resident path not available for this plan");
   return PRS_E_INVALID;
 }
