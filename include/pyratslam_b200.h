@@ -141,6 +141,20 @@ PRS_API int prs_vt_sweep_u8(const uint8_t* lib, long long n, const uint8_t* quer
                     unsigned long long* key_out, uint32_t* scores, void* stream);
 PRS_API int prs_vt_sweep_f32(const float* lib, long long n, const float* query, int mode, long long base_index,
                      unsigned long long* key_out, float* scores, void* stream);
+/* Bit-sliced ("packed") uint8 library: the layout the fast sweep streams.  1088 bytes per template, stored
+ * in groups of 32 (see csrc/view_templates.cu).  Same scores, keys and tie-breaks as prs_vt_sweep_u8.
+ *   prs_vt_packed_bytes(n)  : bytes of a packed library with room for n templates (whole groups)
+ *   prs_vt_pack_u8          : convert n row-major templates src[n][32][32] into slots first..first+n-1
+ *                             (the packed buffer must have been zero-filled once; ViewTemplates' append, :68-71)
+ *   prs_vt_unpack_u8        : one template back to row-major (the ViewTemplate.template attribute)
+ *   prs_vt_sweep_packed_u8  : query is a row-major device uint8[32][32]; scratch is a device buffer of
+ *                             >= 2 KiB; one sweep may be in flight per device (the query planes go through
+ *                             constant memory). */
+PRS_API size_t prs_vt_packed_bytes(long long n);
+PRS_API int prs_vt_pack_u8(const uint8_t* src, long long n, void* packed, long long first, void* stream);
+PRS_API int prs_vt_unpack_u8(const void* packed, long long index, uint8_t* dst, void* stream);
+PRS_API int prs_vt_sweep_packed_u8(const void* packed, long long n, const uint8_t* query, int mode, long long base_index,
+                           unsigned long long* key_out, uint32_t* scores, void* scratch, void* stream);
 /* HOST query in, HOST key out: H2D copy of the 1 KiB query, sweep, D2H of the 8-byte key, sync.
  * lib stays resident on the device; scratch is a device buffer of >= 1024+8 bytes. */
 PRS_API int prs_vt_match_host_u8(const uint8_t* lib, long long n, const uint8_t* query_host, int mode,

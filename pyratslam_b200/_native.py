@@ -54,6 +54,11 @@ _SIGNATURES = {
                                   c_int, c_int, c_void_p]),
     "prs_vt_sweep_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
     "prs_vt_sweep_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
+    "prs_vt_packed_bytes": (c_size_t, [c_longlong]),
+    "prs_vt_pack_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p]),
+    "prs_vt_unpack_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
+    "prs_vt_sweep_packed_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p,
+                                       c_void_p]),
     "prs_vt_match_host_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
 }
 

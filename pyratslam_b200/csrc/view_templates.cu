@@ -304,3 +304,297 @@ extern "C" int prs_vt_match_host_u8(const uint8_t* lib, long long n, const uint8
   PRS_CUDA(cudaStreamSynchronize(st));
   return PRS_OK;
 }
+
+// =============================================================================================
+// Bit-sliced ("packed") uint8 library.
+//
+// The byte-wise SWAR sweep above is bound by the integer pipes (64 lanes/clk/SM on B200, measured):
+// 3 instructions per 4 byte-compares = 0.50 of the HBM roof at best.  The reference score only needs
+//     sum((a - b) mod 256) = sum(a) - sum(b) + 256 * #{a < b}            (checked in the CPU tests)
+// so the library is stored as bit planes: for every template row, 8 words, word k holding bit k of the
+// row's 32 pixels.  #{a < b} over a row pair is then 8 LOP3 (one per plane, LSB to MSB:
+// lt = (~a & b) | (~(a ^ b) & lt)) and one POPC for 32 pixels -- 10 instructions per 32 compares instead
+// of 24.  One lane owns one template, 32 templates are interleaved so that a warp's 128-bit loads are
+// contiguous 512-byte runs, and the query planes are __constant__ operands of the LOP3s (no registers,
+// no loads).  Row sums (uint16 x 32) ride along: 1088 bytes per template.
+//
+// Layout of one group of 32 templates (8704 uint32):
+//   planes : uint4 [32 rows][2 halves][32 lanes]   .x..w = planes 4h..4h+3 of that row of template `lane`
+//   rowsum : uint4 [4][32 lanes]                   16 words per lane, word w = R[2w] | R[2w+1] << 16
+constexpr int kGroupU4 = 32 * 2 * 32 + 4 * 32;  // 2176 uint4 = 34816 bytes per 32 templates
+
+__constant__ uint32_t c_vtq[32 * 8 + 8];  // query planes [row][k], then sum(rows 8..23), sum(all rows)
+
+__global__ void k_vt_pack_u8(const uint8_t* __restrict__ src, long long n, uint4* __restrict__ packed,
+                             long long first) {
+  // one thread per (template, row)
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 32) return;
+  const long long tl = i >> 5;
+  const int t = (int)(i & 31);
+  const long long ti = first + tl;
+  const uint32_t* row = reinterpret_cast<const uint32_t*>(src + tl * 1024 + t * 32);
+  uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t sum = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const uint32_t v = row[w];
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const uint32_t px = (v >> (8 * bb)) & 0xffu;
+      sum += px;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pl[k] |= ((px >> k) & 1u) << (w * 4 + bb);
+    }
+  }
+  uint4* grp = packed + (ti >> 5) * kGroupU4;
+  const int lane = (int)(ti & 31);
+  grp[(t * 2 + 0) * 32 + lane] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  grp[(t * 2 + 1) * 32 + lane] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+  // row sums: 16-bit halves of word w = t/2 of this lane
+  uint16_t* rs = reinterpret_cast<uint16_t*>(grp + 32 * 2 * 32);
+  const int w = t >> 1;
+  rs[(((w >> 2) * 32 + lane) * 4 + (w & 3)) * 2 + (t & 1)] = (uint16_t)sum;
+}
+
+__global__ void k_vt_unpack_u8(const uint4* __restrict__ packed, long long ti, uint8_t* __restrict__ dst) {
+  // 1024 threads: one per pixel of template ti
+  const int t = threadIdx.x >> 5, c = threadIdx.x & 31;
+  const uint4* grp = packed + (ti >> 5) * kGroupU4;
+  const int lane = (int)(ti & 31);
+  const uint4 lo = grp[(t * 2 + 0) * 32 + lane], hi = grp[(t * 2 + 1) * 32 + lane];
+  const uint32_t pl[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  uint32_t px = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) px |= ((pl[k] >> c) & 1u) << k;
+  dst[t * 32 + c] = (uint8_t)px;
+}
+
+__global__ void k_vt_pack_query(const uint8_t* __restrict__ q, uint32_t* __restrict__ out) {
+  // 32 threads: thread t packs row t; then the two sums
+  const int t = threadIdx.x;
+  uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t sum = 0;
+  for (int c = 0; c < 32; ++c) {
+    const uint32_t px = q[t * 32 + c];
+    sum += px;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pl[k] |= ((px >> k) & 1u) << c;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out[t * 8 + k] = pl[k];
+  uint32_t mid = (t >= 8 && t < 24) ? sum : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mid += __shfl_xor_sync(0xffffffffu, mid, o);
+  }
+  if (t == 0) {
+    out[256] = mid;
+    out[257] = sum;
+  }
+}
+
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// #{pixels of the stored row that are smaller than the query row's}: bit planes (lo, hi) of the stored
+// row against query row s, whose planes are constant-bank operands.  LSB to MSB; the last differing bit wins.
+__device__ __forceinline__ uint32_t lt_row(const uint4& lo, const uint4& hi, int s) {
+  const uint32_t* q = c_vtq + s * 8;
+  uint32_t lt = ~lo.x & q[0];
+  lt = (~lo.y & q[1]) | (~(lo.y ^ q[1]) & lt);
+  lt = (~lo.z & q[2]) | (~(lo.z ^ q[2]) & lt);
+  lt = (~lo.w & q[3]) | (~(lo.w ^ q[3]) & lt);
+  lt = (~hi.x & q[4]) | (~(hi.x ^ q[4]) & lt);
+  lt = (~hi.y & q[5]) | (~(hi.y ^ q[5]) & lt);
+  lt = (~hi.z & q[6]) | (~(hi.z ^ q[6]) & lt);
+  lt = (~hi.w & q[7]) | (~(hi.w ^ q[7]) & lt);
+  return (uint32_t)__popc(lt);
+}
+
+// one stored row T against every query row it is paired with in reference mode (o = T - s in [-7, 7], s in [8, 23])
+template <int T>
+__device__ __forceinline__ void ref_row(const uint4& lo, const uint4& hi, uint32_t (&cnt)[15]) {
+  constexpr int s_lo = (T - 7 > 8) ? T - 7 : 8;
+  constexpr int s_hi = (T + 7 < 23) ? T + 7 : 23;
+#pragma unroll
+  for (int s = s_lo; s <= s_hi; ++s) cnt[T - s + 7] += lt_row(lo, hi, s);
+}
+
+template <int T>
+struct RefRows {
+  __device__ __forceinline__ static void run(const uint4* gp, uint4 lo, uint4 hi, uint32_t (&cnt)[15]) {
+    if constexpr (T <= 30) {
+      uint4 nlo = lo, nhi = hi;
+      if constexpr (T < 30) {  // the next row is in flight while this one is compared
+        nlo = ld_stream_u4(gp + ((T + 1) * 2 + 0) * 32);
+        nhi = ld_stream_u4(gp + ((T + 1) * 2 + 1) * 32);
+      }
+      ref_row<T>(lo, hi, cnt);
+      RefRows<T + 1>::run(gp, nlo, nhi, cnt);
+    }
+  }
+};
+
+constexpr int kPkThreads = 128;
+
+// Reference mode (15 windowed row offsets, view_templates.py:16-28) over the packed library.
+__global__ void __launch_bounds__(kPkThreads)
+    k_vt_sweep_packed_ref(const uint4* __restrict__ packed, long long n, long long base_index,
+                          unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const long long n_groups = (n + 31) >> 5;
+  const long long warp0 = ((long long)blockIdx.x * kPkThreads + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * kPkThreads) >> 5;
+  unsigned long long best = ~0ull;
+  for (long long g = warp0; g < n_groups; g += n_warps) {
+    const uint4* gp = packed + g * kGroupU4 + lane;
+    uint32_t cnt[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) cnt[i] = 0;
+    RefRows<1>::run(gp, ld_stream_u4(gp + (1 * 2 + 0) * 32), ld_stream_u4(gp + (1 * 2 + 1) * 32), cnt);
+    // window sums of the stored rows: A(o) = sum_{r=8+o}^{23+o} R[r]
+    uint32_t R[32];
+#pragma unroll
+    for (int w4 = 0; w4 < 4; ++w4) {
+      const uint4 v = ld_stream_u4(gp + 32 * 2 * 32 + w4 * 32);
+      const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        R[(w4 * 4 + j) * 2] = ww[j] & 0xffffu;
+        R[(w4 * 4 + j) * 2 + 1] = ww[j] >> 16;
+      }
+    }
+    uint32_t A = 0;
+#pragma unroll
+    for (int r = 1; r <= 16; ++r) A += R[r];
+    const uint32_t bq = c_vtq[256];
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int o = -7; o <= 7; ++o) {
+      const uint32_t sc = A + 256u * cnt[o + 7] - bq;
+      m = min(m, sc);
+      if (o < 7) A = A - R[8 + o] + R[24 + o];
+    }
+    const long long ti = g * 32 + lane;
+    if (ti < n) {
+      const unsigned long long key = ((unsigned long long)m << 32) | (unsigned long long)(base_index + ti);
+      best = key < best ? key : best;
+      if (scores != nullptr) scores[ti] = m;
+    }
+  }
+  __shared__ unsigned long long sm[kPkThreads / 32];
+  best = warp_min_u64(best);
+  if (lane == 0) sm[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long k = sm[0];
+#pragma unroll
+    for (int i = 1; i < kPkThreads / 32; ++i) k = sm[i] < k ? sm[i] : k;
+    if (k != ~0ull) atomicMin(key_out, k);
+  }
+}
+
+// Circular mode (all 32 cyclic row shifts; extension): per-offset counters live in shared memory because
+// the offset of a (stored row, query row) pair depends on the run-time stored row.
+__global__ void __launch_bounds__(kPkThreads)
+    k_vt_sweep_packed_circ(const uint4* __restrict__ packed, long long n, long long base_index,
+                           unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores) {
+  __shared__ uint32_t s_cnt[kPkThreads / 32][32][32];  // [warp][offset][lane]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long n_groups = (n + 31) >> 5;
+  const long long warp0 = ((long long)blockIdx.x * kPkThreads + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * kPkThreads) >> 5;
+  unsigned long long best = ~0ull;
+  for (long long g = warp0; g < n_groups; g += n_warps) {
+    const uint4* gp = packed + g * kGroupU4 + lane;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) s_cnt[wid][o][lane] = 0;
+    for (int t = 0; t < 32; ++t) {
+      const uint4 lo = ld_stream_u4(gp + (t * 2 + 0) * 32), hi = ld_stream_u4(gp + (t * 2 + 1) * 32);
+#pragma unroll
+      for (int s = 0; s < 32; ++s) {
+        // score(shift) pairs stored row (s + shift) mod 32 with query row s  ->  shift = (t - s) mod 32
+        s_cnt[wid][(t - s) & 31][lane] += lt_row(lo, hi, s);
+      }
+    }
+    uint32_t A = 0;
+#pragma unroll
+    for (int w4 = 0; w4 < 4; ++w4) {
+      const uint4 v = ld_stream_u4(gp + 32 * 2 * 32 + w4 * 32);
+      A += (v.x & 0xffffu) + (v.x >> 16) + (v.y & 0xffffu) + (v.y >> 16) + (v.z & 0xffffu) + (v.z >> 16) +
+           (v.w & 0xffffu) + (v.w >> 16);
+    }
+    const uint32_t bq = c_vtq[257];
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) m = min(m, A + 256u * s_cnt[wid][o][lane] - bq);
+    const long long ti = g * 32 + lane;
+    if (ti < n) {
+      const unsigned long long key = ((unsigned long long)m << 32) | (unsigned long long)(base_index + ti);
+      best = key < best ? key : best;
+      if (scores != nullptr) scores[ti] = m;
+    }
+  }
+  __shared__ unsigned long long sm[kPkThreads / 32];
+  best = warp_min_u64(best);
+  if (lane == 0) sm[wid] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long k = sm[0];
+#pragma unroll
+    for (int i = 1; i < kPkThreads / 32; ++i) k = sm[i] < k ? sm[i] : k;
+    if (k != ~0ull) atomicMin(key_out, k);
+  }
+}
+
+extern "C" size_t prs_vt_packed_bytes(long long n) {
+  return (size_t)((n + 31) / 32) * kGroupU4 * sizeof(uint4);
+}
+
+extern "C" int prs_vt_pack_u8(const uint8_t* src, long long n, void* packed, long long first, void* stream) {
+  PRS_REQUIRE(packed && n >= 0 && first >= 0 && (src || n == 0), "prs_vt_pack_u8: bad argument");
+  if (n == 0) return PRS_OK;
+  const long long threads = n * 32;
+  k_vt_pack_u8<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n, (uint4*)packed, first);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+extern "C" int prs_vt_unpack_u8(const void* packed, long long index, uint8_t* dst, void* stream) {
+  PRS_REQUIRE(packed && dst && index >= 0, "prs_vt_unpack_u8: bad argument");
+  k_vt_unpack_u8<<<1, 1024, 0, (cudaStream_t)stream>>>((const uint4*)packed, index, dst);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+extern "C" int prs_vt_sweep_packed_u8(const void* packed, long long n, const uint8_t* query, int mode,
+                                      long long base_index, unsigned long long* key_out, uint32_t* scores,
+                                      void* scratch, void* stream) {
+  PRS_REQUIRE(query && key_out && scratch && n >= 0 && (packed || n == 0), "prs_vt_sweep_packed_u8: bad argument");
+  PRS_REQUIRE(mode == PRS_VT_MODE_REF || mode == PRS_VT_MODE_CIRCULAR, "prs_vt_sweep_packed_u8: unknown mode %d", mode);
+  PRS_REQUIRE(base_index >= 0 && base_index + n <= 0xffffffffLL,
+              "prs_vt_sweep_packed_u8: template index does not fit 32 bits");
+  cudaStream_t st = (cudaStream_t)stream;
+  PRS_CUDA(cudaMemsetAsync(key_out, 0xff, sizeof(unsigned long long), st));
+  if (n == 0) return PRS_OK;
+  // query -> bit planes -> constant bank (stream ordered; one query in flight per device)
+  k_vt_pack_query<<<1, 32, 0, st>>>(query, (uint32_t*)scratch);
+  PRS_CUDA(cudaMemcpyToSymbolAsync(c_vtq, scratch, (32 * 8 + 2) * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
+  const long long groups = (n + 31) / 32;
+  long long blocks = (groups + (kPkThreads / 32) - 1) / (kPkThreads / 32);
+  const long long cap = 148LL * 16;
+  if (blocks > cap) blocks = cap;
+  if (mode == PRS_VT_MODE_REF)
+    k_vt_sweep_packed_ref<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)packed, n, base_index, key_out, scores);
+  else
+    k_vt_sweep_packed_circ<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)packed, n, base_index, key_out, scores);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}

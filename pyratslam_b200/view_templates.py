@@ -137,6 +137,7 @@ class ViewTemplates:
         self._frame_dev = torch.empty((self.im_x, self.im_y), dtype=torch.uint8, device=self.device)
         self._tpl_u8 = torch.empty((32, 32), dtype=torch.uint8, device=self.device)
         self._frame_pin = torch.empty((self.im_x, self.im_y), dtype=torch.uint8).pin_memory()
+        self._scratch = torch.empty(4096, dtype=torch.uint8, device=self.device)
         self.last_score = None       # best score of the most recent match() (None when the library was empty)
 
     # ------------------------------------------------------------------ reference attributes
@@ -158,13 +159,27 @@ class ViewTemplates:
         return int(v) if self._loc_is_int else float(v)
 
     def _fetch_template(self, i):
+        if self._dtype == torch.uint8:
+            out = torch.empty((32, 32), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                nat.check(nat.lib().prs_vt_unpack_u8(self._lib.data_ptr(), int(i), out.data_ptr(), nat.stream_ptr()),
+                          "prs_vt_unpack_u8")
+            return out.cpu().numpy()
         return self._lib[i].cpu().numpy()
 
     # ------------------------------------------------------------------ library management
+    # uint8 libraries are stored bit-sliced ("packed", 1088 B per template, see csrc/view_templates.cu);
+    # float32 libraries are plain [capacity, 32, 32].
+    def _alloc(self, torch_dtype, capacity):
+        if torch_dtype == torch.uint8:
+            nbytes = int(nat.lib().prs_vt_packed_bytes(int(capacity)))
+            return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        return torch.empty((capacity, 32, 32), dtype=torch_dtype, device=self.device)
+
     def _ensure_lib(self, torch_dtype):
         if self._lib is None:
             self._dtype = torch_dtype
-            self._lib = torch.empty((self._capacity, 32, 32), dtype=torch_dtype, device=self.device)
+            self._lib = self._alloc(torch_dtype, self._capacity)
         elif self._dtype != torch_dtype:
             raise TypeError("library holds %s templates, got a %s frame" % (self._dtype, torch_dtype))
 
@@ -172,13 +187,24 @@ class ViewTemplates:
         if need <= self._capacity:
             return
         cap = max(need, self._capacity * 2)
-        new = torch.empty((cap, 32, 32), dtype=self._dtype, device=self.device)
-        new[: self._n].copy_(self._lib[: self._n])
+        new = self._alloc(self._dtype, cap)
+        if self._dtype == torch.uint8:
+            new[: self._lib.numel()].copy_(self._lib)      # whole 32-template groups, position independent
+        else:
+            new[: self._n].copy_(self._lib[: self._n])
         self._lib = new
         loc = np.zeros((cap, 3), dtype=np.float64)
         loc[: self._n] = self._loc[: self._n]
         self._loc = loc
         self._capacity = cap
+
+    def _store(self, tpl_dev, first, count):
+        """Write ``count`` row-major templates into slots ``first..``."""
+        if self._dtype == torch.uint8:
+            nat.check(nat.lib().prs_vt_pack_u8(tpl_dev.data_ptr(), int(count), self._lib.data_ptr(), int(first),
+                                               nat.stream_ptr()), "prs_vt_pack_u8")
+        else:
+            self._lib[first: first + count].copy_(tpl_dev.reshape(count, 32, 32))
 
     def load_library(self, templates, locations=None):
         """Bulk-load ``templates[n, 32, 32]`` (uint8 or float32; numpy or torch) as templates 0..n-1."""
@@ -187,15 +213,24 @@ class ViewTemplates:
             raise TypeError("templates must be uint8 or float32")
         n = t.shape[0]
         self._dtype = t.dtype
-        self._lib = t.to(self.device).contiguous()
-        self._capacity = n
+        self._capacity = max(n, 32)
+        with torch.cuda.device(self.device):
+            src = t.to(self.device).contiguous()
+            if t.dtype == torch.uint8:
+                self._lib = self._alloc(torch.uint8, self._capacity)
+                self._store(src, 0, n)
+            else:
+                self._lib = src
+                self._capacity = n
         self._n = n
-        self._loc = np.zeros((n, 3), dtype=np.float64) if locations is None else np.asarray(locations, np.float64)
+        self._loc = np.zeros((self._capacity, 3), dtype=np.float64)
+        if locations is not None:
+            self._loc[:n] = np.asarray(locations, np.float64)
         self.templates = _TemplateList(self)
 
     def _append(self, tpl_dev, pc_x, pc_y, pc_th):
         self._grow(self._n + 1)
-        self._lib[self._n].copy_(tpl_dev)
+        self._store(tpl_dev, self._n, 1)
         self._loc[self._n] = (pc_x, pc_y, pc_th)
         if not all(float(v).is_integer() for v in (pc_x, pc_y, pc_th)):
             self._loc_is_int = False
@@ -233,11 +268,15 @@ class ViewTemplates:
             return t[m].reshape(32, 32).contiguous(), torch.float32
         return t[r0: self.y_range[1]: 2, c0: self.x_range[1]: 2].contiguous(), torch.float32
 
-    def _sweep(self, tpl, torch_dtype, key_dev):
-        fn = nat.lib().prs_vt_sweep_u8 if torch_dtype == torch.uint8 else nat.lib().prs_vt_sweep_f32
+    def _sweep(self, tpl, torch_dtype, key_dev, scores_ptr=None):
         lib_ptr = self._lib.data_ptr() if self._n else None
-        nat.check(fn(lib_ptr, self._n, tpl.data_ptr(), self.mode, 0, key_dev.data_ptr(), None, nat.stream_ptr()),
-                  "prs_vt_sweep")
+        if torch_dtype == torch.uint8:
+            nat.check(nat.lib().prs_vt_sweep_packed_u8(lib_ptr, self._n, tpl.data_ptr(), self.mode, 0,
+                                                       key_dev.data_ptr(), scores_ptr, self._scratch.data_ptr(),
+                                                       nat.stream_ptr()), "prs_vt_sweep_packed_u8")
+        else:
+            nat.check(nat.lib().prs_vt_sweep_f32(lib_ptr, self._n, tpl.data_ptr(), self.mode, 0, key_dev.data_ptr(),
+                                                 scores_ptr, nat.stream_ptr()), "prs_vt_sweep_f32")
 
     def _decode(self, key, torch_dtype):
         """``(score, index)`` from the packed key, or ``(None, -1)`` when nothing was compared."""
@@ -255,9 +294,7 @@ class ViewTemplates:
             tpl, td = self._subsample(input)
             self._ensure_lib(td)
             out = torch.empty(self._n, dtype=torch.int32 if td == torch.uint8 else torch.float32, device=self.device)
-            fn = nat.lib().prs_vt_sweep_u8 if td == torch.uint8 else nat.lib().prs_vt_sweep_f32
-            nat.check(fn(self._lib.data_ptr(), self._n, tpl.data_ptr(), self.mode, 0, self._key.data_ptr(),
-                         out.data_ptr(), nat.stream_ptr()), "prs_vt_sweep")
+            self._sweep(tpl, td, self._key, out.data_ptr())
             res = out.cpu().numpy()
             return res.view(np.uint32).astype(np.int64) if td == torch.uint8 else res
 
@@ -304,9 +341,11 @@ class ShardedViewTemplates:
             np.ascontiguousarray(local_templates))
         if t.dtype not in (torch.uint8, torch.float32):
             raise TypeError("templates must be uint8 or float32")
-        self._lib = t.to(self.device).contiguous()
         self._n = int(t.shape[0])
         self._dtype = t.dtype
+        self._rows = t.to(self.device).contiguous()          # row-major copy (appends re-pack from it)
+        self._scratch = torch.empty(4096, dtype=torch.uint8, device=self.device)
+        self._pack()
         self.base_index = int(base_index)
         self.match_threshold = match_threshold
         self.mode = {"ref": nat.VT_MODE_REF, "circular": nat.VT_MODE_CIRCULAR}[mode]
@@ -316,12 +355,27 @@ class ShardedViewTemplates:
         dist.all_gather(allc, counts, group=group)
         self.n_total = int(sum(int(c.item()) for c in allc))
 
+    def _pack(self):
+        if self._dtype == torch.uint8:
+            nbytes = int(nat.lib().prs_vt_packed_bytes(max(self._n, 1)))
+            self._lib = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                nat.check(nat.lib().prs_vt_pack_u8(self._rows.data_ptr() if self._n else None, self._n,
+                                                   self._lib.data_ptr(), 0, nat.stream_ptr()), "prs_vt_pack_u8")
+        else:
+            self._lib = self._rows
+
     def local_sweep(self, query_dev):
         """Launch the local sweep; the packed key is left in ``self._key`` on the device."""
-        fn = nat.lib().prs_vt_sweep_u8 if self._dtype == torch.uint8 else nat.lib().prs_vt_sweep_f32
         lib_ptr = self._lib.data_ptr() if self._n else None
-        nat.check(fn(lib_ptr, self._n, query_dev.data_ptr(), self.mode, self.base_index, self._key.data_ptr(), None,
-                     nat.stream_ptr()), "prs_vt_sweep")
+        if self._dtype == torch.uint8:
+            nat.check(nat.lib().prs_vt_sweep_packed_u8(lib_ptr, self._n, query_dev.data_ptr(), self.mode,
+                                                       self.base_index, self._key.data_ptr(), None,
+                                                       self._scratch.data_ptr(), nat.stream_ptr()),
+                      "prs_vt_sweep_packed_u8")
+        else:
+            nat.check(nat.lib().prs_vt_sweep_f32(lib_ptr, self._n, query_dev.data_ptr(), self.mode, self.base_index,
+                                                 self._key.data_ptr(), None, nat.stream_ptr()), "prs_vt_sweep_f32")
         return self._key
 
     def match_key(self, query_dev):
@@ -338,8 +392,9 @@ class ShardedViewTemplates:
         if created:
             if self.rank == self.world - 1:
                 grown = torch.empty((self._n + 1, 32, 32), dtype=self._dtype, device=self.device)
-                grown[: self._n].copy_(self._lib)
+                grown[: self._n].copy_(self._rows)
                 grown[self._n].copy_(query_dev.reshape(32, 32))
-                self._lib, self._n = grown, self._n + 1
+                self._rows, self._n = grown, self._n + 1
+                self._pack()
             self.n_total += 1
         return index, created

@@ -104,6 +104,62 @@ def test_ragged_library_sizes_u8(mode, n):
     assert key == (int(ref.min()) << 32) | int(np.argmin(ref))
 
 
+def _sweep_packed(lib, q, mode, want_scores=True):
+    """Pack a row-major uint8 library and sweep it through the bit-sliced kernels (C ABI)."""
+    from pyratslam_b200 import _native as nat
+    n = lib.shape[0]
+    L = nat.lib()
+    packed = torch.zeros(int(L.prs_vt_packed_bytes(max(n, 1))), dtype=torch.uint8, device="cuda")
+    lib_t = torch.from_numpy(lib).cuda() if not isinstance(lib, torch.Tensor) else lib
+    q_t = torch.from_numpy(q).cuda()
+    nat.check(L.prs_vt_pack_u8(lib_t.data_ptr() if n else None, n, packed.data_ptr(), 0, None))
+    key = torch.zeros(1, dtype=torch.int64, device="cuda")
+    sc = torch.zeros(max(n, 1), dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    nat.check(L.prs_vt_sweep_packed_u8(packed.data_ptr() if n else None, n, q_t.data_ptr(), mode, 0, key.data_ptr(),
+                                       sc.data_ptr() if want_scores else None, scratch.data_ptr(), None))
+    torch.cuda.synchronize()
+    return int(key.item()) & ((1 << 64) - 1), sc[:n].cpu().numpy().view(np.uint32).astype(np.int64), packed
+
+
+@pytest.mark.parametrize("mode", ["ref", "circular"])
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 64, 1001])
+def test_packed_library_matches_oracle(mode, n):
+    rng = np.random.default_rng(200 + n)
+    lib = rng.integers(0, 256, (n, 32, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (32, 32), dtype=np.uint8)
+    if n > 3:
+        lib[n - 1] = lib[2]                    # a tie: the lower index must win
+        q = np.roll(lib[2], 3, axis=0)
+        lib[0][5:9] = 0                        # extremes of the byte range
+        lib[1][5:9] = 255
+    key, sc, packed = _sweep_packed(lib, q, 0 if mode == "ref" else 1)
+    if n == 0:
+        assert key == (1 << 64) - 1
+        return
+    ref = ovt.library_scores(lib, q, mode=mode)
+    assert sc.tolist() == ref.astype(np.int64).tolist()
+    assert key == (int(ref.min()) << 32) | int(np.argmin(ref))
+    # the packed layout round-trips
+    from pyratslam_b200 import _native as nat
+    out = torch.zeros((32, 32), dtype=torch.uint8, device="cuda")
+    for i in sorted({0, n // 2, n - 1}):
+        nat.check(nat.lib().prs_vt_unpack_u8(packed.data_ptr(), i, out.data_ptr(), None))
+        assert np.array_equal(out.cpu().numpy(), lib[i])
+
+
+def test_packed_equals_bytewise_kernel():
+    """The two uint8 kernels (byte-wise SWAR and bit-sliced) agree on a 20 000-template library."""
+    rng = np.random.default_rng(77)
+    lib = rng.integers(0, 256, (20000, 32, 32), dtype=np.uint8)
+    q = np.clip(lib[12345].astype(np.int16) - 3, 0, 255).astype(np.uint8)
+    for mode in (0, 1):
+        k1, s1 = _sweep(torch.from_numpy(lib).cuda(), torch.from_numpy(q).cuda(), mode)
+        k2, s2, _ = _sweep_packed(lib, q, mode)
+        assert k1 == k2 and s1.view(np.uint32).astype(np.int64).tolist() == s2.tolist()
+    assert k2 & 0xFFFFFFFF == 12345
+
+
 @pytest.mark.parametrize("mode", ["ref", "circular"])
 def test_float32_library(mode):
     rng = np.random.default_rng(5)
@@ -148,6 +204,8 @@ def test_million_template_library_properties():
     key, sc = _sweep(lib, torch.from_numpy(q).cuda(), 0)
     sc = sc.view(np.uint32).astype(np.int64)
     assert key & 0xFFFFFFFF == target == int(np.argmin(sc)) and key >> 32 == int(sc.min())
+    key_p, sc_p, _ = _sweep_packed(lib, q, 0)          # the bit-sliced layout the product streams
+    assert key_p == key and np.array_equal(sc_p, sc)
     lo = 500_000
     ref = ovt.library_scores(lib[lo:lo + 4096].cpu().numpy(), q)
     assert sc[lo:lo + 4096].tolist() == ref.astype(np.int64).tolist()
