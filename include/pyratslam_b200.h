@@ -86,7 +86,8 @@ PRS_API int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out);
 PRS_API int prs_pc_destroy(prs_pc_handle h);
 /* bytes of one full state tensor [B][Th][X][Y] */
 PRS_API size_t prs_pc_state_bytes(prs_pc_handle h);
-/* which kernel family a step uses: 0 = generic multi-kernel path, 1 = fused SMEM-resident kernel */
+/* which kernel family a step uses: 0 = generic multi-kernel path, 1 = fused SMEM-resident kernel,
+ * 2 = tiled large-grid kernels */
 PRS_API int prs_pc_path(prs_pc_handle h);
 /* force the generic path (1) or let the plan choose (0); for tests and profiling */
 PRS_API int prs_pc_force_generic(prs_pc_handle h, int on);

@@ -46,7 +46,7 @@ static void fill_tables(PcTables<T>& t, const prs_pc_config* c) {
 }
 
 static void free_plan(prs_pc_plan* p) {
-  void* ptrs[] = {p->cos_th, p->sin_th, p->s1,       p->s2,        p->s3,     p->s4,       p->shift, p->fsel,
+  void* ptrs[] = {p->cos_th, p->sin_th, p->s1,       nullptr,      p->s3,     nullptr,     p->shift, p->fsel,
                   p->ogi,    p->part_val, p->part_idx, p->inv_total, p->d_odom, p->d_argmax, p->d_err, p->d_total,
                   p->tab_dev};
   for (void* q : ptrs)
@@ -86,7 +86,9 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   const size_t es = cfg->dtype == PRS_F32 ? 4 : 8;
   const size_t sbytes = (size_t)p->B * p->N * es;
   p->nblk_plane = (p->X * p->Y + 255) / 256;
-  const size_t np = (size_t)p->B * p->Th * p->nblk_plane;
+  const int tiles = ((p->X + 31) / 32) * ((p->Y + 31) / 32);
+  p->np_max = p->Th * (p->nblk_plane > tiles ? p->nblk_plane : tiles);
+  const size_t np = (size_t)p->B * p->np_max;
 #define ALLOC(ptr, bytes)                                                        \
   do {                                                                           \
     cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                        \
@@ -110,13 +112,14 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   ALLOC(p->d_total, (size_t)p->B * es);
   ALLOC(p->tab_dev, sizeof(PcTables<float>));
   p->resident_ok = prs_pc_resident_supported(p);
-  // The generic path's four scratch tensors are only allocated when that path can be taken
-  // for this plan; prs_pc_force_generic allocates them lazily otherwise.
+  p->tiled_ok = prs_pc_tiled_supported(p);
+  // The multi-kernel paths need scratch of four state tensors; it is only allocated when such a path
+  // can be taken for this plan (prs_pc_force_generic / path_integration allocate it lazily otherwise).
   if (!p->resident_ok) {
-    ALLOC(p->s1, sbytes);
-    ALLOC(p->s2, sbytes);
-    ALLOC(p->s3, sbytes);
-    ALLOC(p->s4, sbytes);
+    ALLOC(p->s1, 2 * sbytes);
+    ALLOC(p->s3, 2 * sbytes);
+    p->s2 = (char*)p->s1 + sbytes;
+    p->s4 = (char*)p->s3 + sbytes;
   }
 #undef ALLOC
   cudaError_t e = cudaMemcpy(p->cos_th, cfg->cos_th, p->Th * sizeof(double), cudaMemcpyHostToDevice);
@@ -143,13 +146,18 @@ extern "C" size_t prs_pc_state_bytes(prs_pc_handle h) {
 static int ensure_scratch(prs_pc_handle h) {
   if (!h->s1) {
     const size_t sbytes = prs_pc_state_bytes(h);
-    void** slots[] = {&h->s1, &h->s2, &h->s3, &h->s4};
-    for (void** s : slots) PRS_CUDA(cudaMalloc(s, sbytes));
+    PRS_CUDA(cudaMalloc(&h->s1, 2 * sbytes));
+    PRS_CUDA(cudaMalloc(&h->s3, 2 * sbytes));
+    h->s2 = (char*)h->s1 + sbytes;
+    h->s4 = (char*)h->s3 + sbytes;
   }
   return PRS_OK;
 }
 
-extern "C" int prs_pc_path(prs_pc_handle h) { return (h && h->resident_ok && !h->force_generic) ? 1 : 0; }
+extern "C" int prs_pc_path(prs_pc_handle h) {
+  if (!h || h->force_generic) return 0;
+  return h->resident_ok ? 1 : (h->tiled_ok ? 2 : 0);
+}
 
 extern "C" int prs_pc_force_generic(prs_pc_handle h, int on) {
   PRS_REQUIRE(h, "prs_pc_force_generic: null handle");
@@ -164,10 +172,16 @@ extern "C" int prs_pc_force_generic(prs_pc_handle h, int on) {
 static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st) {
   const size_t es = h->dtype == PRS_F32 ? 4 : 8;
-  if (prs_pc_path(h) == 1) return prs_pc_resident_step(h, state, odom, T, gi, argmax, total, err, st);
+  const int path = prs_pc_path(h);
+  if (path == 1) return prs_pc_resident_step(h, state, odom, T, gi, argmax, total, err, st);
   for (int t = 0; t < T; ++t) {
-    int rc = prs_pc_generic_step(h, state, odom + (size_t)t * h->B * 2, gi, argmax + (size_t)t * h->B,
-                                 (char*)total + (size_t)t * h->B * es, err, st);
+    int rc;
+    if (path == 2)
+      rc = prs_pc_tiled_step(h, (float*)state, odom + (size_t)t * h->B * 2, (const float*)gi, argmax + (size_t)t * h->B,
+                             (float*)total + (size_t)t * h->B, err, st);
+    else
+      rc = prs_pc_generic_step(h, state, odom + (size_t)t * h->B * 2, gi, argmax + (size_t)t * h->B,
+                               (char*)total + (size_t)t * h->B * es, err, st);
     if (rc != PRS_OK) return rc;
   }
   return PRS_OK;

@@ -44,12 +44,14 @@ struct prs_pc_plan {
   PcTables<double> td;
   double* cos_th;  // device [Th]
   double* sin_th;
-  // generic path scratch, each [B][N] of dtype
+  // scratch: two allocations of 2*B*N elements; s1|s2 are the halves of the first, s3|s4 of the second
   void *s1, *s2, *s3, *s4;
   int* shift;           // [B][Th][2] integer origins (ox, oy)
   unsigned char* fsel;  // [B][Th] 0 = F0, 1 = F-1
   int* ogi;             // [B] index into f1d
   int nblk_plane;       // blocks per theta plane in the generic kernels
+  int np_max;           // partial-result slots per network (covers the generic and the tiled kernels)
+  int tiled_ok;         // the tiled large-grid kernels support this shape/dtype
   void* part_val;       // [B][Th*nblk_plane] partial sums, later partial maxima
   long long* part_idx;  // [B][Th*nblk_plane]
   void* inv_total;      // [B]
@@ -68,6 +70,13 @@ int prs_pc_generic_step(prs_pc_plan* p, void* state, const double* odom, const v
                         void* total, int* err, cudaStream_t st);
 int prs_pc_generic_path_integration(prs_pc_plan* p, void* state, const double* odom, int* err, cudaStream_t st);
 int prs_pc_generic_argmax(prs_pc_plan* p, const void* state, long long* argmax, cudaStream_t st);
+int prs_pc_tiled_supported(const prs_pc_plan* p);
+int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax, float* total,
+                      int* err, cudaStream_t st);
+// small shared kernels (implemented in posecell_generic.cu)
+int prs_pc_launch_plan(prs_pc_plan* p, const double* odom, int* err, cudaStream_t st);
+int prs_pc_launch_sum_final_f32(prs_pc_plan* p, int np, float* total, cudaStream_t st);
+int prs_pc_launch_argmax_final_f32(prs_pc_plan* p, int np, long long* argmax, cudaStream_t st);
 int prs_pc_resident_supported(const prs_pc_plan* p);
 int prs_pc_resident_step(prs_pc_plan* p, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st);

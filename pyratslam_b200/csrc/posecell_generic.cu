@@ -343,6 +343,26 @@ int generic_path_integration_t(prs_pc_plan* p, const PcTables<T>& tab, T* state,
 
 }  // namespace
 
+int prs_pc_launch_plan(prs_pc_plan* p, const double* odom, int* err, cudaStream_t st) {
+  const int nbt = p->B * p->Th;
+  k_plan<<<(nbt + 127) / 128, 128, 0, st>>>(odom, p->cos_th, p->sin_th, p->B, p->Th, p->X < p->Y ? p->X : p->Y,
+                                            p->vtrans_scale, p->vrot_scale, p->shift, p->fsel, p->ogi, err);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+int prs_pc_launch_sum_final_f32(prs_pc_plan* p, int np, float* total, cudaStream_t st) {
+  k_sum_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, np, total, (float*)p->inv_total);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+int prs_pc_launch_argmax_final_f32(prs_pc_plan* p, int np, long long* argmax, cudaStream_t st) {
+  k_argmax_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, p->part_idx, np, argmax);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
 int prs_pc_generic_path_integration(prs_pc_plan* p, void* state, const double* odom, int* err, cudaStream_t st) {
   if (p->dtype == PRS_F32) return generic_path_integration_t<float>(p, p->tf, (float*)state, odom, err, st);
   return generic_path_integration_t<double>(p, p->td, (double*)state, odom, err, st);

@@ -103,8 +103,8 @@ class PoseCellEnsemble:
 
     @property
     def path(self):
-        """``"resident"`` (fused SMEM-resident kernel) or ``"generic"`` (multi-kernel path)."""
-        return "resident" if nat.lib().prs_pc_path(self._h) == 1 else "generic"
+        """``"resident"`` (fused SMEM-resident kernel), ``"tiled"`` (large-grid kernels) or ``"generic"``."""
+        return {0: "generic", 1: "resident", 2: "tiled"}[nat.lib().prs_pc_path(self._h)]
 
     def force_generic(self, on=True):
         nat.check(nat.lib().prs_pc_force_generic(self._h, 1 if on else 0), "prs_pc_force_generic")
