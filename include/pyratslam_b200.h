@@ -161,6 +161,31 @@ PRS_API int prs_vt_sweep_packed_u8(const void* packed, long long n, const uint8_
 PRS_API int prs_vt_match_host_u8(const uint8_t* lib, long long n, const uint8_t* query_host, int mode,
                          long long base_index, unsigned long long* key_host, void* scratch, void* stream);
 
+/* ------------------------------------------------------------------- one frame */
+
+/* Result of prs_frame_host (32 bytes, written to pinned host memory). */
+typedef struct prs_frame_result {
+  long long argmax;          /* arg-max pose cell after the update (flat index), or the previous one */
+  unsigned long long key;    /* (best score << 32) | best index, UINT64_MAX if the library was empty */
+  int created;               /* 1: the frame became template `template_index` */
+  int template_index;        /* what ViewTemplates.match(...).get_index() returns */
+  int n_templates;           /* library size after this frame */
+  int pc_err;                /* PRS_ERR_* bits of the pose-cell update */
+} prs_frame_result;
+
+PRS_API size_t prs_frame_scratch_bytes(void);
+/* One iteration of the ROS loop (ratslam/ros_simulate.py:98-105,134-137) with a single host sync:
+ * [odom_host != NULL: pose-cell update with (vtrans, vrot)] -> frame H2D -> sub-sample -> sweep of the packed
+ * uint8 library -> create-or-match on the device (a created template is packed into slot n_templates, so
+ * the library must have room for n_templates + 1) -> result D2H.
+ *   pc_work : device, 24 bytes (arg-max, total, err of the single network); persists between frames
+ *   scratch : device, prs_frame_scratch_bytes()
+ *   frame_host / odom_host / result_host : host (pinned for asynchronous copies) */
+PRS_API int prs_frame_host(prs_pc_handle pc, void* pc_state, const void* gi, void* pc_work, const double* odom_host,
+                   void* vt_packed, int n_templates, unsigned threshold, int mode, const uint8_t* frame_host,
+                   int im_rows, int im_cols, int row_lo, int row_hi, int row_step, int col_lo, int col_hi,
+                   int col_step, void* scratch, prs_frame_result* result_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

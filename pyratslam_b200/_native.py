@@ -62,6 +62,17 @@ _SIGNATURES = {
     "prs_vt_match_host_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
 }
 
+_SIGNATURES["prs_frame_scratch_bytes"] = (c_size_t, [])
+_SIGNATURES["prs_frame_host"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_uint,
+                                         c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                         c_void_p, c_void_p])
+
+
+class FrameResult(Structure):
+    _fields_ = [("argmax", c_longlong), ("key", c_uint64), ("created", c_int), ("template_index", c_int),
+                ("n_templates", c_int), ("pc_err", c_int)]
+
+
 _lib = None
 
 

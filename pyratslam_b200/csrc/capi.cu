@@ -87,7 +87,7 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   const size_t sbytes = (size_t)p->B * p->N * es;
   p->nblk_plane = (p->X * p->Y + 255) / 256;
   const int tiles = ((p->X + 31) / 32) * ((p->Y + 31) / 32);
-  p->np_max = p->Th * (p->nblk_plane > tiles ? p->nblk_plane : tiles);
+  p->np_max = p->Th * (p->nblk_plane > tiles ? p->nblk_plane : tiles);  // >= nblk_plane * ceil(Th/8) as well
   const size_t np = (size_t)p->B * p->np_max;
 #define ALLOC(ptr, bytes)                                                        \
   do {                                                                           \

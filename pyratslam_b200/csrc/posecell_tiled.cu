@@ -22,16 +22,23 @@ namespace {
 constexpr int kT = 256;
 
 // ------------------------------------------------------------------------------------------------
+constexpr int kTK = 8;  // theta cells per thread in the two theta kernels (7-register window + 8 new loads)
+
 __global__ void __launch_bounds__(kT) k_tl_theta(const float* __restrict__ P, float2* __restrict__ EI, int XY, int Th,
                                                  PcTables<float> tab) {
   const int p = blockIdx.x * kT + threadIdx.x;
   if (p >= XY) return;
   const size_t base = (size_t)blockIdx.y * Th * XY + p;
+  const int k_lo = blockIdx.z * kTK, k_hi = min(Th, k_lo + kTK);
   const float e0 = tab.ge[3], e1 = tab.ge[2], e2 = tab.ge[1], e3 = tab.ge[0];
   const float i0 = tab.gi[3], i1 = tab.gi[2], i2 = tab.gi[1], i3 = tab.gi[0];
-  float w0 = P[base + (size_t)(Th - 3) * XY], w1 = P[base + (size_t)(Th - 2) * XY], w2 = P[base + (size_t)(Th - 1) * XY];
-  float w3 = P[base], w4 = P[base + (size_t)(1 % Th) * XY], w5 = P[base + (size_t)(2 % Th) * XY];
-  for (int k = 0; k < Th; ++k) {
+  float w0 = P[base + (size_t)modp(k_lo - 3, Th) * XY], w1 = P[base + (size_t)modp(k_lo - 2, Th) * XY];
+  float w2 = P[base + (size_t)modp(k_lo - 1, Th) * XY], w3 = P[base + (size_t)k_lo * XY];
+  float w4 = P[base + (size_t)((k_lo + 1) % Th) * XY], w5 = P[base + (size_t)((k_lo + 2) % Th) * XY];
+#pragma unroll
+  for (int kk = 0; kk < kTK; ++kk) {
+    const int k = k_lo + kk;
+    if (k >= k_hi) break;
     int kn = k + 3;
     kn -= kn >= Th ? Th : 0;
     const float w6 = P[base + (size_t)kn * XY];
@@ -61,9 +68,17 @@ __global__ void __launch_bounds__(kT) k_tl_yx(const float2* __restrict__ EI, flo
   const float2* src = EI + (size_t)plane * XY;
   const int tid = threadIdx.x;
   const int gx0 = modp(x0 - 3, X), gy0 = modp(y0 - 3, Y);
+  const bool nowrapdiv = (X >= kYXH && Y >= kYXH);  // one conditional subtract wraps the index
   for (int i = tid; i < kYXH * kYXH; i += kT) {
     const int r = i / kYXH, c = i - r * kYXH;
-    const int gx = (gx0 + r) % X, gy = (gy0 + c) % Y;
+    int gx = gx0 + r, gy = gy0 + c;
+    if (nowrapdiv) {
+      gx -= gx >= X ? X : 0;
+      gy -= gy >= Y ? Y : 0;
+    } else {
+      gx %= X;
+      gy %= Y;
+    }
     s_in[r * kInStride + c] = src[(size_t)gx * Y + gy];
   }
   __syncthreads();
@@ -142,9 +157,17 @@ __global__ void __launch_bounds__(kT) k_tl_2d(const float* __restrict__ A, float
   const int tid = threadIdx.x;
   // the plane's integer origin displaces the tile that is loaded (convolution.py:329-331)
   const int gx0 = modp(x0 + shift[2 * plane] - 3, X), gy0 = modp(y0 + shift[2 * plane + 1] - 3, Y);
+  const bool nowrapdiv = (X >= k2XH && Y >= k2YH);
   for (int i = tid; i < k2XH * k2YH; i += kT) {
     const int r = i / k2YH, c = i - r * k2YH;
-    const int gx = (gx0 + r) % X, gy = (gy0 + c) % Y;
+    int gx = gx0 + r, gy = gy0 + c;
+    if (nowrapdiv) {
+      gx -= gx >= X ? X : 0;
+      gy -= gy >= Y ? Y : 0;
+    } else {
+      gx %= X;
+      gy %= Y;
+    }
     s_a[r * k2Stride + c] = src[(size_t)gx * Y + gy];
   }
   float F[49];
@@ -215,9 +238,14 @@ __global__ void __launch_bounds__(kT) k_tl_theta_fin(const float* __restrict__ B
     const size_t base = (size_t)blockIdx.y * Th * XY + p;
     const float* f = tab.f1d[ogi[blockIdx.y]];
     const float f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3], f4 = f[4], f5 = f[5], f6 = f[6];
-    float w0 = Bp[base + (size_t)(Th - 3) * XY], w1 = Bp[base + (size_t)(Th - 2) * XY], w2 = Bp[base + (size_t)(Th - 1) * XY];
-    float w3 = Bp[base], w4 = Bp[base + (size_t)(1 % Th) * XY], w5 = Bp[base + (size_t)(2 % Th) * XY];
-    for (int k = 0; k < Th; ++k) {
+    const int k_lo = blockIdx.z * kTK, k_hi = min(Th, k_lo + kTK);
+    float w0 = Bp[base + (size_t)modp(k_lo - 3, Th) * XY], w1 = Bp[base + (size_t)modp(k_lo - 2, Th) * XY];
+    float w2 = Bp[base + (size_t)modp(k_lo - 1, Th) * XY], w3 = Bp[base + (size_t)k_lo * XY];
+    float w4 = Bp[base + (size_t)((k_lo + 1) % Th) * XY], w5 = Bp[base + (size_t)((k_lo + 2) % Th) * XY];
+#pragma unroll
+    for (int kk = 0; kk < kTK; ++kk) {
+      const int k = k_lo + kk;
+      if (k >= k_hi) break;
       int kn = k + 3;
       kn -= kn >= Th ? Th : 0;
       const float w6 = Bp[base + (size_t)kn * XY];
@@ -252,8 +280,9 @@ __global__ void __launch_bounds__(kT) k_tl_theta_fin(const float* __restrict__ B
         best = s_v[w];
         bidx = s_i[w];
       }
-    part_val[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = best;
-    part_idx[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = bidx;
+    const size_t slot = ((size_t)blockIdx.y * gridDim.z + blockIdx.z) * gridDim.x + blockIdx.x;
+    part_val[slot] = best;
+    part_idx[slot] = bidx;
   }
 }
 
@@ -274,15 +303,17 @@ int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const fl
   int rc = prs_pc_launch_plan(p, odom, err, st);
   if (rc != PRS_OK) return rc;
   const int nline = (XY + kT - 1) / kT;
-  k_tl_theta<<<dim3(nline, B), kT, 0, st>>>(state, EI, XY, Th, p->tf);
+  const int nchunk = (Th + kTK - 1) / kTK;
+  k_tl_theta<<<dim3(nline, B, nchunk), kT, 0, st>>>(state, EI, XY, Th, p->tf);
   const dim3 g2((X + kYX - 1) / kYX, (Y + kYX - 1) / kYX, B * Th);
   k_tl_yx<<<g2, kT, 0, st>>>(EI, A, gi, X, Y, Th, p->tf, (float*)p->part_val);
   rc = prs_pc_launch_sum_final_f32(p, Th * g2.x * g2.y, total, st);
   if (rc != PRS_OK) return rc;
   const dim3 g3((X + k2X - 1) / k2X, (Y + k2Y - 1) / k2Y, B * Th);
   k_tl_2d<<<g3, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, p->tf);
-  k_tl_theta_fin<<<dim3(nline, B), kT, 0, st>>>(Bp, state, p->ogi, XY, Th, p->tf, (float*)p->part_val, p->part_idx);
-  rc = prs_pc_launch_argmax_final_f32(p, nline, argmax, st);
+  k_tl_theta_fin<<<dim3(nline, B, nchunk), kT, 0, st>>>(Bp, state, p->ogi, XY, Th, p->tf, (float*)p->part_val,
+                                                        p->part_idx);
+  rc = prs_pc_launch_argmax_final_f32(p, nline * nchunk, argmax, st);
   if (rc != PRS_OK) return rc;
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;

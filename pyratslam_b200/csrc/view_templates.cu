@@ -598,3 +598,99 @@ extern "C" int prs_vt_sweep_packed_u8(const void* packed, long long n, const uin
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
+
+// =============================================================================================
+// One whole frame of the ROS loop (ratslam/ros_simulate.py:98-105,134-137) with a single host
+// synchronisation: odometry H2D -> pose-cell update -> frame H2D -> sub-sample -> library sweep ->
+// create-or-match decided ON THE DEVICE (view_templates.py:67-73; a created template is packed straight
+// into slot n of the library) -> 32-byte result D2H.
+struct FrameScratch {               // device scratch layout (bytes)
+  static constexpr size_t kFrame = 0;                   // uint8 frame, up to 1 MiB
+  static constexpr size_t kTpl = 1 << 20;               // uint8[1024] sub-sampled template
+  static constexpr size_t kPlanes = kTpl + 1024;        // uint32[264] query planes
+  static constexpr size_t kKey = kPlanes + 2048;        // uint64 key
+  static constexpr size_t kResult = kKey + 64;          // prs_frame_result
+  static constexpr size_t kOdom = kResult + 64;         // double[2]
+  static constexpr size_t kBytes = kOdom + 64;
+};
+
+__global__ void k_vt_decide_append(const unsigned long long* __restrict__ key, const uint8_t* __restrict__ tpl,
+                                   uint4* __restrict__ packed, int n, unsigned threshold,
+                                   const long long* __restrict__ argmax, const int* __restrict__ pc_err,
+                                   prs_frame_result* __restrict__ res) {
+  const int t = threadIdx.x;  // 32 threads, one per template row
+  const unsigned long long k = *key;
+  const unsigned score = (unsigned)(k >> 32);
+  const bool create = (n == 0) || (k == ~0ull) || (score > threshold);  // strict '>' (view_templates.py:67)
+  if (create) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(tpl + t * 32);
+    uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t sum = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t v = row[w];
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const uint32_t px = (v >> (8 * bb)) & 0xffu;
+        sum += px;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) pl[kk] |= ((px >> kk) & 1u) << (w * 4 + bb);
+      }
+    }
+    uint4* grp = packed + (size_t)(n >> 5) * kGroupU4;
+    const int lane = n & 31;
+    grp[(t * 2 + 0) * 32 + lane] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    grp[(t * 2 + 1) * 32 + lane] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+    uint16_t* rs = reinterpret_cast<uint16_t*>(grp + 32 * 2 * 32);
+    const int w = t >> 1;
+    rs[(((w >> 2) * 32 + lane) * 4 + (w & 3)) * 2 + (t & 1)] = (uint16_t)sum;
+  }
+  if (t == 0) {
+    res->argmax = argmax ? argmax[0] : -1;
+    res->key = k;
+    res->created = create ? 1 : 0;
+    res->template_index = create ? n : (int)(k & 0xffffffffu);
+    res->n_templates = n + (create ? 1 : 0);
+    res->pc_err = pc_err ? pc_err[0] : 0;
+  }
+}
+
+extern "C" size_t prs_frame_scratch_bytes(void) { return FrameScratch::kBytes; }
+
+extern "C" int prs_frame_host(prs_pc_handle pc, void* pc_state, const void* gi, void* pc_work, const double* odom_host,
+                              void* vt_packed, int n_templates, unsigned threshold, int mode,
+                              const uint8_t* frame_host, int im_rows, int im_cols, int row_lo, int row_hi, int row_step,
+                              int col_lo, int col_hi, int col_step, void* scratch, prs_frame_result* result_host,
+                              void* stream) {
+  PRS_REQUIRE(pc && pc_state && gi && pc_work && vt_packed && frame_host && scratch && result_host,
+              "prs_frame_host: null argument");
+  PRS_REQUIRE((size_t)im_rows * im_cols <= (1u << 20), "prs_frame_host: frame larger than 1 MiB");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* sc = (char*)scratch;
+  uint8_t* d_frame = (uint8_t*)(sc + FrameScratch::kFrame);
+  uint8_t* d_tpl = (uint8_t*)(sc + FrameScratch::kTpl);
+  uint32_t* d_planes = (uint32_t*)(sc + FrameScratch::kPlanes);
+  unsigned long long* d_key = (unsigned long long*)(sc + FrameScratch::kKey);
+  prs_frame_result* d_res = (prs_frame_result*)(sc + FrameScratch::kResult);
+  double* d_odom = (double*)(sc + FrameScratch::kOdom);
+  // pc_work: device int64 argmax[1], float/double total[1] (8 bytes), int err[1]
+  long long* d_argmax = (long long*)pc_work;
+  void* d_total = (char*)pc_work + 8;
+  int* d_err = (int*)((char*)pc_work + 16);
+  int rc;
+  if (odom_host) {  // ros_simulate.py:134-137: one pose-cell update with this twist
+    PRS_CUDA(cudaMemcpyAsync(d_odom, odom_host, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = prs_pc_step(pc, pc_state, d_odom, gi, d_argmax, d_total, d_err, st);
+    if (rc != PRS_OK) return rc;
+  }
+  PRS_CUDA(cudaMemcpyAsync(d_frame, frame_host, (size_t)im_rows * im_cols, cudaMemcpyHostToDevice, st));
+  rc = prs_vt_extract_u8(d_frame, im_rows, im_cols, row_lo, row_hi, row_step, col_lo, col_hi, col_step, d_tpl, 32, 32, st);
+  if (rc != PRS_OK) return rc;
+  rc = prs_vt_sweep_packed_u8(vt_packed, n_templates, d_tpl, mode, 0, d_key, nullptr, d_planes, st);
+  if (rc != PRS_OK) return rc;
+  k_vt_decide_append<<<1, 32, 0, st>>>(d_key, d_tpl, (uint4*)vt_packed, n_templates, threshold, d_argmax, d_err, d_res);
+  PRS_CUDA(cudaGetLastError());
+  PRS_CUDA(cudaMemcpyAsync(result_host, d_res, sizeof(prs_frame_result), cudaMemcpyDeviceToHost, st));
+  PRS_CUDA(cudaStreamSynchronize(st));
+  return PRS_OK;
+}

@@ -14,9 +14,13 @@ odometry first, then the frame (the same order the oracle's ``replay_run`` uses)
 from __future__ import annotations
 
 import math
+import ctypes
 from collections import deque
 
 import numpy as np
+import torch
+
+from . import _native as nat
 
 from .experience_map import ExperienceMap
 from .posecell_network import PoseCellNetwork
@@ -71,6 +75,65 @@ class RatslamRos(object):
         self.em.update(vtrans, vrot, pc_max)
         self.published_pose.append(self.em.get_current_point())
 
+    # ------------------------------------------------------------------ fused fast path
+    # One odometry update + one frame match per call with a single host synchronisation
+    # (prs_frame_host): the create-or-match decision and the library append happen on the device.
+    def _fused_setup(self):
+        e, v = self.pcn._ens, self.vts
+        dev = e.device
+        self._f_scratch = torch.zeros(int(nat.lib().prs_frame_scratch_bytes()), dtype=torch.uint8, device=dev)
+        self._f_pcwork = torch.zeros(3, dtype=torch.int64, device=dev)
+        self._f_frame = torch.zeros((v.im_x, v.im_y), dtype=torch.uint8).pin_memory()
+        self._f_odom = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self._f_res = torch.zeros(32, dtype=torch.uint8).pin_memory()
+        self._f_result = nat.FrameResult.from_address(self._f_res.data_ptr())
+        with torch.cuda.device(dev):
+            nat.check(nat.lib().prs_pc_argmax(e._h, e._state.data_ptr(), self._f_pcwork.data_ptr(), nat.stream_ptr()),
+                      "prs_pc_argmax")
+        v._ensure_lib(torch.uint8)
+        self._fused_ready = True
+
+    def fused_frame(self, twist, im):
+        """``odom_callback(twist)`` + ``spin_once()`` + ``vis_callback(im)`` in one device round trip.
+
+        Returns ``(template_index, created)``.  Same decisions as the three separate calls; a pose-cell
+        error (LUT hole, oversize shift) is raised after the frame instead of before it."""
+        if not getattr(self, "_fused_ready", False):
+            self._fused_setup()
+        e, v = self.pcn._ens, self.vts
+        moved = twist is not None and (abs(twist[0]) > 0.001 or abs(twist[1]) > 0.001)   # ros_simulate.py:128
+        vtrans = vrot = 0.0
+        if moved:
+            vtrans, vrot = twist[0] / self.odom_freq, twist[1] / self.odom_freq          # :157-158
+            o = self._f_odom.numpy()
+            o[0], o[1] = vtrans, vrot
+        v._grow(v._n + 1)
+        self._f_frame.numpy()[...] = im
+        thr = int(min(max(math.floor(v.match_threshold), 0), 0xFFFFFFFF))
+        with torch.cuda.device(e.device):
+            nat.check(nat.lib().prs_frame_host(
+                e._h, e._state.data_ptr(), e._gi.data_ptr(), self._f_pcwork.data_ptr(),
+                self._f_odom.data_ptr() if moved else None, v._lib.data_ptr(), v._n, thr, v.mode,
+                self._f_frame.data_ptr(), v.im_x, v.im_y, v.y_range[0], v.y_range[1], v.y_step,
+                v.x_range[0], v.x_range[1], v.x_step, self._f_scratch.data_ptr(), self._f_res.data_ptr(),
+                nat.stream_ptr()), "prs_frame_host")
+        r = self._f_result
+        if moved:
+            e._raise_on_err(np.array([r.pc_err], dtype=np.int32))
+        X, Y, Th = self.pcn.shape
+        flat = int(r.argmax)
+        pc_max = (flat // (Y * Th), (flat // Th) % Y, flat % Th)
+        self.pcn.max_pc, self.pcn._max_valid = pc_max, True
+        if moved:
+            self.em.update(vtrans, vrot, pc_max)                                          # :136-137
+            self.published_pose.append(self.em.get_current_point())
+        if r.created:
+            v._loc[v._n] = pc_max
+        v._n = int(r.n_templates)
+        v.last_score = None if r.key == (1 << 64) - 1 else int(r.key >> 32)
+        self.published_index.append(int(r.template_index))
+        return int(r.template_index), bool(r.created)
+
     # ros_simulate.py:152-166, one pass of the loop body
     def spin_once(self):
         if self.twist_data:
@@ -80,17 +143,24 @@ class RatslamRos(object):
         return False
 
 
-def replay(frames, odom, **kwargs):
-    """Run the loop over ``frames[T,256,256]`` (uint8) and ``odom[T,2]``; returns per-frame records."""
+def replay(frames, odom, fused=False, **kwargs):
+    """Run the loop over ``frames[T,256,256]`` (uint8) and ``odom[T,2]``; returns per-frame records.
+
+    ``fused=True`` uses ``RatslamRos.fused_frame`` (one device round trip per frame) instead of the three
+    reference-shaped calls; the records are identical."""
     node = RatslamRos(**kwargs)
     T = len(frames)
     rec = {"template": np.zeros(T, np.int64), "created": np.zeros(T, np.bool_),
            "argmax": np.zeros((T, 3), np.int64), "n_exp": np.zeros(T, np.int64), "em_xy": np.zeros((T, 2))}
     for t in range(T):
-        node.odom_callback((float(odom[t, 0]), float(odom[t, 1])))
-        node.spin_once()
-        rec["argmax"][t] = node.pcn.get_pc_max()
-        idx, created = node.vis_callback(frames[t])
+        if fused:
+            idx, created = node.fused_frame((float(odom[t, 0]), float(odom[t, 1])), frames[t])
+            rec["argmax"][t] = node.pcn.max_pc
+        else:
+            node.odom_callback((float(odom[t, 0]), float(odom[t, 1])))
+            node.spin_once()
+            rec["argmax"][t] = node.pcn.get_pc_max()
+            idx, created = node.vis_callback(frames[t])
         rec["template"][t] = idx
         rec["created"][t] = created
         rec["n_exp"][t] = len(node.em.experiences)

@@ -220,8 +220,8 @@ def test_replay_loop_matches_reference_fixture(golden):
     g = golden("replay_ros.npz")
     T = int(g["n_frames"])
     frames = synth_frames(np.random.default_rng(int(g["frame_seed"])), T)
-    for dtype in (np.float32, np.float64):
-        rec = ros_simulate.replay(frames, g["odom"], dtype=dtype)
+    for dtype, fused in ((np.float32, False), (np.float64, False), (np.float32, True), (np.float64, True)):
+        rec = ros_simulate.replay(frames, g["odom"], fused=fused, dtype=dtype)
         assert np.array_equal(rec["template"], g["template"])
         assert np.array_equal(rec["created"], g["created"])
         assert np.array_equal(rec["argmax"], g["argmax"])
@@ -229,3 +229,9 @@ def test_replay_loop_matches_reference_fixture(golden):
         assert np.allclose(rec["em_xy"][-1], g["em_xy"][-1], rtol=0, atol=0)
         fs = rec["node"].pcn.posecells
         assert np.abs(fs - g["final_state"]).max() / g["final_state"].max() <= (1e-5 if dtype == np.float32 else 1e-12)
+        # the library holds the sub-sampled frames and the locations the reference would have stored
+        node = rec["node"]
+        first_created = int(np.flatnonzero(g["created"])[3])
+        tm = node.vts.templates[int(g["template"][first_created])]
+        assert np.array_equal(tm.template, frames[first_created][node.vts.mask].reshape(32, 32))
+        assert tm.location() == tuple(g["argmax"][first_created])
