@@ -445,7 +445,7 @@ struct RefRows {
 constexpr int kPkThreads = 128;
 
 // Reference mode (15 windowed row offsets, view_templates.py:16-28) over the packed library.
-__global__ void __launch_bounds__(kPkThreads)
+__global__ void __launch_bounds__(kPkThreads)  // 96 registers (15 interleaved compare chains); capping them spills
     k_vt_sweep_packed_ref(const uint4* __restrict__ packed, long long n, long long base_index,
                           unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores) {
   const int lane = threadIdx.x & 31;
