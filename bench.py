@@ -94,6 +94,22 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def profiled_traffic():
+    """DRAM bytes per launch of the resident kernel from the committed `ncu --set full` capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "r1_resident_ncu_full.csv")
+    try:
+        import csv
+        rd = wr = None
+        for row in csv.reader(open(path)):
+            if row and row[0] == "dram__bytes_read.sum":
+                rd = float(row[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[row[1]]
+            if row and row[0] == "dram__bytes_write.sum":
+                wr = float(row[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[row[1]]
+        return rd + wr if rd is not None and wr is not None else None
+    except Exception:
+        return None
+
+
 def ensemble_inputs(B, T, seed):
     rng = np.random.default_rng(seed)
     gis = np.linspace(0.05, 0.25, B)
@@ -315,6 +331,9 @@ def run_ours(args):
         alg_bytes = 2 * 4 * B * N_CELLS                  # read + write the float32 state once per update
         gbs = alg_bytes / (ms / K * 1e-3) / 1e9
         fma_per_cell = 98
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12        # TFMA/s at the clock seen during the timed region
+        tfma = B * N_CELLS * fma_per_cell / (ms / K * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -328,11 +347,14 @@ def run_ours(args):
             "gpu_launches": K * launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (profiled_traffic() if path == "resident" else None), "peak_source": peak_src,
+                         "traffic_source": "profiles/r1_resident_ncu_full.csv (dram__bytes_read+write, one launch)",
                          "kernel": "pc_resident_step" if path == "resident" else "generic 8-kernel step (whole step timed)",
                          "algorithmic_bytes_per_cell_update": 8,
-                         "fp32_issue": {"fma_per_cell_update": fma_per_cell,
-                                        "achieved_tfma_per_s": B * N_CELLS * fma_per_cell / (ms / K * 1e-3) / 1e12}},
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "binding_roof": "fp32 issue: 98 FMA per 8 B puts the FP32 pipe roof at 0.46 of the HBM roof",
+                         "fp32_issue": {"fma_per_cell_update": fma_per_cell, "achieved_tfma_per_s": tfma,
+                                        "peak_tfma_per_s": fp32_peak, "frac": tfma / fp32_peak}},
             "networks_alive": alive,
         }
         if world == 1:

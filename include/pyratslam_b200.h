@@ -156,6 +156,12 @@ PRS_API int prs_vt_pack_u8(const uint8_t* src, long long n, void* packed, long l
 PRS_API int prs_vt_unpack_u8(const void* packed, long long index, uint8_t* dst, void* stream);
 PRS_API int prs_vt_sweep_packed_u8(const void* packed, long long n, const uint8_t* query, int mode, long long base_index,
                            unsigned long long* key_out, uint32_t* scores, void* scratch, void* stream);
+/* Any template shape rows x cols (row-major library) and any max_offset (view_templates.py:14): the
+ * reference's windowed match for configurations other than its 32x32 default.  Correctness path. */
+PRS_API int prs_vt_sweep_any_u8(const uint8_t* lib, long long n, const uint8_t* query, int rows, int cols, int max_offset,
+                        long long base_index, unsigned long long* key_out, uint32_t* scores, void* stream);
+PRS_API int prs_vt_sweep_any_f32(const float* lib, long long n, const float* query, int rows, int cols, int max_offset,
+                         long long base_index, unsigned long long* key_out, float* scores, void* stream);
 /* HOST query in, HOST key out: H2D copy of the 1 KiB query, sweep, D2H of the 8-byte key, sync.
  * lib stays resident on the device; scratch is a device buffer of >= 1024+8 bytes. */
 PRS_API int prs_vt_match_host_u8(const uint8_t* lib, long long n, const uint8_t* query_host, int mode,

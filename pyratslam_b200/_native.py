@@ -59,6 +59,10 @@ _SIGNATURES = {
     "prs_vt_unpack_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
     "prs_vt_sweep_packed_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p,
                                        c_void_p]),
+    "prs_vt_sweep_any_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p,
+                                    c_void_p]),
+    "prs_vt_sweep_any_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p,
+                                     c_void_p]),
     "prs_vt_match_host_u8": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
 }
 

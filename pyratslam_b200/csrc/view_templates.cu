@@ -694,3 +694,72 @@ extern "C" int prs_frame_host(prs_pc_handle pc, void* pc_state, const void* gi, 
   PRS_CUDA(cudaStreamSynchronize(st));
   return PRS_OK;
 }
+
+// =============================================================================================
+// Any template shape (rows x cols) and any max_offset: one warp per template, lanes stride over the
+// window's pixels.  Used when ViewTemplates is configured away from the reference's 32x32 / offset 8
+// (view_templates.py:14,44); correctness path, not tuned.
+template <typename T, typename ACC>
+__global__ void __launch_bounds__(256)
+    k_vt_sweep_any(const T* __restrict__ lib, long long n, const T* __restrict__ query, int rows, int cols, int max_offset,
+                   long long base_index, unsigned long long* __restrict__ key_out, ACC* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * 256) >> 5;
+  const int win = rows - 2 * max_offset;  // rows compared per offset
+  unsigned long long best = ~0ull;
+  for (long long ti = warp0; ti < n; ti += n_warps) {
+    const T* tp = lib + ti * rows * cols;
+    ACC m = 0;
+    bool first = true;
+    for (int o = -max_offset + 1; o < max_offset; ++o) {
+      ACC s = 0;
+      for (int i = lane; i < win * cols; i += 32) {
+        const int r = i / cols, c = i - r * cols;
+        const T a = tp[(max_offset + o + r) * cols + c], b = query[(max_offset + r) * cols + c];
+        if constexpr (sizeof(T) == 1)
+          s += (ACC)(uint8_t)(a - b);  // uint8 arithmetic wraps; abs() is the identity (view_templates.py:23)
+        else
+          s += fabsf(a - b);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      if (first || s < m) m = s;
+      first = false;
+    }
+    unsigned hi;
+    if constexpr (sizeof(T) == 1)
+      hi = (unsigned)m;
+    else
+      hi = __float_as_uint(m);
+    const unsigned long long key = ((unsigned long long)hi << 32) | (unsigned long long)(base_index + ti);
+    best = key < best ? key : best;
+    if (scores != nullptr && lane == 0) scores[ti] = m;
+  }
+  block_min_to_global(best, key_out);
+}
+
+template <typename T, typename ACC>
+static int sweep_any(const T* lib, long long n, const T* query, int rows, int cols, int max_offset, long long base_index,
+                     unsigned long long* key_out, ACC* scores, cudaStream_t st) {
+  PRS_REQUIRE(query && key_out && n >= 0 && (lib || n == 0), "prs_vt_sweep_any: bad argument");
+  PRS_REQUIRE(rows > 0 && cols > 0 && max_offset >= 1 && rows - 2 * max_offset >= 0,
+              "prs_vt_sweep_any: %dx%d templates cannot be compared with max_offset %d", rows, cols, max_offset);
+  PRS_REQUIRE(base_index >= 0 && base_index + n <= 0xffffffffLL, "prs_vt_sweep_any: template index does not fit 32 bits");
+  PRS_CUDA(cudaMemsetAsync(key_out, 0xff, sizeof(unsigned long long), st));
+  if (n == 0) return PRS_OK;
+  k_vt_sweep_any<T, ACC><<<sweep_grid(n), 256, 0, st>>>(lib, n, query, rows, cols, max_offset, base_index, key_out, scores);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+extern "C" int prs_vt_sweep_any_u8(const uint8_t* lib, long long n, const uint8_t* query, int rows, int cols,
+                                   int max_offset, long long base_index, unsigned long long* key_out, uint32_t* scores,
+                                   void* stream) {
+  return sweep_any<uint8_t, uint32_t>(lib, n, query, rows, cols, max_offset, base_index, key_out, scores, (cudaStream_t)stream);
+}
+
+extern "C" int prs_vt_sweep_any_f32(const float* lib, long long n, const float* query, int rows, int cols, int max_offset,
+                                    long long base_index, unsigned long long* key_out, float* scores, void* stream) {
+  return sweep_any<float, float>(lib, n, query, rows, cols, max_offset, base_index, key_out, scores, (cudaStream_t)stream);
+}

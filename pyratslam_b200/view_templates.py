@@ -48,19 +48,20 @@ class ViewTemplate:
         nat.require_cuda()
         a = np.ascontiguousarray(self.template)
         b = np.ascontiguousarray(new_template)
-        if a.shape != (32, 32) or b.shape != (32, 32):
-            raise NotImplementedError("the CUDA matcher handles 32x32 templates (the reference configuration)")
+        if a.ndim != 2 or a.shape != b.shape:
+            raise ValueError("operands could not be broadcast together with shapes %r %r" % (a.shape, b.shape))
+        R, C = a.shape
         dev = torch.device("cuda", torch.cuda.current_device())
         key = torch.empty(1, dtype=torch.int64, device=dev)
         if a.dtype == np.uint8 and b.dtype == np.uint8:
             ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
-            nat.check(nat.lib().prs_vt_sweep_u8(ta.data_ptr(), 1, tb.data_ptr(), nat.VT_MODE_REF, 0, key.data_ptr(),
-                                                None, nat.stream_ptr()), "prs_vt_sweep_u8")
+            nat.check(nat.lib().prs_vt_sweep_any_u8(ta.data_ptr(), 1, tb.data_ptr(), R, C, self.max_offset, 0,
+                                                    key.data_ptr(), None, nat.stream_ptr()), "prs_vt_sweep_any_u8")
             return np.uint64(int(key.item()) >> 32)
         ta = torch.from_numpy(a.astype(np.float32)).to(dev)
         tb = torch.from_numpy(b.astype(np.float32)).to(dev)
-        nat.check(nat.lib().prs_vt_sweep_f32(ta.data_ptr(), 1, tb.data_ptr(), nat.VT_MODE_REF, 0, key.data_ptr(),
-                                             None, nat.stream_ptr()), "prs_vt_sweep_f32")
+        nat.check(nat.lib().prs_vt_sweep_any_f32(ta.data_ptr(), 1, tb.data_ptr(), R, C, self.max_offset, 0,
+                                                 key.data_ptr(), None, nat.stream_ptr()), "prs_vt_sweep_any_f32")
         return np.array([int(key.item()) >> 32], dtype=np.uint32).view(np.float32)[0]
 
     def location(self):
@@ -121,10 +122,12 @@ class ViewTemplates:
         if self._n_rows * self._n_cols != self.shape[0] * self.shape[1]:
             raise ValueError("cannot reshape array of size %d into shape %r"
                              % (self._n_rows * self._n_cols, self.shape))
-        if self.shape != (32, 32):
-            raise NotImplementedError("the CUDA matcher handles 32x32 templates (the reference configuration), "
-                                      "got %r" % (self.shape,))
+        # 32x32 (the reference configuration) takes the tuned kernels; any other shape the general one
+        self._fast = tuple(self.shape) == (32, 32) and self._n_rows == 32 and self._n_cols == 32
+        if not self._fast and mode != "ref":
+            raise NotImplementedError("circular mode is implemented for 32x32 templates")
         self._mask = None
+        self._mask_dev = None
         self._n = 0
         self._dtype = None           # torch dtype of the library, fixed by the first frame
         self._lib = None             # [capacity, 32, 32]
@@ -135,7 +138,7 @@ class ViewTemplates:
         self._key = torch.empty(1, dtype=torch.int64, device=self.device)
         self._key_pin = torch.empty(1, dtype=torch.int64).pin_memory()
         self._frame_dev = torch.empty((self.im_x, self.im_y), dtype=torch.uint8, device=self.device)
-        self._tpl_u8 = torch.empty((32, 32), dtype=torch.uint8, device=self.device)
+        self._tpl_u8 = torch.empty(tuple(self.shape), dtype=torch.uint8, device=self.device)
         self._frame_pin = torch.empty((self.im_x, self.im_y), dtype=torch.uint8).pin_memory()
         self._scratch = torch.empty(4096, dtype=torch.uint8, device=self.device)
         self.last_score = None       # best score of the most recent match() (None when the library was empty)
@@ -159,7 +162,7 @@ class ViewTemplates:
         return int(v) if self._loc_is_int else float(v)
 
     def _fetch_template(self, i):
-        if self._dtype == torch.uint8:
+        if self._dtype == torch.uint8 and self._fast:
             out = torch.empty((32, 32), dtype=torch.uint8, device=self.device)
             with torch.cuda.device(self.device):
                 nat.check(nat.lib().prs_vt_unpack_u8(self._lib.data_ptr(), int(i), out.data_ptr(), nat.stream_ptr()),
@@ -171,10 +174,10 @@ class ViewTemplates:
     # uint8 libraries are stored bit-sliced ("packed", 1088 B per template, see csrc/view_templates.cu);
     # float32 libraries are plain [capacity, 32, 32].
     def _alloc(self, torch_dtype, capacity):
-        if torch_dtype == torch.uint8:
+        if torch_dtype == torch.uint8 and self._fast:
             nbytes = int(nat.lib().prs_vt_packed_bytes(int(capacity)))
             return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-        return torch.empty((capacity, 32, 32), dtype=torch_dtype, device=self.device)
+        return torch.empty((capacity,) + tuple(self.shape), dtype=torch_dtype, device=self.device)
 
     def _ensure_lib(self, torch_dtype):
         if self._lib is None:
@@ -188,7 +191,7 @@ class ViewTemplates:
             return
         cap = max(need, self._capacity * 2)
         new = self._alloc(self._dtype, cap)
-        if self._dtype == torch.uint8:
+        if self._dtype == torch.uint8 and self._fast:
             new[: self._lib.numel()].copy_(self._lib)      # whole 32-template groups, position independent
         else:
             new[: self._n].copy_(self._lib[: self._n])
@@ -200,23 +203,25 @@ class ViewTemplates:
 
     def _store(self, tpl_dev, first, count):
         """Write ``count`` row-major templates into slots ``first..``."""
-        if self._dtype == torch.uint8:
+        if self._dtype == torch.uint8 and self._fast:
             nat.check(nat.lib().prs_vt_pack_u8(tpl_dev.data_ptr(), int(count), self._lib.data_ptr(), int(first),
                                                nat.stream_ptr()), "prs_vt_pack_u8")
         else:
-            self._lib[first: first + count].copy_(tpl_dev.reshape(count, 32, 32))
+            self._lib[first: first + count].copy_(tpl_dev.reshape((count,) + tuple(self.shape)))
 
     def load_library(self, templates, locations=None):
         """Bulk-load ``templates[n, 32, 32]`` (uint8 or float32; numpy or torch) as templates 0..n-1."""
         t = templates if isinstance(templates, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(templates))
         if t.dtype not in (torch.uint8, torch.float32):
             raise TypeError("templates must be uint8 or float32")
+        if tuple(t.shape[1:]) != tuple(self.shape):
+            raise ValueError("library templates are %r, this matcher uses %r" % (tuple(t.shape[1:]), tuple(self.shape)))
         n = t.shape[0]
         self._dtype = t.dtype
         self._capacity = max(n, 32)
         with torch.cuda.device(self.device):
             src = t.to(self.device).contiguous()
-            if t.dtype == torch.uint8:
+            if t.dtype == torch.uint8 and self._fast:
                 self._lib = self._alloc(torch.uint8, self._capacity)
                 self._store(src, 0, n)
             else:
@@ -248,6 +253,14 @@ class ViewTemplates:
             raise IndexError("boolean index did not match indexed array: frame %r, mask %r"
                              % (tuple(fr.shape), (self.im_x, self.im_y)))
         is_u8 = (fr.dtype == torch.uint8) if isinstance(fr, torch.Tensor) else (fr.dtype == np.uint8)
+        if not self._fast:
+            if self._mask_dev is None:
+                self._mask_dev = torch.from_numpy(self.mask).to(self.device)
+            t = fr if isinstance(fr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(fr))
+            t = t.to(self.device)
+            if not is_u8:
+                t = t.to(torch.float32)
+            return t[self._mask_dev].reshape(tuple(self.shape)).contiguous(), (torch.uint8 if is_u8 else torch.float32)
         if is_u8:
             if isinstance(fr, torch.Tensor):
                 self._frame_dev.copy_(fr, non_blocking=True)
@@ -270,7 +283,11 @@ class ViewTemplates:
 
     def _sweep(self, tpl, torch_dtype, key_dev, scores_ptr=None):
         lib_ptr = self._lib.data_ptr() if self._n else None
-        if torch_dtype == torch.uint8:
+        if not self._fast:
+            fn = nat.lib().prs_vt_sweep_any_u8 if torch_dtype == torch.uint8 else nat.lib().prs_vt_sweep_any_f32
+            nat.check(fn(lib_ptr, self._n, tpl.data_ptr(), int(self.shape[0]), int(self.shape[1]), ViewTemplate.max_offset,
+                         0, key_dev.data_ptr(), scores_ptr, nat.stream_ptr()), "prs_vt_sweep_any")
+        elif torch_dtype == torch.uint8:
             nat.check(nat.lib().prs_vt_sweep_packed_u8(lib_ptr, self._n, tpl.data_ptr(), self.mode, 0,
                                                        key_dev.data_ptr(), scores_ptr, self._scratch.data_ptr(),
                                                        nat.stream_ptr()), "prs_vt_sweep_packed_u8")

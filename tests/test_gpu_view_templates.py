@@ -235,3 +235,29 @@ def test_replay_loop_matches_reference_fixture(golden):
         tm = node.vts.templates[int(g["template"][first_created])]
         assert np.array_equal(tm.template, frames[first_created][node.vts.mask].reshape(32, 32))
         assert tm.location() == tuple(g["argmax"][first_created])
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_other_template_shapes(dtype):
+    """A configuration away from the reference's 32x32: (x_range, y_range) = ((20, 100), (40, 88)), step 2 -> 40x24."""
+    from pyratslam_b200 import ViewTemplates
+    args = ((20, 100), (40, 88), 2, 2, 128, 128, 30000 if dtype == np.uint8 else 9000.0)
+    ref = ovt.ViewTemplates(*args)
+    got = ViewTemplates(*args)
+    assert got.shape == ref.shape == (40, 24) and np.array_equal(got.mask, ref.mask)
+    rng = np.random.default_rng(8)
+    frames = []
+    for t in range(14):
+        if t % 3 == 2:
+            f = np.clip(frames[rng.integers(0, t)].astype(np.int16) - rng.integers(0, 3, (128, 128)), 0, 255)
+        else:
+            f = rng.integers(0, 256, (128, 128))
+        frames.append(f.astype(dtype))
+    for t, f in enumerate(frames):
+        a = ref.match(f, t, 0, 0)
+        b = got.match(f, t, 0, 0)
+        assert a.get_index() == b.get_index() and len(ref.templates) == len(got.templates), t
+    assert 3 < len(got.templates) < 14
+    assert np.array_equal(got.templates[1].template, ref.templates[1].template)
+    q = frames[5][ref.mask].reshape(ref.shape)
+    assert float(got.templates[0].match(q)) == float(ref.templates[0].match(q))
