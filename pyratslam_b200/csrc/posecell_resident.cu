@@ -110,6 +110,25 @@ __device__ __forceinline__ void plan_plane(int k, const double* __restrict__ od,
   if (e) atomicOr(err_b, e);
 }
 
+// Optional in-kernel stage timing (profiling builds of this file only: -DPRS_RESIDENT_TIMING).  Thread 0 of
+// CTA 0 accumulates the cycles between consecutive barriers into timing[0..6].
+#ifdef PRS_RESIDENT_TIMING
+__device__ unsigned long long g_stage_cycles[8];
+#define PRS_STAMP(i)                                                   \
+  do {                                                                 \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                         \
+      const long long now_ = clock64();                                \
+      if ((i) > 0) g_stage_cycles[(i)-1] += now_ - stamp_;             \
+      else if (stamp_) g_stage_cycles[6] += now_ - stamp_;             \
+      stamp_ = now_;                                                   \
+    }                                                                  \
+  } while (0)
+#else
+#define PRS_STAMP(i) \
+  do {               \
+  } while (0)
+#endif
+
 template <int X, int Y, int T, int NT>
 __global__ void __launch_bounds__(NT, 1)
     k_pc_resident(float* state, const double* __restrict__ odom, int n_steps, const float* __restrict__ gi,
@@ -166,6 +185,9 @@ __global__ void __launch_bounds__(NT, 1)
   __syncthreads();
   uint32_t parity = 0;
   int slot = 0;
+#ifdef PRS_RESIDENT_TIMING
+  long long stamp_ = 0;
+#endif
 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     float* gst = state + (size_t)b * N;
@@ -173,6 +195,7 @@ __global__ void __launch_bounds__(NT, 1)
     for (int step = 0; step < n_steps; ++step) {
       const int* plan = s_plan + slot * L::kPlanInts;
       const int4* plan4 = reinterpret_cast<const int4*>(plan);
+      PRS_STAMP(0);
 
       // ---- 1. theta pass of the separable DoG: stage (or global on later steps) -> (E, I) pairs.
       //      The pair of plane k is stored at (x - ox_k, y - oy_k): the integer origin the reference adds
@@ -209,6 +232,7 @@ __global__ void __launch_bounds__(NT, 1)
         }
       }
       __syncthreads();
+      PRS_STAMP(1);
       // the staging buffer is free again: fetch the next network while this one is computed
       if (tid == 0 && step == 0) {
         const int nb = b + gridDim.x;
@@ -244,6 +268,7 @@ __global__ void __launch_bounds__(NT, 1)
         }
       }
       __syncthreads();
+      PRS_STAMP(2);
 
       // ---- 3. x pass + global inhibition (posecell_network.py:339-340) + sum (:343).
       //      A thread takes the same (y) column of BOTH planes of a pair (kp, kp+NP), so that the result is
@@ -286,6 +311,7 @@ __global__ void __launch_bounds__(NT, 1)
       for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
       if (lane == 0) red_f[wid] = psum;
       __syncthreads();  // every (E, I) pair has been consumed: the bytes become A2 / B2
+      PRS_STAMP(3);
       if (!(ablate & 8) && tid < NP * Y) {
         float2* dst = A2 + kp3 * PS + y3;  // row r of the halo layout is grid row r - 3
 #pragma unroll
@@ -302,6 +328,7 @@ __global__ void __launch_bounds__(NT, 1)
         if (lane == 0) s_val[0] = sacc;
       }
       __syncthreads();  // publishes A2 and the total
+      PRS_STAMP(4);
       const float tot = s_val[0];
       const float inv = (tot != 0.f) ? 1.f / tot : 1.f;  // posecell_network.py:344-345
 
@@ -346,6 +373,7 @@ __global__ void __launch_bounds__(NT, 1)
         }
       }
       __syncthreads();
+      PRS_STAMP(5);
 
       // ---- 5. theta pass (convolution.py:344-359), clamp, arg-max, registers -> global
       float best = -INFINITY;
@@ -434,6 +462,7 @@ __global__ void __launch_bounds__(NT, 1)
         red_i[wid] = bidx;
       }
       __syncthreads();  // the state in global memory and every SMEM slot are consistent for the next update
+      PRS_STAMP(6);
       if (wid == 0) {
         float v = lane < (NT + 31) / 32 ? red_f[lane] : -INFINITY;
         int ix = lane < (NT + 31) / 32 ? red_i[lane] : 0x7fffffff;
@@ -482,6 +511,18 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
 }
 
 }  // namespace
+
+#ifdef PRS_RESIDENT_TIMING
+extern "C" __attribute__((visibility("default"))) int prs_debug_stage_cycles(unsigned long long* out8, int reset) {
+  PRS_CUDA(cudaDeviceSynchronize());
+  PRS_CUDA(cudaMemcpyFromSymbol(out8, g_stage_cycles, 8 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    PRS_CUDA(cudaMemcpyToSymbol(g_stage_cycles, z, sizeof(z)));
+  }
+  return PRS_OK;
+}
+#endif
 
 int prs_pc_resident_supported(const prs_pc_plan* p) {
   if (p->dtype != PRS_F32) return 0;
