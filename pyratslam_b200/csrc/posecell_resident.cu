@@ -12,9 +12,13 @@
 //   stage[N] float        the next network's state as it lies in HBM, theta-major [th][x][y]   4N bytes
 //   buf2[N]  float2       (E, I) pairs of the separable DoG, [th][x][y]                        8N bytes
 //     after the x pass the same bytes are reused as two plane-pair-interleaved tensors
-//       A2[NP][x+halo][y] float2 = (A'[kp], A'[kp+NP])  inhibited activity, already moved by the integer
+//       A2[NP][x+halo][y] float2 = (A'[mid+m], A'[mid-m])  inhibited activity, already moved by the integer
 //                                                   (x, y) origin of its plane, 3 periodic halo rows each side
-//       B2[NP][x][y] float2 = (B[kp],  B[kp+NP])    after the 2-D correlate
+//       B2[NP][x][y] float2 = (B[mid+m], B[mid-m])    after the 2-D correlate
+//     Plane pairs are MIRROR pairs about mid = Th/2 (pair 0 is (mid, 0)): cos((k-mid)*2pi/Th) is the same for
+//     both, hence the same x origin and the same LUT filter (a variant of stage 4 that adds the tap rows sharing
+//     coefficients first -- 4 or 5 row groups instead of 7 -- was measured and was NOT faster: the stage is bound
+//     by the sum of its shared-memory and FMA time, not by the FMA count).
 // Stages (a __syncthreads between each):
 //   1 theta pass   thread = one (x,y) line of Th cells in registers, stage -> buf2         11 op / cell
 //   2 y pass       thread = one (th,x) line, in place, packed FFMA2 on (E,I)               7 FFMA2 / cell
@@ -142,6 +146,9 @@ __global__ void __launch_bounds__(NT, 1)
   static_assert((N * 4) % 16 == 0, "bulk copies move multiples of 16 bytes");
   static_assert(kPlanT0 >= NP * X && T <= 64, "the planning threads must be idle in stage 4");
   static_assert(NP * X <= NT && NP * Y <= NT && XY <= NT, "one work item per thread in stages 1, 3, 4, 5");
+  static_assert(T % 2 == 0 && T >= 8, "mirror plane pairs need an even number of theta planes");
+  constexpr int MID = T / 2;  // posecell_network.py:257: mid = floor(Th / 2); pair m = (MID + m, MID - m), pair 0 = (MID, 0)
+  constexpr int NW = (NT + 31) / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   float* stage = reinterpret_cast<float*>(smem + L::kStageOff);
   float2* buf2 = reinterpret_cast<float2*>(smem + L::kBufOff);
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(NT, 1)
   float2* s_cf_ty = reinterpret_cast<float2*>(smem + L::kCfOff);
   float2* s_cf_x = s_cf_ty + 7;
   int* s_plan = reinterpret_cast<int*>(smem + L::kPlanOff);
-  int* red_i = reinterpret_cast<int*>(smem + L::kRedOff);
+  int* red_i = reinterpret_cast<int*>(smem + L::kRedOff);  // [0..NW) warp maxima, [30], [31] the two arg-max slots
   float* red_f = reinterpret_cast<float*>(smem + L::kRedOff + 32 * 4);
   float* s_val = red_f + 32;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + L::kBarOff);
@@ -185,6 +192,10 @@ __global__ void __launch_bounds__(NT, 1)
   __syncthreads();
   uint32_t parity = 0;
   int slot = 0;
+  bool pend_valid = false;
+  int pend_slot = 0;
+  size_t pend_off = 0;
+  float pend_tot = 0.f;
 #ifdef PRS_RESIDENT_TIMING
   long long stamp_ = 0;
 #endif
@@ -233,6 +244,11 @@ __global__ void __launch_bounds__(NT, 1)
       }
       __syncthreads();
       PRS_STAMP(1);
+      if (tid == 0 && pend_valid) {  // every winner of the previous update has done its atomicMin by now
+        argmax[pend_off] = (long long)red_i[30 + pend_slot];
+        total[pend_off] = pend_tot;
+      }
+      pend_valid = false;
       // the staging buffer is free again: fetch the next network while this one is computed
       if (tid == 0 && step == 0) {
         const int nb = b + gridDim.x;
@@ -271,7 +287,7 @@ __global__ void __launch_bounds__(NT, 1)
       PRS_STAMP(2);
 
       // ---- 3. x pass + global inhibition (posecell_network.py:339-340) + sum (:343).
-      //      A thread takes the same (y) column of BOTH planes of a pair (kp, kp+NP), so that the result is
+      //      A thread takes the same (y) column of BOTH planes of a mirror pair, so that the result is
       //      written as one float2 per cell.  Items are enumerated plane-fastest: a warp's accesses stride by
       //      one plane (an odd number of float2 slots), which is free of bank conflicts.
       float2 keep[X];
@@ -285,8 +301,8 @@ __global__ void __launch_bounds__(NT, 1)
         for (int t = 0; t < 7; ++t) cf[t] = s_cf_x[t];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int k = kp3 + h * NP;
-          if (k < T) {
+          const int k = h == 0 ? MID + kp3 : (kp3 == 0 ? 0 : MID - kp3);
+          {
             const float2* col = buf2 + k * XY + y3;
             float2 in[X];
 #pragma unroll
@@ -343,8 +359,8 @@ __global__ void __launch_bounds__(NT, 1)
                               vrot_scale, s_plan + (slot ^ 1) * L::kPlanInts, err + nb);
       } else if (!(ablate & 16) && tid < NP * X) {
         const int kp = tid / X, x = tid - kp * X;
-        const int k1 = (kp + NP < T) ? kp + NP : kp;
-        const float2* ctab = s_f2p + (plan4[kp].w * 2 + plan4[k1].w) * 56;
+        const int fsA = plan4[MID + kp].w, fsB = plan4[kp == 0 ? 0 : MID - kp].w;
+        const float2* ctab = s_f2p + (fsA * 2 + fsB) * 56;
         const float2* rows = A2 + kp * PS + x * Y;  // halo layout: tap row a of output row x is row x + a
         float2 acc[Y];
 #pragma unroll
@@ -375,9 +391,12 @@ __global__ void __launch_bounds__(NT, 1)
       __syncthreads();
       PRS_STAMP(5);
 
-      // ---- 5. theta pass (convolution.py:344-359), clamp, arg-max, registers -> global
-      float best = -INFINITY;
-      int bidx = 0x7fffffff;
+      // ---- 5. theta pass (convolution.py:344-359), clamp (:314), registers -> global, maximum.
+      //      For the mirror pair m = (MID+m, MID-m) the tap at offset u reads planes MID+(m+u) and MID-(m-u):
+      //      the same pair m+u for both halves when the second half takes the taps in reverse, i.e.
+      //      acc += pair(m+u) * (f[3+u], f[3-u]).  Pairs that fall off either end are swapped or pair 0.
+      float2 out[NP];
+      float vmax = 0.f;
       if (!(ablate & 32) && tid < XY) {
         const int p = tid;
         float fc[7];
@@ -387,101 +406,84 @@ __global__ void __launch_bounds__(NT, 1)
         float2 pin[NP];
 #pragma unroll
         for (int kk = 0; kk < NP; ++kk) pin[kk] = B2[kk * XY + p];
-        if constexpr (T % 2 == 0) {
-          // planes kk and kk+NP advance together; a tap that leaves [0, NP) lands in the partner half
-          float2 cf2[7];
+        float2 cf2[7];
 #pragma unroll
-          for (int t = 0; t < 7; ++t) cf2[t] = make_float2(fc[t], fc[t]);
-          float2 out[NP];
+        for (int u = -3; u <= 3; ++u) cf2[u + 3] = make_float2(fc[3 + u], fc[3 - u]);
 #pragma unroll
-          for (int kk = 0; kk < NP; ++kk) {
-            float2 acc = make_float2(0.f, 0.f);
+        for (int m = 1; m < NP; ++m) {
+          float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < 7; ++t) {
-              const int m = kk + t - 3;
-              float2 v;
-              if (m < 0)
-                v = make_float2(pin[m + NP].y, pin[m + NP].x);
-              else if (m >= NP)
-                v = make_float2(pin[m - NP].y, pin[m - NP].x);
-              else
-                v = pin[m];
-              acc = ffma2(v, cf2[t], acc);
-            }
-            out[kk] = make_float2(acc.x < 0.f ? 0.f : acc.x, acc.y < 0.f ? 0.f : acc.y);  // posecell_network.py:314
+          for (int u = -3; u <= 3; ++u) {
+            const int j = m + u;
+            float2 v;
+            if (j >= 1 && j <= NP - 1)
+              v = pin[j];
+            else if (j == 0)
+              v = make_float2(pin[0].x, pin[0].x);                    // plane MID on both sides
+            else if (j == NP)
+              v = make_float2(pin[0].y, pin[0].y);                    // plane 0 == plane T on both sides
+            else if (j < 0)
+              v = make_float2(pin[-j].y, pin[-j].x);                  // crossed the middle: halves swap
+            else
+              v = make_float2(pin[2 * NP - j].y, pin[2 * NP - j].x);  // crossed plane 0: halves swap
+            acc = ffma2(v, cf2[u + 3], acc);
           }
+          out[m] = make_float2(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f));
+        }
+        {  // pair 0 = (MID, 0)
+          float a = 0.f, c = 0.f;
 #pragma unroll
-          for (int kk = 0; kk < NP; ++kk) {
-            gst[kk * XY + p] = out[kk].x;
-            if (out[kk].x > best) {  // theta ascending: strict '>' keeps the lowest flat index of this line
-              best = out[kk].x;
-              bidx = p * T + kk;
-            }
+          for (int u = -3; u <= 3; ++u) {
+            const float va = u > 0 ? pin[u].x : (u < 0 ? pin[-u].y : pin[0].x);
+            const float vc = u > 0 ? pin[NP - u].y : (u < 0 ? pin[NP + u].x : pin[0].y);
+            a = fmaf(fc[3 + u], va, a);
+            c = fmaf(fc[3 + u], vc, c);
           }
+          out[0] = make_float2(fmaxf(a, 0.f), fmaxf(c, 0.f));
+        }
+        gst[MID * XY + p] = out[0].x;
+        gst[p] = out[0].y;
+        vmax = fmaxf(out[0].x, out[0].y);
 #pragma unroll
-          for (int kk = 0; kk < NP; ++kk) {
-            gst[(kk + NP) * XY + p] = out[kk].y;
-            if (out[kk].y > best) {
-              best = out[kk].y;
-              bidx = p * T + kk + NP;
-            }
-          }
-        } else {
-          float in[T];
-#pragma unroll
-          for (int kk = 0; kk < NP; ++kk) {
-            in[kk] = pin[kk].x;
-            if (kk + NP < T) in[kk + NP] = pin[kk].y;
-          }
-#pragma unroll
-          for (int k = 0; k < T; ++k) {
-            float c = 0.f;
-#pragma unroll
-            for (int t = 0; t < 7; ++t) c = fmaf(fc[t], in[(k + t + T - 3) % T], c);
-            c = (c < 0.f) ? 0.f : c;
-            gst[k * XY + p] = c;
-            if (c > best) {
-              best = c;
-              bidx = p * T + k;
-            }
-          }
+        for (int m = 1; m < NP; ++m) {
+          gst[(MID + m) * XY + p] = out[m].x;
+          gst[(MID - m) * XY + p] = out[m].y;
+          vmax = fmaxf(vmax, fmaxf(out[m].x, out[m].y));
         }
       }
-      // block arg-max: value descending, reference flat index ascending (numpy.argmax)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float v2 = __shfl_xor_sync(0xffffffffu, best, o);
-        const int i2 = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (v2 > best || (v2 == best && i2 < bidx)) {
-          best = v2;
-          bidx = i2;
-        }
-      }
-      if (lane == 0) {
-        red_f[wid] = best;
-        red_i[wid] = bidx;
-      }
+      // arg-max (numpy.argmax: first maximum in [x][y][th] order).  Values are >= 0, so their bit patterns order
+      // like the values: one REDUX per warp, one per block; then only the thread(s) holding the maximum look
+      // for its lowest theta and race with atomicMin on the flat index.
+      const unsigned vbits = __float_as_uint(vmax);
+      const unsigned wmax = __reduce_max_sync(0xffffffffu, vbits);
+      if (lane == 0) red_i[wid] = (int)wmax;
+      if (tid == 0) red_i[30 + slot] = 0x7fffffff;
       __syncthreads();  // the state in global memory and every SMEM slot are consistent for the next update
       PRS_STAMP(6);
-      if (wid == 0) {
-        float v = lane < (NT + 31) / 32 ? red_f[lane] : -INFINITY;
-        int ix = lane < (NT + 31) / 32 ? red_i[lane] : 0x7fffffff;
+      {
+        const unsigned gmax = __reduce_max_sync(0xffffffffu, lane < NW ? (unsigned)red_i[lane] : 0u);
+        if (tid < XY && vbits == gmax) {
+          int kbest = T;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
-          const int i2 = __shfl_xor_sync(0xffffffffu, ix, o);
-          if (v2 > v || (v2 == v && i2 < ix)) {
-            v = v2;
-            ix = i2;
+          for (int k = T - 1; k >= 0; --k) {  // descending, so the lowest matching theta is what remains
+            const float v = k == 0 ? out[0].y : (k < MID ? out[MID - k].y : (k == MID ? out[0].x : out[k - MID].x));
+            if (v == vmax) kbest = k;
           }
-        }
-        if (lane == 0) {
-          argmax[(size_t)step * B + b] = (long long)ix;
-          total[(size_t)step * B + b] = tot;
+          atomicMin(&red_i[30 + slot], tid * T + kbest);
         }
       }
+      // the result of this update is complete after the next barrier; thread 0 publishes it there
+      pend_valid = true;
+      pend_slot = slot;
+      pend_off = (size_t)step * B + b;
+      pend_tot = tot;
       slot ^= 1;
     }
+  }
+  __syncthreads();
+  if (tid == 0 && pend_valid) {
+    argmax[pend_off] = (long long)red_i[30 + pend_slot];
+    total[pend_off] = pend_tot;
   }
 }
 
