@@ -288,13 +288,13 @@ __global__ void __launch_bounds__(NT, 1)
 
       // ---- 3. x pass + global inhibition (posecell_network.py:339-340) + sum (:343).
       //      A thread takes the same (y) column of BOTH planes of a mirror pair, so that the result is
-      //      written as one float2 per cell.  Items are enumerated plane-fastest: a warp's accesses stride by
-      //      one plane (an odd number of float2 slots), which is free of bank conflicts.
+      //      written as one float2 per cell.  Items are enumerated y-fastest (measured: a plane-fastest
+      //      enumeration costs 2x shared-memory wavefronts on these 64-bit accesses).
       float2 keep[X];
       float psum = 0.f;
 #pragma unroll
       for (int x = 0; x < X; ++x) keep[x] = make_float2(0.f, 0.f);
-      const int y3 = tid / NP, kp3 = tid - y3 * NP;
+      const int kp3 = tid / Y, y3 = tid - kp3 * Y;  // y fastest: a warp reads contiguous float2 runs
       if (!(ablate & 4) && tid < NP * Y) {
         float2 cf[7];
 #pragma unroll
