@@ -343,7 +343,7 @@ def run_ours(args):
                        "l2": "state per GPU (260 MB) exceeds L2 (126 MB): every step streams from HBM",
                        "parallelism": "networks sharded by rank, no collective"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * 16,
-                    "d2h_bytes_per_step": B * 12},
+                    "d2h_bytes_per_step": B * 16},
             "gpu_launches": K * launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,

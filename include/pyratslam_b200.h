@@ -111,6 +111,11 @@ PRS_API int prs_pc_run(prs_pc_handle h, void* state, const double* odom, int T, 
 PRS_API int prs_pc_step_host(prs_pc_handle h, void* state, const double* odom_host, const void* gi,
                      long long* argmax_host, int* err_host, void* stream);
 
+/* As prs_pc_step_host, but the result comes back as ONE array int32 result_host[B][4] = (x, y, th, err):
+ * the arg-max already unravelled the way get_pc_max does (posecell_network.py:318) plus the PRS_ERR_* bits. */
+PRS_API int prs_pc_step_host_xyz(prs_pc_handle h, void* state, const double* odom_host, const void* gi, int* result_host,
+                         void* stream);
+
 /* PoseCellNetwork.path_integration() alone (posecell_network.py:252-314): per-plane shifted 7x7
  * correlate + clamp, theta correlate + clamp; no attractor dynamics, no normalisation. */
 PRS_API int prs_pc_path_integration(prs_pc_handle h, void* state, const double* odom, int* err, void* stream);

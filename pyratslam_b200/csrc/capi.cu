@@ -48,7 +48,7 @@ static void fill_tables(PcTables<T>& t, const prs_pc_config* c) {
 static void free_plan(prs_pc_plan* p) {
   void* ptrs[] = {p->cos_th, p->sin_th, p->s1,       nullptr,      p->s3,     nullptr,     p->shift, p->fsel,
                   p->ogi,    p->part_val, p->part_idx, p->inv_total, p->d_odom, p->d_argmax, p->d_err, p->d_total,
-                  p->tab_dev};
+                  p->tab_dev, p->d_xyze};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   delete p;
@@ -110,6 +110,7 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   ALLOC(p->d_argmax, (size_t)p->B * sizeof(long long));
   ALLOC(p->d_err, (size_t)p->B * sizeof(int));
   ALLOC(p->d_total, (size_t)p->B * es);
+  ALLOC(p->d_xyze, (size_t)p->B * 4 * sizeof(int));
   ALLOC(p->tab_dev, sizeof(PcTables<float>));
   p->resident_ok = prs_pc_resident_supported(p);
   p->tiled_ok = prs_pc_tiled_supported(p);
@@ -223,6 +224,20 @@ extern "C" int prs_pc_step_host(prs_pc_handle h, void* state, const double* odom
   if (rc != PRS_OK) return rc;
   PRS_CUDA(cudaMemcpyAsync(argmax_host, h->d_argmax, (size_t)h->B * sizeof(long long), cudaMemcpyDeviceToHost, st));
   PRS_CUDA(cudaMemcpyAsync(err_host, h->d_err, (size_t)h->B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  PRS_CUDA(cudaStreamSynchronize(st));
+  return PRS_OK;
+}
+
+extern "C" int prs_pc_step_host_xyz(prs_pc_handle h, void* state, const double* odom_host, const void* gi,
+                                    int* result_host, void* stream) {
+  PRS_REQUIRE(h && state && odom_host && gi && result_host, "prs_pc_step_host_xyz: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PRS_CUDA(cudaMemcpyAsync(h->d_odom, odom_host, (size_t)h->B * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = prs_pc_step(h, state, h->d_odom, gi, h->d_argmax, h->d_total, h->d_err, st);
+  if (rc != PRS_OK) return rc;
+  rc = prs_pc_launch_unravel_pack(h, h->d_argmax, h->d_err, h->d_xyze, st);
+  if (rc != PRS_OK) return rc;
+  PRS_CUDA(cudaMemcpyAsync(result_host, h->d_xyze, (size_t)h->B * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   PRS_CUDA(cudaStreamSynchronize(st));
   return PRS_OK;
 }

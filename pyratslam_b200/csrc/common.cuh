@@ -60,6 +60,7 @@ struct prs_pc_plan {
   long long* d_argmax;
   int* d_err;
   void* d_total;
+  int* d_xyze;          // [B][4] int32 (x, y, th, err) for prs_pc_step_host_xyz
   int force_generic;
   int resident_ok;      // the fused SMEM-resident kernel supports this shape/dtype
   void* tab_dev;        // device copy of PcTables<float> for the resident kernel
@@ -74,6 +75,7 @@ int prs_pc_tiled_supported(const prs_pc_plan* p);
 int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax, float* total,
                       int* err, cudaStream_t st);
 // small shared kernels (implemented in posecell_generic.cu)
+int prs_pc_launch_unravel_pack(prs_pc_plan* p, const long long* argmax, const int* err, int* out, cudaStream_t st);
 int prs_pc_launch_plan(prs_pc_plan* p, const double* odom, int* err, cudaStream_t st);
 int prs_pc_launch_sum_final_f32(prs_pc_plan* p, int np, float* total, cudaStream_t st);
 int prs_pc_launch_argmax_final_f32(prs_pc_plan* p, int np, long long* argmax, cudaStream_t st);

@@ -408,6 +408,22 @@ extern "C" int prs_pc_inject(prs_pc_handle h, void* state, int b, int x, int y, 
   return PRS_OK;
 }
 
+__global__ void k_unravel_pack(const long long* __restrict__ argmax, const int* __restrict__ err, int B, int Y, int Th,
+                               int4* __restrict__ out) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const long long f = argmax[b];
+  const int th = (int)(f % Th);
+  const long long xy = f / Th;
+  out[b] = make_int4((int)(xy / Y), (int)(xy % Y), th, err[b]);
+}
+
+int prs_pc_launch_unravel_pack(prs_pc_plan* p, const long long* argmax, const int* err, int* out, cudaStream_t st) {
+  k_unravel_pack<<<(p->B + 127) / 128, 128, 0, st>>>(argmax, err, p->B, p->Y, p->Th, (int4*)out);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
 extern "C" int prs_pc_argmax(prs_pc_handle h, const void* state, long long* argmax, void* stream) {
   PRS_REQUIRE(h && state && argmax, "prs_pc_argmax: null argument");
   return prs_pc_generic_argmax(h, state, argmax, (cudaStream_t)stream);

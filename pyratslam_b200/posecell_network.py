@@ -77,8 +77,9 @@ class PoseCellEnsemble:
         self._total = torch.zeros(B, dtype=td, device=dev)
         self._err = torch.zeros(B, dtype=torch.int32, device=dev)
         self._odom_pin = torch.zeros((B, 2), dtype=torch.float64).pin_memory()
-        self._argmax_pin = torch.zeros(B, dtype=torch.int64).pin_memory()
-        self._err_pin = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self._res_pin = torch.zeros((B, 4), dtype=torch.int32).pin_memory()   # (x, y, th, err) per network
+        self._res_np = self._res_pin.numpy()
+        self._odom_np = self._odom_pin.numpy()
         self.max_pc = np.zeros((B, 3), dtype=np.int64)
 
     def __del__(self):
@@ -175,14 +176,15 @@ class PoseCellEnsemble:
         Raises ``KeyError`` / ``ValueError`` if any network hit the conditions under which the reference
         raises or reads unwritten memory (see PRS_ERR_* in the header).
         """
-        vv = np.asarray(v, dtype=np.float64).reshape(self.n_networks, 2)
-        self._odom_pin.numpy()[...] = vv
+        self._odom_np[...] = np.asarray(v, dtype=np.float64).reshape(self.n_networks, 2)
         with torch.cuda.device(self.device):
-            nat.check(nat.lib().prs_pc_step_host(self._h, self._state.data_ptr(), self._odom_pin.data_ptr(),
-                                                 self._gi.data_ptr(), self._argmax_pin.data_ptr(),
-                                                 self._err_pin.data_ptr(), nat.stream_ptr()), "prs_pc_step_host")
-        self._raise_on_err(self._err_pin.numpy())
-        self.max_pc = self._unravel(self._argmax_pin.numpy())
+            nat.check(nat.lib().prs_pc_step_host_xyz(self._h, self._state.data_ptr(), self._odom_pin.data_ptr(),
+                                                     self._gi.data_ptr(), self._res_pin.data_ptr(), nat.stream_ptr()),
+                      "prs_pc_step_host_xyz")
+        res = self._res_np
+        if res[:, 3].any():
+            self._raise_on_err(res[:, 3])
+        self.max_pc = res[:, :3].astype(np.int64)
         return self.max_pc
 
     def path_integration(self, v):
