@@ -197,6 +197,19 @@ PRS_API int prs_frame_host(prs_pc_handle pc, void* pc_state, const void* gi, voi
                    int im_rows, int im_cols, int row_lo, int row_hi, int row_step, int col_lo, int col_hi,
                    int col_step, void* scratch, prs_frame_result* result_host, void* stream);
 
+/* The same frame as a replayed CUDA graph: all pointers (pinned host buffers included) are fixed at creation and
+ * the library size lives in device memory, so one frame = one graph launch + one synchronisation.
+ * The library must keep a free slot: recreate the plan when ViewTemplates grows its buffer.
+ * prs_frame_run(plan, moved, stream): moved != 0 -> odom_host holds (vtrans, vrot) and the pose cells update first;
+ * `stream` must be a non-default stream for the graph to be captured (otherwise every frame is enqueued eagerly). */
+typedef struct prs_frame_plan prs_frame_plan;
+PRS_API int prs_frame_create(prs_pc_handle pc, void* pc_state, const void* gi, void* pc_work, void* vt_packed,
+                     int n_templates, int capacity, unsigned threshold, int mode, int im_rows, int im_cols,
+                     int row_lo, int row_hi, int row_step, int col_lo, int col_hi, int col_step, void* scratch,
+                     double* odom_host, uint8_t* frame_host, prs_frame_result* result_host, prs_frame_plan** out);
+PRS_API int prs_frame_destroy(prs_frame_plan* plan);
+PRS_API int prs_frame_run(prs_frame_plan* plan, int moved, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,8 @@
 //
 // float32 ("profiles", BASELINE config 5): one template per warp, lane == column,
 // score = sum |T - q| accumulated in float32.
+#include <new>
+
 #include "common.cuh"
 
 namespace {
@@ -447,7 +449,9 @@ constexpr int kPkThreads = 128;
 // Reference mode (15 windowed row offsets, view_templates.py:16-28) over the packed library.
 __global__ void __launch_bounds__(kPkThreads)  // 96 registers (15 interleaved compare chains); capping them spills
     k_vt_sweep_packed_ref(const uint4* __restrict__ packed, long long n, long long base_index,
-                          unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores) {
+                          unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores,
+                          const int* __restrict__ n_dev) {
+  if (n_dev != nullptr) n = *n_dev;  // graph replays: the library size lives on the device
   const int lane = threadIdx.x & 31;
   const long long n_groups = (n + 31) >> 5;
   const long long warp0 = ((long long)blockIdx.x * kPkThreads + threadIdx.x) >> 5;
@@ -505,7 +509,9 @@ __global__ void __launch_bounds__(kPkThreads)  // 96 registers (15 interleaved c
 // the offset of a (stored row, query row) pair depends on the run-time stored row.
 __global__ void __launch_bounds__(kPkThreads)
     k_vt_sweep_packed_circ(const uint4* __restrict__ packed, long long n, long long base_index,
-                           unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores) {
+                           unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores,
+                           const int* __restrict__ n_dev) {
+  if (n_dev != nullptr) n = *n_dev;
   __shared__ uint32_t s_cnt[kPkThreads / 32][32][32];  // [warp][offset][lane]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long n_groups = (n + 31) >> 5;
@@ -592,9 +598,10 @@ extern "C" int prs_vt_sweep_packed_u8(const void* packed, long long n, const uin
   const long long cap = 148LL * 16;
   if (blocks > cap) blocks = cap;
   if (mode == PRS_VT_MODE_REF)
-    k_vt_sweep_packed_ref<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)packed, n, base_index, key_out, scores);
+    k_vt_sweep_packed_ref<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)packed, n, base_index, key_out, scores, nullptr);
   else
-    k_vt_sweep_packed_circ<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)packed, n, base_index, key_out, scores);
+    k_vt_sweep_packed_circ<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)packed, n, base_index, key_out, scores,
+                                                              nullptr);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
@@ -617,8 +624,10 @@ struct FrameScratch {               // device scratch layout (bytes)
 __global__ void k_vt_decide_append(const unsigned long long* __restrict__ key, const uint8_t* __restrict__ tpl,
                                    uint4* __restrict__ packed, int n, unsigned threshold,
                                    const long long* __restrict__ argmax, const int* __restrict__ pc_err,
-                                   prs_frame_result* __restrict__ res) {
+                                   prs_frame_result* __restrict__ res, int* __restrict__ n_dev) {
   const int t = threadIdx.x;  // 32 threads, one per template row
+  if (n_dev != nullptr) n = *n_dev;
+  __syncwarp();
   const unsigned long long k = *key;
   const unsigned score = (unsigned)(k >> 32);
   const bool create = (n == 0) || (k == ~0ull) || (score > threshold);  // strict '>' (view_templates.py:67)
@@ -652,6 +661,7 @@ __global__ void k_vt_decide_append(const unsigned long long* __restrict__ key, c
     res->template_index = create ? n : (int)(k & 0xffffffffu);
     res->n_templates = n + (create ? 1 : 0);
     res->pc_err = pc_err ? pc_err[0] : 0;
+    if (n_dev != nullptr) *n_dev = n + (create ? 1 : 0);
   }
 }
 
@@ -688,7 +698,8 @@ extern "C" int prs_frame_host(prs_pc_handle pc, void* pc_state, const void* gi, 
   if (rc != PRS_OK) return rc;
   rc = prs_vt_sweep_packed_u8(vt_packed, n_templates, d_tpl, mode, 0, d_key, nullptr, d_planes, st);
   if (rc != PRS_OK) return rc;
-  k_vt_decide_append<<<1, 32, 0, st>>>(d_key, d_tpl, (uint4*)vt_packed, n_templates, threshold, d_argmax, d_err, d_res);
+  k_vt_decide_append<<<1, 32, 0, st>>>(d_key, d_tpl, (uint4*)vt_packed, n_templates, threshold, d_argmax, d_err, d_res,
+                                       nullptr);
   PRS_CUDA(cudaGetLastError());
   PRS_CUDA(cudaMemcpyAsync(result_host, d_res, sizeof(prs_frame_result), cudaMemcpyDeviceToHost, st));
   PRS_CUDA(cudaStreamSynchronize(st));
@@ -762,4 +773,132 @@ extern "C" int prs_vt_sweep_any_u8(const uint8_t* lib, long long n, const uint8_
 extern "C" int prs_vt_sweep_any_f32(const float* lib, long long n, const float* query, int rows, int cols, int max_offset,
                                     long long base_index, unsigned long long* key_out, float* scores, void* stream) {
   return sweep_any<float, float>(lib, n, query, rows, cols, max_offset, base_index, key_out, scores, (cudaStream_t)stream);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// The same frame as a CUDA graph: every pointer is fixed at creation (pinned host buffers included), the
+// library size lives in device memory, so a frame is ONE graph launch + one synchronisation instead of
+// eleven stream operations.  Two executables: with and without the pose-cell update (ros_simulate.py:128
+// drops near-zero twists).
+struct prs_frame_plan {
+  prs_pc_handle pc;
+  void *pc_state, *pc_work, *vt_packed, *scratch;
+  const void* gi;
+  double* odom_host;
+  uint8_t* frame_host;
+  prs_frame_result* result_host;
+  unsigned threshold;
+  int mode, capacity;
+  int im_rows, im_cols, row_lo, row_hi, row_step, col_lo, col_hi, col_step;
+  cudaGraphExec_t exec[2];
+  bool ready[2];
+  int* d_n;
+  int warm[2];
+};
+
+static int frame_enqueue(prs_frame_plan* f, bool moved, cudaStream_t st) {
+  char* sc = (char*)f->scratch;
+  uint8_t* d_frame = (uint8_t*)(sc + FrameScratch::kFrame);
+  uint8_t* d_tpl = (uint8_t*)(sc + FrameScratch::kTpl);
+  uint32_t* d_planes = (uint32_t*)(sc + FrameScratch::kPlanes);
+  unsigned long long* d_key = (unsigned long long*)(sc + FrameScratch::kKey);
+  prs_frame_result* d_res = (prs_frame_result*)(sc + FrameScratch::kResult);
+  double* d_odom = (double*)(sc + FrameScratch::kOdom);
+  long long* d_argmax = (long long*)f->pc_work;
+  void* d_total = (char*)f->pc_work + 8;
+  int* d_err = (int*)((char*)f->pc_work + 16);
+  int rc;
+  if (moved) {
+    PRS_CUDA(cudaMemcpyAsync(d_odom, f->odom_host, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = prs_pc_step(f->pc, f->pc_state, d_odom, f->gi, d_argmax, d_total, d_err, st);
+    if (rc != PRS_OK) return rc;
+  }
+  PRS_CUDA(cudaMemcpyAsync(d_frame, f->frame_host, (size_t)f->im_rows * f->im_cols, cudaMemcpyHostToDevice, st));
+  rc = prs_vt_extract_u8(d_frame, f->im_rows, f->im_cols, f->row_lo, f->row_hi, f->row_step, f->col_lo, f->col_hi,
+                         f->col_step, d_tpl, 32, 32, st);
+  if (rc != PRS_OK) return rc;
+  PRS_CUDA(cudaMemsetAsync(d_key, 0xff, sizeof(unsigned long long), st));
+  k_vt_pack_query<<<1, 32, 0, st>>>(d_tpl, d_planes);
+  PRS_CUDA(cudaMemcpyToSymbolAsync(c_vtq, d_planes, (32 * 8 + 2) * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
+  // grid sized for the capacity; the kernels read the live count from device memory
+  const long long groups = ((long long)f->capacity + 31) / 32;
+  long long blocks = (groups + (kPkThreads / 32) - 1) / (kPkThreads / 32);
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (blocks < 1) blocks = 1;
+  if (f->mode == PRS_VT_MODE_REF)
+    k_vt_sweep_packed_ref<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)f->vt_packed, 0, 0, d_key, nullptr, f->d_n);
+  else
+    k_vt_sweep_packed_circ<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)f->vt_packed, 0, 0, d_key, nullptr, f->d_n);
+  k_vt_decide_append<<<1, 32, 0, st>>>(d_key, d_tpl, (uint4*)f->vt_packed, 0, f->threshold, d_argmax, d_err, d_res, f->d_n);
+  PRS_CUDA(cudaGetLastError());
+  PRS_CUDA(cudaMemcpyAsync(f->result_host, d_res, sizeof(prs_frame_result), cudaMemcpyDeviceToHost, st));
+  return PRS_OK;
+}
+
+extern "C" int prs_frame_create(prs_pc_handle pc, void* pc_state, const void* gi, void* pc_work, void* vt_packed,
+                                int n_templates, int capacity, unsigned threshold, int mode, int im_rows, int im_cols,
+                                int row_lo, int row_hi, int row_step, int col_lo, int col_hi, int col_step,
+                                void* scratch, double* odom_host, uint8_t* frame_host, prs_frame_result* result_host,
+                                prs_frame_plan** out) {
+  PRS_REQUIRE(pc && pc_state && gi && pc_work && vt_packed && scratch && odom_host && frame_host && result_host && out,
+              "prs_frame_create: null argument");
+  PRS_REQUIRE((size_t)im_rows * im_cols <= (1u << 20), "prs_frame_create: frame larger than 1 MiB");
+  PRS_REQUIRE(capacity >= 1 && n_templates >= 0 && n_templates < capacity, "prs_frame_create: library has no free slot");
+  prs_frame_plan* f = new (std::nothrow) prs_frame_plan();
+  PRS_REQUIRE(f, "prs_frame_create: out of host memory");
+  *f = prs_frame_plan{pc, pc_state, pc_work, vt_packed, scratch, gi, odom_host, frame_host, result_host, threshold, mode,
+                      capacity, im_rows, im_cols, row_lo, row_hi, row_step, col_lo, col_hi, col_step, {nullptr, nullptr},
+                      {false, false}, nullptr, {0, 0}};
+  f->d_n = (int*)((char*)scratch + FrameScratch::kOdom + 32);
+  cudaError_t e = cudaMemcpy(f->d_n, &n_templates, sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    prs_set_error("prs_frame_create: %s", cudaGetErrorString(e));
+    delete f;
+    return PRS_E_CUDA;
+  }
+  *out = f;
+  return PRS_OK;
+}
+
+extern "C" int prs_frame_destroy(prs_frame_plan* f) {
+  if (f) {
+    for (int i = 0; i < 2; ++i)
+      if (f->ready[i]) cudaGraphExecDestroy(f->exec[i]);
+    delete f;
+  }
+  return PRS_OK;
+}
+
+// One frame.  `moved` != 0: odom_host (given at creation) holds (vtrans, vrot) and the pose cells are updated first.
+// The first call of each kind runs eagerly (it also warms every lazily initialised kernel attribute), the second
+// captures the graph, later ones replay it.
+extern "C" int prs_frame_run(prs_frame_plan* f, int moved, void* stream) {
+  PRS_REQUIRE(f, "prs_frame_run: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int v = moved ? 1 : 0;
+  int rc = PRS_OK;
+  if (f->ready[v]) {
+    PRS_CUDA(cudaGraphLaunch(f->exec[v], st));
+  } else if (f->warm[v] < 1 || st == nullptr) {  // the legacy default stream cannot be captured
+    ++f->warm[v];
+    rc = frame_enqueue(f, moved != 0, st);
+    if (rc != PRS_OK) return rc;
+  } else {
+    cudaGraph_t g = nullptr;
+    PRS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = frame_enqueue(f, moved != 0, st);
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc != PRS_OK || e != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      if (rc == PRS_OK) prs_set_error("prs_frame_run: capture failed: %s", cudaGetErrorString(e));
+      return rc != PRS_OK ? rc : PRS_E_CUDA;
+    }
+    PRS_CUDA(cudaGraphInstantiate(&f->exec[v], g, 0));
+    cudaGraphDestroy(g);
+    f->ready[v] = true;
+    PRS_CUDA(cudaGraphLaunch(f->exec[v], st));
+  }
+  PRS_CUDA(cudaStreamSynchronize(st));
+  return PRS_OK;
 }

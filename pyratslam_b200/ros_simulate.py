@@ -91,7 +91,36 @@ class RatslamRos(object):
             nat.check(nat.lib().prs_pc_argmax(e._h, e._state.data_ptr(), self._f_pcwork.data_ptr(), nat.stream_ptr()),
                       "prs_pc_argmax")
         v._ensure_lib(torch.uint8)
+        self._f_stream = torch.cuda.Stream(device=dev)
+        self._f_plan = ctypes.c_void_p()
+        self._f_plan_key = None
         self._fused_ready = True
+
+    def _fused_plan(self):
+        """(Re)create the CUDA-graph frame plan; needed again whenever the library buffer was reallocated."""
+        e, v = self.pcn._ens, self.vts
+        key = (v._lib.data_ptr(), v._capacity, v.match_threshold)
+        if self._f_plan_key == key:
+            return
+        if self._f_plan:
+            nat.lib().prs_frame_destroy(self._f_plan)
+            self._f_plan = ctypes.c_void_p()
+        torch.cuda.synchronize(e.device)
+        thr = int(min(max(math.floor(v.match_threshold), 0), 0xFFFFFFFF))
+        nat.check(nat.lib().prs_frame_create(
+            e._h, e._state.data_ptr(), e._gi.data_ptr(), self._f_pcwork.data_ptr(), v._lib.data_ptr(), v._n, v._capacity,
+            thr, v.mode, v.im_x, v.im_y, v.y_range[0], v.y_range[1], v.y_step, v.x_range[0], v.x_range[1], v.x_step,
+            self._f_scratch.data_ptr(), self._f_odom.data_ptr(), self._f_frame.data_ptr(), self._f_res.data_ptr(),
+            ctypes.byref(self._f_plan)), "prs_frame_create")
+        self._f_plan_key = key
+
+    def __del__(self):
+        p = getattr(self, "_f_plan", None)
+        if p:
+            try:
+                nat.lib().prs_frame_destroy(p)
+            except Exception:
+                pass
 
     def fused_frame(self, twist, im):
         """``odom_callback(twist)`` + ``spin_once()`` + ``vis_callback(im)`` in one device round trip.
@@ -107,16 +136,11 @@ class RatslamRos(object):
             vtrans, vrot = twist[0] / self.odom_freq, twist[1] / self.odom_freq          # :157-158
             o = self._f_odom.numpy()
             o[0], o[1] = vtrans, vrot
-        v._grow(v._n + 1)
+        v._grow(v._n + 2)
+        self._fused_plan()
         self._f_frame.numpy()[...] = im
-        thr = int(min(max(math.floor(v.match_threshold), 0), 0xFFFFFFFF))
-        with torch.cuda.device(e.device):
-            nat.check(nat.lib().prs_frame_host(
-                e._h, e._state.data_ptr(), e._gi.data_ptr(), self._f_pcwork.data_ptr(),
-                self._f_odom.data_ptr() if moved else None, v._lib.data_ptr(), v._n, thr, v.mode,
-                self._f_frame.data_ptr(), v.im_x, v.im_y, v.y_range[0], v.y_range[1], v.y_step,
-                v.x_range[0], v.x_range[1], v.x_step, self._f_scratch.data_ptr(), self._f_res.data_ptr(),
-                nat.stream_ptr()), "prs_frame_host")
+        nat.check(nat.lib().prs_frame_run(self._f_plan, 1 if moved else 0, ctypes.c_void_p(self._f_stream.cuda_stream)),
+                  "prs_frame_run")
         r = self._f_result
         if moved:
             e._raise_on_err(np.array([r.pc_err], dtype=np.int32))
