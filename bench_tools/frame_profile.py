@@ -19,7 +19,7 @@ odom = np.stack([rng.uniform(0, 3, T), rng.uniform(-1, 1, T)], axis=1)
 node = ros_simulate.RatslamRos()
 for t in range(50):
     node.fused_frame((float(odom[t, 0]), float(odom[t, 1])), frames[t])
-orig = nat.lib().prs_frame_host
+orig = nat.lib().prs_frame_run
 acc = {"c": 0.0}
 
 
@@ -32,7 +32,7 @@ def timed_call(*a):
 
 class L:
     def __getattr__(self, k):
-        return timed_call if k == "prs_frame_host" else getattr(nat._lib, k)
+        return timed_call if k == "prs_frame_run" else getattr(nat._lib, k)
 
 
 real = nat._lib
@@ -42,7 +42,7 @@ for t in range(50, T):
     node.fused_frame((float(odom[t, 0]), float(odom[t, 1])), frames[t])
 tot = time.perf_counter() - t0
 n = T - 50
-print("per frame: total %.1f us, inside prs_frame_host %.1f us, python around it %.1f us"
+print("per frame: total %.1f us, inside prs_frame_run %.1f us, python around it %.1f us"
       % (tot / n * 1e6, acc["c"] / n * 1e6, (tot - acc["c"]) / n * 1e6))
 # device-only time of the same sequence (no sync inside): events around 200 fused frames is not possible (the call syncs);
 # instead time the pose-cell step alone and the sweep alone

@@ -795,6 +795,8 @@ struct prs_frame_plan {
   bool ready[2];
   int* d_n;
   int warm[2];
+  cudaStream_t side;       // the pose-cell update runs here, concurrently with the template branch
+  cudaEvent_t ev_fork, ev_join;
 };
 
 static int frame_enqueue(prs_frame_plan* f, bool moved, cudaStream_t st) {
@@ -809,10 +811,13 @@ static int frame_enqueue(prs_frame_plan* f, bool moved, cudaStream_t st) {
   void* d_total = (char*)f->pc_work + 8;
   int* d_err = (int*)((char*)f->pc_work + 16);
   int rc;
-  if (moved) {
-    PRS_CUDA(cudaMemcpyAsync(d_odom, f->odom_host, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    rc = prs_pc_step(f->pc, f->pc_state, d_odom, f->gi, d_argmax, d_total, d_err, st);
+  if (moved) {  // fork: the pose-cell update does not depend on the frame until the decision
+    PRS_CUDA(cudaEventRecord(f->ev_fork, st));
+    PRS_CUDA(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
+    PRS_CUDA(cudaMemcpyAsync(d_odom, f->odom_host, 2 * sizeof(double), cudaMemcpyHostToDevice, f->side));
+    rc = prs_pc_step(f->pc, f->pc_state, d_odom, f->gi, d_argmax, d_total, d_err, f->side);
     if (rc != PRS_OK) return rc;
+    PRS_CUDA(cudaEventRecord(f->ev_join, f->side));
   }
   PRS_CUDA(cudaMemcpyAsync(d_frame, f->frame_host, (size_t)f->im_rows * f->im_cols, cudaMemcpyHostToDevice, st));
   rc = prs_vt_extract_u8(d_frame, f->im_rows, f->im_cols, f->row_lo, f->row_hi, f->row_step, f->col_lo, f->col_hi,
@@ -830,6 +835,7 @@ static int frame_enqueue(prs_frame_plan* f, bool moved, cudaStream_t st) {
     k_vt_sweep_packed_ref<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)f->vt_packed, 0, 0, d_key, nullptr, f->d_n);
   else
     k_vt_sweep_packed_circ<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)f->vt_packed, 0, 0, d_key, nullptr, f->d_n);
+  if (moved) PRS_CUDA(cudaStreamWaitEvent(st, f->ev_join, 0));  // join: the decision reports the new arg-max
   k_vt_decide_append<<<1, 32, 0, st>>>(d_key, d_tpl, (uint4*)f->vt_packed, 0, f->threshold, d_argmax, d_err, d_res, f->d_n);
   PRS_CUDA(cudaGetLastError());
   PRS_CUDA(cudaMemcpyAsync(f->result_host, d_res, sizeof(prs_frame_result), cudaMemcpyDeviceToHost, st));
@@ -849,9 +855,12 @@ extern "C" int prs_frame_create(prs_pc_handle pc, void* pc_state, const void* gi
   PRS_REQUIRE(f, "prs_frame_create: out of host memory");
   *f = prs_frame_plan{pc, pc_state, pc_work, vt_packed, scratch, gi, odom_host, frame_host, result_host, threshold, mode,
                       capacity, im_rows, im_cols, row_lo, row_hi, row_step, col_lo, col_hi, col_step, {nullptr, nullptr},
-                      {false, false}, nullptr, {0, 0}};
+                      {false, false}, nullptr, {0, 0}, nullptr, nullptr, nullptr};
   f->d_n = (int*)((char*)scratch + FrameScratch::kOdom + 32);
-  cudaError_t e = cudaMemcpy(f->d_n, &n_templates, sizeof(int), cudaMemcpyHostToDevice);
+  cudaError_t e = cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMemcpy(f->d_n, &n_templates, sizeof(int), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     prs_set_error("prs_frame_create: %s", cudaGetErrorString(e));
     delete f;
@@ -865,6 +874,9 @@ extern "C" int prs_frame_destroy(prs_frame_plan* f) {
   if (f) {
     for (int i = 0; i < 2; ++i)
       if (f->ready[i]) cudaGraphExecDestroy(f->exec[i]);
+    if (f->side) cudaStreamDestroy(f->side);
+    if (f->ev_fork) cudaEventDestroy(f->ev_fork);
+    if (f->ev_join) cudaEventDestroy(f->ev_join);
     delete f;
   }
   return PRS_OK;
