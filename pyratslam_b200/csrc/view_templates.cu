@@ -505,14 +505,26 @@ __global__ void __launch_bounds__(kPkThreads)  // 96 registers (15 interleaved c
   }
 }
 
-// Circular mode (all 32 cyclic row shifts; extension): per-offset counters live in shared memory because
-// the offset of a (stored row, query row) pair depends on the run-time stored row.
-__global__ void __launch_bounds__(kPkThreads)
+// Circular mode (all 32 cyclic row shifts; extension).  The shift of a (stored row t, query row s) pair is
+// (t - s) mod 32, which depends on the run-time row t -- but only through t mod 8 once the 32 counters are kept
+// in registers and ROTATED by eight places after every eight stored rows: inside a block of eight rows the
+// pair (i, s) always adds into register (i - s) mod 32, and the rotation re-labels the registers for the next
+// block.  32 register MOVs per block replace 256 shared-memory read-modify-writes.
+// eight stored rows (t0 .. t0+7, held in registers) against every query row; query row outermost so that only
+// its eight plane words are live as (uniform-register) operands at a time
+__device__ __forceinline__ void circ_block(const uint4 (&lo)[8], const uint4 (&hi)[8], uint32_t (&cnt)[32]) {
+#pragma unroll
+  for (int s = 0; s < 32; ++s) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cnt[(i - s) & 31] += lt_row(lo[i], hi[i], s);
+  }
+}
+
+__global__ void __launch_bounds__(kPkThreads, 4)
     k_vt_sweep_packed_circ(const uint4* __restrict__ packed, long long n, long long base_index,
                            unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores,
                            const int* __restrict__ n_dev) {
   if (n_dev != nullptr) n = *n_dev;
-  __shared__ uint32_t s_cnt[kPkThreads / 32][32][32];  // [warp][offset][lane]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long n_groups = (n + 31) >> 5;
   const long long warp0 = ((long long)blockIdx.x * kPkThreads + threadIdx.x) >> 5;
@@ -520,16 +532,26 @@ __global__ void __launch_bounds__(kPkThreads)
   unsigned long long best = ~0ull;
   for (long long g = warp0; g < n_groups; g += n_warps) {
     const uint4* gp = packed + g * kGroupU4 + lane;
+    uint32_t cnt[32];
 #pragma unroll
-    for (int o = 0; o < 32; ++o) s_cnt[wid][o][lane] = 0;
-    for (int t = 0; t < 32; ++t) {
-      const uint4 lo = ld_stream_u4(gp + (t * 2 + 0) * 32), hi = ld_stream_u4(gp + (t * 2 + 1) * 32);
+    for (int o = 0; o < 32; ++o) cnt[o] = 0;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      // during block c register r counts shift (r + 8c) mod 32
+      uint4 lo[8], hi[8];
 #pragma unroll
-      for (int s = 0; s < 32; ++s) {
-        // score(shift) pairs stored row (s + shift) mod 32 with query row s  ->  shift = (t - s) mod 32
-        s_cnt[wid][(t - s) & 31][lane] += lt_row(lo, hi, s);
+      for (int i = 0; i < 8; ++i) {
+        lo[i] = ld_stream_u4(gp + ((8 * c + i) * 2 + 0) * 32);
+        hi[i] = ld_stream_u4(gp + ((8 * c + i) * 2 + 1) * 32);
       }
+      circ_block(lo, hi, cnt);
+      uint32_t rot[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) rot[r] = cnt[(r + 8) & 31];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) cnt[r] = rot[r];
     }
+    // four rotations by eight: register r counts shift r again
     uint32_t A = 0;
 #pragma unroll
     for (int w4 = 0; w4 < 4; ++w4) {
@@ -540,7 +562,7 @@ __global__ void __launch_bounds__(kPkThreads)
     const uint32_t bq = c_vtq[257];
     uint32_t m = 0xffffffffu;
 #pragma unroll
-    for (int o = 0; o < 32; ++o) m = min(m, A + 256u * s_cnt[wid][o][lane] - bq);
+    for (int o = 0; o < 32; ++o) m = min(m, A + 256u * cnt[o] - bq);
     const long long ti = g * 32 + lane;
     if (ti < n) {
       const unsigned long long key = ((unsigned long long)m << 32) | (unsigned long long)(base_index + ti);
