@@ -124,6 +124,15 @@ PRS_API int prs_pc_path_integration(prs_pc_handle h, void* state, const double* 
 PRS_API int prs_pc_inject(prs_pc_handle h, void* state, int b, int x, int y, int th, double energy, void* stream);
 /* arg-max without an update (get_pc_max, posecell_network.py:317-319) */
 PRS_API int prs_pc_argmax(prs_pc_handle h, const void* state, long long* argmax, void* stream);
+/* Sparse read-back: the cells of network b with activity > threshold, in the reference's C order -- what the
+ * viewers draw (`nonzero(pc > .002)`, simulate.py:61; ratslam_viewer.py:137) -- instead of copying the whole grid.
+ *   idx_out : device int32 [max_out] flat indices x*Y*Th + y*Th + th (ascending)
+ *   val_out : device [max_out] of the plan's dtype
+ *   count_out : device int32, the number of cells above the threshold (may exceed max_out; the rest is dropped)
+ *   work : device scratch of prs_pc_active_work_bytes(h) */
+PRS_API size_t prs_pc_active_work_bytes(prs_pc_handle h);
+PRS_API int prs_pc_active_cells(prs_pc_handle h, const void* state, int b, double threshold, int max_out, int* idx_out,
+                        void* val_out, int* count_out, void* work, void* stream);
 /* layout conversion between the reference's [B][x][y][th] and theta-major [B][th][x][y] (device to device) */
 PRS_API int prs_pc_import_xyt(prs_pc_handle h, void* state, const void* xyt, void* stream);
 PRS_API int prs_pc_export_xyt(prs_pc_handle h, const void* state, void* xyt, void* stream);

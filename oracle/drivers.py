@@ -54,10 +54,12 @@ def simulate_run(data=None, shape=POSE_SIZE_SIM, keep_states=False):
     return amax, totals, (np.stack(states) if keep_states else pcn.posecells)
 
 
-def replay_run(frames, odom, shape=POSE_SIZE_ROS, match_threshold=MATCH_THRESHOLD):
+def replay_run(frames, odom, shape=POSE_SIZE_ROS, match_threshold=MATCH_THRESHOLD, inject_energy=None):
     """Offline replay of the ROS loop.
 
     ``frames``: uint8[T,256,256]; ``odom``: float64[T,2] = (linear.x, angular.z).
+    ``inject_energy``: if set, the coupling the reference left commented out at ``ros_simulate.py:106-108`` is
+    enabled: ``pcn.inject(energy, template_match.location())`` after every match.
     Returns a dict of per-frame records.
     """
     pcn = PoseCellNetwork(shape)
@@ -80,6 +82,8 @@ def replay_run(frames, odom, shape=POSE_SIZE_ROS, match_threshold=MATCH_THRESHOL
         pc_max = pcn.get_pc_max()                          # :103
         n_before = len(vts.templates)
         tm = vts.match(frames[t], pc_max[0], pc_max[1], pc_max[2])  # :104
+        if inject_energy is not None:
+            pcn.inject(inject_energy, tm.location())       # :106-108 (commented out in the reference)
         rec["template"][t] = tm.get_index()
         rec["created"][t] = len(vts.templates) > n_before
         rec["argmax"][t] = pc_max

@@ -48,6 +48,9 @@ _SIGNATURES = {
     "prs_pc_step_host_xyz": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_path_integration": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_inject": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p]),
+    "prs_pc_active_work_bytes": (c_size_t, [c_void_p]),
+    "prs_pc_active_cells": (c_int, [c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "prs_pc_argmax": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_import_xyt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_export_xyt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -408,6 +408,72 @@ extern "C" int prs_pc_inject(prs_pc_handle h, void* state, int b, int x, int y, 
   return PRS_OK;
 }
 
+// Cells of network b whose activity exceeds `thr`, in the reference's C order [x][y][th] -- what both viewers
+// draw (simulate.py:61 `nonzero(pc > .002)`, ratslam_viewer.py:137).  Two passes keep the order deterministic:
+// per-block counts, then an exclusive scan by block 0 and a compacting pass.
+template <typename T>
+__global__ void __launch_bounds__(256) k_active_count(const T* __restrict__ state, int XY, int Th, double thr,
+                                                      int* __restrict__ counts) {
+  // one block per 256 consecutive reference-order cells; cell c = (x*Y + y)*Th + th lives at state[th*XY + x*Y + y]
+  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long N = (long long)XY * Th;
+  int hit = 0;
+  if (c < N) {
+    const int th = (int)(c % Th);
+    const long long p = c / Th;
+    hit = ((double)state[(size_t)th * XY + p] > thr) ? 1 : 0;
+  }
+  const int total = __syncthreads_count(hit);
+  if (threadIdx.x == 0) counts[blockIdx.x] = total;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_active_write(const T* __restrict__ state, int XY, int Th, double thr,
+                                                      const int* __restrict__ offsets, int max_out,
+                                                      int* __restrict__ idx_out, T* __restrict__ val_out) {
+  __shared__ int s_warp[8];
+  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long N = (long long)XY * Th;
+  T v = 0;
+  int hit = 0;
+  if (c < N) {
+    const int th = (int)(c % Th);
+    const long long p = c / Th;
+    v = state[(size_t)th * XY + p];
+    hit = ((double)v > thr) ? 1 : 0;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, hit);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) s_warp[w] = __popc(bal);
+  __syncthreads();
+  int base = offsets[blockIdx.x];
+  for (int i = 0; i < w; ++i) base += s_warp[i];
+  const int pos = base + __popc(bal & ((1u << lane) - 1));
+  if (hit && pos < max_out) {
+    idx_out[pos] = (int)c;
+    val_out[pos] = v;
+  }
+}
+
+__global__ void k_exclusive_scan_small(const int* __restrict__ counts, int n, int* __restrict__ offsets,
+                                       int* __restrict__ total) {
+  // single thread block, sequential chunks: n is (cells / 256), at most a few tens of thousands
+  __shared__ int s_part[256];
+  const int per = (n + 255) / 256;
+  const int lo = threadIdx.x * per, hi = min(n, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += counts[i];
+  s_part[threadIdx.x] = s;
+  __syncthreads();
+  int base = 0;
+  for (int i = 0; i < threadIdx.x; ++i) base += s_part[i];
+  for (int i = lo; i < hi; ++i) {
+    offsets[i] = base;
+    base += counts[i];
+  }
+  if (threadIdx.x == 255) *total = base;
+}
+
 __global__ void k_unravel_pack(const long long* __restrict__ argmax, const int* __restrict__ err, int B, int Y, int Th,
                                int4* __restrict__ out) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,6 +488,34 @@ int prs_pc_launch_unravel_pack(prs_pc_plan* p, const long long* argmax, const in
   k_unravel_pack<<<(p->B + 127) / 128, 128, 0, st>>>(argmax, err, p->B, p->Y, p->Th, (int4*)out);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
+}
+
+extern "C" int prs_pc_active_cells(prs_pc_handle h, const void* state, int b, double threshold, int max_out, int* idx_out,
+                                   void* val_out, int* count_out, void* work, void* stream) {
+  PRS_REQUIRE(h && state && idx_out && val_out && count_out && work, "prs_pc_active_cells: null argument");
+  PRS_REQUIRE(b >= 0 && b < h->B && max_out >= 0, "prs_pc_active_cells: bad network index or capacity");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int XY = h->X * h->Y;
+  const int nblk = (int)((h->N + 255) / 256);
+  int* counts = (int*)work;
+  int* offsets = counts + nblk;
+  if (h->dtype == PRS_F32) {
+    const float* s = (const float*)state + (size_t)b * h->N;
+    k_active_count<float><<<nblk, 256, 0, st>>>(s, XY, h->Th, threshold, counts);
+    k_exclusive_scan_small<<<1, 256, 0, st>>>(counts, nblk, offsets, count_out);
+    k_active_write<float><<<nblk, 256, 0, st>>>(s, XY, h->Th, threshold, offsets, max_out, idx_out, (float*)val_out);
+  } else {
+    const double* s = (const double*)state + (size_t)b * h->N;
+    k_active_count<double><<<nblk, 256, 0, st>>>(s, XY, h->Th, threshold, counts);
+    k_exclusive_scan_small<<<1, 256, 0, st>>>(counts, nblk, offsets, count_out);
+    k_active_write<double><<<nblk, 256, 0, st>>>(s, XY, h->Th, threshold, offsets, max_out, idx_out, (double*)val_out);
+  }
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+extern "C" size_t prs_pc_active_work_bytes(prs_pc_handle h) {
+  return h ? (size_t)((h->N + 255) / 256) * 2 * sizeof(int) : 0;
 }
 
 extern "C" int prs_pc_argmax(prs_pc_handle h, const void* state, long long* argmax, void* stream) {

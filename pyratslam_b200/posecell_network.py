@@ -146,6 +146,24 @@ class PoseCellEnsemble:
             nat.check(nat.lib().prs_pc_inject(self._h, self._state.data_ptr(), b, x, y, th, float(energy),
                                               nat.stream_ptr()), "prs_pc_inject")
 
+    def active_cells(self, threshold=0.002, network=0, max_cells=None):
+        """Cells with activity above ``threshold`` as ``(index int64[n, 3], value float64[n])`` in the reference's
+        C order -- ``nonzero(pc > threshold)`` and ``pc[...]`` of ``simulate.py:60-62`` without moving the whole
+        grid to the host (compaction runs on the device)."""
+        N = int(np.prod(self.shape))
+        cap = N if max_cells is None else int(max_cells)
+        with torch.cuda.device(self.device):
+            idx = torch.empty(cap, dtype=torch.int32, device=self.device)
+            val = torch.empty(cap, dtype=self.torch_dtype, device=self.device)
+            cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+            work = torch.empty(int(nat.lib().prs_pc_active_work_bytes(self._h)), dtype=torch.uint8, device=self.device)
+            nat.check(nat.lib().prs_pc_active_cells(self._h, self._state.data_ptr(), int(network), float(threshold), cap,
+                                                    idx.data_ptr(), val.data_ptr(), cnt.data_ptr(), work.data_ptr(),
+                                                    nat.stream_ptr()), "prs_pc_active_cells")
+            n = min(int(cnt.item()), cap)
+            flat = idx[:n].cpu().numpy().astype(np.int64)
+            return self._unravel(flat), val[:n].cpu().numpy().astype(np.float64)
+
     def _unravel(self, flat):
         X, Y, Th = self.shape
         flat = np.asarray(flat, dtype=np.int64)
@@ -304,6 +322,10 @@ class PoseCellNetwork:
     def inject(self, energy, loc):
         self._ens.inject(energy, loc, network=0)
         self._max_valid = False
+
+    def active_cells(self, threshold=0.002, max_cells=None):
+        """``(index[n, 3], value[n])`` of the cells above ``threshold`` (what ``simulate.py:60-62`` plots)."""
+        return self._ens.active_cells(threshold, 0, max_cells)
 
     def get_pc_max(self):
         """Arg-max cell (posecell_network.py:317-319).  Right after ``update`` this is the value the step

@@ -39,7 +39,10 @@ ODOM_FREQ = 10
 class RatslamRos(object):
     """The node's state and callbacks, fed from arrays instead of ROS topics."""
 
-    def __init__(self, pose_size=POSE_SIZE, match_threshold=MATCH_THRESHOLD, **pcn_kwargs):
+    def __init__(self, pose_size=POSE_SIZE, match_threshold=MATCH_THRESHOLD, inject_energy=None, **pcn_kwargs):
+        # inject_energy: enable the view-template -> pose-cell coupling the reference left commented out
+        # (ros_simulate.py:106-108): pcn.inject(energy, template_match.location()) after every match
+        self.inject_energy = inject_energy
         self.im_count = 0
         self.pcn = PoseCellNetwork(shape=pose_size, **pcn_kwargs)
         self.pc_count = 0
@@ -61,6 +64,8 @@ class RatslamRos(object):
         n0 = len(self.vts.templates)
         tm = self.vts.match(input=im, pc_x=pc_max[0], pc_y=pc_max[1], pc_th=pc_max[2])
         index = tm.get_index()
+        if self.inject_energy is not None:
+            self.pcn.inject(self.inject_energy, tm.location())                              # :106-108
         self.published_index.append(index)
         return index, len(self.vts.templates) > n0
 
@@ -155,6 +160,14 @@ class RatslamRos(object):
             v._loc[v._n] = pc_max
         v._n = int(r.n_templates)
         v.last_score = None if r.key == (1 << 64) - 1 else int(r.key >> 32)
+        if self.inject_energy is not None:
+            loc = tuple(int(c) for c in v._loc[int(r.template_index)])
+            with torch.cuda.stream(self._f_stream):
+                self.pcn.inject(self.inject_energy, loc)
+                with torch.cuda.device(e.device):    # keep the cached arg-max in step with the injected state
+                    nat.check(nat.lib().prs_pc_argmax(e._h, e._state.data_ptr(), self._f_pcwork.data_ptr(),
+                                                      nat.stream_ptr()), "prs_pc_argmax")
+            self._f_stream.synchronize()
         self.published_index.append(int(r.template_index))
         return int(r.template_index), bool(r.created)
 

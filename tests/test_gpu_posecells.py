@@ -194,3 +194,20 @@ def test_full_size_ensemble_replicas_and_samples():
     assert torch.equal(st[7], st[1000])
     pc = ens.posecells
     assert _rel(pc[pick], ref_states) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_active_cells_sparse_readback(dtype):
+    """The device-side compaction returns exactly nonzero(pc > thr) in C order (simulate.py:60-62)."""
+    net = _make((50, 50, 10), dtype, "auto")
+    net.inject(1, (25, 25, 5))
+    for v in [(3.0, 0.0), (3.0, 0.0), (3.0, math.pi / 4)]:
+        net.update(v)
+    pc = net.posecells
+    for thr in (0.002, 0.0, 0.05, 10.0):
+        idx, val = net.active_cells(thr)
+        ref = np.stack(np.nonzero(pc > thr), axis=-1)
+        assert np.array_equal(idx, ref)
+        assert np.array_equal(val, pc[pc > thr])
+    idx, val = net.active_cells(0.0, max_cells=5)      # truncated output keeps the first cells
+    assert np.array_equal(idx, np.stack(np.nonzero(pc > 0), axis=-1)[:5])

@@ -261,3 +261,22 @@ def test_other_template_shapes(dtype):
     assert np.array_equal(got.templates[1].template, ref.templates[1].template)
     q = frames[5][ref.mask].reshape(ref.shape)
     assert float(got.templates[0].match(q)) == float(ref.templates[0].match(q))
+
+
+def test_replay_with_template_injection():
+    """the match -> pose-cell injection the reference left commented out (ros_simulate.py:106-108),
+    against the oracle's replay with the same coupling; both the three-call and the fused loop."""
+    from oracle import drivers as odrv
+    from pyratslam_b200 import ros_simulate
+    T = 20
+    frames = synth_frames(np.random.default_rng(77), T)
+    rng = np.random.default_rng(78)
+    odom = np.stack([rng.uniform(0, 3.0, T), rng.uniform(-1, 1, T)], axis=1)
+    odom[7] = 0.0
+    ref = odrv.replay_run(frames, odom, inject_energy=0.02)
+    for fused in (False, True):
+        rec = ros_simulate.replay(frames, odom, fused=fused, inject_energy=0.02)
+        assert np.array_equal(rec["template"], ref["template"]) and np.array_equal(rec["created"], ref["created"])
+        assert np.array_equal(rec["argmax"], ref["argmax"])
+        fs = rec["node"].pcn.posecells
+        assert np.abs(fs - ref["final_state"]).max() / ref["final_state"].max() <= 1e-5
