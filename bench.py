@@ -264,6 +264,22 @@ def extra_single_gpu(torch, peak, steps):
     out["large_grid_256x256x72"] = {"metric": METRIC, "value": cells / (ms * 1e-3), "ms_per_step": ms, "path": net.path,
                                     "note": "18.9 MB state is L2-resident; HBM roofline does not apply"}
     del net
+    # ---- BASELINE config 1: simulate.py's own scenario (50x50x10, 40 steps), every step through update()
+    from pyratslam_b200 import simulate
+    from oracle import drivers as odrv
+    simulate.main(steps=40, verbose=False)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        trace = simulate.main(steps=40, verbose=False)
+    dt_sim = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter()
+    ref_amax, _, _ = odrv.simulate_run()
+    dt_cpu = time.perf_counter() - t0
+    assert [tuple(t) for t in trace] == [tuple(t) for t in ref_amax.tolist()]
+    out["simulate_50x50x10"] = {"metric": "pose-cell cell-updates/s", "value": 40 * 25000 / dt_sim,
+                                "ms_per_step": dt_sim / 40 * 1e3, "cpu_oracle_ms_per_step": dt_cpu / 40 * 1e3,
+                                "note": "simulate.py:36-58 loop incl. construction and one host sync per update(); "
+                                        "arg-max trace identical to the oracle's"}
     # ---- BASELINE config 2: frame-by-frame replay (odometry update + template match per frame)
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     from synth import synth_frames
@@ -286,6 +302,29 @@ def extra_single_gpu(torch, peak, steps):
                               "note": "host frames: 64 KiB H2D + pose-cell update + template match + 32 B D2H per frame, "
                                       "wall clock; value = fused one-round-trip entry (prs_frame_host), the other figure "
                                       "= separate PoseCellNetwork.update / ViewTemplates.match calls"}
+    return out
+
+
+def extra_sharded_library(torch, dist, world, rank, peak, steps):
+    """BASELINE config 5 across ranks: 2^20 uint8 templates per GPU (weak scaling), contiguous global index
+    ranges, one 8-byte MIN all-reduce of the packed key per query (NCCL for N > 1)."""
+    from pyratslam_b200 import ShardedViewTemplates
+    n = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(40 + rank)
+    lib = torch.randint(0, 256, (n, 32, 32), dtype=torch.uint8, device="cuda", generator=g)
+    gq = torch.Generator(device="cuda").manual_seed(99)
+    qs = torch.randint(0, 256, (8, 32, 32), dtype=torch.uint8, device="cuda", generator=gq)
+    out = {}
+    for mode, offs in (("ref", 15), ("circular", 32)):
+        svt = ShardedViewTemplates(lib, rank * n, match_threshold=45000, mode=mode)
+        fn = lambda t: svt.match_key(qs[t % 8])  # noqa: E731
+        k = max(5, min(steps, 20))
+        timed(torch, dist, world, fn, 3)
+        ms = timed(torch, dist, world, fn, k) / k
+        out["vt_sharded_u8_" + mode] = {"metric": "VT shift-compares/s", "value": world * n * offs / (ms * 1e-3),
+                                        "ms_per_query": ms, "templates_per_gpu": n,
+                                        "note": "local sweep + MIN all-reduce of the packed key + 8-byte read-back per query"}
+        del svt
     return out
 
 
@@ -357,10 +396,16 @@ def run_ours(args):
                                         "peak_tfma_per_s": fp32_peak, "frac": tfma / fp32_peak}},
             "networks_alive": alive,
         }
+        line["extra_sharded"] = None
         if world == 1:
             line["cpu_baseline"] = cpu_baseline()
             if not args.no_extra:
                 line["extra"] = extra_single_gpu(torch, peak, K)
+    if not args.no_extra:
+        shard = extra_sharded_library(torch, dist if world > 1 else None, world, rank, peak, K)
+        if rank == 0:
+            line["extra_sharded"] = shard
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

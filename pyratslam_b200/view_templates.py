@@ -351,8 +351,9 @@ class ShardedViewTemplates:
         nat.require_cuda()
         self._dist = dist
         self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
+        self._distributed = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self._distributed else 0
+        self.world = dist.get_world_size(group) if self._distributed else 1
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         t = local_templates if isinstance(local_templates, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(local_templates))
@@ -367,10 +368,13 @@ class ShardedViewTemplates:
         self.match_threshold = match_threshold
         self.mode = {"ref": nat.VT_MODE_REF, "circular": nat.VT_MODE_CIRCULAR}[mode]
         self._key = torch.empty(1, dtype=torch.int64, device=self.device)
-        counts = torch.tensor([self._n], dtype=torch.int64, device=self.device)
-        allc = [torch.zeros_like(counts) for _ in range(self.world)]
-        dist.all_gather(allc, counts, group=group)
-        self.n_total = int(sum(int(c.item()) for c in allc))
+        if self._distributed:
+            counts = torch.tensor([self._n], dtype=torch.int64, device=self.device)
+            allc = [torch.zeros_like(counts) for _ in range(self.world)]
+            dist.all_gather(allc, counts, group=group)
+            self.n_total = int(sum(int(c.item()) for c in allc))
+        else:
+            self.n_total = self._n
 
     def _pack(self):
         if self._dtype == torch.uint8:
