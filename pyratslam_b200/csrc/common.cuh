@@ -61,6 +61,12 @@ struct prs_pc_plan {
   int* d_err;
   void* d_total;
   int* d_xyze;          // [B][4] int32 (x, y, th, err) for prs_pc_step_host_xyz
+  // prs_pc_step_host_xyz replays its copy -> step -> unravel -> copy sequence as a CUDA graph on a private stream
+  cudaStream_t hs;
+  cudaEvent_t hev;
+  cudaGraphExec_t hgraph;
+  const void* hkey[4];  // (state, odom_host, gi, result_host) the graph was captured with
+  int hwarm;
   int force_generic;
   int resident_ok;      // the fused SMEM-resident kernel supports this shape/dtype
   void* tab_dev;        // device copy of PcTables<float> for the resident kernel
