@@ -192,6 +192,11 @@ __global__ void __launch_bounds__(NT, 1)
   __syncthreads();
   uint32_t parity = 0;
   int slot = 0;
+  // Results of stage 5 are written to global memory lazily: when the CTA moves on to another network, the
+  // 36 stores per thread are interleaved with the next network's stage 1 instead of bursting at the end of
+  // stage 5 (measured: the burst stalls on the LSU queue, "stall_lg").
+  float2 out[NP];
+  float* st_gst = nullptr;  // where the deferred results go, nullptr if none are pending
   bool pend_valid = false;
   int pend_slot = 0;
   size_t pend_off = 0;
@@ -240,7 +245,12 @@ __global__ void __launch_bounds__(NT, 1)
           const int4 pl = plan4[k];
           const int dst = k * XY + p - pl.z + (x < pl.x ? XY : 0) + (y < pl.y ? Y : 0);
           buf2[dst] = make_float2(e, i);
+          if (st_gst != nullptr) {  // the previous network's plane k (mirror pair layout of out[])
+            const float v = k == 0 ? out[0].y : (k < MID ? out[MID - k].y : (k == MID ? out[0].x : out[k - MID].x));
+            st_gst[k * XY + p] = v;
+          }
         }
+        st_gst = nullptr;
       }
       __syncthreads();
       PRS_STAMP(1);
@@ -395,7 +405,6 @@ __global__ void __launch_bounds__(NT, 1)
       //      For the mirror pair m = (MID+m, MID-m) the tap at offset u reads planes MID+(m+u) and MID-(m-u):
       //      the same pair m+u for both halves when the second half takes the taps in reverse, i.e.
       //      acc += pair(m+u) * (f[3+u], f[3-u]).  Pairs that fall off either end are swapped or pair 0.
-      float2 out[NP];
       float vmax = 0.f;
       if (!(ablate & 32) && tid < XY) {
         const int p = tid;
@@ -441,14 +450,19 @@ __global__ void __launch_bounds__(NT, 1)
           }
           out[0] = make_float2(fmaxf(a, 0.f), fmaxf(c, 0.f));
         }
-        gst[MID * XY + p] = out[0].x;
-        gst[p] = out[0].y;
         vmax = fmaxf(out[0].x, out[0].y);
 #pragma unroll
-        for (int m = 1; m < NP; ++m) {
-          gst[(MID + m) * XY + p] = out[m].x;
-          gst[(MID - m) * XY + p] = out[m].y;
-          vmax = fmaxf(vmax, fmaxf(out[m].x, out[m].y));
+        for (int m = 1; m < NP; ++m) vmax = fmaxf(vmax, fmaxf(out[m].x, out[m].y));
+        if (step + 1 < n_steps) {  // the next update of this network reads the state back from global memory
+          gst[MID * XY + p] = out[0].x;
+          gst[p] = out[0].y;
+#pragma unroll
+          for (int m = 1; m < NP; ++m) {
+            gst[(MID + m) * XY + p] = out[m].x;
+            gst[(MID - m) * XY + p] = out[m].y;
+          }
+        } else {
+          st_gst = gst;  // deferred into the next network's stage 1 (or the kernel's epilogue)
         }
       }
       // arg-max (numpy.argmax: first maximum in [x][y][th] order).  Values are >= 0, so their bit patterns order
@@ -478,6 +492,15 @@ __global__ void __launch_bounds__(NT, 1)
       pend_off = (size_t)step * B + b;
       pend_tot = tot;
       slot ^= 1;
+    }
+  }
+  if (st_gst != nullptr && tid < XY) {
+    st_gst[MID * XY + tid] = out[0].x;
+    st_gst[tid] = out[0].y;
+#pragma unroll
+    for (int m = 1; m < NP; ++m) {
+      st_gst[(MID + m) * XY + tid] = out[m].x;
+      st_gst[(MID - m) * XY + tid] = out[m].y;
     }
   }
   __syncthreads();
