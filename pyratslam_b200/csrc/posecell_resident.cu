@@ -194,7 +194,9 @@ __global__ void __launch_bounds__(NT, 1)
   int slot = 0;
   // Results of stage 5 are written to global memory lazily: when the CTA moves on to another network, the
   // 36 stores per thread are interleaved with the next network's stage 1 instead of bursting at the end of
-  // stage 5 (measured: the burst stalls on the LSU queue, "stall_lg").
+  // stage 5 (measured: the burst stalls on the LSU queue, "stall_lg"; -4.7 % per update).  Staging them in the
+  // consumed lines of the TMA buffer and writing them with one cp.async.bulk store was also measured: not faster
+  // (stage 1 is bound by issue slots and registers, not by the store path).
   float2 out[NP];
   float* st_gst = nullptr;  // where the deferred results go, nullptr if none are pending
   bool pend_valid = false;
