@@ -51,6 +51,10 @@ static void free_plan(prs_pc_plan* p) {
                   p->tab_dev, p->d_xyze};
   for (void* q : ptrs)
     if (q) cudaFree(q);
+  if (p->sgraph) cudaGraphExecDestroy(p->sgraph);
+  if (p->sev_in) cudaEventDestroy(p->sev_in);
+  if (p->sev_out) cudaEventDestroy(p->sev_out);
+  if (p->ss) cudaStreamDestroy(p->ss);
   if (p->hgraph) cudaGraphExecDestroy(p->hgraph);
   if (p->hev) cudaEventDestroy(p->hev);
   if (p->hs) cudaStreamDestroy(p->hs);
@@ -174,6 +178,10 @@ extern "C" int prs_pc_force_generic(prs_pc_handle h, int on) {
     cudaGraphExecDestroy(h->hgraph);
     h->hgraph = nullptr;
   }
+  if (h->sgraph) {
+    cudaGraphExecDestroy(h->sgraph);
+    h->sgraph = nullptr;
+  }
   return PRS_OK;
 }
 
@@ -195,12 +203,62 @@ static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T
   return PRS_OK;
 }
 
+static int step_enqueue(prs_pc_handle h, void* state, const double* odom, const void* gi, long long* argmax, void* total,
+                        int* err, cudaStream_t st) {
+  PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
+  return step_dispatch(h, state, odom, 1, gi, argmax, total, err, st);
+}
+
 extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, const void* gi, long long* argmax,
                            void* total, int* err, void* stream) {
   PRS_REQUIRE(h && state && odom && gi && argmax && total && err, "prs_pc_step: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
-  return step_dispatch(h, state, odom, 1, gi, argmax, total, err, st);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
+  // The fused kernel is one launch; a caller that is capturing its own graph gets plain launches as well.
+  if (prs_pc_path(h) == 1 || cap != cudaStreamCaptureStatusNone) return step_enqueue(h, state, odom, gi, argmax, total, err, st);
+  // Multi-kernel paths: replay the launch sequence as a graph on a private stream, ordered after the caller's
+  // stream on entry and before it on exit (no host synchronisation).
+  if (!h->ss) {
+    PRS_CUDA(cudaStreamCreateWithFlags(&h->ss, cudaStreamNonBlocking));
+    PRS_CUDA(cudaEventCreateWithFlags(&h->sev_in, cudaEventDisableTiming));
+    PRS_CUDA(cudaEventCreateWithFlags(&h->sev_out, cudaEventDisableTiming));
+  }
+  // the odometry pointer usually changes from call to call: it is staged into the plan's own buffer outside the
+  // graph, so that the captured launches only see fixed addresses
+  const void* key[6] = {state, h->d_odom, gi, argmax, total, err};
+  bool same = h->sgraph != nullptr;
+  for (int i = 0; i < 6 && same; ++i) same = key[i] == h->skey[i];
+  if (!same && h->swarm < 2) {  // first calls: eager on the caller's stream (lazy attributes, and short-lived users)
+    ++h->swarm;
+    return step_enqueue(h, state, odom, gi, argmax, total, err, st);
+  }
+  PRS_CUDA(cudaEventRecord(h->sev_in, st));
+  PRS_CUDA(cudaStreamWaitEvent(h->ss, h->sev_in, 0));
+  if (odom != h->d_odom)
+    PRS_CUDA(cudaMemcpyAsync(h->d_odom, odom, (size_t)h->B * 2 * sizeof(double), cudaMemcpyDeviceToDevice, h->ss));
+  if (!same) {
+    if (h->sgraph) {
+      cudaGraphExecDestroy(h->sgraph);
+      h->sgraph = nullptr;
+    }
+    cudaGraph_t g = nullptr;
+    PRS_CUDA(cudaStreamBeginCapture(h->ss, cudaStreamCaptureModeThreadLocal));
+    int rc = step_enqueue(h, state, h->d_odom, gi, argmax, total, err, h->ss);
+    cudaError_t e = cudaStreamEndCapture(h->ss, &g);
+    if (rc != PRS_OK || e != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      if (rc == PRS_OK) prs_set_error("prs_pc_step: graph capture failed: %s", cudaGetErrorString(e));
+      return rc != PRS_OK ? rc : PRS_E_CUDA;
+    }
+    PRS_CUDA(cudaGraphInstantiate(&h->sgraph, g, 0));
+    cudaGraphDestroy(g);
+    for (int i = 0; i < 6; ++i) h->skey[i] = key[i];
+  }
+  PRS_CUDA(cudaGraphLaunch(h->sgraph, h->ss));
+  PRS_CUDA(cudaEventRecord(h->sev_out, h->ss));
+  PRS_CUDA(cudaStreamWaitEvent(st, h->sev_out, 0));
+  return PRS_OK;
 }
 
 extern "C" int prs_pc_path_integration(prs_pc_handle h, void* state, const double* odom, int* err, void* stream) {

@@ -67,6 +67,13 @@ struct prs_pc_plan {
   cudaGraphExec_t hgraph;
   const void* hkey[4];  // (state, odom_host, gi, result_host) the graph was captured with
   int hwarm;
+  // prs_pc_step on the multi-kernel paths (tiled, generic) is replayed as a graph too: eight dependent launches
+  // are CPU-enqueue bound otherwise
+  cudaStream_t ss;
+  cudaEvent_t sev_in, sev_out;
+  cudaGraphExec_t sgraph;
+  const void* skey[6];  // (state, odom, gi, argmax, total, err)
+  int swarm;
   int force_generic;
   int resident_ok;      // the fused SMEM-resident kernel supports this shape/dtype
   void* tab_dev;        // device copy of PcTables<float> for the resident kernel
