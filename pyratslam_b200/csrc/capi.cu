@@ -48,7 +48,7 @@ static void fill_tables(PcTables<T>& t, const prs_pc_config* c) {
 static void free_plan(prs_pc_plan* p) {
   void* ptrs[] = {p->cos_th, p->sin_th, p->s1,       nullptr,      p->s3,     nullptr,     p->shift, p->fsel,
                   p->ogi,    p->part_val, p->part_idx, p->inv_total, p->d_odom, p->d_argmax, p->d_err, p->d_total,
-                  p->tab_dev, p->d_xyze};
+                  p->tab_dev, p->d_xyze, p->done_ctr};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   if (p->sgraph) cudaGraphExecDestroy(p->sgraph);
@@ -93,7 +93,7 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   const size_t es = cfg->dtype == PRS_F32 ? 4 : 8;
   const size_t sbytes = (size_t)p->B * p->N * es;
   p->nblk_plane = (p->X * p->Y + 255) / 256;
-  const int tiles = ((p->X + 31) / 32) * ((p->Y + 31) / 32);
+  const int tiles = ((p->X + 31) / 32) * ((p->Y + 31) / 32);  // an upper bound of the tiled path's tile count
   p->np_max = p->Th * (p->nblk_plane > tiles ? p->nblk_plane : tiles);  // >= nblk_plane * ceil(Th/8) as well
   const size_t np = (size_t)p->B * p->np_max;
 #define ALLOC(ptr, bytes)                                                        \
@@ -118,6 +118,8 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   ALLOC(p->d_err, (size_t)p->B * sizeof(int));
   ALLOC(p->d_total, (size_t)p->B * es);
   ALLOC(p->d_xyze, (size_t)p->B * 4 * sizeof(int));
+  ALLOC(p->done_ctr, (size_t)p->B * 2 * sizeof(unsigned));
+  cudaMemset(p->done_ctr, 0, (size_t)p->B * 2 * sizeof(unsigned));
   ALLOC(p->tab_dev, sizeof(PcTables<float>));
   p->resident_ok = prs_pc_resident_supported(p);
   p->tiled_ok = prs_pc_tiled_supported(p);

@@ -55,6 +55,7 @@ struct prs_pc_plan {
   void* part_val;       // [B][Th*nblk_plane] partial sums, later partial maxima
   long long* part_idx;  // [B][Th*nblk_plane]
   void* inv_total;      // [B]
+  unsigned* done_ctr;   // [2*B] last-block-done counters of the tiled kernels (atomicInc wraps them back to 0)
   // staging for the *_host entry points
   double* d_odom;
   long long* d_argmax;
@@ -97,6 +98,44 @@ int prs_pc_resident_step(prs_pc_plan* p, void* state, const double* odom, int T,
                          void* total, int* err, cudaStream_t st);
 
 // ---- small device helpers -------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ int prs_modp_dev(int v, int n) {
+  int r = v % n;
+  return r < 0 ? r + n : r;
+}
+// Decisions of one path-integration step for (network b, plane k): bit-for-bit the float64 arithmetic numpy
+// does on the host (posecell_network.py:252-267,249,304); explicit _rn intrinsics keep the compiler from
+// contracting mul+sub into an FMA.
+__device__ __forceinline__ void prs_plan_cell(int b, int k, int Th, int minXY, const double* __restrict__ odom,
+                                              const double* __restrict__ cos_th, const double* __restrict__ sin_th,
+                                              double vtrans_scale, double vrot_scale, int* __restrict__ shift,
+                                              unsigned char* __restrict__ fsel, int* __restrict__ ogi,
+                                              int* __restrict__ err) {
+  const int i = b * Th + k;
+  const double vt = __ddiv_rn(odom[2 * b], vtrans_scale);
+  const double ex = __dmul_rn(vt, cos_th[k]);
+  const double ey = __dmul_rn(vt, sin_th[k]);
+  const double oxd = rint(ex), oyd = rint(ey);  // numpy.around: half to even
+  const double dx = __dsub_rn(ex, oxd);
+  const int key = (int)__dmul_rn(dx, 10.0);  // int(): truncation toward zero
+  shift[2 * i] = (int)oxd;
+  shift[2 * i + 1] = (int)oyd;
+  fsel[i] = key < 0 ? 1 : 0;
+  int e = 0;
+  if (key >= 5) e |= PRS_ERR_LUT_KEY;
+  if (k == 0) {
+    const double radius = ceil(fabs(vt));
+    if (!(3.0 + radius <= (double)minXY)) e |= PRS_ERR_RADIUS;
+    const double vr = __ddiv_rn(odom[2 * b + 1], vrot_scale);
+    const double og = floor(__dadd_rn(vr, 0.5));
+    if (!(fabs(og) <= 64.0)) e |= PRS_ERR_THETA;
+    const int ogc = og < -(double)PRS_OG_RANGE ? -PRS_OG_RANGE : (og > (double)PRS_OG_RANGE ? PRS_OG_RANGE : (int)og);
+    ogi[b] = ogc + PRS_OG_RANGE;
+  }
+  if (e) atomicOr(&err[b], e);  // err[] is zeroed by the caller (prs_pc_step) and OR-ed across steps (prs_pc_run)
+}
+#endif
+
 __device__ __forceinline__ int wrap1(int v, int n) {  // valid for -n <= v < 2n
   v = v < 0 ? v + n : v;
   return v >= n ? v - n : v;

@@ -39,28 +39,7 @@ __global__ void k_plan(const double* __restrict__ odom, const double* __restrict
                        int* __restrict__ ogi, int* __restrict__ err) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * Th) return;
-  int b = i / Th, k = i - b * Th;
-  double vt = __ddiv_rn(odom[2 * b], vtrans_scale);
-  double ex = __dmul_rn(vt, cos_th[k]);
-  double ey = __dmul_rn(vt, sin_th[k]);
-  double oxd = rint(ex), oyd = rint(ey);  // numpy.around: half to even
-  double dx = __dsub_rn(ex, oxd);
-  int key = (int)__dmul_rn(dx, 10.0);  // int(): truncation toward zero
-  shift[2 * i] = (int)oxd;
-  shift[2 * i + 1] = (int)oyd;
-  fsel[i] = key < 0 ? 1 : 0;
-  int e = 0;
-  if (key >= 5) e |= PRS_ERR_LUT_KEY;
-  if (k == 0) {
-    double radius = ceil(fabs(vt));
-    if (!(3.0 + radius <= (double)minXY)) e |= PRS_ERR_RADIUS;
-    double vr = __ddiv_rn(odom[2 * b + 1], vrot_scale);
-    double og = floor(__dadd_rn(vr, 0.5));
-    if (!(fabs(og) <= 64.0)) e |= PRS_ERR_THETA;
-    int ogc = og < -(double)PRS_OG_RANGE ? -PRS_OG_RANGE : (og > (double)PRS_OG_RANGE ? PRS_OG_RANGE : (int)og);
-    ogi[b] = ogc + PRS_OG_RANGE;
-  }
-  if (e) atomicOr(&err[b], e);  // err[] is zeroed by the caller (prs_pc_step) and OR-ed across steps (prs_pc_run)
+  prs_plan_cell(i / Th, i % Th, Th, minXY, odom, cos_th, sin_th, vtrans_scale, vrot_scale, shift, fsel, ogi, err);
 }
 
 // ---------------------------------------------------------------------------

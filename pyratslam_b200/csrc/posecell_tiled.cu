@@ -12,7 +12,9 @@
 //                   rows arrive by LDS.128; * 1/total, clamp (:300)                            5.3 + 4 B / cell
 //   k_tl_theta_fin  shifted 7-tap theta pass (convolution.py:344-359), clamp (:314), block arg-max  8 B / cell
 //
-// plus the shared k_plan / k_sum_final / k_argmax_final.  Any X, Y, Th >= 3 (edge tiles are masked, halos
+// Four launches per update: the decisions (k_plan's arithmetic) run inside k_tl_theta, and the grid-wide sum
+// and arg-max are finished by the last block of k_tl_yx / k_tl_theta_fin to retire (atomicInc counters that
+// wrap back to zero, partials added in a fixed order).  Any X, Y, Th >= 3 (edge tiles are masked, halos
 // wrap by modulo); chosen by the plan for float32 grids of at least 1024 cells per plane that the fused
 // SMEM-resident kernel does not cover.
 #include "common.cuh"
@@ -21,70 +23,111 @@ namespace {
 
 constexpr int kT = 256;
 
+// v in [-n, 2n): one conditional add/sub instead of an integer division (the kernels below are issue bound)
+__device__ __forceinline__ int wrap_near(int v, int n) {
+  v += v < 0 ? n : 0;
+  v -= v >= n ? n : 0;
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------
 constexpr int kTK = 8;  // theta cells per thread in the two theta kernels (7-register window + 8 new loads)
 
+struct PlanArgs {  // what prs_plan_cell needs; the theta kernel runs it for its network in one of its blocks
+  const double *odom, *cos_th, *sin_th;
+  double vtrans_scale, vrot_scale;
+  int* shift;
+  unsigned char* fsel;
+  int *ogi, *err;
+  int minXY;
+};
+
 __global__ void __launch_bounds__(kT) k_tl_theta(const float* __restrict__ P, float2* __restrict__ EI, int XY, int Th,
-                                                 PcTables<float> tab) {
+                                                 PcTables<float> tab, PlanArgs pa) {
+  if (blockIdx.x == 0 && blockIdx.z == 0) {  // decisions of this update, needed from k_tl_2d on
+    for (int k = threadIdx.x; k < Th; k += kT)
+      prs_plan_cell(blockIdx.y, k, Th, pa.minXY, pa.odom, pa.cos_th, pa.sin_th, pa.vtrans_scale, pa.vrot_scale, pa.shift,
+                    pa.fsel, pa.ogi, pa.err);
+  }
   const int p = blockIdx.x * kT + threadIdx.x;
   if (p >= XY) return;
   const size_t base = (size_t)blockIdx.y * Th * XY + p;
-  const int k_lo = blockIdx.z * kTK, k_hi = min(Th, k_lo + kTK);
+  const float* Pb = P + base;
+  float2* Eb = EI + base;
+  const int k_lo = blockIdx.z * kTK;
+  const bool near = Th >= kTK + 3;  // k_lo - 3 + j stays within [-Th, 2 Th)
   const float e0 = tab.ge[3], e1 = tab.ge[2], e2 = tab.ge[1], e3 = tab.ge[0];
   const float i0 = tab.gi[3], i1 = tab.gi[2], i2 = tab.gi[1], i3 = tab.gi[0];
-  float w0 = P[base + (size_t)modp(k_lo - 3, Th) * XY], w1 = P[base + (size_t)modp(k_lo - 2, Th) * XY];
-  float w2 = P[base + (size_t)modp(k_lo - 1, Th) * XY], w3 = P[base + (size_t)k_lo * XY];
-  float w4 = P[base + (size_t)((k_lo + 1) % Th) * XY], w5 = P[base + (size_t)((k_lo + 2) % Th) * XY];
+  float w[kTK + 6];  // planes k_lo-3 .. k_lo+kTK+2, all loads issued before the first use
+#pragma unroll
+  for (int j = 0; j < kTK + 6; ++j) {
+    const int kq = near ? wrap_near(k_lo - 3 + j, Th) : modp(k_lo - 3 + j, Th);
+    w[j] = Pb[kq * XY];
+  }
 #pragma unroll
   for (int kk = 0; kk < kTK; ++kk) {
     const int k = k_lo + kk;
-    if (k >= k_hi) break;
-    int kn = k + 3;
-    kn -= kn >= Th ? Th : 0;
-    const float w6 = P[base + (size_t)kn * XY];
-    const float s1 = w2 + w4, s2 = w1 + w5, s3 = w0 + w6;
-    const float e = fmaf(e0, w3, fmaf(e1, s1, fmaf(e2, s2, e3 * s3)));
-    const float i = fmaf(i0, w3, fmaf(i1, s1, fmaf(i2, s2, i3 * s3)));
-    EI[base + (size_t)k * XY] = make_float2(e, i);
-    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
+    if (k < Th) {
+      const float s1 = w[kk + 2] + w[kk + 4], s2 = w[kk + 1] + w[kk + 5], s3 = w[kk] + w[kk + 6];
+      const float e = fmaf(e0, w[kk + 3], fmaf(e1, s1, fmaf(e2, s2, e3 * s3)));
+      const float i = fmaf(i0, w[kk + 3], fmaf(i1, s1, fmaf(i2, s2, i3 * s3)));
+      Eb[k * XY] = make_float2(e, i);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int kYX = 32;           // tile edge
-constexpr int kYXH = kYX + 6;     // with halo
-constexpr int kInStride = kYXH + 1;   // 39: odd, so that lanes walking down rows hit distinct banks
-constexpr int kMidStride = kYX + 1;   // 33
+constexpr int kYXx = 56, kYXy = 32;      // outputs per tile (x rows, y columns)
+constexpr int kYXrows = kYXx + 6;        // 62 halo rows
+constexpr int kYXcols = kYXy + 6;        // 38 halo columns
+constexpr int kInStride = kYXcols + 1;   // 39: odd, so that lanes walking down rows hit distinct banks
+constexpr int kMidStride = kYXy + 1;     // 33
 
 __global__ void __launch_bounds__(kT) k_tl_yx(const float2* __restrict__ EI, float* __restrict__ A,
                                               const float* __restrict__ gi, int X, int Y, int Th, PcTables<float> tab,
-                                              float* __restrict__ part) {
-  __shared__ float2 s_in[kYXH * kInStride];
-  __shared__ float2 s_mid[kYXH * kMidStride];
+                                              float* __restrict__ part, unsigned* __restrict__ done_ctr,
+                                              float* __restrict__ total, float* __restrict__ inv_total) {
+  __shared__ float2 s_in[kYXrows * kInStride];
+  __shared__ int s_last;
+  __shared__ float2 s_mid[kYXrows * kMidStride];
   __shared__ float s_red[kT / 32];
   const int XY = X * Y;
-  const int x0 = blockIdx.x * kYX, y0 = blockIdx.y * kYX;
+  const int x0 = blockIdx.x * kYXx, y0 = blockIdx.y * kYXy;
   const int plane = blockIdx.z;  // b * Th + k
   const float2* src = EI + (size_t)plane * XY;
-  const int tid = threadIdx.x;
-  const int gx0 = modp(x0 - 3, X), gy0 = modp(y0 - 3, Y);
-  const bool nowrapdiv = (X >= kYXH && Y >= kYXH);  // one conditional subtract wraps the index
-  for (int i = tid; i < kYXH * kYXH; i += kT) {
-    const int r = i / kYXH, c = i - r * kYXH;
-    int gx = gx0 + r, gy = gy0 + c;
-    if (nowrapdiv) {
-      gx -= gx >= X ? X : 0;
-      gy -= gy >= Y ? Y : 0;
-    } else {
-      gx %= X;
-      gy %= Y;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // halo tile: one warp per row, the row's wrapped x index is computed once, lanes walk along y
+  {
+    const int gy0 = modp(y0 - 3, Y);
+    int gya = gy0 + lane, gyb = gy0 + lane + 32;
+    gya = gya >= Y ? gya % Y : gya;
+    gyb = gyb >= Y ? gyb % Y : gyb;
+    constexpr int NR = (kYXrows + kT / 32 - 1) / (kT / 32);
+    const bool xnear = X >= kYXrows;
+    float2 va[NR], vb[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = wid + i * (kT / 32);
+      if (r < kYXrows) {
+        const int gx = xnear ? wrap_near(x0 - 3 + r, X) : modp(x0 - 3 + r, X);
+        const float2* row = src + gx * Y;
+        va[i] = row[gya];
+        if (lane + 32 < kYXcols) vb[i] = row[gyb];
+      }
     }
-    s_in[r * kInStride + c] = src[(size_t)gx * Y + gy];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = wid + i * (kT / 32);
+      if (r < kYXrows) {
+        s_in[r * kInStride + lane] = va[i];
+        if (lane + 32 < kYXcols) s_in[r * kInStride + lane + 32] = vb[i];
+      }
+    }
   }
   __syncthreads();
-  // y pass: item = (segment of 8 outputs, halo row); lanes walk down the rows
-  if (tid < 4 * kYXH) {
-    const int seg = tid / kYXH, r = tid - seg * kYXH;
+  // y pass: item = (segment of 8 outputs, halo row); lanes walk down the rows (248 of 256 threads busy)
+  if (tid < 4 * kYXrows) {
+    const int seg = tid / kYXrows, r = tid - seg * kYXrows;
     float2 cf[7];
 #pragma unroll
     for (int t = 0; t < 7; ++t) cf[t] = make_float2(tab.ge[t], tab.gi[t]);
@@ -100,10 +143,10 @@ __global__ void __launch_bounds__(kT) k_tl_yx(const float2* __restrict__ EI, flo
     }
   }
   __syncthreads();
-  // x pass: item = (segment of 8 outputs, column); lanes walk along y
+  // x pass: item = (segment of 8 outputs, column); lanes walk along y (224 of 256 threads busy)
   float psum = 0.f;
-  if (tid < 4 * kYX) {
-    const int seg = tid / kYX, y = tid - seg * kYX;
+  if (tid < (kYXx / 8) * kYXy) {
+    const int seg = tid / kYXy, y = tid - seg * kYXy;
     float2 cf[7];
 #pragma unroll
     for (int t = 0; t < 7; ++t) cf[t] = make_float2(tab.gex[t], tab.gix[t]);
@@ -112,6 +155,7 @@ __global__ void __launch_bounds__(kT) k_tl_yx(const float2* __restrict__ EI, flo
     for (int j = 0; j < 14; ++j) in[j] = s_mid[(seg * 8 + j) * kMidStride + y];
     const float g = gi[plane / Th];
     const int gy = y0 + y;
+    float* Ap = A + (size_t)plane * XY;
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       float2 acc = make_float2(0.f, 0.f);
@@ -121,14 +165,14 @@ __global__ void __launch_bounds__(kT) k_tl_yx(const float2* __restrict__ EI, flo
       a = (a < g) ? 0.f : a - g;  // posecell_network.py:339-340
       const int gx = x0 + seg * 8 + jj;
       if (gx < X && gy < Y) {
-        A[(size_t)plane * XY + (size_t)gx * Y + gy] = a;
+        Ap[gx * Y + gy] = a;
         psum += a;
       }
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
-  if ((tid & 31) == 0) s_red[tid >> 5] = psum;
+  if (lane == 0) s_red[wid] = psum;
   __syncthreads();
   if (tid == 0) {
     float s = 0.f;
@@ -137,6 +181,28 @@ __global__ void __launch_bounds__(kT) k_tl_yx(const float2* __restrict__ EI, flo
     const int ntiles = gridDim.x * gridDim.y;
     const int k = plane % Th, b = plane / Th;
     part[(size_t)b * Th * ntiles + (size_t)k * ntiles + blockIdx.y * gridDim.x + blockIdx.x] = s;
+    __threadfence();
+    // the last block of this network to finish adds the partial sums up (fixed order: deterministic)
+    s_last = (atomicInc(&done_ctr[b], (unsigned)(Th * ntiles - 1)) == (unsigned)(Th * ntiles - 1)) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    const int ntiles = gridDim.x * gridDim.y, np = Th * ntiles, b = plane / Th;
+    const volatile float* pp = part + (size_t)b * np;
+    float acc = 0.f;
+    for (int i = tid; i < np; i += kT) acc += pp[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __syncthreads();
+    if (lane == 0) s_red[wid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kT / 32; ++w) t += s_red[w];
+      total[b] = t;
+      inv_total[b] = (t != 0.f) ? 1.f / t : 1.f;  // posecell_network.py:344-345
+    }
   }
 }
 
@@ -157,18 +223,33 @@ __global__ void __launch_bounds__(kT) k_tl_2d(const float* __restrict__ A, float
   const int tid = threadIdx.x;
   // the plane's integer origin displaces the tile that is loaded (convolution.py:329-331)
   const int gx0 = modp(x0 + shift[2 * plane] - 3, X), gy0 = modp(y0 + shift[2 * plane + 1] - 3, Y);
-  const bool nowrapdiv = (X >= k2XH && Y >= k2YH);
-  for (int i = tid; i < k2XH * k2YH; i += kT) {
-    const int r = i / k2YH, c = i - r * k2YH;
-    int gx = gx0 + r, gy = gy0 + c;
-    if (nowrapdiv) {
-      gx -= gx >= X ? X : 0;
-      gy -= gy >= Y ? Y : 0;
-    } else {
-      gx %= X;
-      gy %= Y;
+  {
+    const int lane = tid & 31, wid = tid >> 5;
+    int gya = gy0 + lane, gyb = gy0 + lane + 32;
+    gya = gya >= Y ? gya % Y : gya;
+    gyb = gyb >= Y ? gyb % Y : gyb;
+    constexpr int NR = (k2XH + kT / 32 - 1) / (kT / 32);
+    const bool xnear = X >= k2XH;
+    float va[NR], vb[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = wid + i * (kT / 32);
+      if (r < k2XH) {
+        int gx = gx0 + r;
+        gx = xnear ? (gx >= X ? gx - X : gx) : gx % X;
+        const float* row = src + gx * Y;
+        va[i] = row[gya];
+        if (lane + 32 < k2YH) vb[i] = row[gyb];
+      }
     }
-    s_a[r * k2Stride + c] = src[(size_t)gx * Y + gy];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = wid + i * (kT / 32);
+      if (r < k2XH) {
+        s_a[r * k2Stride + lane] = va[i];
+        if (lane + 32 < k2YH) s_a[r * k2Stride + lane + 32] = vb[i];
+      }
+    }
   }
   float F[49];
   {
@@ -228,61 +309,111 @@ __global__ void __launch_bounds__(kT) k_tl_2d(const float* __restrict__ A, float
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kT) k_tl_theta_fin(const float* __restrict__ Bp, float* __restrict__ S,
                                                      const int* __restrict__ ogi, int XY, int Th, PcTables<float> tab,
-                                                     float* __restrict__ part_val, long long* __restrict__ part_idx) {
+                                                     float* __restrict__ part_val, long long* __restrict__ part_idx,
+                                                     unsigned* __restrict__ done_ctr, long long* __restrict__ argmax) {
   __shared__ float s_v[kT / 32];
   __shared__ long long s_i[kT / 32];
   const int p = blockIdx.x * kT + threadIdx.x;
   float best = -INFINITY;
-  long long bidx = 0x7fffffffffffffffLL;
+  int bidx = 0x7fffffff;  // the plan guarantees X*Y*Th < 2^31
   if (p < XY) {
     const size_t base = (size_t)blockIdx.y * Th * XY + p;
+    const float* Bb = Bp + base;
+    float* Sb = S + base;
     const float* f = tab.f1d[ogi[blockIdx.y]];
     const float f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3], f4 = f[4], f5 = f[5], f6 = f[6];
-    const int k_lo = blockIdx.z * kTK, k_hi = min(Th, k_lo + kTK);
-    float w0 = Bp[base + (size_t)modp(k_lo - 3, Th) * XY], w1 = Bp[base + (size_t)modp(k_lo - 2, Th) * XY];
-    float w2 = Bp[base + (size_t)modp(k_lo - 1, Th) * XY], w3 = Bp[base + (size_t)k_lo * XY];
-    float w4 = Bp[base + (size_t)((k_lo + 1) % Th) * XY], w5 = Bp[base + (size_t)((k_lo + 2) % Th) * XY];
+    const int k_lo = blockIdx.z * kTK;
+    const bool near = Th >= kTK + 3;
+    float w[kTK + 6];
+#pragma unroll
+    for (int j = 0; j < kTK + 6; ++j) {
+      const int kq = near ? wrap_near(k_lo - 3 + j, Th) : modp(k_lo - 3 + j, Th);
+      w[j] = Bb[kq * XY];
+    }
+    const int flat0 = p * Th + k_lo;
 #pragma unroll
     for (int kk = 0; kk < kTK; ++kk) {
       const int k = k_lo + kk;
-      if (k >= k_hi) break;
-      int kn = k + 3;
-      kn -= kn >= Th ? Th : 0;
-      const float w6 = Bp[base + (size_t)kn * XY];
-      float c = fmaf(f0, w0, fmaf(f1, w1, fmaf(f2, w2, fmaf(f3, w3, fmaf(f4, w4, fmaf(f5, w5, f6 * w6))))));
-      c = (c < 0.f) ? 0.f : c;  // posecell_network.py:314
-      S[base + (size_t)k * XY] = c;
-      if (c > best) {  // theta ascending: strict '>' keeps the lowest flat index of this line
-        best = c;
-        bidx = (long long)p * Th + k;
+      if (k < Th) {
+        float c = fmaf(f0, w[kk], fmaf(f1, w[kk + 1], fmaf(f2, w[kk + 2], fmaf(f3, w[kk + 3],
+                  fmaf(f4, w[kk + 4], fmaf(f5, w[kk + 5], f6 * w[kk + 6]))))));
+        c = fmaxf(c, 0.f);  // posecell_network.py:314
+        Sb[k * XY] = c;
+        if (c > best) {  // theta ascending: strict '>' keeps the lowest flat index of this line
+          best = c;
+          bidx = flat0 + kk;
+        }
       }
-      w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float v2 = __shfl_xor_sync(0xffffffffu, best, o);
-    const long long i2 = __shfl_xor_sync(0xffffffffu, bidx, o);
-    if (v2 > best || (v2 == best && i2 < bidx)) {
-      best = v2;
-      bidx = i2;
+  // block arg-max (first maximum in [x][y][th] order): values are >= 0, so their bit patterns order like the
+  // values -- REDUX.MAX on the bits, then REDUX.MIN on the index among the lanes that hold the maximum
+  {
+    const unsigned vb = best >= 0.f ? __float_as_uint(best) : 0u;
+    const int ib = best >= 0.f ? bidx : 0x7fffffff;
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, vb);
+    const int widx = __reduce_min_sync(0xffffffffu, vb == wmax ? ib : 0x7fffffff);
+    if ((threadIdx.x & 31) == 0) {
+      s_v[threadIdx.x >> 5] = __uint_as_float(wmax);
+      s_i[threadIdx.x >> 5] = widx;
     }
-  }
-  if ((threadIdx.x & 31) == 0) {
-    s_v[threadIdx.x >> 5] = best;
-    s_i[threadIdx.x >> 5] = bidx;
   }
   __syncthreads();
+  __shared__ int s_last;
+  const int nslots = gridDim.x * gridDim.z;
   if (threadIdx.x == 0) {
+    float bv = s_v[0];
+    long long bi = s_i[0];
 #pragma unroll
-    for (int w = 1; w < kT / 32; ++w)
-      if (s_v[w] > best || (s_v[w] == best && s_i[w] < bidx)) {
-        best = s_v[w];
-        bidx = s_i[w];
+    for (int w2 = 1; w2 < kT / 32; ++w2)
+      if (s_v[w2] > bv || (s_v[w2] == bv && s_i[w2] < bi)) {
+        bv = s_v[w2];
+        bi = s_i[w2];
       }
-    const size_t slot = ((size_t)blockIdx.y * gridDim.z + blockIdx.z) * gridDim.x + blockIdx.x;
-    part_val[slot] = best;
-    part_idx[slot] = bidx;
+    const size_t slot = (size_t)blockIdx.y * nslots + (size_t)blockIdx.z * gridDim.x + blockIdx.x;
+    part_val[slot] = bv;
+    part_idx[slot] = bi;
+    __threadfence();
+    s_last = (atomicInc(&done_ctr[blockIdx.y], (unsigned)(nslots - 1)) == (unsigned)(nslots - 1)) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {  // the last block of this network: final arg-max over the per-block candidates
+    const volatile float* pv = part_val + (size_t)blockIdx.y * nslots;
+    const volatile long long* pi = part_idx + (size_t)blockIdx.y * nslots;
+    float bv = -1.f;
+    long long bi = 0x7fffffffffffffffLL;
+    for (int i = threadIdx.x; i < nslots; i += kT) {
+      const float v = pv[i];
+      const long long ix = pi[i];
+      if (v > bv || (v == bv && ix < bi)) {
+        bv = v;
+        bi = ix;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const long long i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (v2 > bv || (v2 == bv && i2 < bi)) {
+        bv = v2;
+        bi = i2;
+      }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      s_v[threadIdx.x >> 5] = bv;
+      s_i[threadIdx.x >> 5] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w2 = 1; w2 < kT / 32; ++w2)
+        if (s_v[w2] > bv || (s_v[w2] == bv && s_i[w2] < bi)) {
+          bv = s_v[w2];
+          bi = s_i[w2];
+        }
+      argmax[blockIdx.y] = bi;
+    }
   }
 }
 
@@ -300,21 +431,17 @@ int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const fl
   float2* EI = (float2*)p->s1;  // s1|s2 are contiguous: 2*B*N floats
   float* A = (float*)p->s3;
   float* Bp = (float*)p->s4;
-  int rc = prs_pc_launch_plan(p, odom, err, st);
-  if (rc != PRS_OK) return rc;
   const int nline = (XY + kT - 1) / kT;
   const int nchunk = (Th + kTK - 1) / kTK;
-  k_tl_theta<<<dim3(nline, B, nchunk), kT, 0, st>>>(state, EI, XY, Th, p->tf);
-  const dim3 g2((X + kYX - 1) / kYX, (Y + kYX - 1) / kYX, B * Th);
-  k_tl_yx<<<g2, kT, 0, st>>>(EI, A, gi, X, Y, Th, p->tf, (float*)p->part_val);
-  rc = prs_pc_launch_sum_final_f32(p, Th * g2.x * g2.y, total, st);
-  if (rc != PRS_OK) return rc;
+  const PlanArgs pa{odom, p->cos_th, p->sin_th, p->vtrans_scale, p->vrot_scale, p->shift, p->fsel, p->ogi, err,
+                    X < Y ? X : Y};
+  k_tl_theta<<<dim3(nline, B, nchunk), kT, 0, st>>>(state, EI, XY, Th, p->tf, pa);
+  const dim3 g2((X + kYXx - 1) / kYXx, (Y + kYXy - 1) / kYXy, B * Th);
+  k_tl_yx<<<g2, kT, 0, st>>>(EI, A, gi, X, Y, Th, p->tf, (float*)p->part_val, p->done_ctr, total, (float*)p->inv_total);
   const dim3 g3((X + k2X - 1) / k2X, (Y + k2Y - 1) / k2Y, B * Th);
   k_tl_2d<<<g3, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, p->tf);
   k_tl_theta_fin<<<dim3(nline, B, nchunk), kT, 0, st>>>(Bp, state, p->ogi, XY, Th, p->tf, (float*)p->part_val,
-                                                        p->part_idx);
-  rc = prs_pc_launch_argmax_final_f32(p, nline * nchunk, argmax, st);
-  if (rc != PRS_OK) return rc;
+                                                        p->part_idx, p->done_ctr + B, argmax);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
