@@ -307,6 +307,135 @@ __global__ void __launch_bounds__(kT) k_tl_2d(const float* __restrict__ A, float
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same 7x7 stage on TWO adjacent theta planes at once with packed FFMA2 (the kernel above is bound by
+// instruction issue: 49 FFMA per cell).  The two planes' tiles -- each displaced by its own origin -- are
+// interleaved as float2 in shared memory, the coefficient pairs (F_k0[a][q], F_k1[a][q]) are read by LDS.128.
+constexpr int k2pStride = 40;  // float2 per halo row
+
+__global__ void __launch_bounds__(kT) k_tl_2d_pair(const float* __restrict__ A, float* __restrict__ Bp,
+                                                   const int* __restrict__ shift, const unsigned char* __restrict__ fsel,
+                                                   const float* __restrict__ inv_total, int X, int Y, int Th, int NPh,
+                                                   PcTables<float> tab) {
+  __shared__ __align__(16) float2 s_a[k2XH * k2pStride];
+  __shared__ __align__(16) float2 s_cf[7 * 8];
+  const int XY = X * Y;
+  const int x0 = blockIdx.x * k2X, y0 = blockIdx.y * k2Y;
+  const int b = blockIdx.z / NPh, kp = blockIdx.z - b * NPh;
+  const int k0 = 2 * kp, k1 = (2 * kp + 1 < Th) ? 2 * kp + 1 : 2 * kp;
+  const int pl0 = b * Th + k0, pl1 = b * Th + k1;
+  const float* src0 = A + (size_t)pl0 * XY;
+  const float* src1 = A + (size_t)pl1 * XY;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid < 56) {
+    const int a = tid >> 3, q = tid & 7;
+    s_cf[tid] = q < 7 ? make_float2(tab.f2d[fsel[pl0]][a * 7 + q], tab.f2d[fsel[pl1]][a * 7 + q]) : make_float2(0.f, 0.f);
+  }
+  {
+    // each plane's integer origin displaces the tile that is loaded (convolution.py:329-331)
+    const int gx00 = modp(x0 + shift[2 * pl0] - 3, X), gy00 = modp(y0 + shift[2 * pl0 + 1] - 3, Y);
+    const int gx01 = modp(x0 + shift[2 * pl1] - 3, X), gy01 = modp(y0 + shift[2 * pl1 + 1] - 3, Y);
+    int ya0 = gy00 + lane, yb0 = gy00 + lane + 32, ya1 = gy01 + lane, yb1 = gy01 + lane + 32;
+    ya0 = ya0 >= Y ? ya0 % Y : ya0;
+    yb0 = yb0 >= Y ? yb0 % Y : yb0;
+    ya1 = ya1 >= Y ? ya1 % Y : ya1;
+    yb1 = yb1 >= Y ? yb1 % Y : yb1;
+    constexpr int NR = (k2XH + kT / 32 - 1) / (kT / 32);
+    const bool xnear = X >= k2XH;
+    float2 va[NR], vb[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = wid + i * (kT / 32);
+      if (r < k2XH) {
+        int g0 = gx00 + r, g1 = gx01 + r;
+        g0 = xnear ? (g0 >= X ? g0 - X : g0) : g0 % X;
+        g1 = xnear ? (g1 >= X ? g1 - X : g1) : g1 % X;
+        const float* r0 = src0 + g0 * Y;
+        const float* r1 = src1 + g1 * Y;
+        va[i] = make_float2(r0[ya0], r1[ya1]);
+        if (lane + 32 < k2YH) vb[i] = make_float2(r0[yb0], r1[yb1]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = wid + i * (kT / 32);
+      if (r < k2XH) {
+        s_a[r * k2pStride + lane] = va[i];
+        if (lane + 32 < k2YH) s_a[r * k2pStride + lane + 32] = vb[i];
+      }
+    }
+  }
+  __syncthreads();
+  const int xb = tid >> 3, yb = tid & 7;
+  const int x = 2 * xb, y = 4 * yb;
+  float2 acc[2][4];
+#pragma unroll
+  for (int d = 0; d < 2; ++d)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[d][j] = make_float2(0.f, 0.f);
+  float2 cprev[7];
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    const float4* rp = reinterpret_cast<const float4*>(s_a + (x + rr) * k2pStride + y);
+    float2 in[12];
+#pragma unroll
+    for (int h = 0; h < 6; ++h) {
+      const float4 v = rp[h];
+      in[2 * h] = make_float2(v.x, v.y);
+      in[2 * h + 1] = make_float2(v.z, v.w);
+    }
+    float2 ccur[7];
+    if (rr <= 6) {
+      const float4* cp = reinterpret_cast<const float4*>(s_cf + rr * 8);
+      const float4 c01 = cp[0], c23 = cp[1], c45 = cp[2], c6x = cp[3];
+      ccur[0] = make_float2(c01.x, c01.y);
+      ccur[1] = make_float2(c01.z, c01.w);
+      ccur[2] = make_float2(c23.x, c23.y);
+      ccur[3] = make_float2(c23.z, c23.w);
+      ccur[4] = make_float2(c45.x, c45.y);
+      ccur[5] = make_float2(c45.z, c45.w);
+      ccur[6] = make_float2(c6x.x, c6x.y);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 7; ++q) acc[0][j] = __ffma2_rn(in[j + q], ccur[q], acc[0][j]);
+    }
+    if (rr >= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 7; ++q) acc[1][j] = __ffma2_rn(in[j + q], cprev[q], acc[1][j]);
+    }
+#pragma unroll
+    for (int q = 0; q < 7; ++q) cprev[q] = ccur[q];
+  }
+  const float inv = inv_total[b];
+  const int gy = y0 + y;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const int gx = x0 + x + d;
+    if (gx >= X) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && k1 == k0) continue;  // odd Th: the last pair has one plane
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = (h == 0 ? acc[d][j].x : acc[d][j].y) * inv;
+        o[j] = fmaxf(v, 0.f);  // posecell_network.py:300
+      }
+      float* dst = Bp + (size_t)(h == 0 ? pl0 : pl1) * XY + gx * Y + gy;
+      if ((Y & 3) == 0 && gy + 3 < Y) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gy + j < Y) dst[j] = o[j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kT) k_tl_theta_fin(const float* __restrict__ Bp, float* __restrict__ S,
                                                      const int* __restrict__ ogi, int XY, int Th, PcTables<float> tab,
                                                      float* __restrict__ part_val, long long* __restrict__ part_idx,
@@ -438,8 +567,14 @@ int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const fl
   k_tl_theta<<<dim3(nline, B, nchunk), kT, 0, st>>>(state, EI, XY, Th, p->tf, pa);
   const dim3 g2((X + kYXx - 1) / kYXx, (Y + kYXy - 1) / kYXy, B * Th);
   k_tl_yx<<<g2, kT, 0, st>>>(EI, A, gi, X, Y, Th, p->tf, (float*)p->part_val, p->done_ctr, total, (float*)p->inv_total);
-  const dim3 g3((X + k2X - 1) / k2X, (Y + k2Y - 1) / k2Y, B * Th);
-  k_tl_2d<<<g3, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, p->tf);
+  const int NPh = (Th + 1) / 2;
+  const dim3 g3p((X + k2X - 1) / k2X, (Y + k2Y - 1) / k2Y, B * NPh);
+  if ((long long)g3p.x * g3p.y * g3p.z >= 2 * 148) {  // enough plane pairs to fill the chip: packed FFMA2 variant
+    k_tl_2d_pair<<<g3p, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, NPh, p->tf);
+  } else {
+    const dim3 g3(g3p.x, g3p.y, B * Th);
+    k_tl_2d<<<g3, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, p->tf);
+  }
   k_tl_theta_fin<<<dim3(nline, B, nchunk), kT, 0, st>>>(Bp, state, p->ogi, XY, Th, p->tf, (float*)p->part_val,
                                                         p->part_idx, p->done_ctr + B, argmax);
   PRS_CUDA(cudaGetLastError());
