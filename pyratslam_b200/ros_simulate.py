@@ -206,3 +206,107 @@ def replay(frames, odom, fused=False, **kwargs):
     rec["n_templates"] = len(node.vts.templates)
     rec["node"] = node
     return rec
+
+
+def replay_events(events, fused=False, record=None, **kwargs):
+    """Run the node over a message stream (``rosbag_io.read_events``): ``("odom", stamp, (lin_x, ang_z))`` ->
+    ``odom_callback`` + one pass of ``run``'s loop body, ``("image", stamp, frame)`` -> ``vis_callback``, in the
+    order given.  ``fused=True`` folds every odometry message that is directly followed by an image into one
+    ``fused_frame`` call (same results).  ``record`` = path of a bag to write the node's outputs to, the way
+    RECORD_ROSBAG does (``ros_simulate.py:92-95,116-117,147-148``): ``navbot/templatematches`` (std_msgs/Int32)
+    and ``navbot/experiencemap`` (geometry_msgs/Pose2D)."""
+    from . import rosbag_io as rb
+    events = list(events)
+    first = next((p for k, _, p in events if k == "image"), None)
+    node = RatslamRos(**kwargs)
+    if first is not None and tuple(first.shape) != (node.vts.im_x, node.vts.im_y):
+        raise ValueError("frames are %r, the view-template mask was built for %r"
+                         % (tuple(first.shape), (node.vts.im_x, node.vts.im_y)))
+    writer = rb.BagWriter(record) if record else None
+    rec = {"template": [], "created": [], "argmax": [], "n_exp": [], "em_xy": [], "image_stamp": []}
+
+    def note_pose(stamp):
+        if writer is not None and node.em.current_exp is not None:
+            x, y = node.em.get_current_point()
+            writer.write(rb.EM_TOPIC, "geometry_msgs/Pose2D", stamp, rb.encode_pose2d(x, y))
+
+    def note_image(stamp, idx, created, pc_max):
+        rec["template"].append(idx)
+        rec["created"].append(created)
+        rec["argmax"].append(tuple(int(c) for c in pc_max))       # the cell the match was made with
+        rec["n_exp"].append(len(node.em.experiences))
+        rec["em_xy"].append(node.em.get_current_point() if node.em.current_exp is not None else (0.0, 0.0))
+        rec["image_stamp"].append(stamp[0] + stamp[1] * 1e-9)
+        if writer is not None:
+            writer.write(rb.MATCH_TOPIC, "std_msgs/Int32", stamp, rb.encode_int32(idx))
+
+    try:
+        i, n = 0, len(events)
+        while i < n:
+            kind, stamp, payload = events[i]
+            if kind == "odom":
+                twist = (float(payload[0]), float(payload[1]))
+                if fused and i + 1 < n and events[i + 1][0] == "image":
+                    _, istamp, frame = events[i + 1]
+                    n_pose = len(node.published_pose)
+                    idx, created = node.fused_frame(twist, frame)
+                    if len(node.published_pose) > n_pose:
+                        note_pose(stamp)
+                    note_image(istamp, idx, created, node.pcn.max_pc)
+                    i += 2
+                    continue
+                node.odom_callback(twist)
+                if node.spin_once():
+                    note_pose(stamp)
+            elif kind == "image":
+                if fused:
+                    idx, created = node.fused_frame(None, payload)
+                    pc_max = node.pcn.max_pc
+                else:
+                    pc_max = node.pcn.get_pc_max()
+                    idx, created = node.vis_callback(payload)
+                note_image(stamp, idx, created, pc_max)
+            else:
+                raise ValueError("unknown event kind %r" % (kind,))
+            i += 1
+    finally:
+        if writer is not None:
+            writer.close()
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out["argmax"] = out["argmax"].reshape(-1, 3)
+    out["em_xy"] = out["em_xy"].reshape(-1, 2)
+    out["n_templates"] = len(node.vts.templates)
+    out["node"] = node
+    return out
+
+
+def replay_bag(path, fused=False, record=None, image_topic="navbot/camera/image", odom_topic="navbot/odom", **kwargs):
+    """``replay_events`` over a recorded ROS1 bag (topics of ``ros_simulate.py:82-83``)."""
+    from . import rosbag_io as rb
+    return replay_events(rb.read_events(path, image_topic=image_topic, odom_topic=odom_topic), fused=fused,
+                         record=record, **kwargs)
+
+
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser(description="Replay a ROS1 bag through the pose-cell / view-template loop")
+    ap.add_argument("bag")
+    ap.add_argument("--fused", action="store_true", help="one device round trip per frame")
+    ap.add_argument("--record", default=None, help="write template matches and experience-map points to this bag")
+    ap.add_argument("--npy", default=None, help="also save frames/odom arrays as <prefix>_frames.npy, <prefix>_odom.npy")
+    ap.add_argument("--image-topic", default="navbot/camera/image")
+    ap.add_argument("--odom-topic", default="navbot/odom")
+    a = ap.parse_args(argv)
+    from . import rosbag_io as rb
+    events = rb.read_events(a.bag, image_topic=a.image_topic, odom_topic=a.odom_topic)
+    if a.npy:
+        frames, odom, _ = rb.events_to_arrays(events)
+        np.save(a.npy + "_frames.npy", frames)
+        np.save(a.npy + "_odom.npy", odom)
+    out = replay_events(events, fused=a.fused, record=a.record)
+    print("frames %d  templates %d  experiences %d" % (len(out["template"]), out["n_templates"],
+                                                      len(out["node"].em.experiences)))
+
+
+if __name__ == "__main__":
+    main()

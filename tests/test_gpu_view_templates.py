@@ -280,3 +280,34 @@ def test_replay_with_template_injection():
         assert np.array_equal(rec["argmax"], ref["argmax"])
         fs = rec["node"].pcn.posecells
         assert np.abs(fs - ref["final_state"]).max() / ref["final_state"].max() <= 1e-5
+
+
+@pytest.mark.parametrize("compression", ["none", "bz2"])
+def test_replay_from_rosbag(golden, tmp_path, compression):
+    """the reference fixture's run written as a ROS1 bag (one Odometry + one Image per step),
+    read back and replayed -- same decisions as the array replay; the recorded output topics match too."""
+    from pyratslam_b200 import ros_simulate, rosbag_io as rb
+    g = golden("replay_ros.npz")
+    T = int(g["n_frames"])
+    frames = synth_frames(np.random.default_rng(int(g["frame_seed"])), T)
+    path = str(tmp_path / "run.bag")
+    rb.write_run(path, frames, g["odom"], compression=compression, chunk_threshold=1 << 20)
+    for fused in (False, True):
+        out_path = str(tmp_path / ("out%d.bag" % fused))
+        rec = ros_simulate.replay_bag(path, fused=fused, record=out_path)
+        assert np.array_equal(rec["template"], g["template"]) and np.array_equal(rec["created"], g["created"])
+        assert np.array_equal(rec["argmax"], g["argmax"]) and np.array_equal(rec["n_exp"], g["n_exp"])
+        assert np.array_equal(rec["em_xy"][-1], g["em_xy"][-1])
+        out = rb.BagReader(out_path)
+        idx = [rb.decode_int32(m.data) for m in out.messages([rb.MATCH_TOPIC])]
+        assert idx == g["template"].tolist()
+        poses = [rb.decode_pose2d(m.data) for m in out.messages([rb.EM_TOPIC])]
+        moved = (np.abs(g["odom"]) > 0.001).any(axis=1)
+        assert len(poses) == int(moved.sum()) and poses[-1][:2] == tuple(g["em_xy"][-1])
+    # messages that do not alternate: two twists before a frame, a frame without a twist
+    ev = rb.read_events(path)[:40]
+    ev = [ev[0], ev[2]] + ev[1:2] + ev[3:]
+    a = ros_simulate.replay_events(ev, fused=False)
+    b = ros_simulate.replay_events(ev, fused=True)
+    for k in ("template", "created", "argmax", "n_exp", "em_xy"):
+        assert np.array_equal(a[k], b[k]), k
