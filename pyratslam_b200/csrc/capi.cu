@@ -80,6 +80,11 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   prs_pc_plan* p = new (std::nothrow) prs_pc_plan();
   PRS_REQUIRE(p, "prs_pc_create: out of host memory");
   memset(p, 0, sizeof(*p));
+  if (cudaGetDevice(&p->device) != cudaSuccess) {
+    prs_set_error("prs_pc_create: cudaGetDevice failed");
+    delete p;
+    return PRS_E_CUDA;
+  }
   p->X = cfg->X;
   p->Y = cfg->Y;
   p->Th = cfg->Th;
@@ -90,6 +95,15 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   p->vrot_scale = cfg->vrot_scale;
   fill_tables(p->tf, cfg);
   fill_tables(p->td, cfg);
+  for (int t = 0; t < 7; ++t) {
+    p->tl.ty[t] = make_float2(p->tf.ge[t], p->tf.gi[t]);
+    p->tl.tx[t] = make_float2(p->tf.gex[t], p->tf.gix[t]);
+  }
+  for (int c = 0; c < 4; ++c)
+    for (int a = 0; a < 7; ++a)
+      for (int q = 0; q < 8; ++q)
+        p->tl.f2p[c][a][q] = q < 7 ? make_float2(p->tf.f2d[c >> 1][a * 7 + q], p->tf.f2d[c & 1][a * 7 + q])
+                                   : make_float2(0.f, 0.f);
   const size_t es = cfg->dtype == PRS_F32 ? 4 : 8;
   const size_t sbytes = (size_t)p->B * p->N * es;
   p->nblk_plane = (p->X * p->Y + 255) / 256;
@@ -141,6 +155,13 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
     return PRS_E_CUDA;
   }
   *out = p;
+  return PRS_OK;
+}
+
+int prs_pc_check_device(const prs_pc_plan* p, const char* who) {
+  int dev = -1;
+  PRS_CUDA(cudaGetDevice(&dev));
+  PRS_REQUIRE(dev == p->device, "%s: the plan was created on device %d but device %d is current", who, p->device, dev);
   return PRS_OK;
 }
 
@@ -214,6 +235,7 @@ static int step_enqueue(prs_pc_handle h, void* state, const double* odom, const 
 extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, const void* gi, long long* argmax,
                            void* total, int* err, void* stream) {
   PRS_REQUIRE(h && state && odom && gi && argmax && total && err, "prs_pc_step: null argument");
+  if (int rc_ = prs_pc_check_device(h, "prs_pc_step")) return rc_;
   cudaStream_t st = (cudaStream_t)stream;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
@@ -265,6 +287,7 @@ extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, con
 
 extern "C" int prs_pc_path_integration(prs_pc_handle h, void* state, const double* odom, int* err, void* stream) {
   PRS_REQUIRE(h && state && odom && err, "prs_pc_path_integration: null argument");
+  if (int rc_ = prs_pc_check_device(h, "prs_pc_path_integration")) return rc_;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = ensure_scratch(h);
   if (rc != PRS_OK) return rc;
@@ -275,6 +298,7 @@ extern "C" int prs_pc_path_integration(prs_pc_handle h, void* state, const doubl
 extern "C" int prs_pc_run(prs_pc_handle h, void* state, const double* odom, int T, const void* gi, long long* argmax,
                           void* total, int* err, void* stream) {
   PRS_REQUIRE(h && state && odom && gi && argmax && total && err, "prs_pc_run: null argument");
+  if (int rc_ = prs_pc_check_device(h, "prs_pc_run")) return rc_;
   PRS_REQUIRE(T >= 0, "prs_pc_run: negative step count");
   cudaStream_t st = (cudaStream_t)stream;
   PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
@@ -285,6 +309,7 @@ extern "C" int prs_pc_run(prs_pc_handle h, void* state, const double* odom, int 
 extern "C" int prs_pc_step_host(prs_pc_handle h, void* state, const double* odom_host, const void* gi,
                                 long long* argmax_host, int* err_host, void* stream) {
   PRS_REQUIRE(h && state && odom_host && gi && argmax_host && err_host, "prs_pc_step_host: null argument");
+  if (int rc_ = prs_pc_check_device(h, "prs_pc_step_host")) return rc_;
   cudaStream_t st = (cudaStream_t)stream;
   PRS_CUDA(cudaMemcpyAsync(h->d_odom, odom_host, (size_t)h->B * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   int rc = prs_pc_step(h, state, h->d_odom, gi, h->d_argmax, h->d_total, h->d_err, st);
@@ -309,6 +334,7 @@ static int step_host_xyz_enqueue(prs_pc_handle h, void* state, const double* odo
 extern "C" int prs_pc_step_host_xyz(prs_pc_handle h, void* state, const double* odom_host, const void* gi,
                                     int* result_host, void* stream) {
   PRS_REQUIRE(h && state && odom_host && gi && result_host, "prs_pc_step_host_xyz: null argument");
+  if (int rc_ = prs_pc_check_device(h, "prs_pc_step_host_xyz")) return rc_;
   cudaStream_t caller = (cudaStream_t)stream;
   if (!h->hs) {
     PRS_CUDA(cudaStreamCreateWithFlags(&h->hs, cudaStreamNonBlocking));

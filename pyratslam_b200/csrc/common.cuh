@@ -36,12 +36,23 @@ struct PcTables {
   T f1d[PRS_NOG][7]; // theta filters for og = -PRS_OG_RANGE..PRS_OG_RANGE
 };
 
+// Coefficient PAIRS of the tiled float32 kernels, passed by value (constant bank): a packed FFMA2 can take such a
+// pair straight from two adjacent uniform registers (one LDCU.64), which keeps them out of the register file
+// and off the shared-memory pipe.
+struct TlPairs {
+  float2 ty[7];         // (ge[t], gi[t])      theta / y passes on (E, I)
+  float2 tx[7];         // (aE*ge[t], aI*gi[t])  x pass
+  float2 f2p[4][7][8];  // [(fsel_plane0 * 2 + fsel_plane1)][tap row][tap column (7 used)]: (F_p0, F_p1) of a plane pair
+};
+
 struct prs_pc_plan {
   int X, Y, Th, B, dtype;
+  int device;   // the CUDA device the plan's buffers live on; every entry point checks it is current
   long long N;  // cells per network
   double vtrans_scale, vrot_scale;
   PcTables<float> tf;
   PcTables<double> td;
+  TlPairs tl;
   double* cos_th;  // device [Th]
   double* sin_th;
   // scratch: two allocations of 2*B*N elements; s1|s2 are the halves of the first, s3|s4 of the second
@@ -79,6 +90,8 @@ struct prs_pc_plan {
   int resident_ok;      // the fused SMEM-resident kernel supports this shape/dtype
   void* tab_dev;        // device copy of PcTables<float> for the resident kernel
 };
+
+int prs_pc_check_device(const prs_pc_plan* p, const char* who);
 
 // launchers implemented per translation unit
 int prs_pc_generic_step(prs_pc_plan* p, void* state, const double* odom, const void* gi, long long* argmax,

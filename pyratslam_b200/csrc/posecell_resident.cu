@@ -517,14 +517,16 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
            float* total, int* err, cudaStream_t st) {
   using L = ResLayout<X, Y, T>;
   auto kern = k_pc_resident<X, Y, T, NT>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};  // function attributes are per device
+  static int nsm_of[64] = {};
+  const int dev = p->device;
+  PRS_REQUIRE(dev >= 0 && dev < 64, "resident path: device index %d out of range", dev);
+  if (!configured[dev]) {
     PRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
-    configured = true;
+    PRS_CUDA(cudaDeviceGetAttribute(&nsm_of[dev], cudaDevAttrMultiProcessorCount, dev));
+    configured[dev] = true;
   }
-  int dev = 0, nsm = 148;
-  PRS_CUDA(cudaGetDevice(&dev));
-  PRS_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int nsm = nsm_of[dev];
   const int grid = p->B < nsm ? p->B : nsm;
   // PRS_RESIDENT_ABLATE (profiling only): bit i skips stage i+1 to attribute time; results are then meaningless
   static int ablate = [] {

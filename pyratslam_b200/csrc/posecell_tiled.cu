@@ -17,6 +17,8 @@
 // wrap back to zero, partials added in a fixed order).  Any X, Y, Th >= 3 (edge tiles are masked, halos
 // wrap by modulo); chosen by the plan for float32 grids of at least 1024 cells per plane that the fused
 // SMEM-resident kernel does not cover.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -42,6 +44,84 @@ struct PlanArgs {  // what prs_plan_cell needs; the theta kernel runs it for its
   int minXY;
 };
 
+// A filter coefficient read from the kernel parameters is a constant-bank operand; ptxas re-materialises
+// it with one LDCU/UMOV per use, which costs an issue slot each time in these issue-bound kernels.  Passing
+// the value through an empty asm pins it in an ordinary register for the rest of the kernel.
+__device__ __forceinline__ float pin(float v) {
+  asm volatile("" : "+f"(v));
+  return v;
+}
+
+// Block-level combine without a barrier: every warp publishes its partial result in shared memory and bumps a
+// shared counter; only the warp that arrives last goes on (the others are done and free their issue slots --
+// a __syncthreads here made every warp wait for the slowest memory access of the block).  *cnt must have been
+// zeroed before a barrier that every warp has passed.
+__device__ __forceinline__ bool last_warp_of_block(unsigned* cnt, int nwarps) {
+  unsigned old = 0;
+  if ((threadIdx.x & 31) == 0) {
+    __threadfence_block();
+    old = atomicAdd(cnt, 1u);
+  }
+  old = __shfl_sync(0xffffffffu, old, 0);
+  if (old != (unsigned)(nwarps - 1)) return false;
+  __threadfence_block();
+  return true;
+}
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<1> {
+  using F = float;
+  using F2 = float2;
+};
+template <>
+struct Vec<4> {
+  using F = float4;
+  using F2 = float4;  // two (E,I) pairs
+};
+template <int V>
+__device__ __forceinline__ void ldv(const float* p, float* out);
+template <>
+__device__ __forceinline__ void ldv<1>(const float* p, float* out) {
+  out[0] = *p;
+}
+template <>
+__device__ __forceinline__ void ldv<4>(const float* p, float* out) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  out[0] = v.x, out[1] = v.y, out[2] = v.z, out[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void ldv<2>(const float* p, float* out) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  out[0] = v.x, out[1] = v.y;
+}
+
+// The 7 + kTK - 1 planes a chunk of kTK theta cells reads.  `inner` (block-uniform) = no periodic wrap and no
+// ragged end in this chunk: plane addresses are then one pointer plus multiples of the plane stride.
+template <int V, int TK>
+__device__ __forceinline__ void load_window(const float* base, int k_lo, int XY, int Th, bool inner,
+                                            float (&w)[TK + 6][V]) {
+  if (inner) {
+    const float* q = base + (size_t)(k_lo - 3) * XY;
+#pragma unroll
+    for (int j = 0; j < TK + 6; ++j) {
+      ldv<V>(q, w[j]);
+      q += XY;
+    }
+  } else {
+    const bool near = Th >= TK + 3;  // k_lo - 3 + j stays within [-Th, 2 Th)
+#pragma unroll
+    for (int j = 0; j < TK + 6; ++j) {
+      const int kq = near ? wrap_near(k_lo - 3 + j, Th) : modp(k_lo - 3 + j, Th);
+      ldv<V>(base + (size_t)kq * XY, w[j]);
+    }
+  }
+}
+
+// V = cells per thread along the (x,y) line index p: 2 when X*Y is even (64-bit loads, and the two (E,I) pairs
+// leave as one 128-bit store, so that a warp writes whole 32-byte sectors), else 1.  TK = theta cells per thread.
+template <int V, int TK>
 __global__ void __launch_bounds__(kT) k_tl_theta(const float* __restrict__ P, float2* __restrict__ EI, int XY, int Th,
                                                  PcTables<float> tab, PlanArgs pa) {
   if (blockIdx.x == 0 && blockIdx.z == 0) {  // decisions of this update, needed from k_tl_2d on
@@ -49,159 +129,185 @@ __global__ void __launch_bounds__(kT) k_tl_theta(const float* __restrict__ P, fl
       prs_plan_cell(blockIdx.y, k, Th, pa.minXY, pa.odom, pa.cos_th, pa.sin_th, pa.vtrans_scale, pa.vrot_scale, pa.shift,
                     pa.fsel, pa.ogi, pa.err);
   }
-  const int p = blockIdx.x * kT + threadIdx.x;
+  const int p = (blockIdx.x * kT + threadIdx.x) * V;
   if (p >= XY) return;
   const size_t base = (size_t)blockIdx.y * Th * XY + p;
-  const float* Pb = P + base;
-  float2* Eb = EI + base;
-  const int k_lo = blockIdx.z * kTK;
-  const bool near = Th >= kTK + 3;  // k_lo - 3 + j stays within [-Th, 2 Th)
-  const float e0 = tab.ge[3], e1 = tab.ge[2], e2 = tab.ge[1], e3 = tab.ge[0];
-  const float i0 = tab.gi[3], i1 = tab.gi[2], i2 = tab.gi[1], i3 = tab.gi[0];
-  float w[kTK + 6];  // planes k_lo-3 .. k_lo+kTK+2, all loads issued before the first use
+  const int k_lo = blockIdx.z * TK;
+  const bool inner = k_lo >= 3 && k_lo + TK + 3 <= Th;
+  const float e0 = pin(tab.ge[3]), e1 = pin(tab.ge[2]), e2 = pin(tab.ge[1]), e3 = pin(tab.ge[0]);
+  const float i0 = pin(tab.gi[3]), i1 = pin(tab.gi[2]), i2 = pin(tab.gi[1]), i3 = pin(tab.gi[0]);
+  float w[TK + 6][V];  // planes k_lo-3 .. k_lo+TK+2, all loads issued before the first use
+  load_window<V, TK>(P + base, k_lo, XY, Th, inner, w);
+  float2* q = EI + base + (size_t)k_lo * XY;
 #pragma unroll
-  for (int j = 0; j < kTK + 6; ++j) {
-    const int kq = near ? wrap_near(k_lo - 3 + j, Th) : modp(k_lo - 3 + j, Th);
-    w[j] = Pb[kq * XY];
-  }
+  for (int kk = 0; kk < TK; ++kk) {
+    if (inner || k_lo + kk < Th) {
+      float2 o[V];
 #pragma unroll
-  for (int kk = 0; kk < kTK; ++kk) {
-    const int k = k_lo + kk;
-    if (k < Th) {
-      const float s1 = w[kk + 2] + w[kk + 4], s2 = w[kk + 1] + w[kk + 5], s3 = w[kk] + w[kk + 6];
-      const float e = fmaf(e0, w[kk + 3], fmaf(e1, s1, fmaf(e2, s2, e3 * s3)));
-      const float i = fmaf(i0, w[kk + 3], fmaf(i1, s1, fmaf(i2, s2, i3 * s3)));
-      Eb[k * XY] = make_float2(e, i);
+      for (int v = 0; v < V; ++v) {
+        const float s1 = w[kk + 2][v] + w[kk + 4][v], s2 = w[kk + 1][v] + w[kk + 5][v], s3 = w[kk][v] + w[kk + 6][v];
+        o[v].x = fmaf(e0, w[kk + 3][v], fmaf(e1, s1, fmaf(e2, s2, e3 * s3)));
+        o[v].y = fmaf(i0, w[kk + 3][v], fmaf(i1, s1, fmaf(i2, s2, i3 * s3)));
+      }
+      if (V == 2)
+        *reinterpret_cast<float4*>(q) = make_float4(o[0].x, o[0].y, o[V - 1].x, o[V - 1].y);
+      else
+        q[0] = o[0];
     }
+    q += XY;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int kYXx = 56, kYXy = 32;      // outputs per tile (x rows, y columns)
-constexpr int kYXrows = kYXx + 6;        // 62 halo rows
+constexpr int kYXx = 64, kYXy = 32;      // outputs per tile (x rows, y columns)
+constexpr int kYXrows = kYXx + 6;        // 70 halo rows
 constexpr int kYXcols = kYXy + 6;        // 38 halo columns
 constexpr int kInStride = kYXcols + 1;   // 39: odd, so that lanes walking down rows hit distinct banks
 constexpr int kMidStride = kYXy + 1;     // 33
+constexpr int kTyx = 288;                // 9 warps: 4 x 70 = 280 y-pass items, 8 x 32 = 256 x-pass items
 
-__global__ void __launch_bounds__(kT) k_tl_yx(const float2* __restrict__ EI, float* __restrict__ A,
-                                              const float* __restrict__ gi, int X, int Y, int Th, PcTables<float> tab,
-                                              float* __restrict__ part, unsigned* __restrict__ done_ctr,
-                                              float* __restrict__ total, float* __restrict__ inv_total) {
+__global__ void __launch_bounds__(kTyx) k_tl_yx(const float2* __restrict__ EI, float* __restrict__ A,
+                                                const float* __restrict__ gi, int X, int Y, int Th, TlPairs tp,
+                                                float* __restrict__ part, unsigned* __restrict__ done_ctr,
+                                                float* __restrict__ total, float* __restrict__ inv_total) {
+  constexpr int kT = kTyx;
   __shared__ float2 s_in[kYXrows * kInStride];
-  __shared__ int s_last;
+  __shared__ unsigned s_cnt;
   __shared__ float2 s_mid[kYXrows * kMidStride];
-  __shared__ float s_red[kT / 32];
+  __shared__ float s_red[(kT + 31) / 32];
   const int XY = X * Y;
   const int x0 = blockIdx.x * kYXx, y0 = blockIdx.y * kYXy;
   const int plane = blockIdx.z;  // b * Th + k
   const float2* src = EI + (size_t)plane * XY;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // halo tile: one warp per row, the row's wrapped x index is computed once, lanes walk along y
+  if (tid == 0) s_cnt = 0;
+  // halo tile: one warp per row, lanes walk along y
   {
-    const int gy0 = modp(y0 - 3, Y);
-    int gya = gy0 + lane, gyb = gy0 + lane + 32;
-    gya = gya >= Y ? gya % Y : gya;
-    gyb = gyb >= Y ? gyb % Y : gyb;
-    constexpr int NR = (kYXrows + kT / 32 - 1) / (kT / 32);
-    const bool xnear = X >= kYXrows;
+    constexpr int NW = kT / 32;
+    constexpr int NR = (kYXrows + NW - 1) / NW;
     float2 va[NR], vb[NR];
+    if (x0 >= 3 && x0 - 3 + kYXrows <= X && y0 >= 3 && y0 - 3 + kYXcols <= Y) {  // interior tile: no periodic wrap
+      const float2* q = src + (size_t)(x0 - 3 + wid) * Y + (y0 - 3 + lane);
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
-      const int r = wid + i * (kT / 32);
-      if (r < kYXrows) {
-        const int gx = xnear ? wrap_near(x0 - 3 + r, X) : modp(x0 - 3 + r, X);
-        const float2* row = src + gx * Y;
-        va[i] = row[gya];
-        if (lane + 32 < kYXcols) vb[i] = row[gyb];
+      for (int i = 0; i < NR; ++i) {
+        if (wid + i * NW < kYXrows) {
+          va[i] = q[0];
+          if (lane + 32 < kYXcols) vb[i] = q[32];
+        }
+        q += (size_t)NW * Y;
+      }
+    } else {  // periodic wrap: column offsets once per thread, one conditional subtract per row, 32-bit indices
+      const int gy0 = modp(y0 - 3, Y);
+      int gya = gy0 + lane, gyb = gy0 + lane + 32;
+      gya = gya >= Y ? gya % Y : gya;
+      gyb = gyb >= Y ? gyb % Y : gyb;
+      const bool xnear = X >= kYXrows;
+      int gx = xnear ? wrap_near(x0 - 3 + wid, X) : modp(x0 - 3 + wid, X);
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        if (wid + i * NW < kYXrows) {
+          const unsigned rb = (unsigned)(gx * Y);
+          va[i] = src[rb + (unsigned)gya];
+          if (lane + 32 < kYXcols) vb[i] = src[rb + (unsigned)gyb];
+        }
+        gx += NW;
+        gx = xnear ? (gx >= X ? gx - X : gx) : gx % X;
       }
     }
+    float2* d = s_in + wid * kInStride + lane;
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-      const int r = wid + i * (kT / 32);
-      if (r < kYXrows) {
-        s_in[r * kInStride + lane] = va[i];
-        if (lane + 32 < kYXcols) s_in[r * kInStride + lane + 32] = vb[i];
+      if (wid + i * NW < kYXrows) {
+        d[i * NW * kInStride] = va[i];
+        if (lane + 32 < kYXcols) d[i * NW * kInStride + 32] = vb[i];
       }
     }
   }
   __syncthreads();
-  // y pass: item = (segment of 8 outputs, halo row); lanes walk down the rows (248 of 256 threads busy)
+  // y pass: item = (segment of 8 outputs, halo row); lanes walk down the rows (280 of 288 threads busy)
   if (tid < 4 * kYXrows) {
     const int seg = tid / kYXrows, r = tid - seg * kYXrows;
-    float2 cf[7];
-#pragma unroll
-    for (int t = 0; t < 7; ++t) cf[t] = make_float2(tab.ge[t], tab.gi[t]);
+    const float2* sp = s_in + r * kInStride + seg * 8;
     float2 in[14];
 #pragma unroll
-    for (int j = 0; j < 14; ++j) in[j] = s_in[r * kInStride + seg * 8 + j];
+    for (int j = 0; j < 14; ++j) in[j] = sp[j];
+    float2* mp = s_mid + r * kMidStride + seg * 8;
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int t = 0; t < 7; ++t) acc = __ffma2_rn(in[jj + t], cf[t], acc);
-      s_mid[r * kMidStride + seg * 8 + jj] = acc;
+      for (int t = 0; t < 7; ++t) acc = __ffma2_rn(in[jj + t], tp.ty[t], acc);
+      mp[jj] = acc;
     }
   }
   __syncthreads();
-  // x pass: item = (segment of 8 outputs, column); lanes walk along y (224 of 256 threads busy)
+  // x pass: item = (segment of 8 outputs, column); lanes walk along y (256 of 288 threads busy)
   float psum = 0.f;
   if (tid < (kYXx / 8) * kYXy) {
-    const int seg = tid / kYXy, y = tid - seg * kYXy;
-    float2 cf[7];
-#pragma unroll
-    for (int t = 0; t < 7; ++t) cf[t] = make_float2(tab.gex[t], tab.gix[t]);
+    const int seg = wid, y = lane;
+    const float2* sp = s_mid + seg * 8 * kMidStride + y;
     float2 in[14];
 #pragma unroll
-    for (int j = 0; j < 14; ++j) in[j] = s_mid[(seg * 8 + j) * kMidStride + y];
+    for (int j = 0; j < 14; ++j) in[j] = sp[j * kMidStride];
     const float g = gi[plane / Th];
-    const int gy = y0 + y;
+    const int gy = y0 + y, gx0 = x0 + seg * 8;
     float* Ap = A + (size_t)plane * XY;
+    float a[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int t = 0; t < 7; ++t) acc = __ffma2_rn(in[jj + t], cf[t], acc);
-      float a = acc.x - acc.y;
-      a = (a < g) ? 0.f : a - g;  // posecell_network.py:339-340
-      const int gx = x0 + seg * 8 + jj;
-      if (gx < X && gy < Y) {
-        Ap[gx * Y + gy] = a;
-        psum += a;
+      for (int t = 0; t < 7; ++t) acc = __ffma2_rn(in[jj + t], tp.tx[t], acc);
+      const float d = acc.x - acc.y;
+      a[jj] = (d < g) ? 0.f : d - g;  // posecell_network.py:339-340
+    }
+    unsigned o = (unsigned)(gx0 * Y + gy);
+    if (x0 + kYXx <= X && y0 + kYXy <= Y) {  // block-uniform: a full tile needs no edge masking
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        Ap[o] = a[jj];
+        psum += a[jj];
+        o += Y;
+      }
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        if (gx0 + jj < X && gy < Y) {
+          Ap[o] = a[jj];
+          psum += a[jj];
+        }
+        o += Y;
       }
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
   if (lane == 0) s_red[wid] = psum;
-  __syncthreads();
-  if (tid == 0) {
-    float s = 0.f;
+  if (!last_warp_of_block(&s_cnt, kT / 32)) return;
+  // the last warp of the block: tile sum in a fixed order, then -- in the last block of this network -- the
+  // grid-wide sum, again in a fixed order (deterministic whichever block gets there last)
+  const int ntiles = gridDim.x * gridDim.y, np = Th * ntiles, b = plane / Th;
+  int last = 0;
+  if (lane == 0) {
+    float sum = 0.f;
 #pragma unroll
-    for (int w = 0; w < kT / 32; ++w) s += s_red[w];
-    const int ntiles = gridDim.x * gridDim.y;
-    const int k = plane % Th, b = plane / Th;
-    part[(size_t)b * Th * ntiles + (size_t)k * ntiles + blockIdx.y * gridDim.x + blockIdx.x] = s;
+    for (int w = 0; w < kT / 32; ++w) sum += s_red[w];
+    const int k = plane - b * Th;
+    part[(size_t)b * np + (size_t)k * ntiles + blockIdx.y * gridDim.x + blockIdx.x] = sum;
     __threadfence();
-    // the last block of this network to finish adds the partial sums up (fixed order: deterministic)
-    s_last = (atomicInc(&done_ctr[b], (unsigned)(Th * ntiles - 1)) == (unsigned)(Th * ntiles - 1)) ? 1 : 0;
+    last = (atomicInc(&done_ctr[b], (unsigned)(np - 1)) == (unsigned)(np - 1)) ? 1 : 0;
   }
-  __syncthreads();
-  if (s_last) {
-    const int ntiles = gridDim.x * gridDim.y, np = Th * ntiles, b = plane / Th;
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) {
+    __threadfence();
     const volatile float* pp = part + (size_t)b * np;
     float acc = 0.f;
-    for (int i = tid; i < np; i += kT) acc += pp[i];
+    for (int i = lane; i < np; i += 32) acc += pp[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    __syncthreads();
-    if (lane == 0) s_red[wid] = acc;
-    __syncthreads();
-    if (tid == 0) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kT / 32; ++w) t += s_red[w];
-      total[b] = t;
-      inv_total[b] = (t != 0.f) ? 1.f / t : 1.f;  // posecell_network.py:344-345
+    if (lane == 0) {
+      total[b] = acc;
+      inv_total[b] = (acc != 0.f) ? 1.f / acc : 1.f;  // posecell_network.py:344-345
     }
   }
 }
@@ -309,107 +415,143 @@ __global__ void __launch_bounds__(kT) k_tl_2d(const float* __restrict__ A, float
 // ------------------------------------------------------------------------------------------------
 // The same 7x7 stage on TWO adjacent theta planes at once with packed FFMA2 (the kernel above is bound by
 // instruction issue: 49 FFMA per cell).  The two planes' tiles -- each displaced by its own origin -- are
-// interleaved as float2 in shared memory, the coefficient pairs (F_k0[a][q], F_k1[a][q]) are read by LDS.128.
-constexpr int k2pStride = 40;  // float2 per halo row
+// interleaved as float2 in shared memory; the coefficient pairs (F_k0[a][q], F_k1[a][q]) come from the constant
+// bank as uniform-register operands of the FFMA2 (no registers, no shared-memory traffic).
+// A thread owns a patch of 2 rows x PW columns of outputs: 8 halo rows of PW + 6 float2 feed 98 * PW FFMA2.
+// The eight lanes of a quarter warp read windows that start PW float2 apart; 16-byte unit u of a row is
+// therefore stored at u ^ ((u >> 3) & M) (M = 3 for PW = 8, 1 for PW = 4), which spreads the eight units
+// {h, h + PW/2, ...} over all eight 16-byte bank groups: conflict-free LDS.128 (the unswizzled 2 x 4 patch
+// needed 7.75 wavefronts per LDS.128 and was bound by the shared-memory pipe).
+constexpr int k2pX = 64;  // output rows per tile
+template <int PW>
+struct Pair2D {
+  static constexpr int kY = 8 * PW;                     // output columns per tile
+  static constexpr int kXH = k2pX + 6, kYH = kY + 6;    // halo tile
+  static constexpr int kUnits = ((kYH + 1) / 2 + 7) / 8 * 8;  // 16-byte units per row, a multiple of 8
+  static constexpr int kStride = 2 * kUnits;            // float2 per halo row
+  static constexpr int kMask = PW == 8 ? 3 : 1;
+  static constexpr int kNH = (PW + 6) / 2;              // LDS.128 per window row
+  static constexpr int kNC = (kYH + 31) / 32;           // columns per lane in the fill
+  static constexpr int kMinBlocks = PW == 8 ? 3 : 4;
+  __device__ static __forceinline__ int swz(int u) { return u ^ ((u >> 3) & kMask); }
+};
 
-__global__ void __launch_bounds__(kT) k_tl_2d_pair(const float* __restrict__ A, float* __restrict__ Bp,
-                                                   const int* __restrict__ shift, const unsigned char* __restrict__ fsel,
-                                                   const float* __restrict__ inv_total, int X, int Y, int Th, int NPh,
-                                                   PcTables<float> tab) {
-  __shared__ __align__(16) float2 s_a[k2XH * k2pStride];
-  __shared__ __align__(16) float2 s_cf[7 * 8];
+template <int PW>
+__global__ void __launch_bounds__(kT, Pair2D<PW>::kMinBlocks)
+    k_tl_2d_pair(const float* __restrict__ A, float* __restrict__ Bp, const int* __restrict__ shift,
+                 const unsigned char* __restrict__ fsel, const float* __restrict__ inv_total, int X, int Y, int Th,
+                 int NPh, TlPairs tp) {
+  using C = Pair2D<PW>;
+  __shared__ __align__(16) float2 s_a[C::kXH * C::kStride];
   const int XY = X * Y;
-  const int x0 = blockIdx.x * k2X, y0 = blockIdx.y * k2Y;
+  const int x0 = blockIdx.x * k2pX, y0 = blockIdx.y * C::kY;
   const int b = blockIdx.z / NPh, kp = blockIdx.z - b * NPh;
   const int k0 = 2 * kp, k1 = (2 * kp + 1 < Th) ? 2 * kp + 1 : 2 * kp;
   const int pl0 = b * Th + k0, pl1 = b * Th + k1;
-  const float* src0 = A + (size_t)pl0 * XY;
-  const float* src1 = A + (size_t)pl1 * XY;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid < 56) {
-    const int a = tid >> 3, q = tid & 7;
-    s_cf[tid] = q < 7 ? make_float2(tab.f2d[fsel[pl0]][a * 7 + q], tab.f2d[fsel[pl1]][a * 7 + q]) : make_float2(0.f, 0.f);
-  }
+  const int combo = fsel[pl0] * 2 + fsel[pl1];  // block-uniform: the coefficient pairs come from the constant bank
   {
-    // each plane's integer origin displaces the tile that is loaded (convolution.py:329-331)
-    const int gx00 = modp(x0 + shift[2 * pl0] - 3, X), gy00 = modp(y0 + shift[2 * pl0 + 1] - 3, Y);
-    const int gx01 = modp(x0 + shift[2 * pl1] - 3, X), gy01 = modp(y0 + shift[2 * pl1 + 1] - 3, Y);
-    int ya0 = gy00 + lane, yb0 = gy00 + lane + 32, ya1 = gy01 + lane, yb1 = gy01 + lane + 32;
-    ya0 = ya0 >= Y ? ya0 % Y : ya0;
-    yb0 = yb0 >= Y ? yb0 % Y : yb0;
-    ya1 = ya1 >= Y ? ya1 % Y : ya1;
-    yb1 = yb1 >= Y ? yb1 % Y : yb1;
-    constexpr int NR = (k2XH + kT / 32 - 1) / (kT / 32);
-    const bool xnear = X >= k2XH;
-    float2 va[NR], vb[NR];
+    // each plane's integer origin displaces the tile that is loaded (convolution.py:329-331); one warp per halo
+    // row, lanes along y (columns lane, lane + 32, ...)
+    constexpr int NW = kT / 32;
+    constexpr int NR = (C::kXH + NW - 1) / NW;
+    constexpr int NC = C::kNC;
+    const bool xnear = X >= C::kXH;
+    int dcol[NC];  // where this lane's columns land in the swizzled row
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
-      const int r = wid + i * (kT / 32);
-      if (r < k2XH) {
-        int g0 = gx00 + r, g1 = gx01 + r;
-        g0 = xnear ? (g0 >= X ? g0 - X : g0) : g0 % X;
-        g1 = xnear ? (g1 >= X ? g1 - X : g1) : g1 % X;
-        const float* r0 = src0 + g0 * Y;
-        const float* r1 = src1 + g1 * Y;
-        va[i] = make_float2(r0[ya0], r1[ya1]);
-        if (lane + 32 < k2YH) vb[i] = make_float2(r0[yb0], r1[yb1]);
+    for (int c = 0; c < NC; ++c) {
+      const int col = lane + 32 * c;
+      dcol[c] = C::swz(col >> 1) * 2 + (col & 1);
+    }
+    float v[2][NR][NC];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pl = h == 0 ? pl0 : pl1;
+      const float* src = A + (size_t)pl * XY;
+      const int gx0 = modp(x0 + shift[2 * pl] - 3, X), gy0 = modp(y0 + shift[2 * pl + 1] - 3, Y);
+      if (gy0 + C::kYH <= Y && xnear) {  // no wrap along y (block-uniform): one row pointer, immediate column offsets
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          const int r = wid + i * NW;
+          if (r < C::kXH) {
+            int gx = gx0 + r;
+            gx -= gx >= X ? X : 0;
+            const float* q = src + (size_t)gx * Y + (gy0 + lane);
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+              if (32 * c + 32 <= C::kYH || lane + 32 * c < C::kYH) v[h][i][c] = q[32 * c];
+          }
+        }
+      } else {
+        int gy[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          gy[c] = gy0 + lane + 32 * c;
+          gy[c] = gy[c] >= Y ? gy[c] % Y : gy[c];
+        }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          const int r = wid + i * NW;
+          if (r < C::kXH) {
+            int gx = gx0 + r;
+            gx = xnear ? (gx >= X ? gx - X : gx) : gx % X;
+            const int rb = gx * Y;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+              if (32 * c + 32 <= C::kYH || lane + 32 * c < C::kYH) v[h][i][c] = src[rb + gy[c]];
+          }
+        }
       }
     }
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-      const int r = wid + i * (kT / 32);
-      if (r < k2XH) {
-        s_a[r * k2pStride + lane] = va[i];
-        if (lane + 32 < k2YH) s_a[r * k2pStride + lane + 32] = vb[i];
+      const int r = wid + i * NW;
+      if (r < C::kXH) {
+        float2* d = s_a + r * C::kStride;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (32 * c + 32 <= C::kYH || lane + 32 * c < C::kYH) d[dcol[c]] = make_float2(v[0][i][c], v[1][i][c]);
       }
     }
   }
   __syncthreads();
   const int xb = tid >> 3, yb = tid & 7;
-  const int x = 2 * xb, y = 4 * yb;
-  float2 acc[2][4];
+  const int x = 2 * xb, y = PW * yb;
+  // the 16-byte units of this thread's window, as pointers into row x (rows add immediates)
+  const float4* rp[C::kNH];
+#pragma unroll
+  for (int h = 0; h < C::kNH; ++h)
+    rp[h] = reinterpret_cast<const float4*>(s_a + x * C::kStride) + C::swz((PW / 2) * yb + h);
+  float2 acc[2][PW];
 #pragma unroll
   for (int d = 0; d < 2; ++d)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[d][j] = make_float2(0.f, 0.f);
-  float2 cprev[7];
+    for (int j = 0; j < PW; ++j) acc[d][j] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int rr = 0; rr < 8; ++rr) {
-    const float4* rp = reinterpret_cast<const float4*>(s_a + (x + rr) * k2pStride + y);
-    float2 in[12];
+    float2 in[2 * C::kNH];
 #pragma unroll
-    for (int h = 0; h < 6; ++h) {
-      const float4 v = rp[h];
+    for (int h = 0; h < C::kNH; ++h) {
+      const float4 v = rp[h][rr * (C::kStride / 2)];
       in[2 * h] = make_float2(v.x, v.y);
       in[2 * h + 1] = make_float2(v.z, v.w);
     }
-    float2 ccur[7];
     if (rr <= 6) {
-      const float4* cp = reinterpret_cast<const float4*>(s_cf + rr * 8);
-      const float4 c01 = cp[0], c23 = cp[1], c45 = cp[2], c6x = cp[3];
-      ccur[0] = make_float2(c01.x, c01.y);
-      ccur[1] = make_float2(c01.z, c01.w);
-      ccur[2] = make_float2(c23.x, c23.y);
-      ccur[3] = make_float2(c23.z, c23.w);
-      ccur[4] = make_float2(c45.x, c45.y);
-      ccur[5] = make_float2(c45.z, c45.w);
-      ccur[6] = make_float2(c6x.x, c6x.y);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < PW; ++j)
 #pragma unroll
-        for (int q = 0; q < 7; ++q) acc[0][j] = __ffma2_rn(in[j + q], ccur[q], acc[0][j]);
+        for (int q = 0; q < 7; ++q) acc[0][j] = __ffma2_rn(in[j + q], tp.f2p[combo][rr][q], acc[0][j]);
     }
     if (rr >= 1) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < PW; ++j)
 #pragma unroll
-        for (int q = 0; q < 7; ++q) acc[1][j] = __ffma2_rn(in[j + q], cprev[q], acc[1][j]);
+        for (int q = 0; q < 7; ++q) acc[1][j] = __ffma2_rn(in[j + q], tp.f2p[combo][rr - 1][q], acc[1][j]);
     }
-#pragma unroll
-    for (int q = 0; q < 7; ++q) cprev[q] = ccur[q];
   }
   const float inv = inv_total[b];
   const int gy = y0 + y;
+  const bool vec = (Y & 3) == 0 && gy + PW - 1 < Y;
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
     const int gx = x0 + x + d;
@@ -417,18 +559,16 @@ __global__ void __launch_bounds__(kT) k_tl_2d_pair(const float* __restrict__ A, 
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h == 1 && k1 == k0) continue;  // odd Th: the last pair has one plane
-      float o[4];
+      float o[PW];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float v = (h == 0 ? acc[d][j].x : acc[d][j].y) * inv;
-        o[j] = fmaxf(v, 0.f);  // posecell_network.py:300
-      }
+      for (int j = 0; j < PW; ++j) o[j] = fmaxf((h == 0 ? acc[d][j].x : acc[d][j].y) * inv, 0.f);  // posecell_network.py:300
       float* dst = Bp + (size_t)(h == 0 ? pl0 : pl1) * XY + gx * Y + gy;
-      if ((Y & 3) == 0 && gy + 3 < Y) {
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      if (vec) {
+#pragma unroll
+        for (int j = 0; j < PW; j += 4) reinterpret_cast<float4*>(dst)[j / 4] = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < PW; ++j)
           if (gy + j < Y) dst[j] = o[j];
       }
     }
@@ -436,89 +576,79 @@ __global__ void __launch_bounds__(kT) k_tl_2d_pair(const float* __restrict__ A, 
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kT) k_tl_theta_fin(const float* __restrict__ Bp, float* __restrict__ S,
+template <int V, int TK, int MINB>
+__global__ void __launch_bounds__(kT, MINB) k_tl_theta_fin(const float* __restrict__ Bp, float* __restrict__ S,
                                                      const int* __restrict__ ogi, int XY, int Th, PcTables<float> tab,
                                                      float* __restrict__ part_val, long long* __restrict__ part_idx,
                                                      unsigned* __restrict__ done_ctr, long long* __restrict__ argmax) {
   __shared__ float s_v[kT / 32];
-  __shared__ long long s_i[kT / 32];
-  const int p = blockIdx.x * kT + threadIdx.x;
-  float best = -INFINITY;
-  int bidx = 0x7fffffff;  // the plan guarantees X*Y*Th < 2^31
-  if (p < XY) {
+  __shared__ int s_i[kT / 32];
+  __shared__ unsigned s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();  // the only barrier, before any memory latency has been incurred
+  const int p = (blockIdx.x * kT + threadIdx.x) * V;
+  const int k_lo = blockIdx.z * TK;
+  // values are >= 0 after the clamp, so their bit patterns order like the values.  Per line (p + v) the best value
+  // and its theta are tracked with a strict '>' (theta ascending: the lowest theta of a tie stays).
+  float bestv[V];
+  int bestk[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) bestv[v] = -1.f, bestk[v] = 0;
+  const bool live = p < XY;
+  if (live) {
     const size_t base = (size_t)blockIdx.y * Th * XY + p;
-    const float* Bb = Bp + base;
-    float* Sb = S + base;
+    const bool inner = k_lo >= 3 && k_lo + TK + 3 <= Th;
     const float* f = tab.f1d[ogi[blockIdx.y]];
-    const float f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3], f4 = f[4], f5 = f[5], f6 = f[6];
-    const int k_lo = blockIdx.z * kTK;
-    const bool near = Th >= kTK + 3;
-    float w[kTK + 6];
+    const float f0 = pin(f[0]), f1 = pin(f[1]), f2 = pin(f[2]), f3 = pin(f[3]), f4 = pin(f[4]), f5 = pin(f[5]),
+                f6 = pin(f[6]);
+    float w[TK + 6][V];
+    load_window<V, TK>(Bp + base, k_lo, XY, Th, inner, w);
+    float* q = S + base + (size_t)k_lo * XY;
 #pragma unroll
-    for (int j = 0; j < kTK + 6; ++j) {
-      const int kq = near ? wrap_near(k_lo - 3 + j, Th) : modp(k_lo - 3 + j, Th);
-      w[j] = Bb[kq * XY];
-    }
-    const int flat0 = p * Th + k_lo;
+    for (int kk = 0; kk < TK; ++kk) {
+      if (inner || k_lo + kk < Th) {
+        float c[V];
 #pragma unroll
-    for (int kk = 0; kk < kTK; ++kk) {
-      const int k = k_lo + kk;
-      if (k < Th) {
-        float c = fmaf(f0, w[kk], fmaf(f1, w[kk + 1], fmaf(f2, w[kk + 2], fmaf(f3, w[kk + 3],
-                  fmaf(f4, w[kk + 4], fmaf(f5, w[kk + 5], f6 * w[kk + 6]))))));
-        c = fmaxf(c, 0.f);  // posecell_network.py:314
-        Sb[k * XY] = c;
-        if (c > best) {  // theta ascending: strict '>' keeps the lowest flat index of this line
-          best = c;
-          bidx = flat0 + kk;
+        for (int v = 0; v < V; ++v) {
+          const float r = fmaf(f0, w[kk][v], fmaf(f1, w[kk + 1][v], fmaf(f2, w[kk + 2][v], fmaf(f3, w[kk + 3][v],
+                          fmaf(f4, w[kk + 4][v], fmaf(f5, w[kk + 5][v], f6 * w[kk + 6][v]))))));
+          c[v] = fmaxf(r, 0.f);  // posecell_network.py:314
+          if (c[v] > bestv[v]) bestv[v] = c[v], bestk[v] = kk;
         }
+        if (V == 4)
+          *reinterpret_cast<float4*>(q) = make_float4(c[0], c[1 % V], c[2 % V], c[3 % V]);
+        else if (V == 2)
+          *reinterpret_cast<float2*>(q) = make_float2(c[0], c[1 % V]);
+        else
+          q[0] = c[0];
       }
+      q += XY;
     }
   }
-  // block arg-max (first maximum in [x][y][th] order): values are >= 0, so their bit patterns order like the
-  // values -- REDUX.MAX on the bits, then REDUX.MIN on the index among the lanes that hold the maximum
+  // block arg-max (numpy.argmax: first maximum in [x][y][th] order): lines ascending with a strict '>', then
+  // REDUX.MAX on the bits and REDUX.MIN on the flat index among the lanes that hold the warp's maximum
   {
-    const unsigned vb = best >= 0.f ? __float_as_uint(best) : 0u;
-    const int ib = best >= 0.f ? bidx : 0x7fffffff;
+    float best = bestv[0];
+    int ib = p * Th + k_lo + bestk[0];
+#pragma unroll
+    for (int v = 1; v < V; ++v)
+      if (bestv[v] > best) best = bestv[v], ib = (p + v) * Th + k_lo + bestk[v];
+    const unsigned vb = (live && best >= 0.f) ? __float_as_uint(best) : 0u;
     const unsigned wmax = __reduce_max_sync(0xffffffffu, vb);
-    const int widx = __reduce_min_sync(0xffffffffu, vb == wmax ? ib : 0x7fffffff);
+    if (!(live && best >= 0.f && vb == wmax)) ib = 0x7fffffff;  // the plan guarantees X*Y*Th < 2^31
+    const int widx = __reduce_min_sync(0xffffffffu, ib);
     if ((threadIdx.x & 31) == 0) {
       s_v[threadIdx.x >> 5] = __uint_as_float(wmax);
       s_i[threadIdx.x >> 5] = widx;
     }
   }
-  __syncthreads();
-  __shared__ int s_last;
+  if (!last_warp_of_block(&s_cnt, kT / 32)) return;
+  // last warp of the block: best (value, lowest index) of the block; in the last block of this network, of the grid
+  const int lane = threadIdx.x & 31;
   const int nslots = gridDim.x * gridDim.z;
-  if (threadIdx.x == 0) {
-    float bv = s_v[0];
-    long long bi = s_i[0];
-#pragma unroll
-    for (int w2 = 1; w2 < kT / 32; ++w2)
-      if (s_v[w2] > bv || (s_v[w2] == bv && s_i[w2] < bi)) {
-        bv = s_v[w2];
-        bi = s_i[w2];
-      }
-    const size_t slot = (size_t)blockIdx.y * nslots + (size_t)blockIdx.z * gridDim.x + blockIdx.x;
-    part_val[slot] = bv;
-    part_idx[slot] = bi;
-    __threadfence();
-    s_last = (atomicInc(&done_ctr[blockIdx.y], (unsigned)(nslots - 1)) == (unsigned)(nslots - 1)) ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last) {  // the last block of this network: final arg-max over the per-block candidates
-    const volatile float* pv = part_val + (size_t)blockIdx.y * nslots;
-    const volatile long long* pi = part_idx + (size_t)blockIdx.y * nslots;
-    float bv = -1.f;
-    long long bi = 0x7fffffffffffffffLL;
-    for (int i = threadIdx.x; i < nslots; i += kT) {
-      const float v = pv[i];
-      const long long ix = pi[i];
-      if (v > bv || (v == bv && ix < bi)) {
-        bv = v;
-        bi = ix;
-      }
-    }
+  float bv = lane < kT / 32 ? s_v[lane] : -1.f;
+  long long bi = lane < kT / 32 ? (long long)s_i[lane] : 0x7fffffffffffffffLL;
+  auto warp_best = [&]() {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -528,21 +658,33 @@ __global__ void __launch_bounds__(kT) k_tl_theta_fin(const float* __restrict__ B
         bi = i2;
       }
     }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
-      s_v[threadIdx.x >> 5] = bv;
-      s_i[threadIdx.x >> 5] = bi;
+  };
+  warp_best();
+  int last = 0;
+  if (lane == 0) {
+    const size_t slot = (size_t)blockIdx.y * nslots + (size_t)blockIdx.z * gridDim.x + blockIdx.x;
+    part_val[slot] = bv;
+    part_idx[slot] = bi;
+    __threadfence();
+    last = (atomicInc(&done_ctr[blockIdx.y], (unsigned)(nslots - 1)) == (unsigned)(nslots - 1)) ? 1 : 0;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) {
+    __threadfence();
+    const volatile float* pv = part_val + (size_t)blockIdx.y * nslots;
+    const volatile long long* pi = part_idx + (size_t)blockIdx.y * nslots;
+    bv = -1.f;
+    bi = 0x7fffffffffffffffLL;
+    for (int i = lane; i < nslots; i += 32) {
+      const float v = pv[i];
+      const long long ix = pi[i];
+      if (v > bv || (v == bv && ix < bi)) {
+        bv = v;
+        bi = ix;
+      }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int w2 = 1; w2 < kT / 32; ++w2)
-        if (s_v[w2] > bv || (s_v[w2] == bv && s_i[w2] < bi)) {
-          bv = s_v[w2];
-          bi = s_i[w2];
-        }
-      argmax[blockIdx.y] = bi;
-    }
+    warp_best();
+    if (lane == 0) argmax[blockIdx.y] = bi;
   }
 }
 
@@ -560,23 +702,64 @@ int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const fl
   float2* EI = (float2*)p->s1;  // s1|s2 are contiguous: 2*B*N floats
   float* A = (float*)p->s3;
   float* Bp = (float*)p->s4;
-  const int nline = (XY + kT - 1) / kT;
   const int nchunk = (Th + kTK - 1) / kTK;
   const PlanArgs pa{odom, p->cos_th, p->sin_th, p->vtrans_scale, p->vrot_scale, p->shift, p->fsel, p->ogi, err,
                     X < Y ? X : Y};
-  k_tl_theta<<<dim3(nline, B, nchunk), kT, 0, st>>>(state, EI, XY, Th, p->tf, pa);
+  {
+    const int V = (XY % 2 == 0) ? 2 : 1;
+    const int nline = (XY / V + kT - 1) / kT;
+    if (Th >= 36 && Th % 12 == 0) {  // longer chunks re-read fewer planes: (12 + 6) / 12 loads per cell
+      const dim3 g(nline, B, Th / 12);
+      if (V == 2)
+        k_tl_theta<2, 12><<<g, kT, 0, st>>>(state, EI, XY, Th, p->tf, pa);
+      else
+        k_tl_theta<1, 12><<<g, kT, 0, st>>>(state, EI, XY, Th, p->tf, pa);
+    } else {
+      const dim3 g(nline, B, nchunk);
+      if (V == 2)
+        k_tl_theta<2, kTK><<<g, kT, 0, st>>>(state, EI, XY, Th, p->tf, pa);
+      else
+        k_tl_theta<1, kTK><<<g, kT, 0, st>>>(state, EI, XY, Th, p->tf, pa);
+    }
+  }
   const dim3 g2((X + kYXx - 1) / kYXx, (Y + kYXy - 1) / kYXy, B * Th);
-  k_tl_yx<<<g2, kT, 0, st>>>(EI, A, gi, X, Y, Th, p->tf, (float*)p->part_val, p->done_ctr, total, (float*)p->inv_total);
+  k_tl_yx<<<g2, kTyx, 0, st>>>(EI, A, gi, X, Y, Th, p->tl, (float*)p->part_val, p->done_ctr, total, (float*)p->inv_total);
   const int NPh = (Th + 1) / 2;
-  const dim3 g3p((X + k2X - 1) / k2X, (Y + k2Y - 1) / k2Y, B * NPh);
+  // PRS_TILED_PW (tuning knob): columns per thread patch in the plane-pair kernel, 4 (default) or 8
+  static const int pw = [] {
+    const char* e = getenv("PRS_TILED_PW");
+    return (e && atoi(e) == 8) ? 8 : 4;
+  }();
+  const int tileY = 8 * pw;
+  const dim3 g3p((X + k2pX - 1) / k2pX, (Y + tileY - 1) / tileY, B * NPh);
   if ((long long)g3p.x * g3p.y * g3p.z >= 2 * 148) {  // enough plane pairs to fill the chip: packed FFMA2 variant
-    k_tl_2d_pair<<<g3p, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, NPh, p->tf);
+    if (pw == 8)
+      k_tl_2d_pair<8><<<g3p, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, NPh, p->tl);
+    else
+      k_tl_2d_pair<4><<<g3p, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, NPh, p->tl);
   } else {
-    const dim3 g3(g3p.x, g3p.y, B * Th);
+    const dim3 g3((X + k2X - 1) / k2X, (Y + k2Y - 1) / k2Y, B * Th);
     k_tl_2d<<<g3, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, p->tf);
   }
-  k_tl_theta_fin<<<dim3(nline, B, nchunk), kT, 0, st>>>(Bp, state, p->ogi, XY, Th, p->tf, (float*)p->part_val,
-                                                        p->part_idx, p->done_ctr + B, argmax);
+  {
+    // PRS_TILED_FIN (tuning knob): 0 = 2 cells x 8 planes per thread, 1 = 4 x 8, 2 = 2 x 12
+    static const int fin = [] {
+      const char* e = getenv("PRS_TILED_FIN");
+      return e ? atoi(e) : 0;
+    }();
+#define PRS_FIN(V_, TK_, MB_)                                                                                      \
+  k_tl_theta_fin<V_, TK_, MB_><<<dim3((XY / V_ + kT - 1) / kT, B, (Th + TK_ - 1) / TK_), kT, 0, st>>>(              \
+      Bp, state, p->ogi, XY, Th, p->tf, (float*)p->part_val, p->part_idx, p->done_ctr + B, argmax)
+    if (XY % 4 == 0 && fin == 1)
+      PRS_FIN(4, 8, 4);
+    else if (XY % 2 == 0 && fin == 2)
+      PRS_FIN(2, 12, 5);
+    else if (XY % 2 == 0)
+      PRS_FIN(2, 8, 1);
+    else
+      PRS_FIN(1, 8, 1);
+#undef PRS_FIN
+  }
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }

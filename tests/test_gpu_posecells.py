@@ -158,6 +158,39 @@ def test_large_grid_one_step_against_oracle():
     assert _rel(net.posecells, ref.posecells) <= 1e-5
 
 
+@pytest.mark.parametrize("shape", [(33, 35, 9), (70, 40, 19), (128, 64, 8), (36, 36, 3)])
+def test_tiled_path_shapes_against_oracle(shape):
+    """The large-grid kernels on shapes that exercise their edges: X*Y not a multiple of 4 (scalar accesses),
+    ragged tiles in x and y, theta counts that are not a multiple of the chunk, tiles that wrap on every side.
+    Two packets (one across the periodic corner) and an exact tie for the maximum."""
+    ref = opc.PoseCellNetwork(shape)
+    net = _make(shape, np.float32, "auto")
+    assert net.path == "tiled"
+    X, Y, Th = shape
+    for n in (ref, net):
+        n.inject(1.0, (X // 2, Y // 2, Th // 2))
+        n.inject(0.75, (X - 1, 0, Th - 1))
+    for v in [(0.21, 0.03), (0.12, -0.04), (0.0, 0.0), (0.33, 0.0)]:
+        assert tuple(net.update(v)) == tuple(ref.update(v)), v
+        assert _rel(net.posecells, ref.posecells) <= 1e-5
+    # equal maxima: the lowest flat index must win; then an all-zero grid reports cell (0, 0, 0)
+    st = np.zeros(shape)
+    st[X - 2, 3, 1] = st[1, Y - 1, 1] = 1.0       # translated copies: bit-identical responses
+    ref.posecells = st.copy()
+    net.posecells = st
+    got, want = net.update((0.0, 0.0)), ref.update((0.0, 0.0))
+    assert tuple(got) == tuple(want)
+    pc = net.posecells
+    assert np.array_equal(pc[X - 2, 3], pc[1, Y - 1]) and pc[tuple(got)] == pc.max()   # an exact tie, lowest index won
+    if Th >= 7:
+        assert tuple(got)[:2] == (1, Y - 1)
+    gi0 = ref.global_inhibition
+    ref.global_inhibition = net.global_inhibition = 50.0
+    assert tuple(net.update((0.0, 0.0))) == tuple(ref.update((0.0, 0.0))) == (0, 0, 0)
+    assert net.posecells.max() == 0
+    ref.global_inhibition = net.global_inhibition = gi0
+
+
 def test_translation_equivariance_large():
     """Size-independent property: the update commutes with a cyclic shift of the grid in x and y
     (not in theta: the heading decides which way a plane moves)."""
