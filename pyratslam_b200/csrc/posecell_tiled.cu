@@ -59,12 +59,12 @@ __device__ __forceinline__ float pin(float v) {
 __device__ __forceinline__ bool last_warp_of_block(unsigned* cnt, int nwarps) {
   unsigned old = 0;
   if ((threadIdx.x & 31) == 0) {
-    __threadfence_block();
+    asm volatile("fence.acq_rel.cta;" ::: "memory");  // __threadfence_block() is the sequentially-consistent flavour
     old = atomicAdd(cnt, 1u);
   }
   old = __shfl_sync(0xffffffffu, old, 0);
   if (old != (unsigned)(nwarps - 1)) return false;
-  __threadfence_block();
+  asm volatile("fence.acq_rel.cta;" ::: "memory");
   return true;
 }
 
@@ -168,8 +168,7 @@ constexpr int kTyx = 288;                // 9 warps: 4 x 70 = 280 y-pass items, 
 
 __global__ void __launch_bounds__(kTyx) k_tl_yx(const float2* __restrict__ EI, float* __restrict__ A,
                                                 const float* __restrict__ gi, int X, int Y, int Th, TlPairs tp,
-                                                float* __restrict__ part, unsigned* __restrict__ done_ctr,
-                                                float* __restrict__ total, float* __restrict__ inv_total) {
+                                                float* __restrict__ part) {
   constexpr int kT = kTyx;
   __shared__ float2 s_in[kYXrows * kInStride];
   __shared__ unsigned s_cnt;
@@ -203,12 +202,14 @@ __global__ void __launch_bounds__(kTyx) k_tl_yx(const float2* __restrict__ EI, f
       gyb = gyb >= Y ? gyb % Y : gyb;
       const bool xnear = X >= kYXrows;
       int gx = xnear ? wrap_near(x0 - 3 + wid, X) : modp(x0 - 3 + wid, X);
+      const float2* pa = src + gya;
+      const float2* pb = src + gyb;
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         if (wid + i * NW < kYXrows) {
           const unsigned rb = (unsigned)(gx * Y);
-          va[i] = src[rb + (unsigned)gya];
-          if (lane + 32 < kYXcols) vb[i] = src[rb + (unsigned)gyb];
+          va[i] = pa[rb];
+          if (lane + 32 < kYXcols) vb[i] = pb[rb];
         }
         gx += NW;
         gx = xnear ? (gx >= X ? gx - X : gx) : gx % X;
@@ -261,22 +262,14 @@ __global__ void __launch_bounds__(kTyx) k_tl_yx(const float2* __restrict__ EI, f
       const float d = acc.x - acc.y;
       a[jj] = (d < g) ? 0.f : d - g;  // posecell_network.py:339-340
     }
-    unsigned o = (unsigned)(gx0 * Y + gy);
-    if (x0 + kYXx <= X && y0 + kYXy <= Y) {  // block-uniform: a full tile needs no edge masking
+    // rows of this segment inside the grid (0 when the column is outside): one compare per element masks the edges
+    const int nv = gy < Y ? X - gx0 : 0;
+    float* q = Ap + (unsigned)(gx0 * Y + gy);
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        Ap[o] = a[jj];
+    for (int jj = 0; jj < 8; ++jj) {
+      if (jj < nv) {
+        q[(unsigned)(jj * Y)] = a[jj];
         psum += a[jj];
-        o += Y;
-      }
-    } else {
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        if (gx0 + jj < X && gy < Y) {
-          Ap[o] = a[jj];
-          psum += a[jj];
-        }
-        o += Y;
       }
     }
   }
@@ -284,31 +277,43 @@ __global__ void __launch_bounds__(kTyx) k_tl_yx(const float2* __restrict__ EI, f
   for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
   if (lane == 0) s_red[wid] = psum;
   if (!last_warp_of_block(&s_cnt, kT / 32)) return;
-  // the last warp of the block: tile sum in a fixed order, then -- in the last block of this network -- the
-  // grid-wide sum, again in a fixed order (deterministic whichever block gets there last)
-  const int ntiles = gridDim.x * gridDim.y, np = Th * ntiles, b = plane / Th;
-  int last = 0;
+  // the last warp of the block adds the warp sums in a fixed order and publishes the tile's partial sum; the
+  // grid-wide total is formed by every block of the next kernel (tile_total), so that no block of this one waits
+  // for a grid-scope fence and an atomic before it can retire
   if (lane == 0) {
     float sum = 0.f;
 #pragma unroll
     for (int w = 0; w < kT / 32; ++w) sum += s_red[w];
-    const int k = plane - b * Th;
-    part[(size_t)b * np + (size_t)k * ntiles + blockIdx.y * gridDim.x + blockIdx.x] = sum;
-    __threadfence();
-    last = (atomicInc(&done_ctr[b], (unsigned)(np - 1)) == (unsigned)(np - 1)) ? 1 : 0;
+    const int ntiles = gridDim.x * gridDim.y, b = plane / Th, k = plane - b * Th;
+    part[(size_t)b * Th * ntiles + (size_t)k * ntiles + blockIdx.y * gridDim.x + blockIdx.x] = sum;
   }
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (last) {
-    __threadfence();
-    const volatile float* pp = part + (size_t)b * np;
-    float acc = 0.f;
-    for (int i = lane; i < np; i += 32) acc += pp[i];
+}
+
+// Grid-wide sum of the previous kernel's per-tile partial sums (posecell_network.py:343), formed by ONE block per
+// network -- the first block of the 7x7 kernel, as a side job after its own tile -- in a fixed order.  The 7x7
+// stage itself does not need the total: it is a positive scale factor, max(s*v, 0) = s*max(v, 0), and the theta
+// pass after it is linear, so 1/total is applied by the last kernel.  No block ever waits for a fence or an atomic.
+__device__ __forceinline__ void block_tile_total(const float* __restrict__ part, int np, float* __restrict__ total,
+                                                 float* __restrict__ inv_total, float* s_w) {
+  float acc = 0.f;
+  for (int i0 = threadIdx.x; i0 < np; i0 += kT * 4) {  // four independent loads in flight per thread
+    float v[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      total[b] = acc;
-      inv_total[b] = (acc != 0.f) ? 1.f / acc : 1.f;  // posecell_network.py:344-345
-    }
+    for (int u = 0; u < 4; ++u) v[u] = i0 + kT * u < np ? part[i0 + kT * u] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += v[u];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __syncthreads();  // s_w may alias shared memory the tile stage has just read
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kT / 32; ++w) t += s_w[w];
+    *total = t;
+    *inv_total = (t != 0.f) ? 1.f / t : 1.f;  // posecell_network.py:344-345
   }
 }
 
@@ -319,7 +324,8 @@ constexpr int k2Stride = 40;               // floats per halo row, a multiple of
 
 __global__ void __launch_bounds__(kT) k_tl_2d(const float* __restrict__ A, float* __restrict__ Bp,
                                               const int* __restrict__ shift, const unsigned char* __restrict__ fsel,
-                                              const float* __restrict__ inv_total, int X, int Y, int Th,
+                                              const float* __restrict__ part, int np, float* __restrict__ total,
+                                              float* __restrict__ inv_total, int X, int Y, int Th,
                                               PcTables<float> tab) {
   __shared__ __align__(16) float s_a[k2XH * k2Stride];
   const int XY = X * Y;
@@ -389,7 +395,6 @@ __global__ void __launch_bounds__(kT) k_tl_2d(const float* __restrict__ A, float
         for (int q = 0; q < 7; ++q) acc[1][j] = fmaf(in[j + q], F[(rr - 1) * 7 + q], acc[1][j]);
     }
   }
-  const float inv = inv_total[plane / Th];
   const int gy = y0 + y;
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
@@ -397,10 +402,7 @@ __global__ void __launch_bounds__(kT) k_tl_2d(const float* __restrict__ A, float
     if (gx >= X) continue;
     float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float v = acc[d][j] * inv;
-      o[j] = (v < 0.f) ? 0.f : v;  // posecell_network.py:300
-    }
+    for (int j = 0; j < 4; ++j) o[j] = fmaxf(acc[d][j], 0.f);  // posecell_network.py:300 (1/total: see block_tile_total)
     float* dst = Bp + (size_t)plane * XY + (size_t)gx * Y + gy;
     if ((Y & 3) == 0 && gy + 3 < Y) {
       *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
@@ -410,6 +412,8 @@ __global__ void __launch_bounds__(kT) k_tl_2d(const float* __restrict__ A, float
         if (gy + j < Y) dst[j] = o[j];
     }
   }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && plane % Th == 0)  // side job of one block per network
+    block_tile_total(part + (size_t)(plane / Th) * np, np, total + plane / Th, inv_total + plane / Th, s_a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -439,8 +443,8 @@ struct Pair2D {
 template <int PW>
 __global__ void __launch_bounds__(kT, Pair2D<PW>::kMinBlocks)
     k_tl_2d_pair(const float* __restrict__ A, float* __restrict__ Bp, const int* __restrict__ shift,
-                 const unsigned char* __restrict__ fsel, const float* __restrict__ inv_total, int X, int Y, int Th,
-                 int NPh, TlPairs tp) {
+                 const unsigned char* __restrict__ fsel, const float* __restrict__ part, int np,
+                 float* __restrict__ total, float* __restrict__ inv_total, int X, int Y, int Th, int NPh, TlPairs tp) {
   using C = Pair2D<PW>;
   __shared__ __align__(16) float2 s_a[C::kXH * C::kStride];
   const int XY = X * Y;
@@ -549,7 +553,6 @@ __global__ void __launch_bounds__(kT, Pair2D<PW>::kMinBlocks)
         for (int q = 0; q < 7; ++q) acc[1][j] = __ffma2_rn(in[j + q], tp.f2p[combo][rr - 1][q], acc[1][j]);
     }
   }
-  const float inv = inv_total[b];
   const int gy = y0 + y;
   const bool vec = (Y & 3) == 0 && gy + PW - 1 < Y;
 #pragma unroll
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(kT, Pair2D<PW>::kMinBlocks)
       if (h == 1 && k1 == k0) continue;  // odd Th: the last pair has one plane
       float o[PW];
 #pragma unroll
-      for (int j = 0; j < PW; ++j) o[j] = fmaxf((h == 0 ? acc[d][j].x : acc[d][j].y) * inv, 0.f);  // posecell_network.py:300
+      for (int j = 0; j < PW; ++j) o[j] = fmaxf(h == 0 ? acc[d][j].x : acc[d][j].y, 0.f);  // posecell_network.py:300 (1/total: see block_tile_total)
       float* dst = Bp + (size_t)(h == 0 ? pl0 : pl1) * XY + gx * Y + gy;
       if (vec) {
 #pragma unroll
@@ -573,12 +576,15 @@ __global__ void __launch_bounds__(kT, Pair2D<PW>::kMinBlocks)
       }
     }
   }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && kp == 0)  // side job of one block per network
+    block_tile_total(part + (size_t)b * np, np, total + b, inv_total + b, reinterpret_cast<float*>(s_a));
 }
 
 // ------------------------------------------------------------------------------------------------
 template <int V, int TK, int MINB>
 __global__ void __launch_bounds__(kT, MINB) k_tl_theta_fin(const float* __restrict__ Bp, float* __restrict__ S,
-                                                     const int* __restrict__ ogi, int XY, int Th, PcTables<float> tab,
+                                                     const int* __restrict__ ogi, const float* __restrict__ inv_total,
+                                                     int XY, int Th, PcTables<float> tab,
                                                      float* __restrict__ part_val, long long* __restrict__ part_idx,
                                                      unsigned* __restrict__ done_ctr, long long* __restrict__ argmax) {
   __shared__ float s_v[kT / 32];
@@ -599,8 +605,9 @@ __global__ void __launch_bounds__(kT, MINB) k_tl_theta_fin(const float* __restri
     const size_t base = (size_t)blockIdx.y * Th * XY + p;
     const bool inner = k_lo >= 3 && k_lo + TK + 3 <= Th;
     const float* f = tab.f1d[ogi[blockIdx.y]];
-    const float f0 = pin(f[0]), f1 = pin(f[1]), f2 = pin(f[2]), f3 = pin(f[3]), f4 = pin(f[4]), f5 = pin(f[5]),
-                f6 = pin(f[6]);
+    const float inv = inv_total[blockIdx.y];  // 1/total of the normalisation (posecell_network.py:344-345), folded into the taps
+    const float f0 = pin(f[0] * inv), f1 = pin(f[1] * inv), f2 = pin(f[2] * inv), f3 = pin(f[3] * inv),
+                f4 = pin(f[4] * inv), f5 = pin(f[5] * inv), f6 = pin(f[6] * inv);
     float w[TK + 6][V];
     load_window<V, TK>(Bp + base, k_lo, XY, Th, inner, w);
     float* q = S + base + (size_t)k_lo * XY;
@@ -671,17 +678,27 @@ __global__ void __launch_bounds__(kT, MINB) k_tl_theta_fin(const float* __restri
   last = __shfl_sync(0xffffffffu, last, 0);
   if (last) {
     __threadfence();
-    const volatile float* pv = part_val + (size_t)blockIdx.y * nslots;
-    const volatile long long* pi = part_idx + (size_t)blockIdx.y * nslots;
+    // One warp is left: batches of eight independent L2 loads per lane (a plain loop over volatile pointers costs
+    // one L2 round trip per iteration, at the very end of the kernel where nothing hides it).
+    const float* pv = part_val + (size_t)blockIdx.y * nslots;
+    const long long* pi = part_idx + (size_t)blockIdx.y * nslots;
     bv = -1.f;
     bi = 0x7fffffffffffffffLL;
-    for (int i = lane; i < nslots; i += 32) {
-      const float v = pv[i];
-      const long long ix = pi[i];
-      if (v > bv || (v == bv && ix < bi)) {
-        bv = v;
-        bi = ix;
+    for (int i0 = lane; i0 < nslots; i0 += 32 * 8) {
+      float v[8];
+      long long ix[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + 32 * u;
+        v[u] = i < nslots ? __ldcg(pv + i) : -1.f;
+        ix[u] = i < nslots ? __ldcg(pi + i) : 0x7fffffffffffffffLL;
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (v[u] > bv || (v[u] == bv && ix[u] < bi)) {
+          bv = v[u];
+          bi = ix[u];
+        }
     }
     warp_best();
     if (lane == 0) argmax[blockIdx.y] = bi;
@@ -723,7 +740,8 @@ int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const fl
     }
   }
   const dim3 g2((X + kYXx - 1) / kYXx, (Y + kYXy - 1) / kYXy, B * Th);
-  k_tl_yx<<<g2, kTyx, 0, st>>>(EI, A, gi, X, Y, Th, p->tl, (float*)p->part_val, p->done_ctr, total, (float*)p->inv_total);
+  k_tl_yx<<<g2, kTyx, 0, st>>>(EI, A, gi, X, Y, Th, p->tl, (float*)p->part_val);
+  const int np = Th * (int)(g2.x * g2.y);
   const int NPh = (Th + 1) / 2;
   // PRS_TILED_PW (tuning knob): columns per thread patch in the plane-pair kernel, 4 (default) or 8
   static const int pw = [] {
@@ -734,25 +752,26 @@ int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const fl
   const dim3 g3p((X + k2pX - 1) / k2pX, (Y + tileY - 1) / tileY, B * NPh);
   if ((long long)g3p.x * g3p.y * g3p.z >= 2 * 148) {  // enough plane pairs to fill the chip: packed FFMA2 variant
     if (pw == 8)
-      k_tl_2d_pair<8><<<g3p, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, NPh, p->tl);
+      k_tl_2d_pair<8><<<g3p, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->part_val, np, total, (float*)p->inv_total, X, Y, Th, NPh, p->tl);
     else
-      k_tl_2d_pair<4><<<g3p, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, NPh, p->tl);
+      k_tl_2d_pair<4><<<g3p, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->part_val, np, total, (float*)p->inv_total, X, Y, Th, NPh, p->tl);
   } else {
     const dim3 g3((X + k2X - 1) / k2X, (Y + k2Y - 1) / k2Y, B * Th);
-    k_tl_2d<<<g3, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->inv_total, X, Y, Th, p->tf);
+    k_tl_2d<<<g3, kT, 0, st>>>(A, Bp, p->shift, p->fsel, (const float*)p->part_val, np, total, (float*)p->inv_total, X, Y, Th, p->tf);
   }
   {
-    // PRS_TILED_FIN (tuning knob): 0 = 2 cells x 8 planes per thread, 1 = 4 x 8, 2 = 2 x 12
+    // PRS_TILED_FIN (tuning knob): cells x planes per thread, 0 = 2 x 8, 1 (default) = 4 x 8, 2 = 2 x 12
     static const int fin = [] {
       const char* e = getenv("PRS_TILED_FIN");
-      return e ? atoi(e) : 0;
+      return e ? atoi(e) : 1;
     }();
 #define PRS_FIN(V_, TK_, MB_)                                                                                      \
   k_tl_theta_fin<V_, TK_, MB_><<<dim3((XY / V_ + kT - 1) / kT, B, (Th + TK_ - 1) / TK_), kT, 0, st>>>(              \
-      Bp, state, p->ogi, XY, Th, p->tf, (float*)p->part_val, p->part_idx, p->done_ctr + B, argmax)
+      Bp, state, p->ogi, (const float*)p->inv_total, XY, Th, p->tf, (float*)p->part_val, p->part_idx,              \
+      p->done_ctr + B, argmax)
     if (XY % 4 == 0 && fin == 1)
       PRS_FIN(4, 8, 4);
-    else if (XY % 2 == 0 && fin == 2)
+    else if (XY % 2 == 0 && fin != 0)
       PRS_FIN(2, 12, 5);
     else if (XY % 2 == 0)
       PRS_FIN(2, 8, 1);
