@@ -324,8 +324,7 @@ __global__ void __launch_bounds__(NT, 1)
               float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
               for (int t = 0; t < 7; ++t) acc = ffma2(in[(x + t + X - 3) % X], cf[t], acc);
-              float a = acc.x - acc.y;
-              a = (a < g_inh) ? 0.f : a - g_inh;
+              const float a = fmaxf((acc.x - acc.y) - g_inh, 0.f);  // == (a < gi) ? 0 : a - gi, one FMNMX
               if (h == 0)
                 keep[x].x = a;
               else
@@ -357,8 +356,10 @@ __global__ void __launch_bounds__(NT, 1)
       }
       __syncthreads();  // publishes A2 and the total
       PRS_STAMP(4);
+      // posecell_network.py:344-345.  The normalisation is a positive scale: max(s*v, 0) = s*max(v, 0) and the
+      // theta pass is linear, so stage 4 runs un-normalised and 1/total is folded into stage 5's seven taps.
       const float tot = s_val[0];
-      const float inv = (tot != 0.f) ? 1.f / tot : 1.f;  // posecell_network.py:344-345
+      const float inv = (tot != 0.f) ? 1.f / tot : 1.f;
 
       // ---- 4. 7x7 periodic correlate of both planes of a pair at once (posecell_network.py:273-274,300);
       //      meanwhile two otherwise idle warps prepare the plan of the next update.
@@ -395,10 +396,8 @@ __global__ void __launch_bounds__(NT, 1)
         }
         float2* o = B2 + kp * XY + x * Y;
 #pragma unroll
-        for (int j = 0; j < Y; ++j) {
-          const float v0 = acc[j].x * inv, v1 = acc[j].y * inv;
-          o[j] = make_float2((v0 < 0.f) ? 0.f : v0, (v1 < 0.f) ? 0.f : v1);  // posecell_network.py:300
-        }
+        for (int j = 0; j < Y; ++j)  // posecell_network.py:300; 1/total is applied by stage 5 (see there)
+          o[j] = make_float2(fmaxf(acc[j].x, 0.f), fmaxf(acc[j].y, 0.f));
       }
       __syncthreads();
       PRS_STAMP(5);
@@ -413,7 +412,7 @@ __global__ void __launch_bounds__(NT, 1)
         float fc[7];
         const float* f1 = tab->f1d[plan[4 * T]];
 #pragma unroll
-        for (int t = 0; t < 7; ++t) fc[t] = f1[t];
+        for (int t = 0; t < 7; ++t) fc[t] = f1[t] * inv;
         float2 pin[NP];
 #pragma unroll
         for (int kk = 0; kk < NP; ++kk) pin[kk] = B2[kk * XY + p];

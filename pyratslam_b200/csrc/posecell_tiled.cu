@@ -259,8 +259,7 @@ __global__ void __launch_bounds__(kTyx) k_tl_yx(const float2* __restrict__ EI, f
       float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
       for (int t = 0; t < 7; ++t) acc = __ffma2_rn(in[jj + t], tp.tx[t], acc);
-      const float d = acc.x - acc.y;
-      a[jj] = (d < g) ? 0.f : d - g;  // posecell_network.py:339-340
+      a[jj] = fmaxf((acc.x - acc.y) - g, 0.f);  // posecell_network.py:339-340: (a < gi) ? 0 : a - gi
     }
     // rows of this segment inside the grid (0 when the column is outside): one compare per element masks the edges
     const int nv = gy < Y ? X - gx0 : 0;
