@@ -86,11 +86,19 @@ PRS_API int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out);
 PRS_API int prs_pc_destroy(prs_pc_handle h);
 /* bytes of one full state tensor [B][Th][X][Y] */
 PRS_API size_t prs_pc_state_bytes(prs_pc_handle h);
-/* which kernel family a step uses: 0 = generic multi-kernel path, 1 = fused SMEM-resident kernel,
- * 2 = tiled large-grid kernels */
+/* which kernel family a step uses: 0 = generic multi-kernel path, 1 = fused SMEM-resident kernel (one CTA per
+ * network), 2 = tiled large-grid kernels, 3 = one network per thread-block cluster */
+#define PRS_PATH_AUTO (-1)
+#define PRS_PATH_GENERIC 0
+#define PRS_PATH_RESIDENT 1
+#define PRS_PATH_TILED 2
+#define PRS_PATH_CLUSTER 3
 PRS_API int prs_pc_path(prs_pc_handle h);
 /* force the generic path (1) or let the plan choose (0); for tests and profiling */
 PRS_API int prs_pc_force_generic(prs_pc_handle h, int on);
+/* choose the kernel family explicitly (PRS_PATH_*, PRS_PATH_AUTO = the plan's own choice); PRS_E_INVALID if the
+ * plan's shape / dtype is not supported by that family; for tests and profiling */
+PRS_API int prs_pc_set_path(prs_pc_handle h, int path);
 
 /* One PoseCellNetwork.update() for all B networks (posecell_network.py:326-353):
  *   state  : device, [B][Th][X][Y] of the plan's dtype, updated in place

@@ -135,8 +135,11 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   ALLOC(p->done_ctr, (size_t)p->B * 2 * sizeof(unsigned));
   cudaMemset(p->done_ctr, 0, (size_t)p->B * 2 * sizeof(unsigned));
   ALLOC(p->tab_dev, sizeof(PcTables<float>));
+  p->forced_path = PRS_PATH_AUTO;
   p->resident_ok = prs_pc_resident_supported(p);
   p->tiled_ok = prs_pc_tiled_supported(p);
+  p->cluster_ok = prs_pc_cluster_supported(p);
+  p->cluster_pref = prs_pc_cluster_preferred(p);
   // The multi-kernel paths need scratch of four state tensors; it is only allocated when such a path
   // can be taken for this plan (prs_pc_force_generic / path_integration allocate it lazily otherwise).
   if (!p->resident_ok) {
@@ -186,8 +189,28 @@ static int ensure_scratch(prs_pc_handle h) {
 }
 
 extern "C" int prs_pc_path(prs_pc_handle h) {
-  if (!h || h->force_generic) return 0;
-  return h->resident_ok ? 1 : (h->tiled_ok ? 2 : 0);
+  if (!h || h->force_generic) return PRS_PATH_GENERIC;
+  if (h->forced_path >= 0) return h->forced_path;
+  if (h->cluster_pref) return PRS_PATH_CLUSTER;
+  return h->resident_ok ? PRS_PATH_RESIDENT : (h->tiled_ok ? PRS_PATH_TILED : PRS_PATH_GENERIC);
+}
+
+static void drop_graphs(prs_pc_handle h);
+
+extern "C" int prs_pc_set_path(prs_pc_handle h, int path) {
+  PRS_REQUIRE(h, "prs_pc_set_path: null handle");
+  const bool ok = path == PRS_PATH_AUTO || path == PRS_PATH_GENERIC || (path == PRS_PATH_RESIDENT && h->resident_ok) ||
+                  (path == PRS_PATH_TILED && h->tiled_ok) || (path == PRS_PATH_CLUSTER && h->cluster_ok);
+  PRS_REQUIRE(ok, "prs_pc_set_path: path %d is not available for a %dx%dx%d %s plan", path, h->X, h->Y, h->Th,
+              h->dtype == PRS_F32 ? "float32" : "float64");
+  if (path == PRS_PATH_GENERIC || path == PRS_PATH_TILED) {
+    int rc = ensure_scratch(h);
+    if (rc != PRS_OK) return rc;
+  }
+  h->forced_path = path;
+  h->force_generic = 0;
+  drop_graphs(h);
+  return PRS_OK;
 }
 
 extern "C" int prs_pc_force_generic(prs_pc_handle h, int on) {
@@ -197,6 +220,11 @@ extern "C" int prs_pc_force_generic(prs_pc_handle h, int on) {
     if (rc != PRS_OK) return rc;
   }
   h->force_generic = on ? 1 : 0;
+  drop_graphs(h);
+  return PRS_OK;
+}
+
+static void drop_graphs(prs_pc_handle h) {
   if (h->hgraph) {  // a captured host-step graph holds the other path's kernels
     cudaGraphExecDestroy(h->hgraph);
     h->hgraph = nullptr;
@@ -205,17 +233,19 @@ extern "C" int prs_pc_force_generic(prs_pc_handle h, int on) {
     cudaGraphExecDestroy(h->sgraph);
     h->sgraph = nullptr;
   }
-  return PRS_OK;
 }
 
 static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st) {
   const size_t es = h->dtype == PRS_F32 ? 4 : 8;
   const int path = prs_pc_path(h);
-  if (path == 1) return prs_pc_resident_step(h, state, odom, T, gi, argmax, total, err, st);
+  if (path == PRS_PATH_RESIDENT) return prs_pc_resident_step(h, state, odom, T, gi, argmax, total, err, st);
   for (int t = 0; t < T; ++t) {
     int rc;
-    if (path == 2)
+    if (path == PRS_PATH_CLUSTER)
+      rc = prs_pc_cluster_step(h, (float*)state, odom + (size_t)t * h->B * 2, (const float*)gi,
+                               argmax + (size_t)t * h->B, (float*)total + (size_t)t * h->B, err, st);
+    else if (path == 2)
       rc = prs_pc_tiled_step(h, (float*)state, odom + (size_t)t * h->B * 2, (const float*)gi, argmax + (size_t)t * h->B,
                              (float*)total + (size_t)t * h->B, err, st);
     else
@@ -239,8 +269,10 @@ extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, con
   cudaStream_t st = (cudaStream_t)stream;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
-  // The fused kernel is one launch; a caller that is capturing its own graph gets plain launches as well.
-  if (prs_pc_path(h) == 1 || cap != cudaStreamCaptureStatusNone) return step_enqueue(h, state, odom, gi, argmax, total, err, st);
+  // The fused kernels are one launch; a caller that is capturing its own graph gets plain launches as well.
+  const int path_now = prs_pc_path(h);
+  if (path_now == PRS_PATH_RESIDENT || path_now == PRS_PATH_CLUSTER || cap != cudaStreamCaptureStatusNone)
+    return step_enqueue(h, state, odom, gi, argmax, total, err, st);
   // Multi-kernel paths: replay the launch sequence as a graph on a private stream, ordered after the caller's
   // stream on entry and before it on exit (no host synchronisation).
   if (!h->ss) {

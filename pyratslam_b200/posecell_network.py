@@ -31,6 +31,9 @@ def _as_np_dtype(dtype):
     raise TypeError("Data type specified is not currently supported: %r" % (dtype,))  # convolution.py:25
 
 
+_PATHS = {0: "generic", 1: "resident", 2: "tiled", 3: "cluster"}
+
+
 class PoseCellEnsemble:
     """B independent pose-cell networks of one shape, resident on one GPU."""
 
@@ -104,8 +107,18 @@ class PoseCellEnsemble:
 
     @property
     def path(self):
-        """``"resident"`` (fused SMEM-resident kernel), ``"tiled"`` (large-grid kernels) or ``"generic"``."""
-        return {0: "generic", 1: "resident", 2: "tiled"}[nat.lib().prs_pc_path(self._h)]
+        """``"resident"`` (fused SMEM-resident kernel, one CTA per network), ``"cluster"`` (one network per
+        thread-block cluster), ``"tiled"`` (large-grid kernels) or ``"generic"``."""
+        return _PATHS[nat.lib().prs_pc_path(self._h)]
+
+    def force_path(self, name):
+        """Choose the kernel family (``"auto"`` or one of the ``path`` names); ``ValueError`` if the plan's shape
+        or dtype is not supported by it.  For tests and profiling."""
+        code = {v: k for k, v in _PATHS.items()}.get(name, -1 if name == "auto" else None)
+        if code is None:
+            raise ValueError("unknown path %r" % (name,))
+        if nat.lib().prs_pc_set_path(self._h, code) != 0:
+            raise ValueError(nat.lib().prs_last_error().decode())
 
     def force_generic(self, on=True):
         nat.check(nat.lib().prs_pc_force_generic(self._h, 1 if on else 0), "prs_pc_force_generic")

@@ -16,7 +16,7 @@ from oracle import posecells as opc
 pytestmark = pytest.mark.gpu
 
 RTOL = {np.float32: 1e-5, np.float64: 1e-12}
-PATHS = ["auto", "generic"]
+PATHS = ["auto", "generic", "resident", "tiled", "cluster"]
 
 
 def _rel(a, b):
@@ -26,9 +26,17 @@ def _rel(a, b):
 def _make(shape, dtype, path, **kw):
     from pyratslam_b200 import PoseCellNetwork
     net = PoseCellNetwork(shape, dtype=dtype, **kw)
-    if path == "generic":
-        net._ens.force_generic(True)
+    _force(net._ens, path)
     return net
+
+
+def _force(ens, path):
+    if path == "auto":
+        return
+    try:
+        ens.force_path(path)
+    except ValueError as e:
+        pytest.skip(str(e))
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -135,8 +143,7 @@ def test_ensemble_against_oracle(dtype, path):
     odom = np.stack([rng.uniform(0, 0.3, (T, B)), rng.uniform(-0.1, 0.1, (T, B))], axis=-1)
     ref_amax, ref_states = opc.run_ensemble(shape, gis, odom)
     ens = PoseCellEnsemble(shape, B, global_inhibition=gis, dtype=dtype)
-    if path == "generic":
-        ens.force_generic(True)
+    _force(ens, path)
     ens.inject(1.0, tuple(s // 2 for s in shape))
     # half the steps one at a time through the host entry, the rest as one multi-step run
     got = [ens.update(odom[t]) for t in range(10)]
@@ -159,13 +166,15 @@ def test_large_grid_one_step_against_oracle():
 
 
 @pytest.mark.parametrize("shape", [(33, 35, 9), (70, 40, 19), (128, 64, 8), (36, 36, 3)])
-def test_tiled_path_shapes_against_oracle(shape):
-    """The large-grid kernels on shapes that exercise their edges: X*Y not a multiple of 4 (scalar accesses),
-    ragged tiles in x and y, theta counts that are not a multiple of the chunk, tiles that wrap on every side.
-    Two packets (one across the periodic corner) and an exact tie for the maximum."""
+@pytest.mark.parametrize("path", ["tiled", "cluster"])
+def test_tiled_path_shapes_against_oracle(shape, path):
+    """The large-grid kernels (and the cluster kernel, where it applies) on shapes that exercise their edges: X*Y
+    not a multiple of 4 (scalar accesses), ragged tiles and segments in x and y, theta counts that are not a
+    multiple of the chunk, tiles that wrap on every side.  Two packets (one across the periodic corner) and an
+    exact tie for the maximum."""
     ref = opc.PoseCellNetwork(shape)
-    net = _make(shape, np.float32, "auto")
-    assert net.path == "tiled"
+    net = _make(shape, np.float32, path)
+    assert net.path == path
     X, Y, Th = shape
     for n in (ref, net):
         n.inject(1.0, (X // 2, Y // 2, Th // 2))
@@ -189,6 +198,28 @@ def test_tiled_path_shapes_against_oracle(shape):
     assert tuple(net.update((0.0, 0.0))) == tuple(ref.update((0.0, 0.0))) == (0, 0, 0)
     assert net.posecells.max() == 0
     ref.global_inhibition = net.global_inhibition = gi0
+
+
+@pytest.mark.parametrize("shape,B", [((21, 21, 36), 1), ((21, 21, 36), 5), ((50, 50, 10), 3), ((9, 8, 7), 2),
+                                     ((17, 23, 12), 1), ((30, 24, 16), 2), ((12, 40, 27), 1)])
+def test_cluster_path_against_oracle(shape, B):
+    """One network per thread-block cluster: cluster sizes 2..8, 1..9 planes per CTA, ragged segments, small
+    ensembles with per-network inhibition and odometry (including a network that dies and a theta shift)."""
+    from pyratslam_b200 import PoseCellEnsemble
+    T = 8
+    rng = np.random.default_rng(sum(shape) + B)
+    gis = np.linspace(0.08, 0.22, B)
+    odom = np.stack([rng.uniform(0, 0.3, (T, B)), rng.uniform(-0.3, 0.3, (T, B))], axis=-1)
+    odom[3] = 0.0
+    ref_amax, ref_states = opc.run_ensemble(shape, gis, odom)
+    ens = PoseCellEnsemble(shape, B, global_inhibition=gis)
+    _force(ens, "cluster")
+    assert ens.path == "cluster"
+    ens.inject(1.0, tuple(s // 2 for s in shape))
+    got = [ens.update(odom[t]) for t in range(4)]
+    got = np.concatenate([np.stack(got), ens.run(odom[4:])])
+    assert np.array_equal(got, ref_amax)
+    assert _rel(ens.posecells, ref_states) <= 1e-5
 
 
 def test_translation_equivariance_large():
