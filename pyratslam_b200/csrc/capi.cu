@@ -138,8 +138,11 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   p->forced_path = PRS_PATH_AUTO;
   p->resident_ok = prs_pc_resident_supported(p);
   p->tiled_ok = prs_pc_tiled_supported(p);
-  p->cluster_ok = prs_pc_cluster_supported(p);
-  p->cluster_pref = prs_pc_cluster_preferred(p);
+  p->cluster_C = prs_pc_cluster_choose(p);
+  p->cluster_ok = p->cluster_C >= 2;
+  // one network per cluster pays when one CTA per network (or four grid-wide launches of a few blocks) would leave
+  // most of the chip idle: a single 21x21x36 network takes 12.5 us against 18.5 us, a 50x50x10 one 16 against 19
+  p->cluster_pref = p->cluster_ok && (long long)p->B * p->cluster_C <= 148;
   // The multi-kernel paths need scratch of four state tensors; it is only allocated when such a path
   // can be taken for this plan (prs_pc_force_generic / path_integration allocate it lazily otherwise).
   if (!p->resident_ok) {

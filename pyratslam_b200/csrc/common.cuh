@@ -88,7 +88,8 @@ struct prs_pc_plan {
   int swarm;
   int force_generic;
   int forced_path;      // -1 = automatic choice, else one of the PRS_PATH_* codes (prs_pc_set_path)
-  int cluster_ok;       // the thread-block-cluster kernel supports this shape/dtype
+  int cluster_C;        // CTAs per network of the thread-block-cluster kernel, 0 if it does not apply to this plan
+  int cluster_ok;       // = cluster_C >= 2
   int cluster_pref;     // ... and the network count is small enough for it to be the automatic choice
   int resident_ok;      // the fused SMEM-resident kernel supports this shape/dtype
   void* tab_dev;        // device copy of PcTables<float> for the resident kernel
@@ -109,8 +110,7 @@ int prs_pc_launch_unravel_pack(prs_pc_plan* p, const long long* argmax, const in
 int prs_pc_launch_plan(prs_pc_plan* p, const double* odom, int* err, cudaStream_t st);
 int prs_pc_launch_sum_final_f32(prs_pc_plan* p, int np, float* total, cudaStream_t st);
 int prs_pc_launch_argmax_final_f32(prs_pc_plan* p, int np, long long* argmax, cudaStream_t st);
-int prs_pc_cluster_supported(const prs_pc_plan* p);
-int prs_pc_cluster_preferred(const prs_pc_plan* p);
+int prs_pc_cluster_choose(const prs_pc_plan* p);
 int prs_pc_cluster_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax,
                         float* total, int* err, cudaStream_t st);
 int prs_pc_resident_supported(const prs_pc_plan* p);

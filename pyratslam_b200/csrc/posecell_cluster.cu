@@ -1,6 +1,6 @@
 // One pose-cell network spread over a thread-block cluster (float32, sm_100a): a low-latency path for a single
 // reference-size network -- simulate.py's 50x50x10 and the ROS node's 21x21x36 -- and for ensembles too small
-// to fill the chip with one CTA per network.  Opt-in in round 1 (see prs_pc_cluster_preferred below).
+// to fill the chip with one CTA per network (the automatic choice while B * C <= 148 CTAs).
 //
 // A network update (ratslam/posecell_network.py:326-353) on ONE SM is bound by that SM's FP32 issue rate
 // (98 FMA per cell: 14 us for 21x21x36, the fused resident kernel); as four grid-wide launches it is bound by
@@ -41,6 +41,11 @@ struct FastDiv {
   explicit FastDiv(int d_) : m((unsigned)(0x100000000ULL / (unsigned)d_) + 1u), d(d_) {}  // on the host, once per launch
   __device__ __forceinline__ int div(int n) const { return (int)__umulhi((unsigned)n, m); }
 };
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_shared_f32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 
 struct ClLayout {  // element counts / strides of the shared-memory arrays, identical on host and device
   int X, Y, XY, P;
@@ -96,7 +101,7 @@ struct ClArgs {
   const double *cos_th, *sin_th;
   double vtrans_scale, vrot_scale;
   int X, Y, Th;
-  FastDiv dY, dX, dRows, dNsx, dNxp, dRows2;  // Y, X, P*X, ceil(X/8), ceil(X/2), (P/2)*ceil(X/2)
+  FastDiv dY, dX, dRows, dNsx, dNxp, dRows2;  // Y, X, P*X, ceil(X/8), ceil(X/2), (P/2)*X
 };
 
 template <int P>
@@ -142,20 +147,29 @@ __global__ void __launch_bounds__(kNT, 1) k_pc_cluster(ClArgs a, PcTables<float>
   if (P % 2 != 0)
     for (int i = tid; i < 98; i += kNT) m->f2d[i / 49][i % 49] = tab.f2d[i / 49][i % 49];
 
-  // ---- load the P + 6 planes this CTA's theta pass reads (plane loop outside: no division per element)
-  if ((XY & 3) == 0) {
-    const int n4 = XY >> 2;
+  // ---- load the P + 6 planes this CTA's theta pass reads: all of a thread's loads are issued before the first
+  //      store (one memory round trip per 512 elements of a plane, not one per plane)
+  {
+    const float* srcp[P + 6];
 #pragma unroll
-    for (int j = 0; j < P + 6; ++j) {
-      const float4* src = reinterpret_cast<const float4*>(gst + (size_t)wrap1(k0 - 3 + j, Th) * XY);
-      float4* dst = reinterpret_cast<float4*>(s_in + j * XY);
-      for (int i = tid; i < n4; i += kNT) dst[i] = src[i];
-    }
-  } else {
+    for (int j = 0; j < P + 6; ++j) srcp[j] = gst + (size_t)wrap1(k0 - 3 + j, Th) * XY;  // Th >= 3
+    if ((XY & 3) == 0) {
+      const int n4 = XY >> 2;
+      for (int i = tid; i < n4; i += kNT) {
+        float4 v[P + 6];
 #pragma unroll
-    for (int j = 0; j < P + 6; ++j) {
-      const float* src = gst + (size_t)wrap1(k0 - 3 + j, Th) * XY;
-      for (int i = tid; i < XY; i += kNT) s_in[j * XY + i] = src[i];
+        for (int j = 0; j < P + 6; ++j) v[j] = reinterpret_cast<const float4*>(srcp[j])[i];
+#pragma unroll
+        for (int j = 0; j < P + 6; ++j) reinterpret_cast<float4*>(s_in + j * XY)[i] = v[j];
+      }
+    } else {
+      for (int i = tid; i < XY; i += kNT) {
+        float v[P + 6];
+#pragma unroll
+        for (int j = 0; j < P + 6; ++j) v[j] = srcp[j][i];
+#pragma unroll
+        for (int j = 0; j < P + 6; ++j) s_in[j * XY + i] = v[j];
+      }
     }
   }
   __syncthreads();
@@ -239,8 +253,10 @@ __global__ void __launch_bounds__(kNT, 1) k_pc_cluster(ClArgs a, PcTables<float>
       float* ap = (P % 2 == 0) ? s_a + (p >> 1) * (L.RA * L.SA * 2) + (p & 1) : s_a + p * (L.RA * L.SA);
       int xd = seg * 8 - pl.x;  // destination row of output 0; rows advance with a periodic wrap
       xd += xd < 0 ? X : 0;
-      float* d = ap + ((xd + 3) * L.SA + yd + 3) * ES;
-      const int rstep = L.SA * ES;
+      // byte address in shared memory, advanced incrementally (left to itself the compiler re-derives the closed
+      // form -- some 30 integer instructions -- for every one of the 8 outputs)
+      unsigned sa = smem_u32(ap) + 4u * (unsigned)(((xd + 3) * L.SA + yd + 3) * ES);
+      const int rstepb = 4 * L.SA * ES, yoffb = 4 * yh * ES, Xb = X * rstepb;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         float2 acc = make_float2(0.f, 0.f);
@@ -249,17 +265,18 @@ __global__ void __launch_bounds__(kNT, 1) k_pc_cluster(ClArgs a, PcTables<float>
         if (seg * 8 + jj < X) {
           const float v = fmaxf((acc.x - acc.y) - g, 0.f);
           psum += v;
-          const int xh = xd < 3 ? X : (xd >= X - 3 ? -X : 0);
-          d[0] = v;
-          if (yh != 0) d[yh * ES] = v;
-          if (xh != 0) {
-            d[xh * rstep] = v;
-            if (yh != 0) d[xh * rstep + yh * ES] = v;
+          const int xoffb = xd < 3 ? Xb : (xd >= X - 3 ? -Xb : 0);
+          st_shared_f32(sa, v);
+          if (yh != 0) st_shared_f32(sa + yoffb, v);
+          if (xoffb != 0) {
+            st_shared_f32(sa + xoffb, v);
+            if (yh != 0) st_shared_f32(sa + xoffb + yoffb, v);
           }
         }
         ++xd;
-        d += rstep;
-        if (xd == X) xd = 0, d -= X * rstep;
+        sa += rstepb;
+        if (xd == X) xd = 0, sa -= Xb;
+        asm volatile("" : "+r"(sa), "+r"(xd));
       }
     }
 #pragma unroll
@@ -276,54 +293,36 @@ __global__ void __launch_bounds__(kNT, 1) k_pc_cluster(ClArgs a, PcTables<float>
 
   // ---- 4. 7x7 correlate (posecell_network.py:273-274) of 2 rows x 8 columns per item, clamp (:300); with an even
   //         number of planes two planes go through it at once as float2 (packed FFMA2, coefficient pairs)
-  if (P % 2 == 0) {
-    const int nxp = (X + 1) / 2;
-    const int rows = (P / 2) * nxp;
-    const FastDiv dR = a.dRows2, dN = a.dNxp;
+  if (P % 2 == 0) {  // item = (plane pair, row, 8 columns): a short critical path matters more here than reuse
+    const int rows = (P / 2) * X;
+    const FastDiv dR = a.dRows2;
     for (int it = tid; it < rows * L.nsy; it += kNT) {
       const int seg = dR.div(it), r = it - seg * rows;
-      const int pp = dN.div(r), x = 2 * (r - pp * nxp);
+      const int pp = dX.div(r), x = r - pp * X;
       const float2* F = m->f2p[pp % 4];
       const float2* ap = reinterpret_cast<const float2*>(s_a) + (pp * L.RA + x) * L.SA + seg * 8;
-      float2 acc[2][8];
+      float2 acc[8];
 #pragma unroll
-      for (int d = 0; d < 2; ++d)
+      for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[d][j] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
+      for (int rr = 0; rr < 7; ++rr) {
         float2 in[14];
 #pragma unroll
         for (int j = 0; j < 14; ++j) in[j] = ap[rr * L.SA + j];
-        if (rr <= 6) {
 #pragma unroll
-          for (int q = 0; q < 7; ++q) {
-            const float2 f = F[rr * 7 + q];
+        for (int q = 0; q < 7; ++q) {
+          const float2 f = F[rr * 7 + q];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[0][j] = __ffma2_rn(in[j + q], f, acc[0][j]);
-          }
-        }
-        if (rr >= 1) {
-#pragma unroll
-          for (int q = 0; q < 7; ++q) {
-            const float2 f = F[(rr - 1) * 7 + q];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[1][j] = __ffma2_rn(in[j + q], f, acc[1][j]);
-          }
+          for (int j = 0; j < 8; ++j) acc[j] = __ffma2_rn(in[j + q], f, acc[j]);
         }
       }
+      float* o0 = s_b + (2 * pp) * XY + x * Y + seg * 8;
 #pragma unroll
-      for (int d = 0; d < 2; ++d) {
-        if (x + d < X) {
-          float* o0 = s_b + (2 * pp) * XY + (x + d) * Y + seg * 8;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (seg * 8 + j < Y) {
-              o0[j] = fmaxf(acc[d][j].x, 0.f);
-              o0[XY + j] = fmaxf(acc[d][j].y, 0.f);
-            }
+      for (int j = 0; j < 8; ++j)
+        if (seg * 8 + j < Y) {
+          o0[j] = fmaxf(acc[j].x, 0.f);
+          o0[XY + j] = fmaxf(acc[j].y, 0.f);
         }
-      }
     }
   } else
   {
@@ -381,16 +380,30 @@ __global__ void __launch_bounds__(kNT, 1) k_pc_cluster(ClArgs a, PcTables<float>
 
   // ---- 5. shifted theta pass (convolution.py:344-359), clamp (:314), -> global.  The window's planes -- own ones
   //         and three neighbours each side, which live in other CTAs (DSMEM) -- are first gathered into s_in.
+  {
+    const float* srcp[P + 6];  // plane k0 - 3 + j lives in CTA ((k mod Th) / P) at local index (k mod Th) % P
 #pragma unroll
-  for (int j = 0; j < P + 6; ++j) {  // plane k0 - 3 + j lives in CTA ((k mod Th) / P) at local index (k mod Th) % P
-    const int k = wrap1(k0 - 3 + j, Th);  // Th >= 3: one conditional add / subtract
-    const int owner = k / P;
-    const float* src = (owner == rank ? s_b : cluster.map_shared_rank(s_b, owner)) + (k - owner * P) * XY;
+    for (int j = 0; j < P + 6; ++j) {
+      const int k = wrap1(k0 - 3 + j, Th);
+      const int owner = k / P;
+      srcp[j] = (owner == rank ? s_b : cluster.map_shared_rank(s_b, owner)) + (k - owner * P) * XY;
+    }
     if ((XY & 3) == 0) {
-      for (int i = tid; i < (XY >> 2); i += kNT)
-        reinterpret_cast<float4*>(s_in + j * XY)[i] = reinterpret_cast<const float4*>(src)[i];
+      for (int i = tid; i < (XY >> 2); i += kNT) {
+        float4 v[P + 6];
+#pragma unroll
+        for (int j = 0; j < P + 6; ++j) v[j] = reinterpret_cast<const float4*>(srcp[j])[i];
+#pragma unroll
+        for (int j = 0; j < P + 6; ++j) reinterpret_cast<float4*>(s_in + j * XY)[i] = v[j];
+      }
     } else {
-      for (int i = tid; i < XY; i += kNT) s_in[j * XY + i] = src[i];
+      for (int i = tid; i < XY; i += kNT) {
+        float v[P + 6];
+#pragma unroll
+        for (int j = 0; j < P + 6; ++j) v[j] = srcp[j][i];
+#pragma unroll
+        for (int j = 0; j < P + 6; ++j) s_in[j * XY + i] = v[j];
+      }
     }
   }
   __syncthreads();
@@ -448,67 +461,102 @@ __global__ void __launch_bounds__(kNT, 1) k_pc_cluster(ClArgs a, PcTables<float>
   cluster.sync();  // CTA 0 has read every candidate: shared memory may go away
 }
 
-int cluster_size_for(int Th) {
-  for (int c = 8; c >= 2; --c)
-    if (Th % c == 0) return c;
-  return 0;
-}
-
 template <int P>
-int launch(prs_pc_plan* p, int C, const ClArgs& args, cudaStream_t st) {
-  const ClLayout L(p->X, p->Y, P);
-  auto kern = k_pc_cluster<P>;
-  static size_t smem_set[64] = {};  // largest dynamic shared-memory size enabled so far, per device
-  PRS_REQUIRE(p->device >= 0 && p->device < 64, "cluster path: device index %d out of range", p->device);
-  if (L.bytes > smem_set[p->device]) {
-    PRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
-    smem_set[p->device] = L.bytes;
-  }
+cudaLaunchConfig_t make_config(const prs_pc_plan* p, int C, size_t smem, cudaStream_t st, cudaLaunchAttribute* attr) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p->B * C, 1, 1);
   cfg.blockDim = dim3(kNT, 1, 1);
-  cfg.dynamicSmemBytes = L.bytes;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PRS_CUDA(cudaLaunchKernelEx(&cfg, kern, args, p->tf, p->tl));
+  return cfg;
+}
+
+// Can a cluster of C CTAs with this much shared memory be co-scheduled on the current device?  Sets the function
+// attributes the launch needs (shared-memory opt-in; non-portable cluster sizes above 8) as a side effect.
+template <int P>
+bool cluster_fits(const prs_pc_plan* p, int C) {
+  const ClLayout L(p->X, p->Y, P);
+  if (L.bytes > (size_t)227 * 1024) return false;
+  auto kern = k_pc_cluster<P>;
+  static size_t smem_set[64] = {};  // the opt-in limit is only ever raised: other plans may need the larger value
+  if (p->device < 0 || p->device >= 64) return false;
+  const size_t want = L.bytes > smem_set[p->device] ? L.bytes : smem_set[p->device];
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want) != cudaSuccess ||
+      (C > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  smem_set[p->device] = want;
+  cudaLaunchAttribute attr[1];
+  cudaLaunchConfig_t cfg = make_config<P>(p, C, L.bytes, nullptr, attr);
+  cfg.gridDim = dim3(C, 1, 1);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return n >= 1;
+}
+
+template <int P>
+int launch(prs_pc_plan* p, int C, const ClArgs& args, cudaStream_t st) {
+  const ClLayout L(p->X, p->Y, P);
+  cudaLaunchAttribute attr[1];
+  cudaLaunchConfig_t cfg = make_config<P>(p, C, L.bytes, st, attr);
+  PRS_CUDA(cudaLaunchKernelEx(&cfg, k_pc_cluster<P>, args, p->tf, p->tl));
   return PRS_OK;
+}
+
+bool fits_dispatch(const prs_pc_plan* p, int C, int P) {
+  switch (P) {
+    case 1: return cluster_fits<1>(p, C);
+    case 2: return cluster_fits<2>(p, C);
+    case 3: return cluster_fits<3>(p, C);
+    case 4: return cluster_fits<4>(p, C);
+    case 5: return cluster_fits<5>(p, C);
+    case 6: return cluster_fits<6>(p, C);
+    case 7: return cluster_fits<7>(p, C);
+    case 8: return cluster_fits<8>(p, C);
+    case 9: return cluster_fits<9>(p, C);
+  }
+  return false;
 }
 
 }  // namespace
 
-// Chosen for float32 plans whose theta count splits into 2..8 CTAs of at most 9 planes, whose per-CTA working set
-// fits shared memory, and whose network count is too small for one-CTA-per-network to fill the chip.
-int prs_pc_cluster_supported(const prs_pc_plan* p) {
+// Plan-time choice of the cluster size: the largest divisor C of Th (up to 16; sizes above 8 are "non-portable" and
+// are only taken if the occupancy query confirms them on this device) whose CTAs hold P = Th / C <= 9 planes within
+// the shared-memory limit.  More CTAs mean less work on each one's critical path: measured 16.0 us (C = 10) against
+// 18.4 us (C = 5) for 50x50x10 and 12.5 us (C = 12) against 14.2 us (C = 6) for 21x21x36.  PRS_CLUSTER_MAX lowers
+// the limit (tuning knob).  Returns C, or 0 if the path does not apply to this plan.
+int prs_pc_cluster_choose(const prs_pc_plan* p) {
   if (p->dtype != PRS_F32) return 0;
   if (p->X < 7 || p->Y < 7) return 0;  // a halo of 3 must be a single periodic image
-  const int C = cluster_size_for(p->Th);
-  if (C == 0) return 0;
-  const int P = p->Th / C;
-  if (P < 1 || P > 9) return 0;
-  const ClLayout L(p->X, p->Y, P);
-  if (L.bytes > (size_t)227 * 1024) return 0;
-  return 1;
-}
-
-// Not the automatic choice yet: measured (graph-replayed dependent updates of one network, round 1) 22 us for
-// 50x50x10 against 19 us for the four tiled launches, and 18.3 us for 21x21x36 against 18.5 us for the one-CTA
-// resident kernel.  The kernel issues only 29 % of its cycles -- its stages are short dependent phases on 16 warps
-// per SM -- so the next step is to spread each stage's items over all threads and overlap the load with stage 1.
-// Selected with prs_pc_set_path(h, PRS_PATH_CLUSTER).
-int prs_pc_cluster_preferred(const prs_pc_plan* p) {
-  (void)p;
+  if ((long long)p->X * p->Y >= 65536) return 0;  // FastDiv range
+  static const int cmax = [] {
+    const char* e = getenv("PRS_CLUSTER_MAX");
+    const int v = e ? atoi(e) : 16;
+    return v < 2 ? 2 : (v > 16 ? 16 : v);
+  }();
+  for (int C = cmax; C >= 2; --C) {
+    if (p->Th % C != 0) continue;
+    const int P = p->Th / C;
+    if (P > 9) break;
+    if (fits_dispatch(p, C, P)) return C;
+  }
   return 0;
 }
 
 int prs_pc_cluster_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax,
                         float* total, int* err, cudaStream_t st) {
-  const int C = cluster_size_for(p->Th);
+  const int C = p->cluster_C;
+  PRS_REQUIRE(C >= 2, "cluster path not available for this plan");
   const int P = p->Th / C;
   ClArgs args{state, odom, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale, p->vrot_scale,
               p->X, p->Y, p->Th};
@@ -518,7 +566,7 @@ int prs_pc_cluster_step(prs_pc_plan* p, float* state, const double* odom, const 
   args.dRows = FastDiv(P * p->X);
   args.dNsx = FastDiv((p->X + 7) / 8);
   args.dNxp = FastDiv(nxp);
-  args.dRows2 = FastDiv(P >= 2 ? (P / 2) * nxp : 1);
+  args.dRows2 = FastDiv(P >= 2 ? (P / 2) * p->X : 1);
   switch (P) {
     case 1: return launch<1>(p, C, args, st);
     case 2: return launch<2>(p, C, args, st);
