@@ -226,6 +226,11 @@ PRS_API int prs_frame_create(prs_pc_handle pc, void* pc_state, const void* gi, v
                      double* odom_host, uint8_t* frame_host, prs_frame_result* result_host, prs_frame_plan** out);
 PRS_API int prs_frame_destroy(prs_frame_plan* plan);
 PRS_API int prs_frame_run(prs_frame_plan* plan, int moved, void* stream);
+/* prs_frame_run without the final synchronisation: the caller waits on `stream` (or an event recorded on it) before
+ * reading result_host.  Two plans that share pc / pc_work / scratch / vt_packed (hence the device-side template
+ * count) but have their own pinned host buffers can be launched alternately on ONE stream: the device runs the
+ * frames back to back while the host prepares the next frame and digests the previous result. */
+PRS_API int prs_frame_launch(prs_frame_plan* plan, int moved, void* stream);
 
 #ifdef __cplusplus
 }

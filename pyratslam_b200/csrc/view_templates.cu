@@ -907,8 +907,8 @@ extern "C" int prs_frame_destroy(prs_frame_plan* f) {
 // One frame.  `moved` != 0: odom_host (given at creation) holds (vtrans, vrot) and the pose cells are updated first.
 // The first call of each kind runs eagerly (it also warms every lazily initialised kernel attribute), the second
 // captures the graph, later ones replay it.
-extern "C" int prs_frame_run(prs_frame_plan* f, int moved, void* stream) {
-  PRS_REQUIRE(f, "prs_frame_run: null plan");
+extern "C" int prs_frame_launch(prs_frame_plan* f, int moved, void* stream) {
+  PRS_REQUIRE(f, "prs_frame_launch: null plan");
   cudaStream_t st = (cudaStream_t)stream;
   const int v = moved ? 1 : 0;
   int rc = PRS_OK;
@@ -925,7 +925,7 @@ extern "C" int prs_frame_run(prs_frame_plan* f, int moved, void* stream) {
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (rc != PRS_OK || e != cudaSuccess) {
       if (g) cudaGraphDestroy(g);
-      if (rc == PRS_OK) prs_set_error("prs_frame_run: capture failed: %s", cudaGetErrorString(e));
+      if (rc == PRS_OK) prs_set_error("prs_frame_launch: capture failed: %s", cudaGetErrorString(e));
       return rc != PRS_OK ? rc : PRS_E_CUDA;
     }
     PRS_CUDA(cudaGraphInstantiate(&f->exec[v], g, 0));
@@ -933,6 +933,12 @@ extern "C" int prs_frame_run(prs_frame_plan* f, int moved, void* stream) {
     f->ready[v] = true;
     PRS_CUDA(cudaGraphLaunch(f->exec[v], st));
   }
-  PRS_CUDA(cudaStreamSynchronize(st));
+  return PRS_OK;
+}
+
+extern "C" int prs_frame_run(prs_frame_plan* f, int moved, void* stream) {
+  int rc = prs_frame_launch(f, moved, stream);
+  if (rc != PRS_OK) return rc;
+  PRS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return PRS_OK;
 }

@@ -120,12 +120,13 @@ class RatslamRos(object):
         self._f_plan_key = key
 
     def __del__(self):
-        p = getattr(self, "_f_plan", None)
-        if p:
-            try:
-                nat.lib().prs_frame_destroy(p)
-            except Exception:
-                pass
+        plans = [getattr(self, "_f_plan", None)] + [sl["plan"] for sl in getattr(self, "_p_slots", [])]
+        for p in plans:
+            if p:
+                try:
+                    nat.lib().prs_frame_destroy(p)
+                except Exception:
+                    pass
 
     def fused_frame(self, twist, im):
         """``odom_callback(twist)`` + ``spin_once()`` + ``vis_callback(im)`` in one device round trip.
@@ -171,6 +172,96 @@ class RatslamRos(object):
         self.published_index.append(int(r.template_index))
         return int(r.template_index), bool(r.created)
 
+    # ------------------------------------------------------------------ pipelined frames
+    # Two frame plans with their own pinned host buffers share the device-side state (pose cells, library,
+    # template count) and are launched alternately on one stream: the device runs frame t while the host stages
+    # frame t+1 and digests the result of frame t-1.  Same decisions as fused_frame; results arrive one call late.
+    def _pipe_setup(self):
+        if not getattr(self, "_fused_ready", False):
+            self._fused_setup()
+        e, v = self.pcn._ens, self.vts
+        self._p_slots = []
+        for _ in range(2):
+            frame = torch.zeros((v.im_x, v.im_y), dtype=torch.uint8).pin_memory()
+            odom = torch.zeros(2, dtype=torch.float64).pin_memory()
+            res = torch.zeros(32, dtype=torch.uint8).pin_memory()
+            self._p_slots.append({"frame": frame, "frame_np": frame.numpy(), "odom": odom, "odom_np": odom.numpy(),
+                                  "res": res, "result": nat.FrameResult.from_address(res.data_ptr()),
+                                  "plan": ctypes.c_void_p(), "event": torch.cuda.Event(), "meta": None})
+        self._p_key = None
+        self._p_inflight = 0
+
+    def _pipe_plans(self):
+        e, v = self.pcn._ens, self.vts
+        key = (v._lib.data_ptr(), v._capacity, v.match_threshold)
+        if self._p_key == key:
+            return
+        assert self._p_inflight == 0
+        torch.cuda.synchronize(e.device)
+        thr = int(min(max(math.floor(v.match_threshold), 0), 0xFFFFFFFF))
+        for sl in self._p_slots:
+            if sl["plan"]:
+                nat.lib().prs_frame_destroy(sl["plan"])
+                sl["plan"] = ctypes.c_void_p()
+            nat.check(nat.lib().prs_frame_create(
+                e._h, e._state.data_ptr(), e._gi.data_ptr(), self._f_pcwork.data_ptr(), v._lib.data_ptr(), v._n,
+                v._capacity, thr, v.mode, v.im_x, v.im_y, v.y_range[0], v.y_range[1], v.y_step, v.x_range[0],
+                v.x_range[1], v.x_step, self._f_scratch.data_ptr(), sl["odom"].data_ptr(), sl["frame"].data_ptr(),
+                sl["res"].data_ptr(), ctypes.byref(sl["plan"])), "prs_frame_create")
+        self._p_key = key
+
+    def pipe_submit(self, slot, twist, im):
+        """Stage and launch one frame in ``slot`` (0 or 1) without waiting for it; ``pipe_finish(slot)`` returns its
+        ``(template_index, created)``.  The previous frame of the same slot must have been finished."""
+        v = self.vts
+        sl = self._p_slots[slot]
+        assert sl["meta"] is None, "slot still in flight"
+        if v._n + self._p_inflight + 2 > v._capacity:   # growing reallocates the library: drain, grow, re-plan
+            raise RuntimeError("pipe_submit: library full; finish the frames in flight and call pipe_grow()")
+        moved = twist is not None and (abs(twist[0]) > 0.001 or abs(twist[1]) > 0.001)   # ros_simulate.py:128
+        vtrans = vrot = 0.0
+        if moved:
+            vtrans, vrot = twist[0] / self.odom_freq, twist[1] / self.odom_freq          # :157-158
+            sl["odom_np"][0], sl["odom_np"][1] = vtrans, vrot
+        sl["frame_np"][...] = im
+        nat.check(nat.lib().prs_frame_launch(sl["plan"], 1 if moved else 0, ctypes.c_void_p(self._f_stream.cuda_stream)),
+                  "prs_frame_launch")
+        sl["event"].record(self._f_stream)
+        sl["meta"] = (moved, vtrans, vrot)
+        self._p_inflight += 1
+
+    def pipe_needs_grow(self):
+        return self.vts._n + self._p_inflight + 2 > self.vts._capacity
+
+    def pipe_grow(self):
+        assert self._p_inflight == 0
+        self.vts._grow(max(self.vts._n + 3, 2 * self.vts._capacity))
+        self._pipe_plans()
+
+    def pipe_finish(self, slot):
+        e, v = self.pcn._ens, self.vts
+        sl = self._p_slots[slot]
+        moved, vtrans, vrot = sl["meta"]
+        sl["event"].synchronize()
+        sl["meta"] = None
+        self._p_inflight -= 1
+        r = sl["result"]
+        if moved:
+            e._raise_on_err(np.array([r.pc_err], dtype=np.int32))
+        X, Y, Th = self.pcn.shape
+        flat = int(r.argmax)
+        pc_max = (flat // (Y * Th), (flat // Th) % Y, flat % Th)
+        self.pcn.max_pc, self.pcn._max_valid = pc_max, self._p_inflight == 0
+        if moved:
+            self.em.update(vtrans, vrot, pc_max)                                          # :136-137
+            self.published_pose.append(self.em.get_current_point())
+        if r.created:
+            v._loc[int(r.n_templates) - 1] = pc_max
+        v._n = int(r.n_templates)
+        v.last_score = None if r.key == (1 << 64) - 1 else int(r.key >> 32)
+        self.published_index.append(int(r.template_index))
+        return int(r.template_index), bool(r.created)
+
     # ros_simulate.py:152-166, one pass of the loop body
     def spin_once(self):
         if self.twist_data:
@@ -180,15 +271,47 @@ class RatslamRos(object):
         return False
 
 
-def replay(frames, odom, fused=False, **kwargs):
+def replay(frames, odom, fused=False, pipelined=False, **kwargs):
     """Run the loop over ``frames[T,256,256]`` (uint8) and ``odom[T,2]``; returns per-frame records.
 
     ``fused=True`` uses ``RatslamRos.fused_frame`` (one device round trip per frame) instead of the three
-    reference-shaped calls; the records are identical."""
+    reference-shaped calls; ``pipelined=True`` additionally overlaps the host's staging and bookkeeping of
+    neighbouring frames with the device work (two alternating frame plans).  The records are identical."""
     node = RatslamRos(**kwargs)
     T = len(frames)
     rec = {"template": np.zeros(T, np.int64), "created": np.zeros(T, np.bool_),
            "argmax": np.zeros((T, 3), np.int64), "n_exp": np.zeros(T, np.int64), "em_xy": np.zeros((T, 2))}
+    if pipelined:
+        if node.inject_energy is not None:
+            raise ValueError("pipelined replay does not support inject_energy (the injection needs the match first)")
+        node._pipe_setup()
+        node.vts._grow(64)
+        node._pipe_plans()
+
+        def finish(t):
+            idx, created = node.pipe_finish(t % 2)
+            rec["argmax"][t] = node.pcn.max_pc
+            rec["template"][t] = idx
+            rec["created"][t] = created
+            rec["n_exp"][t] = len(node.em.experiences)
+            if node.em.current_exp is not None:
+                rec["em_xy"][t] = node.em.get_current_point()
+
+        for t in range(T):
+            if node.pipe_needs_grow():
+                if t >= 1:
+                    finish(t - 1)
+                node.pipe_grow()
+                node.pipe_submit(t % 2, (float(odom[t, 0]), float(odom[t, 1])), frames[t])
+                continue
+            node.pipe_submit(t % 2, (float(odom[t, 0]), float(odom[t, 1])), frames[t])
+            if t >= 1 and node._p_slots[(t - 1) % 2]["meta"] is not None:
+                finish(t - 1)
+        if T and node._p_slots[(T - 1) % 2]["meta"] is not None:
+            finish(T - 1)
+        rec["n_templates"] = len(node.vts.templates)
+        rec["node"] = node
+        return rec
     for t in range(T):
         if fused:
             idx, created = node.fused_frame((float(odom[t, 0]), float(odom[t, 1])), frames[t])

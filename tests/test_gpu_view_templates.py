@@ -220,8 +220,9 @@ def test_replay_loop_matches_reference_fixture(golden):
     g = golden("replay_ros.npz")
     T = int(g["n_frames"])
     frames = synth_frames(np.random.default_rng(int(g["frame_seed"])), T)
-    for dtype, fused in ((np.float32, False), (np.float64, False), (np.float32, True), (np.float64, True)):
-        rec = ros_simulate.replay(frames, g["odom"], fused=fused, dtype=dtype)
+    for dtype, fused, piped in ((np.float32, False, False), (np.float64, False, False), (np.float32, True, False),
+                                (np.float64, True, False), (np.float32, True, True), (np.float64, True, True)):
+        rec = ros_simulate.replay(frames, g["odom"], fused=fused, pipelined=piped, dtype=dtype)
         assert np.array_equal(rec["template"], g["template"])
         assert np.array_equal(rec["created"], g["created"])
         assert np.array_equal(rec["argmax"], g["argmax"])
