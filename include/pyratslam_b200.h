@@ -123,6 +123,15 @@ PRS_API int prs_pc_step_host(prs_pc_handle h, void* state, const double* odom_ho
  * the arg-max already unravelled the way get_pc_max does (posecell_network.py:318) plus the PRS_ERR_* bits. */
 PRS_API int prs_pc_step_host_xyz(prs_pc_handle h, void* state, const double* odom_host, const void* gi, int* result_host,
                          void* stream);
+/* The same step WITHOUT the host waiting for it.  The plan keeps two slots of device staging and two copy streams:
+ * the odometry of this step is copied in (from pinned odom_host) on a copy stream, the update runs on `stream`, the
+ * packed result is copied out (to pinned result_host) on another copy stream.  With one step kept in flight -- two
+ * (odom_host, result_host) pairs used alternately -- every step still moves its inputs in and its result out, but
+ * those copies and the launch overhead overlap the neighbouring steps' kernels.  *slot_out (0 or 1) names the step for
+ * prs_pc_host_result_wait, which blocks until result_host of that step is complete.  At most two steps in flight. */
+PRS_API int prs_pc_step_host_xyz_async(prs_pc_handle h, void* state, const double* odom_host, const void* gi,
+                               int* result_host, void* stream, int* slot_out);
+PRS_API int prs_pc_host_result_wait(prs_pc_handle h, int slot);
 
 /* PoseCellNetwork.path_integration() alone (posecell_network.py:252-314): per-plane shifted 7x7
  * correlate + clamp, theta correlate + clamp; no attractor dynamics, no normalisation. */

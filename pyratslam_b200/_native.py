@@ -47,6 +47,9 @@ _SIGNATURES = {
     "prs_pc_run": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_step_host_xyz": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "prs_pc_step_host_xyz_async": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           ctypes.POINTER(c_int)]),
+    "prs_pc_host_result_wait": (c_int, [c_void_p, c_int]),
     "prs_pc_path_integration": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_inject": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p]),
     "prs_pc_active_work_bytes": (c_size_t, [c_void_p]),

@@ -58,6 +58,15 @@ static void free_plan(prs_pc_plan* p) {
   if (p->hgraph) cudaGraphExecDestroy(p->hgraph);
   if (p->hev) cudaEventDestroy(p->hev);
   if (p->hs) cudaStreamDestroy(p->hs);
+  for (int i = 0; i < 2; ++i) {
+    cudaEvent_t evs[4] = {p->ev_h2d[i], p->ev_k[i], p->ev_done[i], p->ev_d2h[i]};
+    for (cudaEvent_t e : evs)
+      if (e) cudaEventDestroy(e);
+    if (p->d_odom2[i]) cudaFree(p->d_odom2[i]);
+    if (p->d_xyze2[i]) cudaFree(p->d_xyze2[i]);
+  }
+  if (p->cs_in) cudaStreamDestroy(p->cs_in);
+  if (p->cs_out) cudaStreamDestroy(p->cs_out);
   delete p;
 }
 
@@ -363,6 +372,52 @@ static int step_host_xyz_enqueue(prs_pc_handle h, void* state, const double* odo
   rc = prs_pc_launch_unravel_pack(h, h->d_argmax, h->d_err, h->d_xyze, st);
   if (rc != PRS_OK) return rc;
   PRS_CUDA(cudaMemcpyAsync(result_host, h->d_xyze, (size_t)h->B * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return PRS_OK;
+}
+
+extern "C" int prs_pc_step_host_xyz_async(prs_pc_handle h, void* state, const double* odom_host, const void* gi,
+                                          int* result_host, void* stream, int* slot_out) {
+  PRS_REQUIRE(h && state && odom_host && gi && result_host && slot_out, "prs_pc_step_host_xyz_async: null argument");
+  if (int rc_ = prs_pc_check_device(h, "prs_pc_step_host_xyz_async")) return rc_;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->cs_in) {
+    PRS_CUDA(cudaStreamCreateWithFlags(&h->cs_in, cudaStreamNonBlocking));
+    PRS_CUDA(cudaStreamCreateWithFlags(&h->cs_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      PRS_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+      PRS_CUDA(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+      PRS_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+      PRS_CUDA(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+      PRS_CUDA(cudaMalloc((void**)&h->d_odom2[i], (size_t)h->B * 2 * sizeof(double)));
+      PRS_CUDA(cudaMalloc((void**)&h->d_xyze2[i], (size_t)h->B * 4 * sizeof(int)));
+    }
+  }
+  const int s = h->pipe_slot;
+  h->pipe_slot ^= 1;
+  // odometry in, on the copy-in stream, once the kernel that last read this slot's buffer is done
+  if (h->pipe_used[s]) PRS_CUDA(cudaStreamWaitEvent(h->cs_in, h->ev_k[s], 0));
+  PRS_CUDA(cudaMemcpyAsync(h->d_odom2[s], odom_host, (size_t)h->B * 2 * sizeof(double), cudaMemcpyHostToDevice, h->cs_in));
+  PRS_CUDA(cudaEventRecord(h->ev_h2d[s], h->cs_in));
+  PRS_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[s], 0));
+  if (h->pipe_used[s]) PRS_CUDA(cudaStreamWaitEvent(st, h->ev_d2h[s], 0));  // this slot's result buffer is free again
+  int rc = prs_pc_step(h, state, h->d_odom2[s], gi, h->d_argmax, h->d_total, h->d_err, st);
+  if (rc != PRS_OK) return rc;
+  PRS_CUDA(cudaEventRecord(h->ev_k[s], st));
+  rc = prs_pc_launch_unravel_pack(h, h->d_argmax, h->d_err, h->d_xyze2[s], st);
+  if (rc != PRS_OK) return rc;
+  PRS_CUDA(cudaEventRecord(h->ev_done[s], st));
+  // result out, on the copy-out stream
+  PRS_CUDA(cudaStreamWaitEvent(h->cs_out, h->ev_done[s], 0));
+  PRS_CUDA(cudaMemcpyAsync(result_host, h->d_xyze2[s], (size_t)h->B * 4 * sizeof(int), cudaMemcpyDeviceToHost, h->cs_out));
+  PRS_CUDA(cudaEventRecord(h->ev_d2h[s], h->cs_out));
+  h->pipe_used[s] = 1;
+  *slot_out = s;
+  return PRS_OK;
+}
+
+extern "C" int prs_pc_host_result_wait(prs_pc_handle h, int slot) {
+  PRS_REQUIRE(h && (slot == 0 || slot == 1) && h->pipe_used[slot], "prs_pc_host_result_wait: no step was submitted in slot %d", slot);
+  PRS_CUDA(cudaEventSynchronize(h->ev_d2h[slot]));
   return PRS_OK;
 }
 

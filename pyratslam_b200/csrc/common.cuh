@@ -86,6 +86,13 @@ struct prs_pc_plan {
   cudaGraphExec_t sgraph;
   const void* skey[6];  // (state, odom, gi, argmax, total, err)
   int swarm;
+  // prs_pc_step_host_xyz_async: two slots of device staging, copies on their own streams so that the odometry of
+  // step t+1 goes in and the result of step t-1 comes out while the kernel of step t runs
+  cudaStream_t cs_in, cs_out;
+  cudaEvent_t ev_h2d[2], ev_k[2], ev_done[2], ev_d2h[2];
+  double* d_odom2[2];
+  int* d_xyze2[2];
+  int pipe_slot, pipe_used[2];
   int force_generic;
   int forced_path;      // -1 = automatic choice, else one of the PRS_PATH_* codes (prs_pc_set_path)
   int cluster_C;        // CTAs per network of the thread-block-cluster kernel, 0 if it does not apply to this plan

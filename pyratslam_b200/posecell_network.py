@@ -218,6 +218,51 @@ class PoseCellEnsemble:
         self.max_pc = res[:, :3].astype(np.int64)
         return self.max_pc
 
+    # Overlapped host stepping: ``update_submit`` stages one step (pinned odometry in, kernels, packed result out) on
+    # the current stream without waiting; ``update_result`` returns the oldest outstanding step's arg-max cells.  With
+    # one step kept in flight the copies and the launch overhead of step t+1 hide behind the kernel of step t.
+    def update_submit(self, v):
+        if not hasattr(self, "_pipe"):
+            B = self.n_networks
+            self._pipe = [{"odom": torch.zeros((B, 2), dtype=torch.float64).pin_memory(),
+                           "res": torch.zeros((B, 4), dtype=torch.int32).pin_memory(),
+                           "slot": ctypes.c_int(0)} for _ in range(2)]
+            for sl in self._pipe:
+                sl["odom_np"], sl["res_np"] = sl["odom"].numpy(), sl["res"].numpy()
+            self._pipe_head = self._pipe_tail = 0
+        if self._pipe_head - self._pipe_tail >= 2:
+            raise RuntimeError("update_submit: two steps are already in flight; call update_result() first")
+        sl = self._pipe[self._pipe_head % 2]
+        sl["odom_np"][...] = np.asarray(v, dtype=np.float64).reshape(self.n_networks, 2)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().prs_pc_step_host_xyz_async(self._h, self._state.data_ptr(), sl["odom"].data_ptr(),
+                                                           self._gi.data_ptr(), sl["res"].data_ptr(), nat.stream_ptr(),
+                                                           ctypes.byref(sl["slot"])), "prs_pc_step_host_xyz_async")
+        self._pipe_head += 1
+
+    def update_result(self):
+        if not hasattr(self, "_pipe") or self._pipe_head == self._pipe_tail:
+            raise RuntimeError("update_result: no step in flight")
+        sl = self._pipe[self._pipe_tail % 2]
+        self._pipe_tail += 1
+        nat.check(nat.lib().prs_pc_host_result_wait(self._h, sl["slot"].value), "prs_pc_host_result_wait")
+        res = sl["res_np"]
+        if res[:, 3].any():
+            self._raise_on_err(res[:, 3])
+        self.max_pc = res[:, :3].astype(np.int64)
+        return self.max_pc
+
+    def update_stream(self, odom_seq):
+        """Generator over ``update`` results for a sequence of host odometry arrays, one step kept in flight."""
+        first = True
+        for v in odom_seq:
+            self.update_submit(v)
+            if not first:
+                yield self.update_result()
+            first = False
+        if not first:
+            yield self.update_result()
+
     def path_integration(self, v):
         """Path integration only (no DoG / inhibition / normalisation) with host odometry ``[B, 2]``."""
         vv = np.asarray(v, dtype=np.float64).reshape(self.n_networks, 2)

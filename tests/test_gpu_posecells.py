@@ -152,6 +152,29 @@ def test_ensemble_against_oracle(dtype, path):
     assert _rel(ens.posecells, ref_states) <= RTOL[dtype]
 
 
+def test_overlapped_host_stepping_matches_blocking_calls():
+    """update_submit / update_result (one step in flight) return exactly what consecutive update() calls return."""
+    from pyratslam_b200 import PoseCellEnsemble
+    shape, B, T = (21, 21, 36), 300, 9
+    rng = np.random.default_rng(5)
+    gis = np.linspace(0.05, 0.25, B)
+    odom = np.stack([rng.uniform(0, 0.3, (T, B)), rng.uniform(-0.1, 0.1, (T, B))], axis=-1)
+    a = PoseCellEnsemble(shape, B, global_inhibition=gis)
+    b = PoseCellEnsemble(shape, B, global_inhibition=gis)
+    for e in (a, b):
+        e.inject(1.0, (10, 10, 18))
+    want = np.stack([a.update(odom[t]) for t in range(T)])
+    got = np.stack(list(b.update_stream(odom[t] for t in range(T))))
+    assert np.array_equal(got, want) and torch.equal(a.state, b.state)
+    with pytest.raises(RuntimeError):
+        b.update_result()
+    b.update_submit(odom[0])
+    b.update_submit(odom[1])
+    with pytest.raises(RuntimeError):
+        b.update_submit(odom[2])
+    b.update_result(), b.update_result()
+
+
 def test_large_grid_one_step_against_oracle():
     """BASELINE config 3 at full size (256x256x72): two steps against the scipy oracle (a few seconds)."""
     shape = (256, 256, 72)
