@@ -241,6 +241,13 @@ int sweep_grid(long long units_per_warp_total) {
 
 }  // namespace
 
+// Tuning knobs of the sweeps (prs_vt_tune): [0] ring depth of the packed reference-mode sweep (0 = the
+// register-prefetch kernel), [1] CTAs per SM its grid is sized for, [2] ring depth of the float32 reference-mode
+// sweep (0 = the register kernel), [3] CTAs per SM of that ring sweep.
+static int g_vt_knob[4] = {4, 5, 2, 3};  // measured best on B200 (bench_tools/vt_tune.py)
+static int launch_f32_ring(int depth, int ctas_per_sm, const float* lib, long long n, const float* query,
+                           long long base_index, unsigned long long* key_out, float* scores, cudaStream_t st);
+
 extern "C" int prs_vt_extract_u8(const uint8_t* frame, int im_rows, int im_cols, int row_lo, int row_hi, int row_step,
                                  int col_lo, int col_hi, int col_step, uint8_t* out, int n_rows, int n_cols,
                                  void* stream) {
@@ -285,6 +292,8 @@ extern "C" int prs_vt_sweep_f32(const float* lib, long long n, const float* quer
   PRS_CUDA(cudaMemsetAsync(key_out, 0xff, sizeof(unsigned long long), st));
   if (n == 0) return PRS_OK;
   int grid = sweep_grid(n);
+  if (mode == PRS_VT_MODE_REF && g_vt_knob[2] != 0)
+    return launch_f32_ring(g_vt_knob[2], g_vt_knob[3], lib, n, query, base_index, key_out, scores, st);
   if (mode == PRS_VT_MODE_REF)
     k_vt_sweep_f32<PRS_VT_MODE_REF><<<grid, kVtThreads, 0, st>>>(lib, n, query, base_index, key_out, scores);
   else
@@ -505,6 +514,262 @@ __global__ void __launch_bounds__(kPkThreads)  // 96 registers (15 interleaved c
   }
 }
 
+// ---- the same sweep fed by warp-private rings of TMA bulk copies -----------------------------------------
+// The register-prefetch kernel above keeps ONE row (1 KB per warp) in flight: 20 warps x 1 KB x 148 SMs = 3 MB,
+// less than half of what Little's law asks for at 6.5 TB/s x ~1 us.  Here every warp owns a ring of D slots of
+// 2 KB (two stored rows of its 32 templates) with one mbarrier each; one elected lane refills a slot with one
+// cp.async.bulk as soon as the warp has consumed it, so 2 D KB per warp are always in flight and the loads cost
+// no registers and no LSU issue slots beyond two LDS.128 per row.  A group is 16 ring items: rows 1..30 in
+// pairs (rows 0 and 31 are never read in reference mode) and the row-sum block; 16 / D fills per slot and
+// group is even, so the mbarrier parity of an item is a compile-time constant.
+__device__ __forceinline__ uint32_t vt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void vt_mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void vt_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// one ring fill: expect BYTES, then the bulk copy global -> shared that completes them on the barrier.  The
+// offset is an immediate of the instruction: handed over as a pointer, every item's address becomes its own
+// loop-carried 64-bit induction variable (measured: 168 registers instead of 96).
+template <int OFF, int BYTES>
+__device__ __forceinline__ void vt_ring_fill(uint32_t dst, const void* base, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(BYTES) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1+%2], %3, [%4];" ::"r"(dst),
+               "l"(base), "n"(OFF), "n"(BYTES), "r"(bar)
+               : "memory");
+}
+// one elected lane of a converged warp (the form ptxas keeps on the uniform datapath)
+__device__ __forceinline__ bool vt_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// A ring item is TWO stored rows (2 KB): rows 2j+1 and 2j+2 for j < 15, then the row-sum block (j = 15).
+constexpr int kItemBytes = 2048;
+constexpr int kItemsPerGroup = 16;
+__host__ __device__ constexpr int pk_item_off(int j) { return (j < 15 ? 2 * j + 1 : 32) * 1024; }
+
+template <int D, int S>
+struct RingPrologue {
+  __device__ __forceinline__ static void run(uint32_t ring, uint32_t bars, const char* gb) {
+    if constexpr (S < D) {
+      vt_ring_fill<pk_item_off(S), kItemBytes>(ring + S * kItemBytes, gb, bars + S * 8);
+      RingPrologue<D, S + 1>::run(ring, bars, gb);
+    }
+  }
+};
+
+template <int D, int J>
+struct RingItems {
+  // ring / bars: shared addresses of this warp's slots and barriers; gb / nb: this group and the warp's next one
+  __device__ __forceinline__ static void run(uint32_t ring, uint32_t bars, const char* gb, const char* nb, int lane,
+                                             uint32_t (&cnt)[15], uint4 (&rs)[4]) {
+    if constexpr (J < kItemsPerGroup) {
+      constexpr int slot = J % D;
+      const uint32_t sl = ring + slot * kItemBytes + lane * 16;
+      vt_mbar_wait(bars + slot * 8, (J / D) & 1);
+      const uint4 lo0 = lds_u4(sl), hi0 = lds_u4(sl + 512), lo1 = lds_u4(sl + 1024), hi1 = lds_u4(sl + 1536);
+      if constexpr (J < 15) {
+        ref_row<2 * J + 1>(lo0, hi0, cnt);
+        ref_row<2 * J + 2>(lo1, hi1, cnt);
+      } else {
+        rs[0] = lo0, rs[1] = hi0, rs[2] = lo1, rs[3] = hi1;
+      }
+      // the slot's contents are in registers (the compares above consumed them): refill it with item J + D
+      __syncwarp();
+      if (vt_elect_one()) {
+        if constexpr (J + D < kItemsPerGroup)
+          vt_ring_fill<pk_item_off(J + D), kItemBytes>(ring + slot * kItemBytes, gb, bars + slot * 8);
+        else if (nb != nullptr)
+          vt_ring_fill<pk_item_off((J + D) % kItemsPerGroup), kItemBytes>(ring + slot * kItemBytes, nb, bars + slot * 8);
+      }
+      RingItems<D, J + 1>::run(ring, bars, gb, nb, lane, cnt, rs);
+    }
+  }
+};
+
+template <int D>
+__global__ void __launch_bounds__(kPkThreads, 5)  // 96 registers: the query planes stay constant-bank operands
+    k_vt_sweep_packed_ref_ring(const uint4* __restrict__ packed, long long n, long long base_index,
+                               unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores,
+                               const int* __restrict__ n_dev) {
+  static_assert(kItemsPerGroup % D == 0 && (kItemsPerGroup / D) % 2 == 0, "the parity of an item must not depend on the group");
+  extern __shared__ __align__(128) unsigned char vt_ring_smem[];
+  if (n_dev != nullptr) n = *n_dev;
+  const int lane = threadIdx.x & 31;
+  const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform, and known to be
+  const long long n_groups = (n + 31) >> 5;
+  const long long warp0 = (long long)blockIdx.x * (kPkThreads / 32) + wid;
+  const long long n_warps = (long long)gridDim.x * (kPkThreads / 32);
+  const uint32_t ring = vt_smem_u32(vt_ring_smem) + wid * D * kItemBytes;
+  const uint32_t bars = vt_smem_u32(vt_ring_smem) + (kPkThreads / 32) * D * kItemBytes + wid * D * 8;
+  constexpr long long kGroupBytes = (long long)kGroupU4 * 16;
+  if (vt_elect_one()) {
+#pragma unroll
+    for (int s = 0; s < D; ++s) vt_mbar_init(bars + s * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp0 < n_groups) {
+      const char* gb = reinterpret_cast<const char*>(packed) + warp0 * kGroupBytes;
+      RingPrologue<D, 0>::run(ring, bars, gb);
+    }
+  }
+  __syncwarp();
+  unsigned long long best = ~0ull;
+  for (long long g = warp0; g < n_groups; g += n_warps) {
+    const char* gb = reinterpret_cast<const char*>(packed) + g * kGroupBytes;
+    const char* nb = (g + n_warps < n_groups) ? gb + n_warps * kGroupBytes : nullptr;
+    uint32_t cnt[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) cnt[i] = 0;
+    uint4 rs[4];
+    RingItems<D, 0>::run(ring, bars, gb, nb, lane, cnt, rs);
+    uint32_t R[32];
+#pragma unroll
+    for (int w4 = 0; w4 < 4; ++w4) {
+      const uint32_t ww[4] = {rs[w4].x, rs[w4].y, rs[w4].z, rs[w4].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        R[(w4 * 4 + j) * 2] = ww[j] & 0xffffu;
+        R[(w4 * 4 + j) * 2 + 1] = ww[j] >> 16;
+      }
+    }
+    uint32_t A = 0;
+#pragma unroll
+    for (int r = 1; r <= 16; ++r) A += R[r];
+    const uint32_t bq = c_vtq[256];
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int o = -7; o <= 7; ++o) {
+      const uint32_t sc = A + 256u * cnt[o + 7] - bq;
+      m = min(m, sc);
+      if (o < 7) A = A - R[8 + o] + R[24 + o];
+    }
+    const long long ti = g * 32 + lane;
+    if (ti < n) {
+      const unsigned long long key = ((unsigned long long)m << 32) | (unsigned long long)(base_index + ti);
+      best = key < best ? key : best;
+      if (scores != nullptr) scores[ti] = m;
+    }
+  }
+  __shared__ unsigned long long sm[kPkThreads / 32];
+  best = warp_min_u64(best);
+  if (lane == 0) sm[wid] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long k = sm[0];
+#pragma unroll
+    for (int i = 1; i < kPkThreads / 32; ++i) k = sm[i] < k ? sm[i] : k;
+    if (k != ~0ull) atomicMin(key_out, k);
+  }
+}
+
+// ---- float32 library, reference mode, fed the same way ----------------------------------------------------
+// k_vt_sweep_f32 loads a template's 30 rows into registers and only then starts to compare: a warp has nothing
+// in flight while it computes.  Here a warp owns a ring of D templates (rows 1..30 = 3840 contiguous bytes each,
+// one bulk copy), so D templates per warp are always on their way while one is being compared out of shared
+// memory.  Same arithmetic in the same order as k_vt_sweep_f32: the scores are bit-identical.
+constexpr int kF32ItemBytes = 30 * 32 * 4;
+constexpr int kF32RingThreads = 128;
+
+template <int D>
+__global__ void __launch_bounds__(kF32RingThreads)
+    k_vt_sweep_f32_ring(const float* __restrict__ lib, long long n, const float* __restrict__ query, long long base_index,
+                        unsigned long long* __restrict__ key_out, float* __restrict__ scores) {
+  using S = VtShape<PRS_VT_MODE_REF>;
+  extern __shared__ __align__(128) unsigned char vt_ring_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const long long warp0 = (long long)blockIdx.x * (kF32RingThreads / 32) + wid;
+  const long long n_warps = (long long)gridDim.x * (kF32RingThreads / 32);
+  const uint32_t ring = vt_smem_u32(vt_ring_smem) + wid * D * kF32ItemBytes;
+  const uint32_t bars = vt_smem_u32(vt_ring_smem) + (kF32RingThreads / 32) * D * kF32ItemBytes + wid * D * 8;
+  const char* base = reinterpret_cast<const char*>(lib) + 128;  // row 1 of template 0
+  if (vt_elect_one()) {
+#pragma unroll
+    for (int s = 0; s < D; ++s) vt_mbar_init(bars + s * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < D; ++s)
+      if (warp0 + s * n_warps < n)
+        vt_ring_fill<0, kF32ItemBytes>(ring + s * kF32ItemBytes, base + (warp0 + s * n_warps) * 4096, bars + s * 8);
+  }
+  __syncwarp();
+  float q[S::NS];
+#pragma unroll
+  for (int s = 0; s < S::NS; ++s) q[s] = query[(S::S0 + s) * 32 + lane];
+  unsigned long long best = ~0ull;
+  int slot = 0;
+  uint32_t parity = 0;
+  for (long long ti = warp0; ti < n; ti += n_warps) {
+    const uint32_t sl = ring + slot * kF32ItemBytes;
+    vt_mbar_wait(bars + slot * 8, parity);
+    float a[S::T1 - S::T0];
+#pragma unroll
+    for (int t = 0; t < S::T1 - S::T0; ++t)
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a[t]) : "r"(sl + t * 128 + lane * 4));
+    __syncwarp();
+    if (vt_elect_one()) {
+      const long long nt = ti + D * n_warps;
+      if (nt < n) vt_ring_fill<0, kF32ItemBytes>(sl, base + nt * 4096, bars + slot * 8);
+    }
+    if (++slot == D) {
+      slot = 0;
+      parity ^= 1u;
+    }
+    float acc[S::NACC];
+#pragma unroll
+    for (int i = 0; i < S::NACC; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int t = S::T0; t < S::T1; ++t) {
+#pragma unroll
+      for (int s = 0; s < S::NS; ++s) {
+        if (S::valid(t, S::S0 + s)) acc[S::off(t, S::S0 + s)] += fabsf(a[t - S::T0] - q[s]);
+      }
+    }
+    int obase = 0;
+    Butterfly<S::NACC, 16, float>::run(acc, lane, obase);
+    float m = (obase < S::NOFF) ? acc[0] : INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    unsigned long long key = ((unsigned long long)__float_as_uint(m) << 32) | (unsigned long long)(base_index + ti);
+    best = key < best ? key : best;
+    if (scores != nullptr && lane == 0) scores[ti] = m;
+  }
+  __shared__ unsigned long long sm[kF32RingThreads / 32];
+  best = warp_min_u64(best);
+  if (lane == 0) sm[wid] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long k = sm[0];
+#pragma unroll
+    for (int i = 1; i < kF32RingThreads / 32; ++i) k = sm[i] < k ? sm[i] : k;
+    if (k != ~0ull) atomicMin(key_out, k);
+  }
+}
+
 // Circular mode (all 32 cyclic row shifts; extension).  The shift of a (stored row t, query row s) pair is
 // (t - s) mod 32, which depends on the run-time row t -- but only through t mod 8 once the 32 counters are kept
 // in registers and ROTATED by eight places after every eight stored rows: inside a block of eight rows the
@@ -582,6 +847,76 @@ __global__ void __launch_bounds__(kPkThreads, 4)
   }
 }
 
+
+extern "C" int prs_vt_tune(int knob, int value) {
+  PRS_REQUIRE(knob >= 0 && knob < 4, "prs_vt_tune: unknown knob %d", knob);
+  if (knob == 0) PRS_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8, "prs_vt_tune: ring depth must be 0, 2, 4 or 8");
+  if (knob == 2) PRS_REQUIRE(value >= 0 && value <= 4, "prs_vt_tune: float32 ring depth must be in 0..4");
+  if (knob == 1 || knob == 3) PRS_REQUIRE(value >= 1 && value <= 32, "prs_vt_tune: CTAs per SM must be in 1..32");
+  g_vt_knob[knob] = value;
+  return PRS_OK;
+}
+
+template <int D>
+static int launch_f32_ring_d(int blocks, const float* lib, long long n, const float* query, long long base_index,
+                             unsigned long long* key_out, float* scores, cudaStream_t st) {
+  constexpr int smem = (kF32RingThreads / 32) * D * (kF32ItemBytes + 8);
+  if (smem > 48 * 1024)
+    PRS_CUDA(cudaFuncSetAttribute(k_vt_sweep_f32_ring<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_vt_sweep_f32_ring<D><<<blocks, kF32RingThreads, smem, st>>>(lib, n, query, base_index, key_out, scores);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
+static int launch_f32_ring(int depth, int ctas_per_sm, const float* lib, long long n, const float* query,
+                           long long base_index, unsigned long long* key_out, float* scores, cudaStream_t st) {
+  long long blocks = (n + (kF32RingThreads / 32) - 1) / (kF32RingThreads / 32);
+  if (blocks > 148LL * ctas_per_sm) blocks = 148LL * ctas_per_sm;
+  switch (depth) {
+    case 1: return launch_f32_ring_d<1>((int)blocks, lib, n, query, base_index, key_out, scores, st);
+    case 2: return launch_f32_ring_d<2>((int)blocks, lib, n, query, base_index, key_out, scores, st);
+    case 3: return launch_f32_ring_d<3>((int)blocks, lib, n, query, base_index, key_out, scores, st);
+    default: return launch_f32_ring_d<4>((int)blocks, lib, n, query, base_index, key_out, scores, st);
+  }
+}
+
+template <int D>
+static int launch_ref_ring(int blocks, const uint4* packed, long long n, long long base_index, unsigned long long* key_out,
+                           uint32_t* scores, const int* n_dev, cudaStream_t st) {
+  constexpr int smem = (kPkThreads / 32) * D * (kItemBytes + 8);
+  if (smem > 48 * 1024)  // per device; cheap enough to repeat
+    PRS_CUDA(cudaFuncSetAttribute(k_vt_sweep_packed_ref_ring<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_vt_sweep_packed_ref_ring<D><<<blocks, kPkThreads, smem, st>>>(packed, n, base_index, key_out, scores, n_dev);
+  return PRS_OK;
+}
+
+// n: the library size the kernel uses when n_dev is NULL; n_grid: the size the grid is laid out for
+static int launch_packed_sweep(const uint4* packed, long long n, long long n_grid, int mode, long long base_index,
+                               unsigned long long* key_out, uint32_t* scores, const int* n_dev, cudaStream_t st) {
+  const long long groups = (n_grid + 31) / 32;
+  long long blocks = (groups + (kPkThreads / 32) - 1) / (kPkThreads / 32);
+  if (blocks < 1) blocks = 1;
+  if (mode == PRS_VT_MODE_REF) {
+    const int depth = g_vt_knob[0];
+    const long long cap = 148LL * (depth ? g_vt_knob[1] : 16);
+    if (blocks > cap) blocks = cap;
+    int rc = PRS_OK;
+    switch (depth) {
+      case 2: rc = launch_ref_ring<2>((int)blocks, packed, n, base_index, key_out, scores, n_dev, st); break;
+      case 4: rc = launch_ref_ring<4>((int)blocks, packed, n, base_index, key_out, scores, n_dev, st); break;
+      case 8: rc = launch_ref_ring<8>((int)blocks, packed, n, base_index, key_out, scores, n_dev, st); break;
+      default:
+        k_vt_sweep_packed_ref<<<(int)blocks, kPkThreads, 0, st>>>(packed, n, base_index, key_out, scores, n_dev);
+    }
+    if (rc != PRS_OK) return rc;
+  } else {
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    k_vt_sweep_packed_circ<<<(int)blocks, kPkThreads, 0, st>>>(packed, n, base_index, key_out, scores, n_dev);
+  }
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
 extern "C" size_t prs_vt_packed_bytes(long long n) {
   return (size_t)((n + 31) / 32) * kGroupU4 * sizeof(uint4);
 }
@@ -615,17 +950,7 @@ extern "C" int prs_vt_sweep_packed_u8(const void* packed, long long n, const uin
   // query -> bit planes -> constant bank (stream ordered; one query in flight per device)
   k_vt_pack_query<<<1, 32, 0, st>>>(query, (uint32_t*)scratch);
   PRS_CUDA(cudaMemcpyToSymbolAsync(c_vtq, scratch, (32 * 8 + 2) * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
-  const long long groups = (n + 31) / 32;
-  long long blocks = (groups + (kPkThreads / 32) - 1) / (kPkThreads / 32);
-  const long long cap = 148LL * 16;
-  if (blocks > cap) blocks = cap;
-  if (mode == PRS_VT_MODE_REF)
-    k_vt_sweep_packed_ref<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)packed, n, base_index, key_out, scores, nullptr);
-  else
-    k_vt_sweep_packed_circ<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)packed, n, base_index, key_out, scores,
-                                                              nullptr);
-  PRS_CUDA(cudaGetLastError());
-  return PRS_OK;
+  return launch_packed_sweep((const uint4*)packed, n, n, mode, base_index, key_out, scores, nullptr, st);
 }
 
 // =============================================================================================
@@ -849,14 +1174,8 @@ static int frame_enqueue(prs_frame_plan* f, bool moved, cudaStream_t st) {
   k_vt_pack_query<<<1, 32, 0, st>>>(d_tpl, d_planes);
   PRS_CUDA(cudaMemcpyToSymbolAsync(c_vtq, d_planes, (32 * 8 + 2) * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
   // grid sized for the capacity; the kernels read the live count from device memory
-  const long long groups = ((long long)f->capacity + 31) / 32;
-  long long blocks = (groups + (kPkThreads / 32) - 1) / (kPkThreads / 32);
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  if (blocks < 1) blocks = 1;
-  if (f->mode == PRS_VT_MODE_REF)
-    k_vt_sweep_packed_ref<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)f->vt_packed, 0, 0, d_key, nullptr, f->d_n);
-  else
-    k_vt_sweep_packed_circ<<<(int)blocks, kPkThreads, 0, st>>>((const uint4*)f->vt_packed, 0, 0, d_key, nullptr, f->d_n);
+  rc = launch_packed_sweep((const uint4*)f->vt_packed, 0, f->capacity, f->mode, 0, d_key, nullptr, f->d_n, st);
+  if (rc != PRS_OK) return rc;
   if (moved) PRS_CUDA(cudaStreamWaitEvent(st, f->ev_join, 0));  // join: the decision reports the new arg-max
   k_vt_decide_append<<<1, 32, 0, st>>>(d_key, d_tpl, (uint4*)f->vt_packed, 0, f->threshold, d_argmax, d_err, d_res, f->d_n);
   PRS_CUDA(cudaGetLastError());
