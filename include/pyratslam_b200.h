@@ -246,6 +246,16 @@ PRS_API int prs_frame_run(prs_frame_plan* plan, int moved, void* stream);
  * frames back to back while the host prepares the next frame and digests the previous result. */
 PRS_API int prs_frame_launch(prs_frame_plan* plan, int moved, void* stream);
 
+/* The whole loop of ros_simulate.py:152-166 over recorded arrays in one call: frame t is staged into the pinned
+ * buffers of plans[t % n_plans] and launched while earlier frames are still running; a plan is reused once its frame
+ * has finished and its result has been copied to results[].  The plans must share pc / pc_state / pc_work / vt_packed /
+ * scratch and differ only in their pinned host buffers; the library needs room for T more templates.
+ *   frames : host uint8 [T][im_rows][im_cols]     odom : host double [T][2] = (vtrans, vrot) as given to update()
+ *   moved  : host uint8 [T], 0 = the twist was below the 0.001 gate (ros_simulate.py:128): no pose-cell update
+ *   results: host prs_frame_result [T]            stream: a non-default stream */
+PRS_API int prs_replay_run(prs_frame_plan* const* plans, int n_plans, const uint8_t* frames, const double* odom,
+                   const uint8_t* moved, int T, prs_frame_result* results, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,7 @@ _SIGNATURES["prs_frame_create"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_
 _SIGNATURES["prs_frame_destroy"] = (c_int, [c_void_p])
 _SIGNATURES["prs_frame_run"] = (c_int, [c_void_p, c_int, c_void_p])
 _SIGNATURES["prs_frame_launch"] = (c_int, [c_void_p, c_int, c_void_p])
+_SIGNATURES["prs_replay_run"] = (c_int, [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p])
 
 
 class FrameResult(Structure):

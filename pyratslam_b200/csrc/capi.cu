@@ -304,7 +304,7 @@ extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, con
   PRS_CUDA(cudaEventRecord(h->sev_in, st));
   PRS_CUDA(cudaStreamWaitEvent(h->ss, h->sev_in, 0));
   if (odom != h->d_odom)
-    PRS_CUDA(cudaMemcpyAsync(h->d_odom, odom, (size_t)h->B * 2 * sizeof(double), cudaMemcpyDeviceToDevice, h->ss));
+    PRS_CUDA(cudaMemcpyAsync(h->d_odom, odom, (size_t)h->B * 2 * sizeof(double), cudaMemcpyDefault, h->ss));
   if (!same) {
     if (h->sgraph) {
       cudaGraphExecDestroy(h->sgraph);

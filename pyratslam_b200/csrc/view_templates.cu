@@ -20,6 +20,7 @@
 // float32 ("profiles", BASELINE config 5): one template per warp, lane == column,
 // score = sum |T - q| accumulated in float32.
 #include <new>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -248,10 +249,9 @@ static int g_vt_knob[4] = {4, 5, 2, 3};  // measured best on B200 (bench_tools/v
 static int launch_f32_ring(int depth, int ctas_per_sm, const float* lib, long long n, const float* query,
                            long long base_index, unsigned long long* key_out, float* scores, cudaStream_t st);
 
-extern "C" int prs_vt_extract_u8(const uint8_t* frame, int im_rows, int im_cols, int row_lo, int row_hi, int row_step,
-                                 int col_lo, int col_hi, int col_step, uint8_t* out, int n_rows, int n_cols,
-                                 void* stream) {
-  PRS_REQUIRE(frame && out, "prs_vt_extract_u8: null argument");
+// the boolean mask of view_templates.py:48-57 must select exactly n_rows x n_cols pixels inside the frame
+static int check_mask(int im_rows, int im_cols, int row_lo, int row_hi, int row_step, int col_lo, int col_hi, int col_step,
+                      int n_rows, int n_cols) {
   PRS_REQUIRE(row_step >= 2 && col_step >= 2, "prs_vt_extract_u8: step must be >= 2 (step 1 selects nothing)");
   auto count = [](int lo, int hi, int step) { return (hi - lo - 1) - (hi - lo - 1) / step; };
   PRS_REQUIRE(row_lo >= 0 && col_lo >= 0 && row_hi <= im_rows && col_hi <= im_cols && row_hi > row_lo && col_hi > col_lo,
@@ -259,6 +259,14 @@ extern "C" int prs_vt_extract_u8(const uint8_t* frame, int im_rows, int im_cols,
   PRS_REQUIRE(count(row_lo, row_hi, row_step) == n_rows && count(col_lo, col_hi, col_step) == n_cols,
               "prs_vt_extract_u8: mask selects %dx%d pixels, not %dx%d", count(row_lo, row_hi, row_step),
               count(col_lo, col_hi, col_step), n_rows, n_cols);
+  return PRS_OK;
+}
+
+extern "C" int prs_vt_extract_u8(const uint8_t* frame, int im_rows, int im_cols, int row_lo, int row_hi, int row_step,
+                                 int col_lo, int col_hi, int col_step, uint8_t* out, int n_rows, int n_cols,
+                                 void* stream) {
+  PRS_REQUIRE(frame && out, "prs_vt_extract_u8: null argument");
+  if (int rc = check_mask(im_rows, im_cols, row_lo, row_hi, row_step, col_lo, col_hi, col_step, n_rows, n_cols)) return rc;
   int total = n_rows * n_cols;
   k_vt_extract_u8<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(frame, im_cols, row_lo, row_step, col_lo,
                                                                          col_step, out, n_rows, n_cols);
@@ -1124,6 +1132,142 @@ extern "C" int prs_vt_sweep_any_f32(const float* lib, long long n, const float* 
 
 
 // ---------------------------------------------------------------------------------------------
+// Short frame chain for replayed frames over small libraries.  With the plan's host buffers pinned (and therefore
+// mapped into the device's address space) the template branch of a frame is three kernels and no copy node:
+//   k_vt_frame_prepare   reads the 32x32 masked pixels straight from the pinned frame (about 2 KB cross the bus
+//                        instead of the whole 64 KB frame), builds the template, its bit planes and row sums,
+//                        resets the key
+//   k_vt_sweep_packed_ref_small   the bit-sliced sweep with the query planes in shared memory instead of the
+//                        constant bank (no cudaMemcpyToSymbol node) and one block per group of 32 templates;
+//                        only used below kSmallLibrary templates
+//   k_vt_decide_append   writes its 32-byte result straight into the pinned result buffer
+// and the pose-cell kernel reads its two doubles of odometry from the pinned buffer as well.
+constexpr int kSmallLibrary = 1 << 16;
+
+__global__ void __launch_bounds__(1024)
+    k_vt_frame_prepare(const uint8_t* __restrict__ frame, int im_cols, int row_lo, int row_step, int col_lo, int col_step,
+                       uint8_t* __restrict__ tpl, uint32_t* __restrict__ planes, unsigned long long* __restrict__ key) {
+  __shared__ uint32_t s_sum[32];
+  const int t = threadIdx.x >> 5, c = threadIdx.x & 31;  // template row, column
+  const int rr = row_lo + (t / (row_step - 1)) * row_step + (t % (row_step - 1)) + 1;
+  const int cc = col_lo + (c / (col_step - 1)) * col_step + (c % (col_step - 1)) + 1;
+  const uint32_t px = frame[(size_t)rr * im_cols + cc];
+  tpl[t * 32 + c] = (uint8_t)px;
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t b = __ballot_sync(0xffffffffu, (px >> k) & 1u);
+    if (c == k) mine = b;
+  }
+  if (c < 8) planes[t * 8 + c] = mine;
+  uint32_t sum = px;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (c == 0) s_sum[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    uint32_t all = s_sum[c], mid = (c >= 8 && c < 24) ? all : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      all += __shfl_xor_sync(0xffffffffu, all, o);
+      mid += __shfl_xor_sync(0xffffffffu, mid, o);
+    }
+    if (c == 0) {
+      planes[256] = mid;
+      planes[257] = all;
+      *key = ~0ull;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t lt_row_q(const uint4& lo, const uint4& hi, const uint32_t* q) {
+  uint32_t lt = ~lo.x & q[0];
+  lt = (~lo.y & q[1]) | (~(lo.y ^ q[1]) & lt);
+  lt = (~lo.z & q[2]) | (~(lo.z ^ q[2]) & lt);
+  lt = (~lo.w & q[3]) | (~(lo.w ^ q[3]) & lt);
+  lt = (~hi.x & q[4]) | (~(hi.x ^ q[4]) & lt);
+  lt = (~hi.y & q[5]) | (~(hi.y ^ q[5]) & lt);
+  lt = (~hi.z & q[6]) | (~(hi.z ^ q[6]) & lt);
+  lt = (~hi.w & q[7]) | (~(hi.w ^ q[7]) & lt);
+  return (uint32_t)__popc(lt);
+}
+
+// Small libraries are latency-bound, not bandwidth-bound: with one warp per group of 32 templates the 30 stored
+// rows are 30 dependent load rounds (measured: 25 us for a 30-template library).  Here a block of 16 warps shares
+// one group: warp w < 15 compares rows 2w+1 and 2w+2 (one load round, 480 compares), warp 15 forms the window sums,
+// and the per-offset counts meet in shared memory (integer adds: exact, order-free).
+constexpr int kSmallThreads = 512;
+
+__global__ void __launch_bounds__(kSmallThreads)
+    k_vt_sweep_packed_ref_small(const uint4* __restrict__ packed, const uint32_t* __restrict__ qplanes,
+                                unsigned long long* __restrict__ key_out, const int* __restrict__ n_dev) {
+  __shared__ uint32_t q[32 * 8 + 8];
+  __shared__ uint32_t s_cnt[15][32];
+  __shared__ uint32_t s_A[15][32];
+  const long long n = *n_dev;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long n_groups = (n + 31) >> 5;
+  if ((long long)blockIdx.x >= n_groups) return;  // the grid is laid out for the capacity, not the live count
+  for (int i = threadIdx.x; i < 32 * 8 + 2; i += kSmallThreads) q[i] = qplanes[i];
+  unsigned long long best = ~0ull;
+  for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    if (threadIdx.x < 15 * 32) s_cnt[wid][lane] = 0;
+    __syncthreads();  // also publishes q on the first pass
+    const uint4* gp = packed + g * kGroupU4 + lane;
+    if (wid < 15) {
+      const int t0 = 2 * wid + 1;
+      const uint4 lo0 = ld_stream_u4(gp + (t0 * 2 + 0) * 32), hi0 = ld_stream_u4(gp + (t0 * 2 + 1) * 32);
+      const uint4 lo1 = ld_stream_u4(gp + (t0 * 2 + 2) * 32), hi1 = ld_stream_u4(gp + (t0 * 2 + 3) * 32);
+#pragma unroll
+      for (int o = -7; o <= 7; ++o) {
+        uint32_t c = 0;
+        const int s0 = t0 - o, s1 = t0 + 1 - o;  // warp-uniform
+        if (s0 >= 8 && s0 <= 23) c += lt_row_q(lo0, hi0, q + s0 * 8);
+        if (s1 >= 8 && s1 <= 23) c += lt_row_q(lo1, hi1, q + s1 * 8);
+        if (c) atomicAdd(&s_cnt[o + 7][lane], c);
+      }
+    } else {
+      uint32_t R[32];
+#pragma unroll
+      for (int w4 = 0; w4 < 4; ++w4) {
+        const uint4 v = ld_stream_u4(gp + 32 * 2 * 32 + w4 * 32);
+        const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          R[(w4 * 4 + j) * 2] = ww[j] & 0xffffu;
+          R[(w4 * 4 + j) * 2 + 1] = ww[j] >> 16;
+        }
+      }
+      uint32_t A = 0;
+#pragma unroll
+      for (int r = 1; r <= 16; ++r) A += R[r];
+#pragma unroll
+      for (int o = -7; o <= 7; ++o) {
+        s_A[o + 7][lane] = A;
+        if (o < 7) A = A - R[8 + o] + R[24 + o];
+      }
+    }
+    __syncthreads();
+    if (wid == 0) {
+      const uint32_t bq = q[256];
+      uint32_t m = 0xffffffffu;
+#pragma unroll
+      for (int o = 0; o < 15; ++o) m = min(m, s_A[o][lane] + 256u * s_cnt[o][lane] - bq);
+      const long long ti = g * 32 + lane;
+      if (ti < n) {
+        const unsigned long long key = ((unsigned long long)m << 32) | (unsigned long long)ti;
+        best = key < best ? key : best;
+      }
+    }
+    __syncthreads();
+  }
+  if (wid == 0) {
+    best = warp_min_u64(best);
+    if (lane == 0 && best != ~0ull) atomicMin(key_out, best);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The same frame as a CUDA graph: every pointer is fixed at creation (pinned host buffers included), the
 // library size lives in device memory, so a frame is ONE graph launch + one synchronisation instead of
 // eleven stream operations.  Two executables: with and without the pose-cell update (ros_simulate.py:128
@@ -1144,6 +1288,11 @@ struct prs_frame_plan {
   int warm[2];
   cudaStream_t side;       // the pose-cell update runs here, concurrently with the template branch
   cudaEvent_t ev_fork, ev_join;
+  cudaEvent_t ev_done;     // recorded behind every frame launched by prs_replay_run
+  // device-side aliases of the pinned host buffers (zero-copy), null when a buffer is not pinned
+  const double* odom_map;
+  const uint8_t* frame_map;
+  prs_frame_result* result_map;
 };
 
 static int frame_enqueue(prs_frame_plan* f, bool moved, cudaStream_t st) {
@@ -1157,29 +1306,48 @@ static int frame_enqueue(prs_frame_plan* f, bool moved, cudaStream_t st) {
   long long* d_argmax = (long long*)f->pc_work;
   void* d_total = (char*)f->pc_work + 8;
   int* d_err = (int*)((char*)f->pc_work + 16);
+  const bool zero_copy = f->odom_map && f->frame_map && f->result_map;
+  // the short chain (see k_vt_frame_prepare): reference mode, 32x32 templates out of a step >= 2 mask, small library
+  const bool short_chain = zero_copy && f->mode == PRS_VT_MODE_REF && f->capacity <= kSmallLibrary;
   int rc;
   if (moved) {  // fork: the pose-cell update does not depend on the frame until the decision
     PRS_CUDA(cudaEventRecord(f->ev_fork, st));
     PRS_CUDA(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
-    PRS_CUDA(cudaMemcpyAsync(d_odom, f->odom_host, 2 * sizeof(double), cudaMemcpyHostToDevice, f->side));
-    rc = prs_pc_step(f->pc, f->pc_state, d_odom, f->gi, d_argmax, d_total, d_err, f->side);
+    const double* od = f->odom_map;
+    if (!zero_copy) {
+      PRS_CUDA(cudaMemcpyAsync(d_odom, f->odom_host, 2 * sizeof(double), cudaMemcpyHostToDevice, f->side));
+      od = d_odom;
+    }
+    rc = prs_pc_step(f->pc, f->pc_state, od, f->gi, d_argmax, d_total, d_err, f->side);
     if (rc != PRS_OK) return rc;
     PRS_CUDA(cudaEventRecord(f->ev_join, f->side));
   }
-  PRS_CUDA(cudaMemcpyAsync(d_frame, f->frame_host, (size_t)f->im_rows * f->im_cols, cudaMemcpyHostToDevice, st));
-  rc = prs_vt_extract_u8(d_frame, f->im_rows, f->im_cols, f->row_lo, f->row_hi, f->row_step, f->col_lo, f->col_hi,
-                         f->col_step, d_tpl, 32, 32, st);
-  if (rc != PRS_OK) return rc;
-  PRS_CUDA(cudaMemsetAsync(d_key, 0xff, sizeof(unsigned long long), st));
-  k_vt_pack_query<<<1, 32, 0, st>>>(d_tpl, d_planes);
-  PRS_CUDA(cudaMemcpyToSymbolAsync(c_vtq, d_planes, (32 * 8 + 2) * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
-  // grid sized for the capacity; the kernels read the live count from device memory
-  rc = launch_packed_sweep((const uint4*)f->vt_packed, 0, f->capacity, f->mode, 0, d_key, nullptr, f->d_n, st);
-  if (rc != PRS_OK) return rc;
+  if (short_chain) {
+    rc = check_mask(f->im_rows, f->im_cols, f->row_lo, f->row_hi, f->row_step, f->col_lo, f->col_hi, f->col_step, 32, 32);
+    if (rc != PRS_OK) return rc;
+    k_vt_frame_prepare<<<1, 1024, 0, st>>>(f->frame_map, f->im_cols, f->row_lo, f->row_step, f->col_lo, f->col_step,
+                                           d_tpl, d_planes, d_key);
+    long long blocks = ((long long)f->capacity + 31) / 32;
+    if (blocks > 148LL * 4) blocks = 148LL * 4;
+    k_vt_sweep_packed_ref_small<<<(int)blocks, kSmallThreads, 0, st>>>((const uint4*)f->vt_packed, d_planes, d_key, f->d_n);
+  } else {
+    PRS_CUDA(cudaMemcpyAsync(d_frame, f->frame_host, (size_t)f->im_rows * f->im_cols, cudaMemcpyHostToDevice, st));
+    rc = prs_vt_extract_u8(d_frame, f->im_rows, f->im_cols, f->row_lo, f->row_hi, f->row_step, f->col_lo, f->col_hi,
+                           f->col_step, d_tpl, 32, 32, st);
+    if (rc != PRS_OK) return rc;
+    PRS_CUDA(cudaMemsetAsync(d_key, 0xff, sizeof(unsigned long long), st));
+    k_vt_pack_query<<<1, 32, 0, st>>>(d_tpl, d_planes);
+    PRS_CUDA(cudaMemcpyToSymbolAsync(c_vtq, d_planes, (32 * 8 + 2) * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
+    // grid sized for the capacity; the kernels read the live count from device memory
+    rc = launch_packed_sweep((const uint4*)f->vt_packed, 0, f->capacity, f->mode, 0, d_key, nullptr, f->d_n, st);
+    if (rc != PRS_OK) return rc;
+  }
   if (moved) PRS_CUDA(cudaStreamWaitEvent(st, f->ev_join, 0));  // join: the decision reports the new arg-max
-  k_vt_decide_append<<<1, 32, 0, st>>>(d_key, d_tpl, (uint4*)f->vt_packed, 0, f->threshold, d_argmax, d_err, d_res, f->d_n);
+  k_vt_decide_append<<<1, 32, 0, st>>>(d_key, d_tpl, (uint4*)f->vt_packed, 0, f->threshold, d_argmax, d_err,
+                                       zero_copy ? f->result_map : d_res, f->d_n);
   PRS_CUDA(cudaGetLastError());
-  PRS_CUDA(cudaMemcpyAsync(f->result_host, d_res, sizeof(prs_frame_result), cudaMemcpyDeviceToHost, st));
+  if (!zero_copy)
+    PRS_CUDA(cudaMemcpyAsync(f->result_host, d_res, sizeof(prs_frame_result), cudaMemcpyDeviceToHost, st));
   return PRS_OK;
 }
 
@@ -1196,11 +1364,25 @@ extern "C" int prs_frame_create(prs_pc_handle pc, void* pc_state, const void* gi
   PRS_REQUIRE(f, "prs_frame_create: out of host memory");
   *f = prs_frame_plan{pc, pc_state, pc_work, vt_packed, scratch, gi, odom_host, frame_host, result_host, threshold, mode,
                       capacity, im_rows, im_cols, row_lo, row_hi, row_step, col_lo, col_hi, col_step, {nullptr, nullptr},
-                      {false, false}, nullptr, {0, 0}, nullptr, nullptr, nullptr};
+                      {false, false}, nullptr, {0, 0}, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  {  // pinned buffers are mapped: kernels can read the inputs and write the result in place
+    auto mapped = [](const void* p) -> void* {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+    };
+    f->odom_map = (const double*)mapped(odom_host);
+    f->frame_map = (const uint8_t*)mapped(frame_host);
+    f->result_map = (prs_frame_result*)mapped(result_host);
+  }
   f->d_n = (int*)((char*)scratch + FrameScratch::kOdom + 32);
   cudaError_t e = cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMemcpy(f->d_n, &n_templates, sizeof(int), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     prs_set_error("prs_frame_create: %s", cudaGetErrorString(e));
@@ -1218,6 +1400,7 @@ extern "C" int prs_frame_destroy(prs_frame_plan* f) {
     if (f->side) cudaStreamDestroy(f->side);
     if (f->ev_fork) cudaEventDestroy(f->ev_fork);
     if (f->ev_join) cudaEventDestroy(f->ev_join);
+    if (f->ev_done) cudaEventDestroy(f->ev_done);
     delete f;
   }
   return PRS_OK;
@@ -1260,4 +1443,51 @@ extern "C" int prs_frame_run(prs_frame_plan* f, int moved, void* stream) {
   if (rc != PRS_OK) return rc;
   PRS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return PRS_OK;
+}
+
+// The whole replay loop (ros_simulate.py:152-166 driven from arrays) on the host side of the C ABI: frame t is
+// staged into the pinned buffers of plan t mod n_plans and launched while the earlier frames are still running;
+// a plan is reused once its event has fired and its 32-byte result has been copied out.  All plans must share the
+// device-side state (pose cells, library, template count, scratch) and differ only in their pinned host buffers;
+// the library must have room for T more templates.
+//   frames  : host uint8 [T][im_rows][im_cols] (pageable is fine: each frame is copied into the plan's pinned buffer)
+//   odom    : host double [T][2] = (vtrans, vrot) as passed to PoseCellNetwork.update
+//   moved   : host uint8 [T], 0 = no pose-cell update for this frame (ros_simulate.py:128)
+//   results : host prs_frame_result [T]
+extern "C" int prs_replay_run(prs_frame_plan* const* plans, int n_plans, const uint8_t* frames, const double* odom,
+                              const uint8_t* moved, int T, prs_frame_result* results, void* stream) {
+  PRS_REQUIRE(plans && n_plans >= 1 && n_plans <= 16 && T >= 0 && results, "prs_replay_run: bad argument");
+  PRS_REQUIRE(T == 0 || (frames && odom && moved), "prs_replay_run: null input");
+  PRS_REQUIRE(stream != nullptr, "prs_replay_run: needs a non-default stream (the frames replay as CUDA graphs)");
+  for (int i = 0; i < n_plans; ++i) PRS_REQUIRE(plans[i], "prs_replay_run: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t fbytes = (size_t)plans[0]->im_rows * plans[0]->im_cols;
+  int rc = PRS_OK;
+  int launched = 0;
+  for (int t = 0; t < T; ++t) {
+    prs_frame_plan* f = plans[t % n_plans];
+    if (t >= n_plans) {
+      PRS_CUDA(cudaEventSynchronize(f->ev_done));
+      results[t - n_plans] = *f->result_host;
+    }
+    memcpy(f->frame_host, frames + (size_t)t * fbytes, fbytes);
+    if (moved[t]) {
+      f->odom_host[0] = odom[2 * t];
+      f->odom_host[1] = odom[2 * t + 1];
+    }
+    rc = prs_frame_launch(f, moved[t] ? 1 : 0, st);
+    if (rc != PRS_OK) break;
+    PRS_CUDA(cudaEventRecord(f->ev_done, st));
+    launched = t + 1;
+  }
+  // drain: the last min(n_plans, launched) frames
+  for (int t = launched > n_plans ? launched - n_plans : 0; t < launched; ++t) {
+    prs_frame_plan* f = plans[t % n_plans];
+    if (cudaEventSynchronize(f->ev_done) != cudaSuccess) {
+      prs_set_error("prs_replay_run: %s", cudaGetErrorString(cudaGetLastError()));
+      return PRS_E_CUDA;
+    }
+    results[t] = *f->result_host;
+  }
+  return rc;
 }

@@ -176,12 +176,12 @@ class RatslamRos(object):
     # Two frame plans with their own pinned host buffers share the device-side state (pose cells, library,
     # template count) and are launched alternately on one stream: the device runs frame t while the host stages
     # frame t+1 and digests the result of frame t-1.  Same decisions as fused_frame; results arrive one call late.
-    def _pipe_setup(self):
+    def _pipe_setup(self, n_slots=2):
         if not getattr(self, "_fused_ready", False):
             self._fused_setup()
         e, v = self.pcn._ens, self.vts
         self._p_slots = []
-        for _ in range(2):
+        for _ in range(n_slots):
             frame = torch.zeros((v.im_x, v.im_y), dtype=torch.uint8).pin_memory()
             odom = torch.zeros(2, dtype=torch.float64).pin_memory()
             res = torch.zeros(32, dtype=torch.uint8).pin_memory()
@@ -262,6 +262,61 @@ class RatslamRos(object):
         self.published_index.append(int(r.template_index))
         return int(r.template_index), bool(r.created)
 
+    # ------------------------------------------------------------------ the loop on the C side
+    _RESULT_DTYPE = np.dtype([("argmax", "<i8"), ("key", "<u8"), ("created", "<i4"), ("template_index", "<i4"),
+                              ("n_templates", "<i4"), ("pc_err", "<i4")])
+
+    def replay_native(self, frames, odom, n_plans=4):
+        """``run``'s loop (ros_simulate.py:152-166) over recorded arrays in ONE library call (``prs_replay_run``):
+        staging, graph launches and result collection happen in C with ``n_plans`` frames in flight; the host-side
+        bookkeeping (experience map, template locations) is replayed from the returned records afterwards.
+        Returns the structured result array (one ``prs_frame_result`` per frame).  Same decisions as the
+        frame-by-frame calls; a pose-cell error is raised for the first offending frame after the batch."""
+        if self.inject_energy is not None:
+            raise ValueError("replay_native does not support inject_energy (the injection needs the match first)")
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        odom = np.asarray(odom, dtype=np.float64)
+        T = len(frames)
+        e, v = self.pcn._ens, self.vts
+        if frames.ndim != 3 or tuple(frames.shape[1:]) != (v.im_x, v.im_y) or odom.shape != (T, 2):
+            raise ValueError("replay_native: frames must be [T,%d,%d] and odom [T,2]" % (v.im_x, v.im_y))
+        if getattr(self, "_p_slots", None) is None or len(self._p_slots) != n_plans:
+            self._pipe_setup(n_plans)
+        assert self._p_inflight == 0
+        v._grow(v._n + T + 2)
+        self._pipe_plans()
+        moved = ((np.abs(odom[:, 0]) > 0.001) | (np.abs(odom[:, 1]) > 0.001)).astype(np.uint8)    # ros_simulate.py:128
+        tw = np.ascontiguousarray(odom / float(self.odom_freq))                                    # :157-158
+        res = np.zeros(T, dtype=self._RESULT_DTYPE)
+        plans = (ctypes.c_void_p * n_plans)(*[sl["plan"].value for sl in self._p_slots])
+        nat.check(nat.lib().prs_replay_run(plans, n_plans, frames.ctypes.data, tw.ctypes.data, moved.ctypes.data, T,
+                                           res.ctypes.data, ctypes.c_void_p(self._f_stream.cuda_stream)),
+                  "prs_replay_run")
+        # host bookkeeping, in frame order
+        X, Y, Th = self.pcn.shape
+        flat = res["argmax"]
+        amax = np.stack([flat // (Y * Th), (flat // Th) % Y, flat % Th], axis=1)
+        bad = np.nonzero((res["pc_err"] != 0) & (moved != 0))[0]
+        stop = int(bad[0]) if len(bad) else T
+        for t in range(stop):
+            pc_max = (int(amax[t, 0]), int(amax[t, 1]), int(amax[t, 2]))
+            if moved[t]:
+                self.em.update(float(tw[t, 0]), float(tw[t, 1]), pc_max)                           # :136-137
+                self.published_pose.append(self.em.get_current_point())
+            if res["created"][t]:
+                v._loc[int(res["n_templates"][t]) - 1] = pc_max
+        self.published_index.extend(int(i) for i in res["template_index"][:stop])
+        if T:
+            last = T - 1
+            v._n = int(res["n_templates"][last])
+            self.pcn.max_pc = tuple(int(c) for c in amax[last])
+            self.pcn._max_valid = True
+            k = int(res["key"][last])
+            v.last_score = None if k == (1 << 64) - 1 else k >> 32
+        if len(bad):
+            e._raise_on_err(np.array([res["pc_err"][stop]], dtype=np.int32))
+        return res
+
     # ros_simulate.py:152-166, one pass of the loop body
     def spin_once(self):
         if self.twist_data:
@@ -271,16 +326,34 @@ class RatslamRos(object):
         return False
 
 
-def replay(frames, odom, fused=False, pipelined=False, **kwargs):
+def replay(frames, odom, fused=False, pipelined=False, native=False, **kwargs):
     """Run the loop over ``frames[T,256,256]`` (uint8) and ``odom[T,2]``; returns per-frame records.
 
     ``fused=True`` uses ``RatslamRos.fused_frame`` (one device round trip per frame) instead of the three
     reference-shaped calls; ``pipelined=True`` additionally overlaps the host's staging and bookkeeping of
-    neighbouring frames with the device work (two alternating frame plans).  The records are identical."""
+    neighbouring frames with the device work (two alternating frame plans); ``native=True`` runs the whole loop in
+    one library call (``prs_replay_run``, four frames in flight) and replays the host bookkeeping from its records.
+    The records are identical."""
     node = RatslamRos(**kwargs)
     T = len(frames)
     rec = {"template": np.zeros(T, np.int64), "created": np.zeros(T, np.bool_),
            "argmax": np.zeros((T, 3), np.int64), "n_exp": np.zeros(T, np.int64), "em_xy": np.zeros((T, 2))}
+    if native:
+        odom = np.asarray(odom, dtype=np.float64)
+        res = node.replay_native(frames, odom)
+        X, Y, Th = node.pcn.shape
+        flat = res["argmax"]
+        rec["argmax"] = np.stack([flat // (Y * Th), (flat // Th) % Y, flat % Th], axis=1).astype(np.int64)
+        rec["template"] = res["template_index"].astype(np.int64)
+        rec["created"] = res["created"] != 0
+        moved = (np.abs(odom[:, 0]) > 0.001) | (np.abs(odom[:, 1]) > 0.001)
+        rec["n_exp"] = np.cumsum(moved).astype(np.int64)          # one experience per pose-cell update
+        pts = np.asarray(node.em.get_points(), dtype=np.float64).reshape(-1, 2)
+        has = rec["n_exp"] > 0
+        rec["em_xy"][has] = pts[rec["n_exp"][has] - 1]
+        rec["n_templates"] = len(node.vts.templates)
+        rec["node"] = node
+        return rec
     if pipelined:
         if node.inject_energy is not None:
             raise ValueError("pipelined replay does not support inject_energy (the injection needs the match first)")

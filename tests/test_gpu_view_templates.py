@@ -220,9 +220,11 @@ def test_replay_loop_matches_reference_fixture(golden):
     g = golden("replay_ros.npz")
     T = int(g["n_frames"])
     frames = synth_frames(np.random.default_rng(int(g["frame_seed"])), T)
-    for dtype, fused, piped in ((np.float32, False, False), (np.float64, False, False), (np.float32, True, False),
-                                (np.float64, True, False), (np.float32, True, True), (np.float64, True, True)):
-        rec = ros_simulate.replay(frames, g["odom"], fused=fused, pipelined=piped, dtype=dtype)
+    for dtype, fused, piped, native in ((np.float32, False, False, False), (np.float64, False, False, False),
+                                        (np.float32, True, False, False), (np.float64, True, False, False),
+                                        (np.float32, True, True, False), (np.float64, True, True, False),
+                                        (np.float32, False, False, True), (np.float64, False, False, True)):
+        rec = ros_simulate.replay(frames, g["odom"], fused=fused, pipelined=piped, native=native, dtype=dtype)
         assert np.array_equal(rec["template"], g["template"])
         assert np.array_equal(rec["created"], g["created"])
         assert np.array_equal(rec["argmax"], g["argmax"])
