@@ -37,6 +37,8 @@ extern "C" {
 #define PRS_E_INVALID (-1) /* bad argument (shape, dtype, null pointer) */
 #define PRS_E_CUDA (-2)    /* CUDA runtime error, see prs_last_error() */
 #define PRS_E_NODEVICE (-3)
+#define PRS_E_LUT_KEY (-4) /* prs_pc_update_host: the reference raises KeyError for this odometry */
+#define PRS_E_RADIUS (-5)  /* prs_pc_update_host: the translation does not fit the grid */
 
 #define PRS_F32 0
 #define PRS_F64 1
@@ -132,6 +134,13 @@ PRS_API int prs_pc_step_host_xyz(prs_pc_handle h, void* state, const double* odo
 PRS_API int prs_pc_step_host_xyz_async(prs_pc_handle h, void* state, const double* odom_host, const void* gi,
                                int* result_host, void* stream, int* slot_out);
 PRS_API int prs_pc_host_result_wait(prs_pc_handle h, int slot);
+/* PoseCellNetwork.update((vtrans, vrot)) of a single-network plan (B == 1) in one call (posecell_network.py:326-353).
+ * The odometry is first checked on the host, in numpy's float64 arithmetic, for the cases the reference cannot
+ * handle -- PRS_E_LUT_KEY: a fractional x offset of exactly +0.5 (KeyError, posecell_network.py:249); PRS_E_RADIUS:
+ * 3 + ceil|vtrans/0.2| > min(X, Y) (convolution.py:661-675 reads unwritten memory) -- and such an update leaves the
+ * state untouched.  Otherwise as prs_pc_step_host_xyz with odom_pinned[0..1] = (vtrans, vrot); both buffers pinned. */
+PRS_API int prs_pc_update_host(prs_pc_handle h, void* state, double vtrans, double vrot, const void* gi,
+                       double* odom_pinned, int* result_pinned, void* stream);
 
 /* PoseCellNetwork.path_integration() alone (posecell_network.py:252-314): per-plane shifted 7x7
  * correlate + clamp, theta correlate + clamp; no attractor dynamics, no normalisation. */

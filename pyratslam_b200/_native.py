@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(PKG, "_lib", "libpyratslam_b200.so")
 
 PRS_F32, PRS_F64 = 0, 1
 ERR_LUT_KEY, ERR_RADIUS, ERR_THETA = 1, 2, 4
+E_LUT_KEY, E_RADIUS = -4, -5   # return codes of prs_pc_update_host
 OG_RANGE = 8
 VT_MODE_REF, VT_MODE_CIRCULAR = 0, 1
 
@@ -50,6 +51,7 @@ _SIGNATURES = {
     "prs_pc_step_host_xyz_async": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            ctypes.POINTER(c_int)]),
     "prs_pc_host_result_wait": (c_int, [c_void_p, c_int]),
+    "prs_pc_update_host": (c_int, [c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_path_integration": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_inject": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p]),
     "prs_pc_active_work_bytes": (c_size_t, [c_void_p]),

@@ -1,7 +1,9 @@
 // C ABI glue: error reporting, plan life-cycle and the dispatch between the generic
 // multi-kernel path and the fused SMEM-resident kernel.  See include/pyratslam_b200.h.
 #include <stdarg.h>
+#include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -67,6 +69,7 @@ static void free_plan(prs_pc_plan* p) {
   }
   if (p->cs_in) cudaStreamDestroy(p->cs_in);
   if (p->cs_out) cudaStreamDestroy(p->cs_out);
+  free(p->h_cos);
   delete p;
 }
 
@@ -161,7 +164,10 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
     p->s4 = (char*)p->s3 + sbytes;
   }
 #undef ALLOC
-  cudaError_t e = cudaMemcpy(p->cos_th, cfg->cos_th, p->Th * sizeof(double), cudaMemcpyHostToDevice);
+  p->h_cos = (double*)malloc(p->Th * sizeof(double));
+  if (p->h_cos) memcpy(p->h_cos, cfg->cos_th, p->Th * sizeof(double));
+  cudaError_t e = p->h_cos ? cudaMemcpy(p->cos_th, cfg->cos_th, p->Th * sizeof(double), cudaMemcpyHostToDevice)
+                           : cudaErrorMemoryAllocation;
   if (e == cudaSuccess) e = cudaMemcpy(p->sin_th, cfg->sin_th, p->Th * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(p->tab_dev, &p->tf, sizeof(PcTables<float>), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -248,7 +254,7 @@ static void drop_graphs(prs_pc_handle h) {
 }
 
 static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T, const void* gi, long long* argmax,
-                         void* total, int* err, cudaStream_t st) {
+                         void* total, int* err, cudaStream_t st, int err_store = 0) {
   const size_t es = h->dtype == PRS_F32 ? 4 : 8;
   const int path = prs_pc_path(h);
   if (path == PRS_PATH_RESIDENT) return prs_pc_resident_step(h, state, odom, T, gi, argmax, total, err, st);
@@ -256,7 +262,7 @@ static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T
     int rc;
     if (path == PRS_PATH_CLUSTER)
       rc = prs_pc_cluster_step(h, (float*)state, odom + (size_t)t * h->B * 2, (const float*)gi,
-                               argmax + (size_t)t * h->B, (float*)total + (size_t)t * h->B, err, st);
+                               argmax + (size_t)t * h->B, (float*)total + (size_t)t * h->B, err, err_store && T == 1, st);
     else if (path == 2)
       rc = prs_pc_tiled_step(h, (float*)state, odom + (size_t)t * h->B * 2, (const float*)gi, argmax + (size_t)t * h->B,
                              (float*)total + (size_t)t * h->B, err, st);
@@ -270,6 +276,8 @@ static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T
 
 static int step_enqueue(prs_pc_handle h, void* state, const double* odom, const void* gi, long long* argmax, void* total,
                         int* err, cudaStream_t st) {
+  // the cluster kernel gathers its error bits and stores them: one node less on a 12 us update
+  if (prs_pc_path(h) == PRS_PATH_CLUSTER) return step_dispatch(h, state, odom, 1, gi, argmax, total, err, st, 1);
   PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
   return step_dispatch(h, state, odom, 1, gi, argmax, total, err, st);
 }
@@ -364,8 +372,29 @@ extern "C" int prs_pc_step_host(prs_pc_handle h, void* state, const double* odom
   return PRS_OK;
 }
 
+// device-side alias of a pinned (hence mapped) host buffer, or null
+static void* mapped_alias(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 static int step_host_xyz_enqueue(prs_pc_handle h, void* state, const double* odom_host, const void* gi, int* result_host,
                                  cudaStream_t st) {
+  // A handful of networks: with pinned host buffers the kernels read the odometry and write the packed result in
+  // place (zero-copy), which takes the two copy nodes -- most of a 12 us update's overhead -- out of the chain.
+  if (h->B <= 64) {
+    const double* od = (const double*)mapped_alias(odom_host);
+    int* res = (int*)mapped_alias(result_host);
+    if (od && res) {
+      int rc = prs_pc_step(h, state, od, gi, h->d_argmax, h->d_total, h->d_err, st);
+      if (rc != PRS_OK) return rc;
+      return prs_pc_launch_unravel_pack(h, h->d_argmax, h->d_err, res, st);
+    }
+  }
   PRS_CUDA(cudaMemcpyAsync(h->d_odom, odom_host, (size_t)h->B * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   int rc = prs_pc_step(h, state, h->d_odom, gi, h->d_argmax, h->d_total, h->d_err, st);
   if (rc != PRS_OK) return rc;
@@ -463,4 +492,32 @@ extern "C" int prs_pc_step_host_xyz(prs_pc_handle h, void* state, const double* 
   }
   PRS_CUDA(cudaStreamSynchronize(h->hs));
   return PRS_OK;
+}
+
+// PoseCellNetwork.update((vtrans, vrot)) of a single-network plan in ONE call (posecell_network.py:326-353): the
+// conditions under which the reference raises or reads unwritten memory are checked on the host first, in the same
+// float64 arithmetic numpy uses (posecell_network.py:249,252-267; convolution.py:661-675), so that a rejected update
+// leaves the state untouched; then the odometry goes into the caller's pinned buffer and the step runs as
+// prs_pc_step_host_xyz does.  Returns PRS_OK, PRS_E_LUT_KEY (the reference's KeyError), PRS_E_RADIUS, or an error.
+extern "C" int prs_pc_update_host(prs_pc_handle h, void* state, double vtrans, double vrot, const void* gi,
+                                  double* odom_pinned, int* result_pinned, void* stream) {
+  PRS_REQUIRE(h && state && gi && odom_pinned && result_pinned, "prs_pc_update_host: null argument");
+  PRS_REQUIRE(h->B == 1, "prs_pc_update_host: the plan holds %d networks, not one", h->B);
+  const volatile double vt = vtrans / h->vtrans_scale;  // volatile: every product below is rounded to double on its own
+  for (int k = 0; k < h->Th; ++k) {
+    const volatile double ex = vt * h->h_cos[k];
+    const volatile double d = ex - rint(ex);             // numpy.around: half to even
+    const volatile double d10 = d * 10.0;
+    if ((long long)d10 >= 5) {
+      prs_set_error("prs_pc_update_host: fractional x offset +0.5 on plane %d (the reference raises KeyError)", k);
+      return PRS_E_LUT_KEY;
+    }
+  }
+  if (3.0 + ceil(fabs(vt)) > (double)(h->X < h->Y ? h->X : h->Y)) {
+    prs_set_error("prs_pc_update_host: translation of %.3g cells does not fit a %dx%d grid", (double)vt, h->X, h->Y);
+    return PRS_E_RADIUS;
+  }
+  odom_pinned[0] = vtrans;
+  odom_pinned[1] = vrot;
+  return prs_pc_step_host_xyz(h, state, odom_pinned, gi, result_pinned, stream);
 }

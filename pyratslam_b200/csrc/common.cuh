@@ -55,6 +55,7 @@ struct prs_pc_plan {
   TlPairs tl;
   double* cos_th;  // device [Th]
   double* sin_th;
+  double* h_cos;   // host copy of cos_th (prs_pc_update_host checks the LUT key before touching the state)
   // scratch: two allocations of 2*B*N elements; s1|s2 are the halves of the first, s3|s4 of the second
   void *s1, *s2, *s3, *s4;
   int* shift;           // [B][Th][2] integer origins (ox, oy)
@@ -118,8 +119,9 @@ int prs_pc_launch_plan(prs_pc_plan* p, const double* odom, int* err, cudaStream_
 int prs_pc_launch_sum_final_f32(prs_pc_plan* p, int np, float* total, cudaStream_t st);
 int prs_pc_launch_argmax_final_f32(prs_pc_plan* p, int np, long long* argmax, cudaStream_t st);
 int prs_pc_cluster_choose(const prs_pc_plan* p);
+// err_store != 0: err[b] is overwritten with the update's bits (needs no zeroed buffer); 0: OR-ed into it
 int prs_pc_cluster_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax,
-                        float* total, int* err, cudaStream_t st);
+                        float* total, int* err, int err_store, cudaStream_t st);
 int prs_pc_resident_supported(const prs_pc_plan* p);
 int prs_pc_resident_step(prs_pc_plan* p, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st);

@@ -88,6 +88,7 @@ struct ClMisc {          // the small per-CTA block at off_misc
   float best_v;          // this CTA's arg-max candidate (read by CTA 0 after the second)
   int best_i;
   int og;                // index into f1d
+  int err;               // PRS_ERR_* bits of this CTA's planes (read by CTA 0 after the second cluster barrier)
 };
 static_assert(sizeof(ClMisc) <= 2048, "misc block must fit its slot");
 
@@ -101,6 +102,7 @@ struct ClArgs {
   const double *cos_th, *sin_th;
   double vtrans_scale, vrot_scale;
   int X, Y, Th;
+  int err_store;  // 1: err[b] is overwritten with this update's bits (no pre-zeroed buffer needed); 0: OR-ed into it
   FastDiv dY, dX, dRows, dNsx, dNxp, dRows2;  // Y, X, P*X, ceil(X/8), ceil(X/2), (P/2)*X
 };
 
@@ -125,24 +127,28 @@ __global__ void __launch_bounds__(kNT, 1) k_pc_cluster(ClArgs a, PcTables<float>
 
   // ---- decisions of this update for the CTA's planes, float64 exactly as numpy computes them on the host
   //      (posecell_network.py:252-267,249,304); LUT filters into shared memory
-  if (tid < P) {
-    const int k = k0 + tid;
-    const double* od = a.odom + (size_t)b * 2;
-    const double vt = __ddiv_rn(od[0], a.vtrans_scale);
-    const double ex = __dmul_rn(vt, a.cos_th[k]);
-    const double ey = __dmul_rn(vt, a.sin_th[k]);
-    const double oxd = rint(ex), oyd = rint(ey);  // numpy.around: half to even
-    const int key = (int)__dmul_rn(__dsub_rn(ex, oxd), 10.0);
-    m->plan[tid] = make_int4(modp((int)oxd, X), modp((int)oyd, Y), key < 0 ? 1 : 0, 0);
-    int e = key >= 5 ? PRS_ERR_LUT_KEY : 0;
-    if (tid == 0) {
-      if (!(3.0 + ceil(fabs(vt)) <= (double)(X < Y ? X : Y))) e |= PRS_ERR_RADIUS;
-      const double og = floor(__dadd_rn(__ddiv_rn(od[1], a.vrot_scale), 0.5));
-      if (!(fabs(og) <= 64.0)) e |= PRS_ERR_THETA;
-      const int ogc = og < -(double)PRS_OG_RANGE ? -PRS_OG_RANGE : (og > (double)PRS_OG_RANGE ? PRS_OG_RANGE : (int)og);
-      m->og = ogc + PRS_OG_RANGE;
+  if (wid == 0) {
+    int e = 0;
+    if (tid < P) {
+      const int k = k0 + tid;
+      const double* od = a.odom + (size_t)b * 2;
+      const double vt = __ddiv_rn(od[0], a.vtrans_scale);
+      const double ex = __dmul_rn(vt, a.cos_th[k]);
+      const double ey = __dmul_rn(vt, a.sin_th[k]);
+      const double oxd = rint(ex), oyd = rint(ey);  // numpy.around: half to even
+      const int key = (int)__dmul_rn(__dsub_rn(ex, oxd), 10.0);
+      m->plan[tid] = make_int4(modp((int)oxd, X), modp((int)oyd, Y), key < 0 ? 1 : 0, 0);
+      e = key >= 5 ? PRS_ERR_LUT_KEY : 0;
+      if (tid == 0) {
+        if (!(3.0 + ceil(fabs(vt)) <= (double)(X < Y ? X : Y))) e |= PRS_ERR_RADIUS;
+        const double og = floor(__dadd_rn(__ddiv_rn(od[1], a.vrot_scale), 0.5));
+        if (!(fabs(og) <= 64.0)) e |= PRS_ERR_THETA;
+        const int ogc = og < -(double)PRS_OG_RANGE ? -PRS_OG_RANGE : (og > (double)PRS_OG_RANGE ? PRS_OG_RANGE : (int)og);
+        m->og = ogc + PRS_OG_RANGE;
+      }
     }
-    if (e) atomicOr(a.err + b, e);
+    e = (int)__reduce_or_sync(0xffffffffu, (unsigned)e);
+    if (tid == 0) m->err = e;
   }
   if (P % 2 != 0)
     for (int i = tid; i < 98; i += kNT) m->f2d[i / 49][i % 49] = tab.f2d[i / 49][i % 49];
@@ -457,6 +463,12 @@ __global__ void __launch_bounds__(kNT, 1) k_pc_cluster(ClArgs a, PcTables<float>
     }
     a.argmax[b] = bi;
     a.total[b] = tot;
+    int e = 0;
+    for (int r = 0; r < C; ++r) e |= cluster.map_shared_rank(&m->err, r)[0];
+    if (a.err_store)
+      a.err[b] = e;
+    else if (e)
+      atomicOr(a.err + b, e);
   }
   cluster.sync();  // CTA 0 has read every candidate: shared memory may go away
 }
@@ -554,12 +566,12 @@ int prs_pc_cluster_choose(const prs_pc_plan* p) {
 }
 
 int prs_pc_cluster_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax,
-                        float* total, int* err, cudaStream_t st) {
+                        float* total, int* err, int err_store, cudaStream_t st) {
   const int C = p->cluster_C;
   PRS_REQUIRE(C >= 2, "cluster path not available for this plan");
   const int P = p->Th / C;
   ClArgs args{state, odom, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale, p->vrot_scale,
-              p->X, p->Y, p->Th};
+              p->X, p->Y, p->Th, err_store};
   const int nxp = (p->X + 1) / 2;
   args.dY = FastDiv(p->Y);
   args.dX = FastDiv(p->X);

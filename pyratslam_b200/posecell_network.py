@@ -34,6 +34,14 @@ def _as_np_dtype(dtype):
 _PATHS = {0: "generic", 1: "resident", 2: "tiled", 3: "cluster"}
 
 
+
+def _raw_stream(dev_index):
+    """The current CUDA stream of ``dev_index`` as an integer handle (torch's C accessor: no Stream object)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(dev_index)
+    except AttributeError:  # pragma: no cover - older torch
+        return torch.cuda.current_stream(dev_index).cuda_stream
+
 class PoseCellEnsemble:
     """B independent pose-cell networks of one shape, resident on one GPU."""
 
@@ -83,6 +91,13 @@ class PoseCellEnsemble:
         self._res_pin = torch.zeros((B, 4), dtype=torch.int32).pin_memory()   # (x, y, th, err) per network
         self._res_np = self._res_pin.numpy()
         self._odom_np = self._odom_pin.numpy()
+        # fixed addresses and the bound entry point of the single-call update (PoseCellNetwork.update)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._state_ptr = self._state.data_ptr()
+        self._gi_ptr = self._gi.data_ptr()
+        self._odom_pin_ptr = self._odom_pin.data_ptr()
+        self._res_pin_ptr = self._res_pin.data_ptr()
+        self._update_host = nat.lib().prs_pc_update_host
         self.max_pc = np.zeros((B, 3), dtype=np.int64)
 
     def __del__(self):
@@ -406,11 +421,29 @@ class PoseCellNetwork:
                              "read unwritten memory)" % (vt, self.shape[0], self.shape[1]))
 
     def update(self, v=(0.0, 0.0)):
-        """One attractor update + path integration; returns the arg-max cell (posecell_network.py:326-353)."""
+        """One attractor update + path integration; returns the arg-max cell (posecell_network.py:326-353).
+
+        One library call (``prs_pc_update_host``): the odometry is checked on the host for the cases in which the
+        reference raises (``KeyError``) or reads unwritten memory (``ValueError``) *before* the device state is
+        touched, then the step runs and the packed ``(x, y, th, err)`` result comes back through pinned memory."""
         vtrans, vrot = float(v[0]), float(v[1])
-        self._precheck(vtrans, vrot)
-        x, y, th = self._ens.update(np.array([[vtrans, vrot]]))[0]
-        self.max_pc = (int(x), int(y), int(th))
+        e = self._ens
+        if torch.cuda.current_device() != e._dev_index:
+            with torch.cuda.device(e.device):
+                return self.update((vtrans, vrot))
+        rc = e._update_host(e._h, e._state_ptr, vtrans, vrot, e._gi_ptr, e._odom_pin_ptr, e._res_pin_ptr,
+                            _raw_stream(e._dev_index))
+        if rc != 0:
+            if rc == nat.E_LUT_KEY:
+                raise KeyError((5, 5))                      # posecell_network.py:249
+            if rc == nat.E_RADIUS:
+                raise ValueError(nat.lib().prs_last_error().decode(errors="replace"))
+            nat.check(rc, "prs_pc_update_host")
+        res = e._res_np
+        if res[0, 3]:
+            e._raise_on_err(res[:, 3])
+        self.max_pc = (int(res[0, 0]), int(res[0, 1]), int(res[0, 2]))
+        e.max_pc = res[:, :3].astype(np.int64)
         self._max_valid = True
         return self.max_pc
 
