@@ -105,6 +105,13 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   p->N = (long long)cfg->X * cfg->Y * cfg->Th;
   p->vtrans_scale = cfg->vtrans_scale;
   p->vrot_scale = cfg->vrot_scale;
+  p->h_cos = (double*)malloc(p->Th * sizeof(double));
+  if (!p->h_cos) {
+    prs_set_error("prs_pc_create: out of host memory");
+    delete p;
+    return PRS_E_INVALID;
+  }
+  memcpy(p->h_cos, cfg->cos_th, p->Th * sizeof(double));
   fill_tables(p->tf, cfg);
   fill_tables(p->td, cfg);
   for (int t = 0; t < 7; ++t) {
@@ -164,10 +171,7 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
     p->s4 = (char*)p->s3 + sbytes;
   }
 #undef ALLOC
-  p->h_cos = (double*)malloc(p->Th * sizeof(double));
-  if (p->h_cos) memcpy(p->h_cos, cfg->cos_th, p->Th * sizeof(double));
-  cudaError_t e = p->h_cos ? cudaMemcpy(p->cos_th, cfg->cos_th, p->Th * sizeof(double), cudaMemcpyHostToDevice)
-                           : cudaErrorMemoryAllocation;
+  cudaError_t e = cudaMemcpy(p->cos_th, cfg->cos_th, p->Th * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(p->sin_th, cfg->sin_th, p->Th * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(p->tab_dev, &p->tf, sizeof(PcTables<float>), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {

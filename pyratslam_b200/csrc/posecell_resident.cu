@@ -12,19 +12,20 @@
 //   stage[N] float        the next network's state as it lies in HBM, theta-major [th][x][y]   4N bytes
 //   buf2[N]  float2       (E, I) pairs of the separable DoG, [th][x][y]                        8N bytes
 //     after the x pass the same bytes are reused as two plane-pair-interleaved tensors
-//       A2[NP][x+halo][y] float2 = (A'[mid+m], A'[mid-m])  inhibited activity, already moved by the integer
-//                                                   (x, y) origin of its plane, 3 periodic halo rows each side
+//       A2[NP][x+halo][y] float2 = (A'[mid+m], A'[mid-m])  inhibited activity; each plane already moved by the y part
+//                                                   of its integer origin, 3 periodic halo rows each side
 //       B2[NP][x][y] float2 = (B[mid+m], B[mid-m])    after the 2-D correlate
 //     Plane pairs are MIRROR pairs about mid = Th/2 (pair 0 is (mid, 0)): cos((k-mid)*2pi/Th) is the same for
-//     both, hence the same x origin and the same LUT filter (a variant of stage 4 that adds the tap rows sharing
+//     both, hence the same x origin -- stage 4 applies it once per thread as the first row it reads -- and the
+//     same LUT filter (a variant of stage 4 that adds the tap rows sharing
 //     coefficients first -- 4 or 5 row groups instead of 7 -- was measured and was NOT faster: the stage is bound
 //     by the sum of its shared-memory and FMA time, not by the FMA count).
 // Stages (a __syncthreads between each):
 //   1 theta pass   thread = one (x,y) line of Th cells in registers, stage -> buf2         11 op / cell
 //   2 y pass       thread = one (th,x) line, in place, packed FFMA2 on (E,I)               7 FFMA2 / cell
-//   3 x pass       thread = one (th,y) line, A = aE*E - aI*I, inhibit, block sum; the store applies
-//                  the plane's integer origin (a rotation of the x and y indices), so that ...
-//   4 7x7 stage    ... is a plain periodic correlate: thread = one x-row of a plane PAIR, packed
+//   3 x pass       thread = one (th,y) line, A = aE*E - aI*I, inhibit, block sum; the column it READS is
+//                  y + oy of its plane (the y part of the integer origin: one wrap per thread)
+//   4 7x7 stage    thread = one x-row of a plane PAIR starting at row x + ox (the x part), packed
 //                  FFMA2 over the pair, rows and coefficient pairs arrive by LDS.64 / LDS.128   24.5 FFMA2 / cell
 //   5 theta pass   thread = one (x,y) line, packed over the plane pair, clamp, arg-max, -> global   3.5 FFMA2 / cell
 // The FMA-heavy stages use the sm_100 packed instruction (fma.rn.f32x2, SASS FFMA2): same FP32 pipe
@@ -216,9 +217,11 @@ __global__ void __launch_bounds__(NT, 1)
       PRS_STAMP(0);
 
       // ---- 1. theta pass of the separable DoG: stage (or global on later steps) -> (E, I) pairs.
-      //      The pair of plane k is stored at (x - ox_k, y - oy_k): the integer origin the reference adds
-      //      to its read index in the 2-D stage (convolution.py:320-340) is applied here, once, as a
-      //      translation of the whole plane; every later stage is a periodic correlate and commutes with it.
+      //      The integer origin the reference adds to its read index in the 2-D stage (convolution.py:320-340)
+      //      is a translation of the whole plane, and every stage up to the 2-D one is a periodic correlate that
+      //      commutes with it.  It is applied where it is free: the y part when stage 3 chooses the column a
+      //      thread reads (one wrap per thread), the x part when stage 4 chooses its first row (one wrap per
+      //      thread) -- not here, where it cost a plan load and six integer instructions per cell.
       if (step == 0) {
         mbar_wait(bar, parity);
         parity ^= 1;
@@ -227,7 +230,11 @@ __global__ void __launch_bounds__(NT, 1)
         const float e0 = tab->ge[3], e1 = tab->ge[2], e2 = tab->ge[1], e3 = tab->ge[0];
         const float i0 = tab->gi[3], i1 = tab->gi[2], i2 = tab->gi[1], i3 = tab->gi[0];
         const int p = tid;
-        const int x = p / Y, y = p - x * Y;
+        // Plane 0 shares pair 0 with plane MID, whose x origin is the opposite one (cos(-pi) = -cos(0)); stage 4
+        // applies the origin of a pair's first plane to both, so plane 0 is stored rotated by the difference.
+        int p0 = p - (plan4[0].x - plan4[MID].x) * Y;
+        p0 += p0 < 0 ? XY : 0;
+        p0 -= p0 >= XY ? XY : 0;
         float in[T];
         if (step == 0) {
 #pragma unroll
@@ -244,9 +251,7 @@ __global__ void __launch_bounds__(NT, 1)
           const float s3 = in[(k + 3) % T] + in[(k + T - 3) % T];
           const float e = fmaf(e0, c, fmaf(e1, s1, fmaf(e2, s2, e3 * s3)));
           const float i = fmaf(i0, c, fmaf(i1, s1, fmaf(i2, s2, i3 * s3)));
-          const int4 pl = plan4[k];
-          const int dst = k * XY + p - pl.z + (x < pl.x ? XY : 0) + (y < pl.y ? Y : 0);
-          buf2[dst] = make_float2(e, i);
+          buf2[k == 0 ? p0 : k * XY + p] = make_float2(e, i);
           if (st_gst != nullptr) {  // the previous network's plane k (mirror pair layout of out[])
             const float v = k == 0 ? out[0].y : (k < MID ? out[MID - k].y : (k == MID ? out[0].x : out[k - MID].x));
             st_gst[k * XY + p] = v;
@@ -315,7 +320,10 @@ __global__ void __launch_bounds__(NT, 1)
         for (int h = 0; h < 2; ++h) {
           const int k = h == 0 ? MID + kp3 : (kp3 == 0 ? 0 : MID - kp3);
           {
-            const float2* col = buf2 + k * XY + y3;
+            // y origin of plane k: output column y3 is computed from input column y3 + oy_k (one wrap per thread)
+            int ys = y3 + plan4[k].y;
+            ys -= ys >= Y ? Y : 0;
+            const float2* col = buf2 + k * XY + ys;
             float2 in[X];
 #pragma unroll
             for (int x = 0; x < X; ++x) in[x] = col[x * Y];
@@ -394,7 +402,12 @@ __global__ void __launch_bounds__(NT, 1)
             for (int q = 0; q < 7; ++q) acc[j] = ffma2(row[(j + q + Y - 3) % Y], cf[q], acc[j]);
           }
         }
-        float2* o = B2 + kp * XY + x * Y;
+        // x origin of the pair (mirror planes have the same cosine, hence the same origin; pair 0: see stage 1):
+        // the row computed from rows x-3..x+3 is row x - ox of the result.  Applied to the 21 stores rather than to
+        // the 175 loads, whose conflict-free bank pattern a rotated row index would break.
+        int xs = x - plan4[MID + kp].x;
+        xs += xs < 0 ? X : 0;
+        float2* o = B2 + kp * XY + xs * Y;
 #pragma unroll
         for (int j = 0; j < Y; ++j)  // posecell_network.py:300; 1/total is applied by stage 5 (see there)
           o[j] = make_float2(fmaxf(acc[j].x, 0.f), fmaxf(acc[j].y, 0.f));
@@ -554,8 +567,13 @@ extern "C" __attribute__((visibility("default"))) int prs_debug_stage_cycles(uns
 
 int prs_pc_resident_supported(const prs_pc_plan* p) {
   if (p->dtype != PRS_F32) return 0;
-  if (p->X == 21 && p->Y == 21 && p->Th == 36) return 1;
-  return 0;
+  if (!(p->X == 21 && p->Y == 21 && p->Th == 36)) return 0;
+  // The kernel applies ONE x origin per mirror pair (MID+m, MID-m), m >= 1: around(vt * cos) must be the same for
+  // both planes, which holds when the host's cosine table is bitwise even about MID (numpy's cos is).
+  const int mid = p->Th / 2;
+  for (int m = 1; m < mid; ++m)
+    if (p->h_cos[mid + m] != p->h_cos[mid - m]) return 0;
+  return 1;
 }
 
 int prs_pc_resident_step(prs_pc_plan* p, void* state, const double* odom, int T, const void* gi, long long* argmax,
