@@ -35,6 +35,10 @@
 
 #include "common.cuh"
 
+#ifndef PRS_RESIDENT_DEFER1
+#define PRS_RESIDENT_DEFER1 35
+#endif
+
 namespace {
 
 template <int X, int Y, int T>
@@ -148,6 +152,9 @@ __global__ void __launch_bounds__(NT, 1)
   static_assert(kPlanT0 >= NP * X && T <= 64, "the planning threads must be idle in stage 4");
   static_assert(NP * X <= NT && NP * Y <= NT && XY <= NT, "one work item per thread in stages 1, 3, 4, 5");
   static_assert(T % 2 == 0 && T >= 8, "mirror plane pairs need an even number of theta planes");
+  // planes of the previous network's deferred result written during stage 1; the rest go out at the head of
+  // stage 2 (the LSU queue, "stall_lg", is what stage 1 waits for once its index arithmetic is gone)
+  constexpr int kDefer1 = PRS_RESIDENT_DEFER1 < T ? PRS_RESIDENT_DEFER1 : T;
   constexpr int MID = T / 2;  // posecell_network.py:257: mid = floor(Th / 2); pair m = (MID + m, MID - m), pair 0 = (MID, 0)
   constexpr int NW = (NT + 31) / 32;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -252,12 +259,12 @@ __global__ void __launch_bounds__(NT, 1)
           const float e = fmaf(e0, c, fmaf(e1, s1, fmaf(e2, s2, e3 * s3)));
           const float i = fmaf(i0, c, fmaf(i1, s1, fmaf(i2, s2, i3 * s3)));
           buf2[k == 0 ? p0 : k * XY + p] = make_float2(e, i);
-          if (st_gst != nullptr) {  // the previous network's plane k (mirror pair layout of out[])
+          if (st_gst != nullptr && k < kDefer1) {  // the previous network's plane k (mirror pair layout of out[])
             const float v = k == 0 ? out[0].y : (k < MID ? out[MID - k].y : (k == MID ? out[0].x : out[k - MID].x));
             st_gst[k * XY + p] = v;
           }
         }
-        st_gst = nullptr;
+        if (kDefer1 == T) st_gst = nullptr;
       }
       __syncthreads();
       PRS_STAMP(1);
@@ -276,7 +283,17 @@ __global__ void __launch_bounds__(NT, 1)
         }
       }
 
-      // ---- 2. y pass, in place on each (theta, x) line
+      // ---- 2. y pass, in place on each (theta, x) line; the remaining deferred result planes leave here
+      if (kDefer1 < T && st_gst != nullptr) {
+        if (tid < XY) {
+#pragma unroll
+          for (int k = kDefer1; k < T; ++k) {
+            const float v = k == 0 ? out[0].y : (k < MID ? out[MID - k].y : (k == MID ? out[0].x : out[k - MID].x));
+            st_gst[k * XY + tid] = v;
+          }
+        }
+        st_gst = nullptr;
+      }
       if (!(ablate & 2)) {
         float2 cf[7];
 #pragma unroll
