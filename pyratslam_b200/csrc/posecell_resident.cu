@@ -35,6 +35,9 @@
 
 #include "common.cuh"
 
+#ifndef PRS_RESIDENT_S3FOLD
+#define PRS_RESIDENT_S3FOLD 1
+#endif
 #ifndef PRS_RESIDENT_DEFER1
 #define PRS_RESIDENT_DEFER1 35
 #endif
@@ -346,18 +349,33 @@ __global__ void __launch_bounds__(NT, 1)
             for (int x = 0; x < X; ++x) in[x] = col[x * Y];
 #pragma unroll
             for (int x = 0; x < X; ++x) {
+#if PRS_RESIDENT_S3FOLD
+              float2 acc = make_float2(-g_inh, 0.f);  // the inhibition rides in the accumulator: one FADD less per cell
+#pragma unroll
+              for (int t = 0; t < 7; ++t) acc = ffma2(in[(x + t + X - 3) % X], cf[t], acc);
+              const float a = fmaxf(acc.x - acc.y, 0.f);  // == (a < gi) ? 0 : a - gi (posecell_network.py:339-340)
+#else
               float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
               for (int t = 0; t < 7; ++t) acc = ffma2(in[(x + t + X - 3) % X], cf[t], acc);
               const float a = fmaxf((acc.x - acc.y) - g_inh, 0.f);  // == (a < gi) ? 0 : a - gi, one FMNMX
+#endif
               if (h == 0)
                 keep[x].x = a;
               else
                 keep[x].y = a;
+#if !PRS_RESIDENT_S3FOLD
               psum += a;
+#endif
             }
           }
         }
+#if PRS_RESIDENT_S3FOLD
+        float2 ps2 = keep[0];  // both planes of the pair at once (add.f32x2)
+#pragma unroll
+        for (int x = 1; x < X; ++x) ps2 = __fadd2_rn(ps2, keep[x]);
+        psum = ps2.x + ps2.y;
+#endif
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
