@@ -315,7 +315,7 @@ def extra_single_gpu(torch, peak, steps):
                               "pipelined_frames_per_s": T / dt_p,
                               "note": "host frames: 64 KiB H2D + pose-cell update + template match + 32 B D2H per frame, "
                                       "wall clock, node construction included; value = the loop on the C side of the ABI "
-                                      "(prs_replay_run: four frame plans in flight, host bookkeeping replayed from the "
+                                      "(prs_replay_run: two frame plans in flight, host bookkeeping replayed from the "
                                       "records); pipelined = two alternating frame plans driven from Python; "
                                       "fused = one CUDA-graph "
                                       "launch and one synchronisation per frame; reference_shaped = separate "

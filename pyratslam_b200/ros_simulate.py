@@ -266,9 +266,9 @@ class RatslamRos(object):
     _RESULT_DTYPE = np.dtype([("argmax", "<i8"), ("key", "<u8"), ("created", "<i4"), ("template_index", "<i4"),
                               ("n_templates", "<i4"), ("pc_err", "<i4")])
 
-    def replay_native(self, frames, odom, n_plans=4):
+    def replay_native(self, frames, odom, n_plans=2):
         """``run``'s loop (ros_simulate.py:152-166) over recorded arrays in ONE library call (``prs_replay_run``):
-        staging, graph launches and result collection happen in C with ``n_plans`` frames in flight; the host-side
+        staging, graph launches and result collection happen in C with ``n_plans`` frames in flight (two already hide the host); the host-side
         bookkeeping (experience map, template locations) is replayed from the returned records afterwards.
         Returns the structured result array (one ``prs_frame_result`` per frame).  Same decisions as the
         frame-by-frame calls; a pose-cell error is raised for the first offending frame after the batch."""
@@ -332,7 +332,7 @@ def replay(frames, odom, fused=False, pipelined=False, native=False, **kwargs):
     ``fused=True`` uses ``RatslamRos.fused_frame`` (one device round trip per frame) instead of the three
     reference-shaped calls; ``pipelined=True`` additionally overlaps the host's staging and bookkeeping of
     neighbouring frames with the device work (two alternating frame plans); ``native=True`` runs the whole loop in
-    one library call (``prs_replay_run``, four frames in flight) and replays the host bookkeeping from its records.
+    one library call (``prs_replay_run``, two frames in flight) and replays the host bookkeeping from its records.
     The records are identical."""
     node = RatslamRos(**kwargs)
     T = len(frames)
