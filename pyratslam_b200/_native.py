@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_longlong, c_size_t, c_uint64, c_void_p
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "_lib", "libpyratslam_b200.so")
+# PYRATSLAM_B200_LIB: another build of the same library (profiling variants, bench_tools/variant_bench.py)
+LIB_PATH = os.environ.get("PYRATSLAM_B200_LIB") or os.path.join(PKG, "_lib", "libpyratslam_b200.so")
 
 PRS_F32, PRS_F64 = 0, 1
 ERR_LUT_KEY, ERR_RADIUS, ERR_THETA = 1, 2, 4
