@@ -341,6 +341,18 @@ extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, con
   return PRS_OK;
 }
 
+int prs_pc_step_mirror(prs_pc_plan* h, void* state, const double* odom, const void* gi, long long* argmax, void* total,
+                       int* err, long long* argmax2, int* err2, int* mirrored, cudaStream_t st) {
+  *mirrored = 0;
+  if (h && argmax2 && err2 && prs_pc_path(h) == PRS_PATH_CLUSTER) {
+    PRS_REQUIRE(state && odom && gi && argmax && total && err, "prs_pc_step: null argument");
+    if (int rc_ = prs_pc_check_device(h, "prs_pc_step")) return rc_;
+    *mirrored = 1;
+    return prs_pc_cluster_step(h, (float*)state, odom, (const float*)gi, argmax, (float*)total, err, 1, st, argmax2, err2);
+  }
+  return prs_pc_step(h, state, odom, gi, argmax, total, err, st);
+}
+
 extern "C" int prs_pc_path_integration(prs_pc_handle h, void* state, const double* odom, int* err, void* stream) {
   PRS_REQUIRE(h && state && odom && err, "prs_pc_path_integration: null argument");
   if (int rc_ = prs_pc_check_device(h, "prs_pc_path_integration")) return rc_;

@@ -120,8 +120,14 @@ int prs_pc_launch_sum_final_f32(prs_pc_plan* p, int np, float* total, cudaStream
 int prs_pc_launch_argmax_final_f32(prs_pc_plan* p, int np, long long* argmax, cudaStream_t st);
 int prs_pc_cluster_choose(const prs_pc_plan* p);
 // err_store != 0: err[b] is overwritten with the update's bits (needs no zeroed buffer); 0: OR-ed into it
+// argmax2 / err2: optional second destination of network b's arg-max and error bits (both or neither)
 int prs_pc_cluster_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax,
-                        float* total, int* err, int err_store, cudaStream_t st);
+                        float* total, int* err, int err_store, cudaStream_t st, long long* argmax2 = nullptr,
+                        int* err2 = nullptr);
+// prs_pc_step that, where the plan's kernel can do it (the cluster path), ALSO writes the arg-max and error bits of
+// every network to argmax2 / err2 (*mirrored = 1); otherwise a plain prs_pc_step (*mirrored = 0)
+int prs_pc_step_mirror(prs_pc_plan* h, void* state, const double* odom, const void* gi, long long* argmax, void* total,
+                       int* err, long long* argmax2, int* err2, int* mirrored, cudaStream_t st);
 int prs_pc_resident_supported(const prs_pc_plan* p);
 int prs_pc_resident_step(prs_pc_plan* p, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st);

@@ -103,6 +103,8 @@ struct ClArgs {
   double vtrans_scale, vrot_scale;
   int X, Y, Th;
   int err_store;  // 1: err[b] is overwritten with this update's bits (no pre-zeroed buffer needed); 0: OR-ed into it
+  long long* argmax2;  // optional second destination of the arg-max and the error bits (e.g. a pinned, mapped host
+  int* err2;           // result record: the frame graph then needs no kernel behind this one to publish them)
   FastDiv dY, dX, dRows, dNsx, dNxp, dRows2;  // Y, X, P*X, ceil(X/8), ceil(X/2), (P/2)*X
 };
 
@@ -469,6 +471,10 @@ __global__ void __launch_bounds__(kNT, 1) k_pc_cluster(ClArgs a, PcTables<float>
       a.err[b] = e;
     else if (e)
       atomicOr(a.err + b, e);
+    if (a.argmax2 != nullptr) {
+      a.argmax2[b] = bi;
+      a.err2[b] = e;
+    }
   }
   cluster.sync();  // CTA 0 has read every candidate: shared memory may go away
 }
@@ -566,12 +572,12 @@ int prs_pc_cluster_choose(const prs_pc_plan* p) {
 }
 
 int prs_pc_cluster_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax,
-                        float* total, int* err, int err_store, cudaStream_t st) {
+                        float* total, int* err, int err_store, cudaStream_t st, long long* argmax2, int* err2) {
   const int C = p->cluster_C;
   PRS_REQUIRE(C >= 2, "cluster path not available for this plan");
   const int P = p->Th / C;
   ClArgs args{state, odom, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale, p->vrot_scale,
-              p->X, p->Y, p->Th, err_store};
+              p->X, p->Y, p->Th, err_store, argmax2, err2};
   const int nxp = (p->X + 1) / 2;
   args.dY = FastDiv(p->Y);
   args.dX = FastDiv(p->X);

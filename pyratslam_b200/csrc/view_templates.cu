@@ -979,7 +979,7 @@ struct FrameScratch {               // device scratch layout (bytes)
 __global__ void k_vt_decide_append(const unsigned long long* __restrict__ key, const uint8_t* __restrict__ tpl,
                                    uint4* __restrict__ packed, int n, unsigned threshold,
                                    const long long* __restrict__ argmax, const int* __restrict__ pc_err,
-                                   prs_frame_result* __restrict__ res, int* __restrict__ n_dev) {
+                                   prs_frame_result* __restrict__ res, int* __restrict__ n_dev, int write_pc = 1) {
   const int t = threadIdx.x;  // 32 threads, one per template row
   if (n_dev != nullptr) n = *n_dev;
   __syncwarp();
@@ -1010,12 +1010,12 @@ __global__ void k_vt_decide_append(const unsigned long long* __restrict__ key, c
     rs[(((w >> 2) * 32 + lane) * 4 + (w & 3)) * 2 + (t & 1)] = (uint16_t)sum;
   }
   if (t == 0) {
-    res->argmax = argmax ? argmax[0] : -1;
+    if (write_pc) res->argmax = argmax ? argmax[0] : -1;  // else the pose-cell kernel writes both fields itself
     res->key = k;
     res->created = create ? 1 : 0;
     res->template_index = create ? n : (int)(k & 0xffffffffu);
     res->n_templates = n + (create ? 1 : 0);
-    res->pc_err = pc_err ? pc_err[0] : 0;
+    if (write_pc) res->pc_err = pc_err ? pc_err[0] : 0;
     if (n_dev != nullptr) *n_dev = n + (create ? 1 : 0);
   }
 }
@@ -1310,6 +1310,7 @@ static int frame_enqueue(prs_frame_plan* f, bool moved, cudaStream_t st) {
   // the short chain (see k_vt_frame_prepare): reference mode, 32x32 templates out of a step >= 2 mask, small library
   const bool short_chain = zero_copy && f->mode == PRS_VT_MODE_REF && f->capacity <= kSmallLibrary;
   int rc;
+  int pc_mirrored = 0;
   if (moved) {  // fork: the pose-cell update does not depend on the frame until the decision
     PRS_CUDA(cudaEventRecord(f->ev_fork, st));
     PRS_CUDA(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
@@ -1318,7 +1319,13 @@ static int frame_enqueue(prs_frame_plan* f, bool moved, cudaStream_t st) {
       PRS_CUDA(cudaMemcpyAsync(d_odom, f->odom_host, 2 * sizeof(double), cudaMemcpyHostToDevice, f->side));
       od = d_odom;
     }
-    rc = prs_pc_step(f->pc, f->pc_state, od, f->gi, d_argmax, d_total, d_err, f->side);
+    // with mapped buffers the cluster kernel writes the arg-max and the error bits into the host record itself:
+    // nothing on the template branch waits for the pose-cell update then
+    if (zero_copy)
+      rc = prs_pc_step_mirror(f->pc, f->pc_state, od, f->gi, d_argmax, d_total, d_err, &f->result_map->argmax,
+                              &f->result_map->pc_err, &pc_mirrored, f->side);
+    else
+      rc = prs_pc_step(f->pc, f->pc_state, od, f->gi, d_argmax, d_total, d_err, f->side);
     if (rc != PRS_OK) return rc;
     PRS_CUDA(cudaEventRecord(f->ev_join, f->side));
   }
@@ -1342,10 +1349,11 @@ static int frame_enqueue(prs_frame_plan* f, bool moved, cudaStream_t st) {
     rc = launch_packed_sweep((const uint4*)f->vt_packed, 0, f->capacity, f->mode, 0, d_key, nullptr, f->d_n, st);
     if (rc != PRS_OK) return rc;
   }
-  if (moved) PRS_CUDA(cudaStreamWaitEvent(st, f->ev_join, 0));  // join: the decision reports the new arg-max
+  if (moved && !pc_mirrored) PRS_CUDA(cudaStreamWaitEvent(st, f->ev_join, 0));  // the decision reports the new arg-max
   k_vt_decide_append<<<1, 32, 0, st>>>(d_key, d_tpl, (uint4*)f->vt_packed, 0, f->threshold, d_argmax, d_err,
-                                       zero_copy ? f->result_map : d_res, f->d_n);
+                                       zero_copy ? f->result_map : d_res, f->d_n, pc_mirrored ? 0 : 1);
   PRS_CUDA(cudaGetLastError());
+  if (moved && pc_mirrored) PRS_CUDA(cudaStreamWaitEvent(st, f->ev_join, 0));  // join: the frame ends with both branches
   if (!zero_copy)
     PRS_CUDA(cudaMemcpyAsync(f->result_host, d_res, sizeof(prs_frame_result), cudaMemcpyDeviceToHost, st));
   return PRS_OK;
