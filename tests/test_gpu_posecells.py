@@ -298,3 +298,31 @@ def test_active_cells_sparse_readback(dtype):
         assert np.array_equal(val, pc[pc > thr])
     idx, val = net.active_cells(0.0, max_cells=5)      # truncated output keeps the first cells
     assert np.array_equal(idx, np.stack(np.nonzero(pc > 0), axis=-1)[:5])
+
+
+def test_single_call_update_checks_match_numpy():
+    """prs_pc_update_host's host-side checks (C doubles) against the numpy expressions of the reference
+    (posecell_network.py:249,252-267): same accept / KeyError decision for odometry on and around the LUT hole."""
+    from pyratslam_b200 import PoseCellNetwork
+    shape = (21, 21, 36)
+    net = PoseCellNetwork(shape)
+    net.inject(1, (10, 10, 18))
+    e = net._ens
+    rng = np.random.default_rng(12)
+    cand = np.concatenate([np.array([0.1, 0.5, 0.9, 0.3, 0.7, 0.1 + 1e-17, 0.1 - 1e-16, 0.5000000000000001]),
+                           np.round(rng.uniform(0, 1.5, 40), 1), rng.uniform(0, 1.5, 40)])
+    n_key = 0
+    for v in cand:
+        vt = v / e.pc_vtrans_scale
+        ex = vt * e._cos
+        want_key = bool(((((ex - np.around(ex)) * 10).astype(np.int64)) >= 5).any())
+        n_key += want_key
+        if want_key:
+            before = net.posecells
+            with pytest.raises(KeyError):
+                net.update((float(v), 0.0))
+            assert np.array_equal(net.posecells, before)
+        else:
+            net.update((float(v), 0.0))
+    assert n_key >= 3
+    assert net.get_pc_max() == net.max_pc

@@ -314,3 +314,82 @@ def test_replay_from_rosbag(golden, tmp_path, compression):
     b = ros_simulate.replay_events(ev, fused=True)
     for k in ("template", "created", "argmax", "n_exp", "em_xy"):
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_sweep_variants_agree():
+    """Every kernel variant behind prs_vt_tune (register-prefetch kernels, ring depths, grid sizes) and the small-library
+    kernel of the frame chain produce the same key and the same per-template scores, on ragged library sizes."""
+    from pyratslam_b200 import _native as nat
+    L = nat.lib()
+    rng = np.random.default_rng(11)
+    key = torch.zeros(1, dtype=torch.int64, device="cuda")
+    scratch = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    try:
+        for n in (1, 31, 33, 2077):
+            lib = torch.from_numpy(rng.integers(0, 256, (n, 32, 32), dtype=np.uint8)).cuda()
+            q = torch.from_numpy(rng.integers(0, 256, (32, 32), dtype=np.uint8)).cuda()
+            packed = torch.zeros(int(L.prs_vt_packed_bytes(n)), dtype=torch.uint8, device="cuda")
+            nat.check(L.prs_vt_pack_u8(lib.data_ptr(), n, packed.data_ptr(), 0, nat.stream_ptr()))
+            want = ovt.library_scores(lib.cpu().numpy(), q.cpu().numpy()).astype(np.int64)
+            for depth, ctas in ((0, 1), (2, 1), (2, 5), (4, 5), (8, 3)):
+                nat.check(L.prs_vt_tune(0, depth))
+                nat.check(L.prs_vt_tune(1, ctas))
+                sc = torch.zeros(n, dtype=torch.int32, device="cuda")
+                nat.check(L.prs_vt_sweep_packed_u8(packed.data_ptr(), n, q.data_ptr(), 0, 0, key.data_ptr(), sc.data_ptr(),
+                                                   scratch.data_ptr(), nat.stream_ptr()))
+                assert sc.cpu().numpy().astype(np.int64).tolist() == want.tolist(), (n, depth, ctas)
+                k = int(key.item()) & (2 ** 64 - 1)
+                assert (k >> 32, k & 0xFFFFFFFF) == (int(want.min()), int(np.argmin(want))), (n, depth, ctas)
+            libf = lib.to(torch.float32) + torch.from_numpy(rng.uniform(0, 1, (n, 32, 32)).astype(np.float32)).cuda()
+            qf = q.to(torch.float32)
+            ref = None
+            for depth, ctas in ((0, 1), (1, 8), (2, 3), (3, 2), (4, 1)):
+                nat.check(L.prs_vt_tune(2, depth))
+                nat.check(L.prs_vt_tune(3, ctas))
+                sc = torch.zeros(n, dtype=torch.float32, device="cuda")
+                nat.check(L.prs_vt_sweep_f32(libf.data_ptr(), n, qf.data_ptr(), 0, 0, key.data_ptr(), sc.data_ptr(),
+                                             nat.stream_ptr()))
+                got = (int(key.item()) & (2 ** 64 - 1), sc.cpu().numpy())
+                if ref is None:
+                    ref = got
+                    exact = ovt.library_scores(libf.cpu().numpy().astype(np.float64), qf.cpu().numpy().astype(np.float64))
+                    assert np.abs(got[1] - exact).max() <= 1e-4 * exact.max()
+                else:   # same arithmetic in the same order: bit-identical
+                    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]), (n, depth, ctas)
+        with pytest.raises(ValueError):
+            nat.check(L.prs_vt_tune(0, 3))
+    finally:   # the measured defaults (csrc/view_templates.cu)
+        for knob, val in enumerate((4, 5, 2, 3)):
+            L.prs_vt_tune(knob, val)
+
+
+def test_native_replay_matches_frame_by_frame():
+    """prs_replay_run (the loop on the C side, zero-copy frame chain, small-library sweep) against the three
+    reference-shaped calls per frame: identical records, library contents and experience map."""
+    from pyratslam_b200 import ros_simulate
+    T = 150
+    frames = synth_frames(np.random.default_rng(5), T)
+    rng = np.random.default_rng(6)
+    odom = np.stack([rng.uniform(0, 3, T), rng.uniform(-1, 1, T)], axis=1)
+    odom[7] = (0.0005, -0.0002)          # below the 0.001 gate: no pose-cell update for this frame
+    odom[8] = (0.0, 0.0)
+    a = ros_simulate.replay(frames, odom)
+    for n_plans in (1, 3):
+        node = ros_simulate.RatslamRos()
+        res = node.replay_native(frames, odom, n_plans=n_plans)
+        assert res["template_index"].tolist() == a["template"].tolist()
+        assert (res["created"] != 0).tolist() == a["created"].tolist()
+        assert len(node.em.experiences) == len(a["node"].em.experiences)
+        assert node.em.get_points() == a["node"].em.get_points()
+        assert len(node.vts.templates) == a["n_templates"]
+        i = int(np.flatnonzero(a["created"])[-1])
+        tm, tr = node.vts.templates[int(a["template"][i])], a["node"].vts.templates[int(a["template"][i])]
+        assert np.array_equal(tm.template, tr.template) and tm.location() == tr.location()
+        assert node.pcn.get_pc_max() == a["node"].pcn.get_pc_max()
+    b = ros_simulate.replay(frames, odom, native=True)
+    for k in ("template", "created", "argmax", "n_exp", "em_xy"):
+        assert np.array_equal(a[k], b[k]), k
+    with pytest.raises(KeyError):       # vtrans = 0.1 after the /10 scaling: the reference's LUT hole
+        bad = odom.copy()
+        bad[20] = (1.0, 0.0)
+        ros_simulate.replay(frames[:30], bad[:30], native=True)
