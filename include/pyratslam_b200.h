@@ -198,8 +198,9 @@ PRS_API int prs_vt_sweep_packed_u8(const void* packed, long long n, const uint8_
                            unsigned long long* key_out, uint32_t* scores, void* scratch, void* stream);
 /* Tuning knobs of the sweeps, for profiling (defaults are the measured best): knob 0 = ring depth of the packed
  * reference-mode sweep (slots of 2 KiB per warp fed by TMA bulk copies; 0 = the register-prefetch kernel, else 2, 4
- * or 8), knob 1 = CTAs per SM that sweep's grid is sized for, knob 2 = ring depth of the float32 sweep (templates in
- * flight per warp; 0 = the register kernel), knob 3 = CTAs per SM of the float32 ring sweep. */
+ * or 8), knob 1 = CTAs per SM that sweep's grid is sized for, knob 2 = ring depth of the float32 sweep (0 = the register
+ * kernel; 1..4 = templates in flight per warp, one template per warp; 11..13 = the column-pair kernel -- two columns per
+ * lane, two templates per warp -- with 1..3 template pairs in flight per warp), knob 3 = CTAs per SM of that sweep. */
 PRS_API int prs_vt_tune(int knob, int value);
 /* Any template shape rows x cols (row-major library) and any max_offset (view_templates.py:14): the
  * reference's windowed match for configurations other than its 32x32 default.  Correctness path. */

@@ -244,8 +244,9 @@ int sweep_grid(long long units_per_warp_total) {
 
 // Tuning knobs of the sweeps (prs_vt_tune): [0] ring depth of the packed reference-mode sweep (0 = the
 // register-prefetch kernel), [1] CTAs per SM its grid is sized for, [2] ring depth of the float32 reference-mode
-// sweep (0 = the register kernel), [3] CTAs per SM of that ring sweep.
-static int g_vt_knob[4] = {4, 5, 2, 3};  // measured best on B200 (bench_tools/vt_tune.py)
+// sweep (0 = the register kernel, 1..4 = one template per warp, 11..13 = the column-pair kernel with depth - 10 slots),
+// [3] CTAs per SM of that ring sweep.
+static int g_vt_knob[4] = {4, 5, 13, 2};  // measured best on B200 (bench_tools/vt_tune.py)
 static int launch_f32_ring(int depth, int ctas_per_sm, const float* lib, long long n, const float* query,
                            long long base_index, unsigned long long* key_out, float* scores, cudaStream_t st);
 
@@ -778,6 +779,116 @@ __global__ void __launch_bounds__(kF32RingThreads)
   }
 }
 
+// ---- float32, two columns per lane -------------------------------------------------------------------------
+// The ring kernel above is bound by instruction issue (ncu: 85 % of the issue slots, 2 instructions per
+// element-difference).  Here a lane owns two adjacent columns, so that the subtraction is one packed add.f32x2 for
+// two differences (3 instructions per two) and a template needs only half a warp: a warp works on templates
+// 2i and 2i+1 at once, a ring slot holds both (two bulk copies on one barrier).  The slot is refilled after it has
+// been compared (the other D - 1 slots are in flight meanwhile).  The sums are formed in another order than in
+// k_vt_sweep_f32: scores agree to rounding (exactly, for integer-valued profiles), not bit for bit.
+template <int D>
+__global__ void __launch_bounds__(kF32RingThreads)
+    k_vt_sweep_f32_pair(const float* __restrict__ lib, long long n, const float* __restrict__ query, long long base_index,
+                        unsigned long long* __restrict__ key_out, float* __restrict__ scores) {
+  using S = VtShape<PRS_VT_MODE_REF>;
+  extern __shared__ __align__(128) unsigned char vt_ring_smem[];
+  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const long long n_pairs = (n + 1) >> 1;
+  const long long warp0 = (long long)blockIdx.x * (kF32RingThreads / 32) + wid;
+  const long long n_warps = (long long)gridDim.x * (kF32RingThreads / 32);
+  constexpr int kSlot = 2 * kF32ItemBytes;
+  const uint32_t ring = vt_smem_u32(vt_ring_smem) + wid * D * kSlot;
+  const uint32_t bars = vt_smem_u32(vt_ring_smem) + (kF32RingThreads / 32) * D * kSlot + wid * D * 8;
+  const char* base = reinterpret_cast<const char*>(lib) + 128;  // row 1 of template 0
+  auto fill = [&](uint32_t slot_addr, long long pi, uint32_t bar) {  // one elected lane
+    const char* src = base + pi * 8192;
+    if (2 * pi + 1 < n) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(kSlot) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       slot_addr),
+                   "l"(src), "n"(kF32ItemBytes), "r"(bar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1+4096], %2, [%3];" ::"r"(
+                       slot_addr + kF32ItemBytes),
+                   "l"(src), "n"(kF32ItemBytes), "r"(bar)
+                   : "memory");
+    } else {  // odd library size: the last pair has one template
+      vt_ring_fill<0, kF32ItemBytes>(slot_addr, src, bar);
+    }
+  };
+  if (vt_elect_one()) {
+#pragma unroll
+    for (int s = 0; s < D; ++s) vt_mbar_init(bars + s * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < D; ++s)
+      if (warp0 + s * n_warps < n_pairs) fill(ring + s * kSlot, warp0 + s * n_warps, bars + s * 8);
+  }
+  __syncwarp();
+  float2 nq[S::NS];  // minus the query's two columns of this lane
+#pragma unroll
+  for (int s = 0; s < S::NS; ++s) {
+    const float2 v = *reinterpret_cast<const float2*>(query + (S::S0 + s) * 32 + 2 * l16);
+    nq[s] = make_float2(-v.x, -v.y);
+  }
+  unsigned long long best = ~0ull;
+  int slot = 0;
+  uint32_t parity = 0;
+  for (long long pi = warp0; pi < n_pairs; pi += n_warps) {
+    const uint32_t sl = ring + slot * kSlot;
+    vt_mbar_wait(bars + slot * 8, parity);
+    const uint32_t mine = sl + half * kF32ItemBytes + l16 * 8;
+    float acc[S::NACC];
+#pragma unroll
+    for (int i = 0; i < S::NACC; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int t = S::T0; t < S::T1; ++t) {
+      float2 a;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a.x), "=f"(a.y) : "r"(mine + (t - S::T0) * 128));
+#pragma unroll
+      for (int s = 0; s < S::NS; ++s) {
+        if (S::valid(t, S::S0 + s)) {
+          const float2 d = __fadd2_rn(a, nq[s]);
+          acc[S::off(t, S::S0 + s)] = (acc[S::off(t, S::S0 + s)] + fabsf(d.x)) + fabsf(d.y);
+        }
+      }
+    }
+    // every lane's loads have been consumed by the sums above: refill the slot with the pair D rounds ahead
+    __syncwarp();
+    if (vt_elect_one()) {
+      const long long np = pi + D * n_warps;
+      if (np < n_pairs) fill(sl, np, bars + slot * 8);
+    }
+    if (++slot == D) {
+      slot = 0;
+      parity ^= 1u;
+    }
+    int obase = 0;
+    Butterfly<S::NACC, 8, float>::run(acc, lane, obase);  // over the 16 lanes of the half-warp
+    float m = (obase < S::NOFF) ? acc[0] : INFINITY;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const long long ti = 2 * pi + half;
+    if (ti < n) {
+      unsigned long long key = ((unsigned long long)__float_as_uint(m) << 32) | (unsigned long long)(base_index + ti);
+      best = key < best ? key : best;
+      if (scores != nullptr && l16 == 0) scores[ti] = m;
+    }
+  }
+  __shared__ unsigned long long sm[kF32RingThreads / 32];
+  best = warp_min_u64(best);
+  if (lane == 0) sm[wid] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long k = sm[0];
+#pragma unroll
+    for (int i = 1; i < kF32RingThreads / 32; ++i) k = sm[i] < k ? sm[i] : k;
+    if (k != ~0ull) atomicMin(key_out, k);
+  }
+}
+
 // Circular mode (all 32 cyclic row shifts; extension).  The shift of a (stored row t, query row s) pair is
 // (t - s) mod 32, which depends on the run-time row t -- but only through t mod 8 once the 32 counters are kept
 // in registers and ROTATED by eight places after every eight stored rows: inside a block of eight rows the
@@ -859,7 +970,9 @@ __global__ void __launch_bounds__(kPkThreads, 4)
 extern "C" int prs_vt_tune(int knob, int value) {
   PRS_REQUIRE(knob >= 0 && knob < 4, "prs_vt_tune: unknown knob %d", knob);
   if (knob == 0) PRS_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8, "prs_vt_tune: ring depth must be 0, 2, 4 or 8");
-  if (knob == 2) PRS_REQUIRE(value >= 0 && value <= 4, "prs_vt_tune: float32 ring depth must be in 0..4");
+  if (knob == 2)
+    PRS_REQUIRE((value >= 0 && value <= 4) || (value >= 11 && value <= 13),
+                "prs_vt_tune: float32 ring depth must be in 0..4, or 11..13 for the column-pair kernel");
   if (knob == 1 || knob == 3) PRS_REQUIRE(value >= 1 && value <= 32, "prs_vt_tune: CTAs per SM must be in 1..32");
   g_vt_knob[knob] = value;
   return PRS_OK;
@@ -876,8 +989,29 @@ static int launch_f32_ring_d(int blocks, const float* lib, long long n, const fl
   return PRS_OK;
 }
 
+template <int D>
+static int launch_f32_pair_d(int blocks, const float* lib, long long n, const float* query, long long base_index,
+                             unsigned long long* key_out, float* scores, cudaStream_t st) {
+  constexpr int smem = (kF32RingThreads / 32) * D * (2 * kF32ItemBytes + 8);
+  if (smem > 48 * 1024)
+    PRS_CUDA(cudaFuncSetAttribute(k_vt_sweep_f32_pair<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_vt_sweep_f32_pair<D><<<blocks, kF32RingThreads, smem, st>>>(lib, n, query, base_index, key_out, scores);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
 static int launch_f32_ring(int depth, int ctas_per_sm, const float* lib, long long n, const float* query,
                            long long base_index, unsigned long long* key_out, float* scores, cudaStream_t st) {
+  if (depth >= 11) {  // two columns per lane, two templates per warp; ring depth = depth - 10
+    const long long pairs = (n + 1) / 2;
+    long long blocks = (pairs + (kF32RingThreads / 32) - 1) / (kF32RingThreads / 32);
+    if (blocks > 148LL * ctas_per_sm) blocks = 148LL * ctas_per_sm;
+    switch (depth - 10) {
+      case 1: return launch_f32_pair_d<1>((int)blocks, lib, n, query, base_index, key_out, scores, st);
+      case 2: return launch_f32_pair_d<2>((int)blocks, lib, n, query, base_index, key_out, scores, st);
+      default: return launch_f32_pair_d<3>((int)blocks, lib, n, query, base_index, key_out, scores, st);
+    }
+  }
   long long blocks = (n + (kF32RingThreads / 32) - 1) / (kF32RingThreads / 32);
   if (blocks > 148LL * ctas_per_sm) blocks = 148LL * ctas_per_sm;
   switch (depth) {

@@ -343,7 +343,7 @@ def test_sweep_variants_agree():
             libf = lib.to(torch.float32) + torch.from_numpy(rng.uniform(0, 1, (n, 32, 32)).astype(np.float32)).cuda()
             qf = q.to(torch.float32)
             ref = None
-            for depth, ctas in ((0, 1), (1, 8), (2, 3), (3, 2), (4, 1)):
+            for depth, ctas in ((0, 1), (1, 8), (2, 3), (3, 2), (4, 1), (11, 6), (12, 3), (13, 2)):
                 nat.check(L.prs_vt_tune(2, depth))
                 nat.check(L.prs_vt_tune(3, ctas))
                 sc = torch.zeros(n, dtype=torch.float32, device="cuda")
@@ -354,12 +354,16 @@ def test_sweep_variants_agree():
                     ref = got
                     exact = ovt.library_scores(libf.cpu().numpy().astype(np.float64), qf.cpu().numpy().astype(np.float64))
                     assert np.abs(got[1] - exact).max() <= 1e-4 * exact.max()
-                else:   # same arithmetic in the same order: bit-identical
+                elif depth < 10:   # same arithmetic in the same order: bit-identical
                     assert got[0] == ref[0] and np.array_equal(got[1], ref[1]), (n, depth, ctas)
+                else:              # column-pair kernel: another summation order, same arg-min
+                    assert got[0] & 0xFFFFFFFF == ref[0] & 0xFFFFFFFF, (n, depth, ctas)
+                    assert np.abs(got[1] - ref[1]).max() <= 1e-5 * ref[1].max(), (n, depth, ctas)
+                    assert np.abs(got[1] - exact).max() <= 1e-4 * exact.max()
         with pytest.raises(ValueError):
             nat.check(L.prs_vt_tune(0, 3))
     finally:   # the measured defaults (csrc/view_templates.cu)
-        for knob, val in enumerate((4, 5, 2, 3)):
+        for knob, val in enumerate((4, 5, 13, 2)):
             L.prs_vt_tune(knob, val)
 
 
