@@ -248,6 +248,7 @@ def extra_single_gpu(torch, peak, steps):
     gbs = nf * 4096 / (ms * 1e-3) / 1e9
     out["vt_f32_ref"] = {"metric": "VT shift-compares/s", "value": nf * 15 / (ms * 1e-3), "ms_per_query": ms,
                          "library": "2^18 x 32x32 float32 (1 GiB)",
+                         "note": "read-only stream: can exceed the peak, which is a measured COPY (read + write) bandwidth",
                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak}}
     del libf
     # ---- BASELINE config 3: one 256x256x72 network
