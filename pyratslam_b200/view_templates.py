@@ -386,18 +386,32 @@ class ShardedViewTemplates:
         else:
             self._lib = self._rows
 
-    def local_sweep(self, query_dev):
-        """Launch the local sweep; the packed key is left in ``self._key`` on the device."""
+    def local_sweep(self, query_dev, key=None):
+        """Launch the local sweep; the packed key is left in ``key`` (a one-element int64 device tensor, default
+        ``self._key``) on the device."""
+        key = self._key if key is None else key
         lib_ptr = self._lib.data_ptr() if self._n else None
         if self._dtype == torch.uint8:
             nat.check(nat.lib().prs_vt_sweep_packed_u8(lib_ptr, self._n, query_dev.data_ptr(), self.mode,
-                                                       self.base_index, self._key.data_ptr(), None,
+                                                       self.base_index, key.data_ptr(), None,
                                                        self._scratch.data_ptr(), nat.stream_ptr()),
                       "prs_vt_sweep_packed_u8")
         else:
             nat.check(nat.lib().prs_vt_sweep_f32(lib_ptr, self._n, query_dev.data_ptr(), self.mode, self.base_index,
-                                                 self._key.data_ptr(), None, nat.stream_ptr()), "prs_vt_sweep_f32")
-        return self._key
+                                                 key.data_ptr(), None, nat.stream_ptr()), "prs_vt_sweep_f32")
+        return key
+
+    def match_keys(self, queries_dev):
+        """``match_key`` for a batch of queries ``[Q, 32, 32]``: Q local sweeps, ONE MIN all-reduce of the Q packed
+        keys and one read-back -- the exchange and the synchronisation are paid once per batch, not once per query.
+        Returns a list of ``(score, index)``, identical on every rank."""
+        Q = int(queries_dev.shape[0])
+        keys = torch.empty(Q, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            for i in range(Q):
+                self.local_sweep(queries_dev[i], keys[i:i + 1])
+            host = reduce_packed_key(keys, self.group).cpu().numpy()
+        return [unpack_key(int(k), is_float=self._dtype != torch.uint8) for k in host]
 
     def match_key(self, query_dev):
         """Global ``(score, index)`` of the best match over all shards; identical on every rank."""

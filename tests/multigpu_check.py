@@ -44,6 +44,8 @@ def main():
             ref = ovt.library_scores(lib, q, mode=mode)
             score, idx = svt.match_key(torch.from_numpy(q).cuda())
             assert (score, idx) == (int(ref.min()), int(np.argmin(ref))), (rank, mode, qi, score, idx)
+        batch = svt.match_keys(torch.from_numpy(np.stack(queries)).cuda())     # one all-reduce for the three queries
+        assert batch == [(int(r.min()), int(np.argmin(r))) for r in (ovt.library_scores(lib, q, mode=mode) for q in queries)]
         index, created = svt.match(torch.from_numpy(queries[2]).cuda())
         assert created and index == n and svt.n_total == n + 1
         index, created = svt.match(torch.from_numpy(queries[2]).cuda())     # now it is in the last shard

@@ -397,3 +397,24 @@ def test_native_replay_matches_frame_by_frame():
         bad = odom.copy()
         bad[20] = (1.0, 0.0)
         ros_simulate.replay(frames[:30], bad[:30], native=True)
+
+
+def test_sharded_batch_matches_per_query():
+    """ShardedViewTemplates.match_keys (one reduction and one read-back per batch) against match_key per query and the
+    oracle, on a single rank (the multi-rank path runs in tests/multigpu_check.py)."""
+    from pyratslam_b200 import ShardedViewTemplates
+    rng = np.random.default_rng(21)
+    n = 3001
+    lib = rng.integers(0, 256, (n, 32, 32), dtype=np.uint8)
+    qs = np.stack([np.clip(lib[1234].astype(np.int16) - 2, 0, 255).astype(np.uint8),
+                   np.roll(lib[77], 3, axis=0), rng.integers(0, 256, (32, 32), dtype=np.uint8)])
+    for mode in ("ref", "circular"):
+        svt = ShardedViewTemplates(lib, 100, match_threshold=45000, mode=mode)      # base index 100: global indices
+        got = svt.match_keys(torch.from_numpy(qs).cuda())
+        assert got == [svt.match_key(torch.from_numpy(q).cuda()) for q in qs]
+        for (score, idx), q in zip(got, qs):
+            ref = ovt.library_scores(lib, q, mode=mode)
+            assert (score, idx) == (int(ref.min()), 100 + int(np.argmin(ref)))
+    svf = ShardedViewTemplates(lib.astype(np.float32), 0, match_threshold=9000.0)
+    gotf = svf.match_keys(torch.from_numpy(qs.astype(np.float32)).cuda())
+    assert [i for _, i in gotf] == [int(np.argmin(ovt.library_scores(lib.astype(np.float64), q.astype(np.float64)))) for q in qs]
