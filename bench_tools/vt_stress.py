@@ -13,7 +13,7 @@ L = nat.lib()
 g = torch.Generator(device="cuda").manual_seed(9)
 key = torch.zeros(1, dtype=torch.int64, device="cuda")
 scratch = torch.zeros(4096, dtype=torch.uint8, device="cuda")
-DEF = (4, 5, 13, 2)
+DEF = (34, 5, 13, 2)
 bad = 0
 # ---- bit-sliced uint8
 n = (1 << 19) + 77
@@ -35,7 +35,7 @@ for q in qs:
     sc = torch.zeros(n, dtype=torch.int32, device="cuda")
     sweep_u8(q, sc)
     want.append(sc)
-for depth, ctas in ((4, 5), (4, 6), (8, 3), (2, 5)):
+for depth, ctas in ((34, 5), (34, 6), (44, 1), (4, 5), (8, 3), (2, 5)):
     nat.check(L.prs_vt_tune(0, depth))
     nat.check(L.prs_vt_tune(1, ctas))
     for r in range(rounds):

@@ -54,9 +54,9 @@ def main():
         for t in range(3):
             sweep(t, scores)
             want.append((int(key.item()), scores.clone()))
-        for depth in (0, 2, 4, 8):
-            for ctas in ((16,) if depth == 0 else (3, 4, 5, 6)):
-                if depth * 4 * 2056 * ctas > 225 * 1024:
+        for depth in (0, 2, 4, 8, 34, 44):
+            for ctas in ((16,) if depth == 0 else (1,) if depth == 44 else (3, 4, 5, 6)):
+                if (depth % 10) * 4 * 2056 * ctas > 225 * 1024:
                     continue
                 nat.check(L.prs_vt_tune(0, depth))
                 nat.check(L.prs_vt_tune(1, ctas))
@@ -74,7 +74,7 @@ def main():
                 break
         del packed, scores
     # ---- float32, reference mode
-    for nf in ((1 << 18) - 5, 1 << 18):
+    for nf in (() if "--u8-only" in sys.argv else ((1 << 18) - 5, 1 << 18)):
         libf = torch.rand((nf, 32, 32), dtype=torch.float32, device="cuda", generator=g) * 255
         qf = torch.rand((32, 32), dtype=torch.float32, device="cuda", generator=g) * 255
         sc = torch.zeros(nf, dtype=torch.float32, device="cuda")

@@ -198,7 +198,8 @@ PRS_API int prs_vt_sweep_packed_u8(const void* packed, long long n, const uint8_
                            unsigned long long* key_out, uint32_t* scores, void* scratch, void* stream);
 /* Tuning knobs of the sweeps, for profiling (defaults are the measured best): knob 0 = ring depth of the packed
  * reference-mode sweep (slots of 2 KiB per warp fed by TMA bulk copies; 0 = the register-prefetch kernel, else 2, 4
- * or 8), knob 1 = CTAs per SM that sweep's grid is sized for, knob 2 = ring depth of the float32 sweep (0 = the register
+ * or 8; 34 = four slots and the warps of a CTA kept in lock step by a barrier per ring item, 44 = the same with one
+ * 640-thread CTA per SM), knob 1 = CTAs per SM that sweep's grid is sized for, knob 2 = ring depth of the float32 sweep (0 = the register
  * kernel; 1..4 = templates in flight per warp, one template per warp; 11..13 = the column-pair kernel -- two columns per
  * lane, two templates per warp -- with 1..3 template pairs in flight per warp), knob 3 = CTAs per SM of that sweep. */
 PRS_API int prs_vt_tune(int knob, int value);

@@ -243,10 +243,11 @@ int sweep_grid(long long units_per_warp_total) {
 }  // namespace
 
 // Tuning knobs of the sweeps (prs_vt_tune): [0] ring depth of the packed reference-mode sweep (0 = the
-// register-prefetch kernel), [1] CTAs per SM its grid is sized for, [2] ring depth of the float32 reference-mode
+// register-prefetch kernel; 2, 4, 8 = slots per warp; 34 = 4 slots with the CTA's warps in lock step, 44 = the same
+// with one 640-thread CTA per SM), [1] CTAs per SM its grid is sized for, [2] ring depth of the float32 reference-mode
 // sweep (0 = the register kernel, 1..4 = one template per warp, 11..13 = the column-pair kernel with depth - 10 slots),
 // [3] CTAs per SM of that ring sweep.
-static int g_vt_knob[4] = {4, 5, 13, 2};  // measured best on B200 (bench_tools/vt_tune.py)
+static int g_vt_knob[4] = {34, 5, 13, 2};  // measured best on B200 (bench_tools/vt_tune.py)
 static int launch_f32_ring(int depth, int ctas_per_sm, const float* lib, long long n, const float* query,
                            long long base_index, unsigned long long* key_out, float* scores, cudaStream_t st);
 
@@ -597,37 +598,42 @@ struct RingPrologue {
   }
 };
 
-template <int D, int J>
+template <int D, int J, bool LOCK>
 struct RingItems {
-  // ring / bars: shared addresses of this warp's slots and barriers; gb / nb: this group and the warp's next one
+  // ring / bars: shared addresses of this warp's slots and barriers; gb / nb: this group and the warp's next one.
+  // LOCK: the warps of the CTA meet at a barrier after every item, so that all of them execute the same stretch of
+  // the (48 KB, straight-line) code at the same time; `active` is false for a warp that has run out of groups.
   __device__ __forceinline__ static void run(uint32_t ring, uint32_t bars, const char* gb, const char* nb, int lane,
-                                             uint32_t (&cnt)[15], uint4 (&rs)[4]) {
+                                             bool active, uint32_t (&cnt)[15], uint4 (&rs)[4]) {
     if constexpr (J < kItemsPerGroup) {
       constexpr int slot = J % D;
-      const uint32_t sl = ring + slot * kItemBytes + lane * 16;
-      vt_mbar_wait(bars + slot * 8, (J / D) & 1);
-      const uint4 lo0 = lds_u4(sl), hi0 = lds_u4(sl + 512), lo1 = lds_u4(sl + 1024), hi1 = lds_u4(sl + 1536);
-      if constexpr (J < 15) {
-        ref_row<2 * J + 1>(lo0, hi0, cnt);
-        ref_row<2 * J + 2>(lo1, hi1, cnt);
-      } else {
-        rs[0] = lo0, rs[1] = hi0, rs[2] = lo1, rs[3] = hi1;
+      if (!LOCK || active) {
+        const uint32_t sl = ring + slot * kItemBytes + lane * 16;
+        vt_mbar_wait(bars + slot * 8, (J / D) & 1);
+        const uint4 lo0 = lds_u4(sl), hi0 = lds_u4(sl + 512), lo1 = lds_u4(sl + 1024), hi1 = lds_u4(sl + 1536);
+        if constexpr (J < 15) {
+          ref_row<2 * J + 1>(lo0, hi0, cnt);
+          ref_row<2 * J + 2>(lo1, hi1, cnt);
+        } else {
+          rs[0] = lo0, rs[1] = hi0, rs[2] = lo1, rs[3] = hi1;
+        }
+        // the slot's contents are in registers (the compares above consumed them): refill it with item J + D
+        __syncwarp();
+        if (vt_elect_one()) {
+          if constexpr (J + D < kItemsPerGroup)
+            vt_ring_fill<pk_item_off(J + D), kItemBytes>(ring + slot * kItemBytes, gb, bars + slot * 8);
+          else if (nb != nullptr)
+            vt_ring_fill<pk_item_off((J + D) % kItemsPerGroup), kItemBytes>(ring + slot * kItemBytes, nb, bars + slot * 8);
+        }
       }
-      // the slot's contents are in registers (the compares above consumed them): refill it with item J + D
-      __syncwarp();
-      if (vt_elect_one()) {
-        if constexpr (J + D < kItemsPerGroup)
-          vt_ring_fill<pk_item_off(J + D), kItemBytes>(ring + slot * kItemBytes, gb, bars + slot * 8);
-        else if (nb != nullptr)
-          vt_ring_fill<pk_item_off((J + D) % kItemsPerGroup), kItemBytes>(ring + slot * kItemBytes, nb, bars + slot * 8);
-      }
-      RingItems<D, J + 1>::run(ring, bars, gb, nb, lane, cnt, rs);
+      if constexpr (LOCK) __syncthreads();
+      RingItems<D, J + 1, LOCK>::run(ring, bars, gb, nb, lane, active, cnt, rs);
     }
   }
 };
 
-template <int D>
-__global__ void __launch_bounds__(kPkThreads, 5)  // 96 registers: the query planes stay constant-bank operands
+template <int D, int NT, bool LOCK>
+__global__ void __launch_bounds__(NT, NT == 128 ? 5 : 1)  // 96 registers: the query planes stay constant-bank operands
     k_vt_sweep_packed_ref_ring(const uint4* __restrict__ packed, long long n, long long base_index,
                                unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores,
                                const int* __restrict__ n_dev) {
@@ -637,10 +643,10 @@ __global__ void __launch_bounds__(kPkThreads, 5)  // 96 registers: the query pla
   const int lane = threadIdx.x & 31;
   const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform, and known to be
   const long long n_groups = (n + 31) >> 5;
-  const long long warp0 = (long long)blockIdx.x * (kPkThreads / 32) + wid;
-  const long long n_warps = (long long)gridDim.x * (kPkThreads / 32);
+  const long long warp0 = (long long)blockIdx.x * (NT / 32) + wid;
+  const long long n_warps = (long long)gridDim.x * (NT / 32);
   const uint32_t ring = vt_smem_u32(vt_ring_smem) + wid * D * kItemBytes;
-  const uint32_t bars = vt_smem_u32(vt_ring_smem) + (kPkThreads / 32) * D * kItemBytes + wid * D * 8;
+  const uint32_t bars = vt_smem_u32(vt_ring_smem) + (NT / 32) * D * kItemBytes + wid * D * 8;
   constexpr long long kGroupBytes = (long long)kGroupU4 * 16;
   if (vt_elect_one()) {
 #pragma unroll
@@ -654,14 +660,16 @@ __global__ void __launch_bounds__(kPkThreads, 5)  // 96 registers: the query pla
   }
   __syncwarp();
   unsigned long long best = ~0ull;
-  for (long long g = warp0; g < n_groups; g += n_warps) {
+  // LOCK: every warp of the CTA makes as many rounds as its first warp (the one with the lowest group index)
+  for (long long g = warp0; (LOCK ? g - wid : g) < n_groups; g += n_warps) {
+    const bool active = g < n_groups;
     const char* gb = reinterpret_cast<const char*>(packed) + g * kGroupBytes;
     const char* nb = (g + n_warps < n_groups) ? gb + n_warps * kGroupBytes : nullptr;
     uint32_t cnt[15];
 #pragma unroll
     for (int i = 0; i < 15; ++i) cnt[i] = 0;
-    uint4 rs[4];
-    RingItems<D, 0>::run(ring, bars, gb, nb, lane, cnt, rs);
+    uint4 rs[4] = {};
+    RingItems<D, 0, LOCK>::run(ring, bars, gb, nb, lane, active, cnt, rs);
     uint32_t R[32];
 #pragma unroll
     for (int w4 = 0; w4 < 4; ++w4) {
@@ -684,20 +692,20 @@ __global__ void __launch_bounds__(kPkThreads, 5)  // 96 registers: the query pla
       if (o < 7) A = A - R[8 + o] + R[24 + o];
     }
     const long long ti = g * 32 + lane;
-    if (ti < n) {
+    if (active && ti < n) {
       const unsigned long long key = ((unsigned long long)m << 32) | (unsigned long long)(base_index + ti);
       best = key < best ? key : best;
       if (scores != nullptr) scores[ti] = m;
     }
   }
-  __shared__ unsigned long long sm[kPkThreads / 32];
+  __shared__ unsigned long long sm[NT / 32];
   best = warp_min_u64(best);
   if (lane == 0) sm[wid] = best;
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long k = sm[0];
 #pragma unroll
-    for (int i = 1; i < kPkThreads / 32; ++i) k = sm[i] < k ? sm[i] : k;
+    for (int i = 1; i < NT / 32; ++i) k = sm[i] < k ? sm[i] : k;
     if (k != ~0ull) atomicMin(key_out, k);
   }
 }
@@ -977,7 +985,8 @@ __global__ void __launch_bounds__(kPkThreads, 4)
 
 extern "C" int prs_vt_tune(int knob, int value) {
   PRS_REQUIRE(knob >= 0 && knob < 4, "prs_vt_tune: unknown knob %d", knob);
-  if (knob == 0) PRS_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8, "prs_vt_tune: ring depth must be 0, 2, 4 or 8");
+  if (knob == 0) PRS_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8 || value == 34 || value == 44,
+                             "prs_vt_tune: ring depth must be 0, 2, 4 or 8, or 34 / 44 for the lock-step variants");
   if (knob == 2)
     PRS_REQUIRE((value >= 0 && value <= 4) || (value >= 11 && value <= 13),
                 "prs_vt_tune: float32 ring depth must be in 0..4, or 11..13 for the column-pair kernel");
@@ -1030,13 +1039,16 @@ static int launch_f32_ring(int depth, int ctas_per_sm, const float* lib, long lo
   }
 }
 
-template <int D>
-static int launch_ref_ring(int blocks, const uint4* packed, long long n, long long base_index, unsigned long long* key_out,
-                           uint32_t* scores, const int* n_dev, cudaStream_t st) {
-  constexpr int smem = (kPkThreads / 32) * D * (kItemBytes + 8);
+template <int D, int NT, bool LOCK>
+static int launch_ref_ring(long long groups, int ctas_per_sm, const uint4* packed, long long n, long long base_index,
+                           unsigned long long* key_out, uint32_t* scores, const int* n_dev, cudaStream_t st) {
+  constexpr int smem = (NT / 32) * D * (kItemBytes + 8);
   if (smem > 48 * 1024)  // per device; cheap enough to repeat
-    PRS_CUDA(cudaFuncSetAttribute(k_vt_sweep_packed_ref_ring<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_vt_sweep_packed_ref_ring<D><<<blocks, kPkThreads, smem, st>>>(packed, n, base_index, key_out, scores, n_dev);
+    PRS_CUDA(cudaFuncSetAttribute(k_vt_sweep_packed_ref_ring<D, NT, LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  long long blocks = (groups + (NT / 32) - 1) / (NT / 32);
+  if (blocks > 148LL * ctas_per_sm) blocks = 148LL * ctas_per_sm;
+  if (blocks < 1) blocks = 1;
+  k_vt_sweep_packed_ref_ring<D, NT, LOCK><<<(int)blocks, NT, smem, st>>>(packed, n, base_index, key_out, scores, n_dev);
   return PRS_OK;
 }
 
@@ -1051,10 +1063,14 @@ static int launch_packed_sweep(const uint4* packed, long long n, long long n_gri
     const long long cap = 148LL * (depth ? g_vt_knob[1] : 16);
     if (blocks > cap) blocks = cap;
     int rc = PRS_OK;
+    const int cps = g_vt_knob[1];
     switch (depth) {
-      case 2: rc = launch_ref_ring<2>((int)blocks, packed, n, base_index, key_out, scores, n_dev, st); break;
-      case 4: rc = launch_ref_ring<4>((int)blocks, packed, n, base_index, key_out, scores, n_dev, st); break;
-      case 8: rc = launch_ref_ring<8>((int)blocks, packed, n, base_index, key_out, scores, n_dev, st); break;
+      case 2: rc = launch_ref_ring<2, 128, false>(groups, cps, packed, n, base_index, key_out, scores, n_dev, st); break;
+      case 4: rc = launch_ref_ring<4, 128, false>(groups, cps, packed, n, base_index, key_out, scores, n_dev, st); break;
+      case 8: rc = launch_ref_ring<8, 128, false>(groups, cps, packed, n, base_index, key_out, scores, n_dev, st); break;
+      // lock-step variants: the warps of a CTA meet at a barrier after every ring item
+      case 34: rc = launch_ref_ring<4, 128, true>(groups, cps, packed, n, base_index, key_out, scores, n_dev, st); break;
+      case 44: rc = launch_ref_ring<4, 640, true>(groups, 1, packed, n, base_index, key_out, scores, n_dev, st); break;
       default:
         k_vt_sweep_packed_ref<<<(int)blocks, kPkThreads, 0, st>>>(packed, n, base_index, key_out, scores, n_dev);
     }

@@ -331,7 +331,7 @@ def test_sweep_variants_agree():
             packed = torch.zeros(int(L.prs_vt_packed_bytes(n)), dtype=torch.uint8, device="cuda")
             nat.check(L.prs_vt_pack_u8(lib.data_ptr(), n, packed.data_ptr(), 0, nat.stream_ptr()))
             want = ovt.library_scores(lib.cpu().numpy(), q.cpu().numpy()).astype(np.int64)
-            for depth, ctas in ((0, 1), (2, 1), (2, 5), (4, 5), (8, 3)):
+            for depth, ctas in ((0, 1), (2, 1), (2, 5), (4, 5), (8, 3), (34, 5), (34, 2), (44, 1)):
                 nat.check(L.prs_vt_tune(0, depth))
                 nat.check(L.prs_vt_tune(1, ctas))
                 sc = torch.zeros(n, dtype=torch.int32, device="cuda")
@@ -363,7 +363,7 @@ def test_sweep_variants_agree():
         with pytest.raises(ValueError):
             nat.check(L.prs_vt_tune(0, 3))
     finally:   # the measured defaults (csrc/view_templates.cu)
-        for knob, val in enumerate((4, 5, 13, 2)):
+        for knob, val in enumerate((34, 5, 13, 2)):
             L.prs_vt_tune(knob, val)
 
 
