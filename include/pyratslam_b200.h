@@ -201,7 +201,8 @@ PRS_API int prs_vt_sweep_packed_u8(const void* packed, long long n, const uint8_
  * or 8; 34 = four slots and the warps of a CTA kept in lock step by a barrier per ring item, 44 = the same with one
  * 640-thread CTA per SM), knob 1 = CTAs per SM that sweep's grid is sized for, knob 2 = ring depth of the float32 sweep (0 = the register
  * kernel; 1..4 = templates in flight per warp, one template per warp; 11..13 = the column-pair kernel -- two columns per
- * lane, two templates per warp -- with 1..3 template pairs in flight per warp), knob 3 = CTAs per SM of that sweep. */
+ * lane, two templates per warp -- with 1..3 template pairs in flight per warp), knob 3 = CTAs per SM of that sweep, knob 4 = the
+ * circular-mode sweep keeps the warps of a CTA in lock step (1, default) or not (0). */
 PRS_API int prs_vt_tune(int knob, int value);
 /* Any template shape rows x cols (row-major library) and any max_offset (view_templates.py:14): the
  * reference's windowed match for configurations other than its 32x32 default.  Correctness path. */

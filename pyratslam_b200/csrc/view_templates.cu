@@ -912,14 +912,24 @@ __global__ void __launch_bounds__(kF32RingThreads)
 // block.  32 register MOVs per block replace 256 shared-memory read-modify-writes.
 // eight stored rows (t0 .. t0+7, held in registers) against every query row; query row outermost so that only
 // its eight plane words are live as (uniform-register) operands at a time
-__device__ __forceinline__ void circ_block(const uint4 (&lo)[8], const uint4 (&hi)[8], uint32_t (&cnt)[32]) {
+#ifndef PRS_VT_CIRC_SYNC_MASK
+#define PRS_VT_CIRC_SYNC_MASK 3
+#endif
+// LOCK: the warps of the CTA meet at a barrier after every four query rows (32 row pairs), so that they fetch the
+// same stretch of the unrolled code together; `active` is false for a warp that has run out of groups.
+template <bool LOCK>
+__device__ __forceinline__ void circ_block(const uint4 (&lo)[8], const uint4 (&hi)[8], uint32_t (&cnt)[32], bool active) {
 #pragma unroll
   for (int s = 0; s < 32; ++s) {
+    if (!LOCK || active) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cnt[(i - s) & 31] += lt_row(lo[i], hi[i], s);
+      for (int i = 0; i < 8; ++i) cnt[(i - s) & 31] += lt_row(lo[i], hi[i], s);
+    }
+    if (LOCK && (s & PRS_VT_CIRC_SYNC_MASK) == PRS_VT_CIRC_SYNC_MASK) __syncthreads();
   }
 }
 
+template <bool LOCK>
 __global__ void __launch_bounds__(kPkThreads, 4)
     k_vt_sweep_packed_circ(const uint4* __restrict__ packed, long long n, long long base_index,
                            unsigned long long* __restrict__ key_out, uint32_t* __restrict__ scores,
@@ -930,8 +940,10 @@ __global__ void __launch_bounds__(kPkThreads, 4)
   const long long warp0 = ((long long)blockIdx.x * kPkThreads + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * kPkThreads) >> 5;
   unsigned long long best = ~0ull;
-  for (long long g = warp0; g < n_groups; g += n_warps) {
-    const uint4* gp = packed + g * kGroupU4 + lane;
+  // LOCK: every warp of the CTA makes as many rounds as its first warp; one without a group only keeps the barriers
+  for (long long g = warp0; (LOCK ? g - wid : g) < n_groups; g += n_warps) {
+    const bool active = g < n_groups;
+    const uint4* gp = packed + (active ? g : 0) * kGroupU4 + lane;
     uint32_t cnt[32];
 #pragma unroll
     for (int o = 0; o < 32; ++o) cnt[o] = 0;
@@ -944,7 +956,7 @@ __global__ void __launch_bounds__(kPkThreads, 4)
         lo[i] = ld_stream_u4(gp + ((8 * c + i) * 2 + 0) * 32);
         hi[i] = ld_stream_u4(gp + ((8 * c + i) * 2 + 1) * 32);
       }
-      circ_block(lo, hi, cnt);
+      circ_block<LOCK>(lo, hi, cnt, active);
       uint32_t rot[32];
 #pragma unroll
       for (int r = 0; r < 32; ++r) rot[r] = cnt[(r + 8) & 31];
@@ -964,7 +976,7 @@ __global__ void __launch_bounds__(kPkThreads, 4)
 #pragma unroll
     for (int o = 0; o < 32; ++o) m = min(m, A + 256u * cnt[o] - bq);
     const long long ti = g * 32 + lane;
-    if (ti < n) {
+    if (active && ti < n) {
       const unsigned long long key = ((unsigned long long)m << 32) | (unsigned long long)(base_index + ti);
       best = key < best ? key : best;
       if (scores != nullptr) scores[ti] = m;
@@ -982,9 +994,14 @@ __global__ void __launch_bounds__(kPkThreads, 4)
   }
 }
 
+static int g_vt_circ_lock = 1;  // knob 4: warps of a CTA in lock step in the circular sweep
 
 extern "C" int prs_vt_tune(int knob, int value) {
-  PRS_REQUIRE(knob >= 0 && knob < 4, "prs_vt_tune: unknown knob %d", knob);
+  PRS_REQUIRE(knob >= 0 && knob <= 4, "prs_vt_tune: unknown knob %d", knob);
+  if (knob == 4) {
+    g_vt_circ_lock = value != 0;
+    return PRS_OK;
+  }
   if (knob == 0) PRS_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8 || value == 34 || value == 44,
                              "prs_vt_tune: ring depth must be 0, 2, 4 or 8, or 34 / 44 for the lock-step variants");
   if (knob == 2)
@@ -1077,7 +1094,10 @@ static int launch_packed_sweep(const uint4* packed, long long n, long long n_gri
     if (rc != PRS_OK) return rc;
   } else {
     if (blocks > 148LL * 16) blocks = 148LL * 16;
-    k_vt_sweep_packed_circ<<<(int)blocks, kPkThreads, 0, st>>>(packed, n, base_index, key_out, scores, n_dev);
+    if (g_vt_circ_lock)
+      k_vt_sweep_packed_circ<true><<<(int)blocks, kPkThreads, 0, st>>>(packed, n, base_index, key_out, scores, n_dev);
+    else
+      k_vt_sweep_packed_circ<false><<<(int)blocks, kPkThreads, 0, st>>>(packed, n, base_index, key_out, scores, n_dev);
   }
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
