@@ -19,6 +19,14 @@
 //
 // float32 ("profiles", BASELINE config 5): one template per warp, lane == column,
 // score = sum |T - q| accumulated in float32.
+//
+// Those two are the row-major kernels.  What the product runs on big libraries (further down in this file):
+//   k_vt_sweep_packed_ref_ring   bit-sliced uint8 library, reference mode: 8 LOP3 + 1 POPC per 32 byte-compares,
+//                                warp-private rings of TMA bulk copies, the warps of a CTA in lock step
+//   k_vt_sweep_packed_circ       the same library, all 32 cyclic shifts (counters rotated in registers)
+//   k_vt_sweep_f32_pair          float32 library: two columns per lane (add.f32x2), two templates per warp, rings
+//   k_vt_sweep_packed_ref_small  small libraries inside replayed frames: one block per group of 32 templates
+// and the frame entry points (prs_frame_*, prs_replay_run) that chain them with the pose-cell update.
 #include <new>
 #include <string.h>
 
