@@ -52,6 +52,20 @@ def _worker(rank, world, port, q):
                 full = ovt.library_scores(lib[:n_total], qv)
                 assert score == int(full.min()) and idx == int(np.argmin(full)), (rank, n_total, score, idx)
                 out.append(sh.decide(score, idx, n_total, 45000))
+            # the batched form (ShardedViewTemplates.match_keys): ONE reduction for all the queries' keys
+            keys = []
+            for qv in queries:
+                if hi > lo:
+                    s = ovt.library_scores(lib[lo:hi], qv)
+                    j = int(np.argmin(s))
+                    keys.append(sh.pack_key(int(s[j]), lo + j))
+                else:
+                    keys.append(-1)
+            kt = torch.tensor(keys, dtype=torch.int64)
+            sh.reduce_packed_key(kt)
+            for k, qv in zip(kt.tolist(), queries):
+                full = ovt.library_scores(lib[:n_total], qv)
+                assert sh.unpack_key(k) == (int(full.min()), int(np.argmin(full)))
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
