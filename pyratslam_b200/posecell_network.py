@@ -35,6 +35,24 @@ _PATHS = {0: "generic", 1: "resident", 2: "tiled", 3: "cluster"}
 
 
 
+_HOST_TABLES = None
+
+
+def _host_tables():
+    """The filter tables of ``PoseCellNetwork.__init__`` (posecell_network.py:24-59), computed once per process."""
+    global _HOST_TABLES
+    if _HOST_TABLES is None:
+        fd = K.build_diff_gaussian_set_2d()
+        _HOST_TABLES = {
+            "kernel_3d": K.diff_gaussian(order=3),
+            "filter_dict_2d": fd,
+            "separable": K.separable_dog_factors(),
+            "f2d": np.ascontiguousarray(np.stack([fd[(0, 0)], fd[(-1, -1)]])),
+            "f1d": np.ascontiguousarray(K.theta_filter_table(nat.OG_RANGE)),
+        }
+    return _HOST_TABLES
+
+
 def _raw_stream(dev_index):
     """The current CUDA stream of ``dev_index`` as an integer handle (torch's C accessor: no Stream object)."""
     try:
@@ -57,15 +75,16 @@ class PoseCellEnsemble:
         X, Y, Th = self.shape
         B = self.n_networks
 
-        # host tables, float64, as the reference computes them
-        self.kernel_3d = K.diff_gaussian(order=3)
+        # host tables, float64, as the reference computes them (they depend on the module constants only: computed
+        # once per process, every network gets its own copies of what it exposes as attributes)
+        tables = _host_tables()
+        self.kernel_3d = tables["kernel_3d"].copy()
         self.pc_vtrans_scale = K.PC_CELL_X_SIZE
         self.pc_vrot_scale = 2.0 * math.pi / Th
-        self.filter_dict_2d = K.build_diff_gaussian_set_2d()
+        self.filter_dict_2d = {k: v.copy() for k, v in tables["filter_dict_2d"].items()}
         self.filter_dict_2d_precision = 10
-        ge, gi, aE, aI = K.separable_dog_factors()
-        f2d = np.ascontiguousarray(np.stack([self.filter_dict_2d[(0, 0)], self.filter_dict_2d[(-1, -1)]]))
-        f1d = np.ascontiguousarray(K.theta_filter_table(nat.OG_RANGE))
+        ge, gi, aE, aI = tables["separable"]
+        f2d, f1d = tables["f2d"], tables["f1d"]
         mid = Th // 2
         ang = (np.arange(Th) - mid) * self.pc_vrot_scale
         self._cos = np.ascontiguousarray(np.cos(ang))
