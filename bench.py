@@ -5,14 +5,21 @@
   python bench.py --impl reference --gpus N --steps K --warmup W
 
 Headline workload (config.workload): BASELINE.json config 4 -- an ensemble of 4096 independent
-reference-size (21, 21, 36) pose-cell networks per GPU, float32, per-network global inhibition in
-[0.05, 0.25] and per-network odometry.  A *step* is one PoseCellNetwork.update() of every network.
+reference-size (21, 21, 36) pose-cell networks IN TOTAL, float32, per-network global inhibition in
+[0.05, 0.25] and per-network odometry, sharded by network over the N ranks (``scaling: "strong"``:
+4096 / N networks per GPU, no collective).  A *step* is one PoseCellNetwork.update() of every network.
 ``value`` = cell-updates/s with odometry already on the device; ``e2e`` = the same through
-``PoseCellEnsemble.update`` with HOST odometry (pinned H2D in, arg-max D2H out, sync every step).
-The state (260 MB per GPU) is larger than L2 (126 MB), so every step streams it from HBM.
+``PoseCellEnsemble.update_submit / update_result`` with HOST odometry (pinned H2D in, arg-max D2H out).
+Every rank keeps N replicas of its shard (260 MB of state per GPU at every N, more than the 126 MB L2)
+and steps them in turn, so that every timed step streams its state from HBM at every N.
 
-At N = 1 the line also carries, under ``extra``: the 2^20-template library sweep (shift-compares/s),
-the single 256x256x72 network, and the frame-by-frame replay (frames/s).
+Before anything is timed every rank runs tests/multigpu_check.run_checks -- sharded library and sharded
+ensemble against the oracle on the ranks of this very job -- and the line carries ``parity_nranks``.
+
+Under ``extra_sharded``: BASELINE config 5, a 2^20-template library IN TOTAL split by contiguous ranges
+(strong scaling; the weak-scaling variants of both configs are reported next to it).  At N = 1 the line also
+carries, under ``extra``: the library sweeps, the single 256x256x72 network, float64 and 50x50x10 ensembles,
+and the frame-by-frame replay (frames/s).
 """
 from __future__ import annotations
 
@@ -32,7 +39,8 @@ sys.path.insert(0, ROOT)
 
 SHAPE = (21, 21, 36)
 N_CELLS = SHAPE[0] * SHAPE[1] * SHAPE[2]
-B_PER_GPU = 4096
+B_TOTAL = 4096
+REF_CORES = 16   # the reference arm uses at most this many host cores (per-core rate reported as well)
 METRIC = "pose-cell cell-updates/s"
 UNIT = "cell-updates/s"
 
@@ -94,20 +102,27 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def kernel_source_sha():
+    """sha256 over the sources of the headline kernel (what a committed ncu capture must have been taken from)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("posecell_resident.cu", "common.cuh"):
+        h.update(open(os.path.join(ROOT, "pyratslam_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
 def profiled_traffic():
-    """DRAM bytes per launch of the resident kernel from the committed `ncu --set full` capture (or None)."""
-    path = os.path.join(ROOT, "profiles", "r1_resident_ncu_full.csv")
+    """DRAM bytes per launch of the headline kernel from the committed `ncu --set full` capture
+    (profiles/r2_resident_traffic.json, written by bench_tools/ncu_traffic.py in the same gpurun as the capture).
+    The record carries the sha256 of the kernel sources it was measured on; a mismatch returns (None, reason)."""
+    path = os.path.join(ROOT, "profiles", "r2_resident_traffic.json")
     try:
-        import csv
-        rd = wr = None
-        for row in csv.reader(open(path)):
-            if row and row[0] == "dram__bytes_read.sum":
-                rd = float(row[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[row[1]]
-            if row and row[0] == "dram__bytes_write.sum":
-                wr = float(row[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[row[1]]
-        return rd + wr if rd is not None and wr is not None else None
+        d = json.load(open(path))
     except Exception:
-        return None
+        return None, "no capture committed for this round"
+    if d.get("kernel_source_sha256") != kernel_source_sha():
+        return None, "profiles/r2_resident_traffic.json was captured on other kernel sources (stale)"
+    return float(d["dram_bytes_per_launch"]), "profiles/r2_resident_traffic.json (%s, dram__bytes_read+write per launch)" % d.get("kernel", "?")
 
 
 def ensemble_inputs(B, T, seed):
@@ -154,12 +169,15 @@ def cpu_baseline(budget_s=12.0):
 
 
 def run_reference(args):
-    """--impl reference: the oracle port on all host cores; each step = a bounded sample of networks."""
+    """--impl reference: the oracle port on min(REF_CORES, available) host cores; each step = a bounded sample of
+    networks.  The core count is pinned so that the number does not float with the box; the per-core rate is printed
+    as well."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = len(os.sched_getaffinity(0))
+    avail = len(os.sched_getaffinity(0))
+    cores = min(REF_CORES, avail)
     per_core = 4                                          # networks per core (about 50 ms of CPU per step)
     nets = cores * per_core
     W, K = args.warmup, args.steps
@@ -168,14 +186,16 @@ def run_reference(args):
     with mp.get_context("fork").Pool(cores) as pool:
         dt = max(pool.map(_oracle_worker, jobs))          # slowest core bounds the step rate
     val = nets * args.steps * N_CELLS / dt
-    sample = ("each step = one update of %d persistent networks (%d per core, all cores) of the %dx%dx%d grid; numpy/scipy float64 "
-              "oracle port of the reference (the Python-2/OpenCL reference cannot run here)" % ((nets, per_core) + SHAPE))
+    sample = ("each step = one update of %d persistent networks (%d per core on %d of the box's %d cores) of the %dx%dx%d "
+              "grid; numpy/scipy float64 oracle port of the reference (the Python-2/OpenCL reference cannot run here)"
+              % ((nets, per_core, cores, avail) + SHAPE))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "ensemble of %d-cell pose-cell networks (BASELINE config 4), CPU sample" % N_CELLS,
                        "shape": list(SHAPE), "networks_per_step": nets},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "cores_available": avail,
+                             "value_per_core": val / cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -262,9 +282,42 @@ def extra_single_gpu(torch, peak, steps):
     k = max(10, min(steps, 50))
     ms = timed(torch, None, 1, stepf, k) / k
     cells = shape[0] * shape[1] * shape[2]
+    gbs = 8 * cells / (ms * 1e-3) / 1e9
+    tf = cells * 98 / (ms * 1e-3) / 1e12
     out["large_grid_256x256x72"] = {"metric": METRIC, "value": cells / (ms * 1e-3), "ms_per_step": ms, "path": net.path,
-                                    "note": "18.9 MB state is L2-resident; HBM roofline does not apply"}
+                                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                                 "frac": gbs / peak, "algorithmic_bytes_per_cell_update": 8,
+                                                 "fp32_issue": {"achieved_tfma_per_s": tf, "peak_tfma_per_s": 148 * 128 * 1.965e-3,
+                                                                "frac": tf / (148 * 128 * 1.965e-3)}},
+                                    "note": "the 18.9 MB state and its intermediates are L2-resident between the kernels "
+                                            "of an update; L2 traffic per update is in profiles/"}
     del net
+    # ---- the reference's own precision (float64, posecell_network.py:27,41) and simulate.py's grid (50x50x10) as
+    #      ensembles larger than L2
+    from pyratslam_b200 import PoseCellEnsemble
+    for name, shp, B, dt, nbytes in (("ensemble_f64_21x21x36", SHAPE, 2048, np.float64, 8),
+                                     ("ensemble_f32_50x50x10", (50, 50, 10), 2600, np.float32, 4)):
+        cells = shp[0] * shp[1] * shp[2]
+        gis = np.linspace(0.05, 0.25, B)
+        e = PoseCellEnsemble(shp, B, global_inhibition=gis, dtype=dt)
+        e.inject(1.0, tuple(v // 2 for v in shp))
+        rng = np.random.default_rng(5)
+        od = torch.from_numpy(np.stack([rng.uniform(0, 0.3, (16, B)), rng.uniform(-0.1, 0.1, (16, B))], axis=-1)).cuda()
+        fn = lambda t: e.update_async(od[t % 16])  # noqa: E731
+        timed(torch, None, 1, fn, 3)
+        k = max(5, min(steps, 20))
+        ms = timed(torch, None, 1, fn, k) / k
+        gbs = 2 * nbytes * B * cells / (ms * 1e-3) / 1e9
+        fma_peak = 148 * (128 if nbytes == 4 else 64) * 1.965e9 / 1e12
+        tf = B * cells * 98 / (ms * 1e-3) / 1e12
+        out[name] = {"metric": METRIC, "value": B * cells / (ms * 1e-3), "ms_per_step": ms, "networks": B, "path": e.path,
+                     "state_mb": B * cells * nbytes / 1e6,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                  "algorithmic_bytes_per_cell_update": 2 * nbytes,
+                                  "fma_pipe": {"achieved_tfma_per_s": tf, "peak_tfma_per_s": fma_peak,
+                                               "frac": tf / fma_peak,
+                                               "pipe": "FP32 (128 FMA/clk/SM)" if nbytes == 4 else "FP64 (64 DFMA/clk/SM, measured)"}}}
+        del e, od
     # ---- BASELINE config 1: simulate.py's own scenario (50x50x10, 40 steps), every step through update()
     from pyratslam_b200 import simulate
     from oracle import drivers as odrv
@@ -324,35 +377,97 @@ def extra_single_gpu(torch, peak, steps):
     return out
 
 
-def extra_sharded_library(torch, dist, world, rank, peak, steps):
-    """BASELINE config 5 across ranks: 2^20 uint8 templates per GPU (weak scaling), contiguous global index
-    ranges, one 8-byte MIN all-reduce of the packed key per query (NCCL for N > 1)."""
-    from pyratslam_b200 import ShardedViewTemplates
-    n = 1 << 20
+def extra_sharded_library(torch, dist, world, rank, peak, steps, n_total, label):
+    """BASELINE config 5 across ranks: ``n_total`` uint8 templates split into contiguous global index ranges, one
+    device-side MIN exchange of the packed key per query (csrc/sharded.cu over CUDA-IPC peer memory; the NCCL
+    all-reduce path is timed next to it).  Planted templates make the answers known without a 10^6-template oracle
+    sweep: a planted match in the first shard, and a pattern stored twice -- in the first and in the last shard --
+    whose query must resolve to the LOWER index (numpy.argmin)."""
+    from oracle import view_templates as ovt                      # checker only
+    from pyratslam_b200 import ShardedViewTemplates, _native as nat
+    from pyratslam_b200.sharding import shard_range
+    lo, hi = shard_range(n_total, rank, world)
+    n = hi - lo
     g = torch.Generator(device="cuda").manual_seed(40 + rank)
     lib = torch.randint(0, 256, (n, 32, 32), dtype=torch.uint8, device="cuda", generator=g)
-    gq = torch.Generator(device="cuda").manual_seed(99)
-    qs = torch.randint(0, 256, (8, 32, 32), dtype=torch.uint8, device="cuda", generator=gq)
-    out = {}
+    rp = np.random.default_rng(1234)
+    P0, P1 = (rp.integers(0, 256, (32, 32), dtype=np.uint8) for _ in range(2))
+    j0, jdup, j1 = 12345, 4242, n_total - 777
+    for j, P in ((j0, P0), (jdup, P1), (j1, P1)):
+        if lo <= j < hi:
+            lib[j - lo] = torch.from_numpy(P).cuda()
+    dark = lambda P: np.clip(P.astype(np.int16) - rp.integers(0, 4, P.shape), 0, 255).astype(np.uint8)  # noqa: E731
+    q_np = [dark(P0), np.roll(dark(P1), 3, axis=0)] + [rp.integers(0, 256, (32, 32), dtype=np.uint8) for _ in range(6)]
+    qs = torch.from_numpy(np.stack(q_np)).cuda()
+    svt = ShardedViewTemplates(lib, lo, match_threshold=45000, mode="ref")
+    del lib
+    out = {"templates_total": n_total, "templates_per_gpu": n, "exchange": svt.exchange,
+           "library": "%d x 32x32 uint8 in total, bit-sliced, %.0f MB per GPU (> L2)" % (n_total, n * 1088 / 1e6)}
     for mode, offs in (("ref", 15), ("circular", 32)):
-        svt = ShardedViewTemplates(lib, rank * n, match_threshold=45000, mode=mode)
-        fn = lambda t: svt.match_key(qs[t % 8])  # noqa: E731
+        svt.mode = {"ref": nat.VT_MODE_REF, "circular": nat.VT_MODE_CIRCULAR}[mode]
+        # parity inside the run: planted answers against the oracle's score of the planted template alone
+        want0 = int(ovt.library_scores(P0[None], q_np[0], mode=mode)[0])
+        want1 = int(ovt.library_scores(P1[None], q_np[1], mode=mode)[0])
+        assert svt.match_key(qs[0]) == (want0, j0), (mode, svt.match_key(qs[0]), want0, j0)
+        assert svt.match_key(qs[1]) == (want1, jdup), (mode, svt.match_key(qs[1]), want1, jdup)
+        keys = svt.match_keys(qs)
+        assert keys[:2] == [(want0, j0), (want1, jdup)] and keys == [svt.match_key(q) for q in qs]
         k = max(5, min(steps, 20))
+        fn = lambda t: svt.match_key(qs[t % 8])  # noqa: E731
         timed(torch, dist, world, fn, 3)
         ms = timed(torch, dist, world, fn, k) / k
         fnb = lambda t: svt.match_keys(qs)  # noqa: E731
-        assert svt.match_keys(qs) == [svt.match_key(q) for q in qs]
         timed(torch, dist, world, fnb, 2)
         kb = max(2, k // 4)
         ms_b = timed(torch, dist, world, fnb, kb) / (kb * len(qs))
-        out["vt_sharded_u8_" + mode] = {"metric": "VT shift-compares/s", "value": world * n * offs / (ms_b * 1e-3),
-                                        "ms_per_query": ms_b, "templates_per_gpu": n,
-                                        "one_query_per_call": {"value": world * n * offs / (ms * 1e-3), "ms_per_query": ms},
-                                        "note": "value: batches of 8 queries (match_keys): 8 local sweeps, ONE MIN all-reduce "
-                                                "of the 8 packed keys and one read-back per batch; one_query_per_call "
-                                                "(match_key): sweep + all-reduce + 8-byte read-back for every query"}
-        del svt
+        fns = lambda t: svt.local_sweep(qs[t % 8])  # noqa: E731      the shard's sweep alone, no exchange, no read-back
+        timed(torch, dist, world, fns, 3)
+        ms_s = timed(torch, dist, world, fns, k) / k
+        rec = {"metric": "VT shift-compares/s", "value": n_total * offs / (ms * 1e-3), "ms_per_query": ms,
+               "local_sweep_only_ms": ms_s, "exchange_and_readback_ms": ms - ms_s,
+               "batched_8_queries": {"value": n_total * offs / (ms_b * 1e-3), "ms_per_query": ms_b},
+               "roofline": {"bound": "hbm", "achieved": n * 1024 / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": n * 1024 / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_template": 1024},
+               "note": "value: ONE query per call (match_key): local sweep + device-side MIN over the ranks + 8-byte "
+                       "result in pinned host memory + stream sync, every query; batched: 8 sweeps, one exchange"}
+        if world > 1 and svt.exchange == "fused":
+            svt.set_exchange("nccl")
+            assert svt.match_key(qs[0]) == (want0, j0)
+            timed(torch, dist, world, fn, 3)
+            rec["nccl_allreduce_ms_per_query"] = timed(torch, dist, world, fn, k) / k
+            svt.set_exchange("fused")
+        out["vt_u8_" + mode] = rec
+    # create-or-match through the exchange: the random queries are novel, the planted ones match
+    svt.mode = nat.VT_MODE_REF
+    assert svt.match(qs[0]) == (j0, False) and svt.match(qs[1]) == (jdup, False)
+    assert svt.match(qs[2]) == (n_total, True) and svt.match(qs[2]) == (n_total, False)
+    out["parity"] = "planted match, cross-shard tie -> lowest index, novel -> created: checked against the oracle (%s)" % label
+    svt.close()
     return out
+
+
+def check_sampled_networks(ens, odom_dev, gis, rank):
+    """Two networks of this rank's shard, three updates, against the oracle (arg-max bit-exact, state <= 1e-5)."""
+    from oracle import posecells as opc                           # checker only
+    import torch
+    B = ens.n_networks
+    pick = sorted({0, B - 1})
+    before = ens.state[pick].clone()
+    od = odom_dev[:3].cpu().numpy()
+    got = []
+    for t in range(3):
+        ens.update_async(odom_dev[t])
+        got.append(ens._unravel(ens._argmax[pick].cpu().numpy()))
+    after = ens.state[pick].permute(0, 2, 3, 1).cpu().numpy().astype(np.float64)   # [th][x][y] -> [x][y][th]
+    for i, b in enumerate(pick):
+        ref = opc.PoseCellNetwork(SHAPE, global_inhibition=float(gis[b]))
+        ref.posecells = before[i].permute(1, 2, 0).cpu().numpy().astype(np.float64)
+        for t in range(3):
+            assert tuple(ref.update(od[t, b])) == tuple(got[t][i]), (rank, b, t)
+        err = np.abs(after[i] - ref.posecells).max() / max(ref.posecells.max(), 1e-30)
+        assert err <= 1e-5, (rank, b, err)
+    torch.cuda.synchronize()
+    return len(pick)
 
 
 def run_ours(args):
@@ -367,53 +482,92 @@ def run_ours(args):
     import __graft_entry__ as ge
     ge.build()
     from pyratslam_b200 import PoseCellEnsemble
+    from pyratslam_b200.sharding import shard_range
     peak, peak_src = measured_peaks()
+    d = dist if world > 1 else None
 
-    B = B_PER_GPU
+    # ---- parity on the ranks of this job, before anything is timed
+    parity = None
+    if not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import multigpu_check
+        exch = multigpu_check.run_checks(rank, world)
+        parity = {"parity_nranks": world, "exchange": exch,
+                  "what": "tests/multigpu_check.run_checks: sharded 5003-template library (ref + circular + float32; ties, "
+                          "appends) == numpy argmin of the oracle; sharded 64-network ensemble == oracle arg-max"}
+
+    # ---- BASELINE config 4, strong scaling: 4096 networks in total, contiguous shards
+    lo, hi = shard_range(B_TOTAL, rank, world)
+    B = hi - lo
+    R = world                                            # replicas of the shard: 260 MB of state per GPU at every N
     K, W = args.steps, max(args.warmup, 3)
-    gis, odom = ensemble_inputs(B, 64, 3 + rank)
-    ens = PoseCellEnsemble(SHAPE, B, global_inhibition=gis)
-    ens.inject(1.0, tuple(s // 2 for s in SHAPE))
+    gis_all, odom_all = ensemble_inputs(B_TOTAL, 64, 3)
+    gis, odom = gis_all[lo:hi], np.ascontiguousarray(odom_all[:, lo:hi])
+    ens = [PoseCellEnsemble(SHAPE, B, global_inhibition=gis) for _ in range(R)]
+    for e in ens:
+        e.inject(1.0, tuple(s // 2 for s in SHAPE))
     od_dev = torch.from_numpy(odom).cuda()
-    path = ens.path
-    launches_per_step = 1 if path == "resident" else 8
-    step_dev = lambda t: ens.update_async(od_dev[t % 64])  # noqa: E731
-    step_block = lambda t: ens.update(odom[t % 64])  # noqa: E731
+    path = ens[0].path
+    launches_per_step = 1 if path in ("resident", "pair") else 8
+    if parity is not None:
+        parity["sampled_networks_per_rank"] = check_sampled_networks(ens[0], od_dev, gis, rank)
+    step_dev = lambda t: ens[t % R].update_async(od_dev[t % 64])  # noqa: E731
+    step_hot = lambda t: ens[0].update_async(od_dev[t % 64])  # noqa: E731
+    step_block = lambda t: ens[t % R].update(odom[t % 64])  # noqa: E731
 
     def step_host(t):
         # the public overlapped stepping API: every step copies its odometry in from pinned memory and its packed
         # result out, one step is kept in flight so that the copies hide behind the previous step's kernel
-        ens.update_submit(odom[t % 64])
+        ens[t % R].update_submit(odom[t % 64])
         if t > 0:
-            ens.update_result()
+            ens[(t - 1) % R].update_result()
         if t == last_step[0]:  # the last step's result is read inside the timed region as well
-            ens.update_result()
+            ens[t % R].update_result()
 
     def drain():
-        while ens._pipe_head > ens._pipe_tail:
-            ens.update_result()
+        for e in ens:
+            while getattr(e, "_pipe_head", 0) > getattr(e, "_pipe_tail", 0):
+                e.update_result()
 
-    timed(torch, dist, world, step_dev, W)
+    timed(torch, d, world, step_dev, W)
     with ClockSampler(local) as clk:
-        ms = timed(torch, dist, world, step_dev, K)
+        ms = timed(torch, d, world, step_dev, K)
         # keep the sampler alive for at least a few samples on very short runs
         if ms < 400:
-            timed(torch, dist, world, step_dev, max(K, int(400 / max(ms / K, 1e-3))))
+            timed(torch, d, world, step_dev, max(K, int(400 / max(ms / K, 1e-3))))
     clocks = clk.summary()
-    value = world * B * N_CELLS * K / (ms * 1e-3)
+    value = B_TOTAL * N_CELLS * K / (ms * 1e-3)
     # end to end through the public API with host odometry
     last_step = [W - 1]
-    timed(torch, dist, world, step_host, W)
+    timed(torch, d, world, step_host, W)
     drain()
     last_step[0] = K - 1
-    ms_e2e = timed(torch, dist, world, step_host, K)
+    ms_e2e = timed(torch, d, world, step_host, K)
     drain()
-    e2e = world * B * N_CELLS * K / (ms_e2e * 1e-3)
-    timed(torch, dist, world, step_block, W)
-    ms_blk = timed(torch, dist, world, step_block, K)
-    e2e_blk = world * B * N_CELLS * K / (ms_blk * 1e-3)
-    alive = int((ens.state.amax(dim=(1, 2, 3)) > 0).sum().item())
+    e2e = B_TOTAL * N_CELLS * K / (ms_e2e * 1e-3)
+    timed(torch, d, world, step_block, W)
+    ms_blk = timed(torch, d, world, step_block, K)
+    e2e_blk = B_TOTAL * N_CELLS * K / (ms_blk * 1e-3)
+    alive = int(sum(int((e.state.amax(dim=(1, 2, 3)) > 0).sum().item()) for e in ens)) // R
+    ms_hot = None
+    weak = None
+    if world > 1:
+        timed(torch, d, world, step_hot, W)
+        ms_hot = timed(torch, d, world, step_hot, K) / K
+        del ens[1:]
+        # weak-scaling variant of the same config (4096 networks PER GPU), reported as an extra
+        gw, ow = ensemble_inputs(B_TOTAL, 64, 3 + rank)
+        ew = PoseCellEnsemble(SHAPE, B_TOTAL, global_inhibition=gw)
+        ew.inject(1.0, tuple(s // 2 for s in SHAPE))
+        odw = torch.from_numpy(ow).cuda()
+        stepw = lambda t: ew.update_async(odw[t % 64])  # noqa: E731
+        timed(torch, d, world, stepw, W)
+        msw = timed(torch, d, world, stepw, K) / K
+        weak = {"value": world * B_TOTAL * N_CELLS / (msw * 1e-3), "ms_per_step": msw, "networks_per_gpu": B_TOTAL,
+                "scaling": "weak"}
+        del ew, odw
 
+    line = None
     if rank == 0:
         alg_bytes = 2 * 4 * B * N_CELLS                  # read + write the float32 state once per update
         gbs = alg_bytes / (ms / K * 1e-3) / 1e9
@@ -421,27 +575,31 @@ def run_ours(args):
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12        # TFMA/s at the clock seen during the timed region
         tfma = B * N_CELLS * fma_per_cell / (ms / K * 1e-3) / 1e12
+        traffic, traffic_src = profiled_traffic() if world == 1 else (None, "N > 1: shard sizes differ from the capture")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ensemble of 4096 independent 21x21x36 pose-cell networks per GPU (BASELINE config 4)",
-                       "shape": list(SHAPE), "networks_per_gpu": B, "path": path,
-                       "l2": "state per GPU (260 MB) exceeds L2 (126 MB): every step streams from HBM",
+            "config": {"workload": "ensemble of 4096 independent 21x21x36 pose-cell networks in total, sharded by "
+                                   "network over the GPUs (BASELINE config 4)",
+                       "shape": list(SHAPE), "networks_total": B_TOTAL, "networks_per_gpu": B, "path": path,
+                       "l2": "every rank steps %d replica(s) of its shard in turn: %.0f MB of distinct state per GPU, more "
+                             "than L2 (126 MB), so every timed step streams from HBM" % (R, R * B * N_CELLS * 4 / 1e6),
                        "parallelism": "networks sharded by rank, no collective"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * 16,
                     "d2h_bytes_per_step": B * 16,
                     "api": "PoseCellEnsemble.update_submit / update_result (prs_pc_step_host_xyz_async): pinned odometry "
-                           "H2D + step + packed (x, y, th, err) D2H every step, one step in flight",
+                           "H2D + step + packed (x, y, th, err) D2H every step, one step in flight; the blocking call "
+                           "(PoseCellEnsemble.update, host waits for every step) is blocking_call",
                     "blocking_call": {"value": e2e_blk, "ms_per_step": ms_blk / K,
                                       "api": "PoseCellEnsemble.update (prs_pc_step_host_xyz): same copies, host waits "
                                              "for every step"}},
             "gpu_launches": K * launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                         "traffic": (profiled_traffic() if path == "resident" else None), "peak_source": peak_src,
-                         "traffic_source": "profiles/r1_resident_ncu_full.csv (dram__bytes_read+write, one launch)",
-                         "kernel": "pc_resident_step" if path == "resident" else "generic 8-kernel step (whole step timed)",
+                         "traffic": traffic, "peak_source": peak_src, "traffic_source": traffic_src,
+                         "kernel": "k_pc_resident / k_pc_pair (one launch per step)" if launches_per_step == 1
+                                   else "generic 8-kernel step (whole step timed)",
                          "algorithmic_bytes_per_cell_update": 8,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "binding_roof": "fp32 issue: 98 FMA per 8 B puts the FP32 pipe roof at 0.46 of the HBM roof",
@@ -449,13 +607,26 @@ def run_ours(args):
                                         "peak_tfma_per_s": fp32_peak, "frac": tfma / fp32_peak}},
             "networks_alive": alive,
         }
+        if parity is not None:
+            line.update(parity)
+        if ms_hot is not None:
+            line["l2_resident_shard"] = {"ms_per_step": ms_hot, "value": B_TOTAL * N_CELLS / (ms_hot * 1e-3),
+                                         "note": "the same step on ONE replica: the shard (%.0f MB) stays in L2 between "
+                                                 "steps, which is what a user stepping this ensemble gets" % (B * N_CELLS * 4 / 1e6)}
+        if weak is not None:
+            line["extra_weak_ensemble"] = weak
         line["extra_sharded"] = None
         if world == 1:
             line["cpu_baseline"] = cpu_baseline()
             if not args.no_extra:
                 line["extra"] = extra_single_gpu(torch, peak, K)
+    del ens
     if not args.no_extra:
-        shard = extra_sharded_library(torch, dist if world > 1 else None, world, rank, peak, K)
+        shard = {"strong_2^20_total": extra_sharded_library(torch, d, world, rank, peak, K, 1 << 20,
+                                                            "%d rank(s)" % world)}
+        if world > 1:
+            shard["weak_2^20_per_gpu"] = extra_sharded_library(torch, d, world, rank, peak, K, world << 20,
+                                                                "%d rank(s), weak" % world)
         if rank == 0:
             line["extra_sharded"] = shard
     if rank == 0:
@@ -491,6 +662,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (profiling runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle checks (profiling runs)")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":

@@ -42,6 +42,7 @@ extern "C" {
 
 #define PRS_F32 0
 #define PRS_F64 1
+#define PRS_U8 2 /* view-template libraries only */
 
 /* per-network error bits written by the step kernels into `err[b]` */
 #define PRS_ERR_LUT_KEY 1 /* fractional x offset exactly +0.5: the reference raises KeyError
@@ -189,8 +190,10 @@ PRS_API int prs_vt_sweep_f32(const float* lib, long long n, const float* query, 
  *                             (the packed buffer must have been zero-filled once; ViewTemplates' append, :68-71)
  *   prs_vt_unpack_u8        : one template back to row-major (the ViewTemplate.template attribute)
  *   prs_vt_sweep_packed_u8  : query is a row-major device uint8[32][32]; scratch is a device buffer of
- *                             >= 2 KiB; one sweep may be in flight per device (the query planes go through
- *                             constant memory). */
+ *                             >= 2 KiB, private to the caller.  The query planes go through one constant-memory
+ *                             buffer per device: sweeps issued on different streams (or host threads) of a device
+ *                             are correct but run one after the other on the device (event-ordered, the host
+ *                             does not block). */
 PRS_API size_t prs_vt_packed_bytes(long long n);
 PRS_API int prs_vt_pack_u8(const uint8_t* src, long long n, void* packed, long long first, void* stream);
 PRS_API int prs_vt_unpack_u8(const void* packed, long long index, uint8_t* dst, void* stream);
@@ -214,6 +217,50 @@ PRS_API int prs_vt_sweep_any_f32(const float* lib, long long n, const float* que
  * lib stays resident on the device; scratch is a device buffer of >= 1024+8 bytes. */
 PRS_API int prs_vt_match_host_u8(const uint8_t* lib, long long n, const uint8_t* query_host, int mode,
                          long long base_index, unsigned long long* key_host, void* scratch, void* stream);
+
+/* ------------------------------------------- sharded library: the MIN over ranks, on the device */
+
+/* A very large library is split by contiguous template ranges over the ranks of a job, one process per GPU
+ * (BASELINE config 5).  The reference has no counterpart (it is single-process); the semantics to keep are those of
+ * `vals.index(min(vals))` / numpy.argmin over the whole list (ratslam/view_templates.py:65-73): minimum score, lowest
+ * global index among equals -- i.e. the MIN of the ranks' packed keys -- followed by the strict '>' threshold test.
+ *
+ * prs_xchg is a small exchange buffer in device memory that the peers map through CUDA IPC (NVLink peer access):
+ *   prs_xchg_create   allocate this rank's buffer (world <= 16)
+ *   prs_xchg_export   64-byte cudaIpcMemHandle_t of the buffer, to be all-gathered by the host (any transport)
+ *   prs_xchg_connect  open the peers' handles, handles = [world][64] in rank order (the own entry is ignored);
+ *                     a world of 1 needs neither export nor connect
+ *   prs_xchg_set_timeout  bound of the device-side wait for the peers (default 10 s; then status = 1)
+ * One kernel per query publishes the rank's key(s) into every peer's buffer with system-scope stores, waits for the
+ * peers' keys of the same query, and reduces them; every rank must issue the same sequence of exchange calls. */
+typedef struct prs_xchg prs_xchg;
+#define PRS_XCHG_HANDLE_BYTES 64
+typedef struct prs_shard_result {
+  unsigned long long key;   /* MIN over the ranks of (score << 32 | global index); UINT64_MAX: nothing compared */
+  int created;              /* 1: the query became template `template_index` (appended on the owning rank) */
+  int template_index;       /* what ViewTemplates.match(...).get_index() returns; -1 from prs_vt_shard_exchange */
+  int n_total;              /* library size over all ranks after this query */
+  int status;               /* 0 = fine, 1 = a peer did not publish within the timeout */
+  unsigned long long seq;   /* sequence number of the exchange (1, 2, ...) */
+} prs_shard_result;
+PRS_API int prs_xchg_create(int world, int rank, prs_xchg** out);
+PRS_API int prs_xchg_export(prs_xchg* x, void* handle64);
+PRS_API int prs_xchg_connect(prs_xchg* x, const void* handles);
+PRS_API int prs_xchg_set_timeout(prs_xchg* x, double seconds);
+PRS_API int prs_xchg_destroy(prs_xchg* x);
+/* MIN over the ranks of n_keys (<= 64) packed keys: keys_local is this rank's (device), keys_out receives the global
+ * minima (device memory or pinned host memory), result (optional, device or pinned host) the status record. */
+PRS_API int prs_vt_shard_exchange(prs_xchg* x, const unsigned long long* keys_local, int n_keys,
+                          unsigned long long* keys_out, prs_shard_result* result, void* stream);
+/* ViewTemplates.match's decision for a sharded library (view_templates.py:67-73), taken on the device by every rank
+ * from the MIN of the ranks' keys: create when the library is empty or score > threshold (strict; the score is the
+ * integer sum for PRS_U8, the float32 sum for PRS_F32, compared in double), else match the key's index.  On the
+ * owning rank (owner != 0) a created template -- tpl, the query as a row-major 32x32 template on the device -- is
+ * stored in slot n_local of lib (bit-sliced for PRS_U8, row-major for PRS_F32; the buffer must have room).
+ * result: device or pinned host memory, valid once `stream` has completed. */
+PRS_API int prs_vt_shard_decide(prs_xchg* x, const unsigned long long* key_local, double threshold, int dtype,
+                        const void* tpl, void* lib, long long n_local, long long n_total, int owner,
+                        prs_shard_result* result, void* stream);
 
 /* ------------------------------------------------------------------- one frame */
 

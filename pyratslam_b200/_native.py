@@ -91,6 +91,23 @@ _SIGNATURES["prs_frame_launch"] = (c_int, [c_void_p, c_int, c_void_p])
 _SIGNATURES["prs_replay_run"] = (c_int, [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p])
 
 
+_SIGNATURES["prs_xchg_create"] = (c_int, [c_int, c_int, POINTER(c_void_p)])
+_SIGNATURES["prs_xchg_export"] = (c_int, [c_void_p, c_void_p])
+_SIGNATURES["prs_xchg_connect"] = (c_int, [c_void_p, c_void_p])
+_SIGNATURES["prs_xchg_set_timeout"] = (c_int, [c_void_p, c_double])
+_SIGNATURES["prs_xchg_destroy"] = (c_int, [c_void_p])
+_SIGNATURES["prs_vt_shard_exchange"] = (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p])
+_SIGNATURES["prs_vt_shard_decide"] = (c_int, [c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p, c_longlong,
+                                              c_longlong, c_int, c_void_p, c_void_p])
+XCHG_HANDLE_BYTES = 64
+PRS_U8 = 2
+
+
+class ShardResult(Structure):
+    _fields_ = [("key", c_uint64), ("created", c_int), ("template_index", c_int), ("n_total", c_int),
+                ("status", c_int), ("seq", c_uint64)]
+
+
 class FrameResult(Structure):
     _fields_ = [("argmax", c_longlong), ("key", c_uint64), ("created", c_int), ("template_index", c_int),
                 ("n_templates", c_int), ("pc_err", c_int)]

@@ -30,7 +30,10 @@
 #include <new>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
+#include "vt_pack.cuh"
 
 namespace {
 
@@ -350,9 +353,54 @@ extern "C" int prs_vt_match_host_u8(const uint8_t* lib, long long n, const uint8
 // Layout of one group of 32 templates (8704 uint32):
 //   planes : uint4 [32 rows][2 halves][32 lanes]   .x..w = planes 4h..4h+3 of that row of template `lane`
 //   rowsum : uint4 [4][32 lanes]                   16 words per lane, word w = R[2w] | R[2w+1] << 16
-constexpr int kGroupU4 = 32 * 2 * 32 + 4 * 32;  // 2176 uint4 = 34816 bytes per 32 templates
+constexpr int kGroupU4 = kVtGroupU4;  // 2176 uint4 = 34816 bytes per 32 templates (vt_pack.cuh)
 
 __constant__ uint32_t c_vtq[32 * 8 + 8];  // query planes [row][k], then sum(rows 8..23), sum(all rows)
+
+// c_vtq is ONE buffer per device, and the sweeps need the planes as constant-bank operands of their LOP3s (read from
+// anywhere else they cost registers the kernels do not have).  Sweeps issued on different streams -- or from different
+// host threads -- of a device are therefore ordered through it: a sweep records an event behind its kernel, and the
+// next writer of the buffer on another stream waits for that event on the device (no host blocking).  The host mutex
+// is held from the wait to the record, so two threads cannot interleave their (write planes, sweep) pairs either.
+struct VtqGuard {
+  std::mutex mu;
+  cudaEvent_t ev[64] = {};
+  cudaStream_t last[64] = {};
+  bool pending[64] = {};
+};
+VtqGuard g_vtq;
+
+struct VtqScope {
+  cudaStream_t st = nullptr;
+  int dev = -1;
+  bool locked = false;
+  // `st` must not be capturing (a graph that contains a sweep is bracketed by its launcher, prs_frame_launch)
+  int begin(cudaStream_t s) {
+    st = s;
+    PRS_CUDA(cudaGetDevice(&dev));
+    PRS_REQUIRE(dev >= 0 && dev < 64, "view-template sweep: device index %d out of range", dev);
+    g_vtq.mu.lock();
+    locked = true;
+    if (!g_vtq.ev[dev]) PRS_CUDA(cudaEventCreateWithFlags(&g_vtq.ev[dev], cudaEventDisableTiming));
+    if (g_vtq.pending[dev] && g_vtq.last[dev] != st) PRS_CUDA(cudaStreamWaitEvent(st, g_vtq.ev[dev], 0));
+    return PRS_OK;
+  }
+  int end() {
+    if (!locked) return PRS_OK;
+    cudaError_t e = cudaEventRecord(g_vtq.ev[dev], st);
+    if (e == cudaSuccess) {
+      g_vtq.pending[dev] = true;
+      g_vtq.last[dev] = st;
+    }
+    locked = false;
+    g_vtq.mu.unlock();
+    PRS_CUDA(e);
+    return PRS_OK;
+  }
+  ~VtqScope() {
+    if (locked) g_vtq.mu.unlock();
+  }
+};
 
 __global__ void k_vt_pack_u8(const uint8_t* __restrict__ src, long long n, uint4* __restrict__ packed,
                              long long first) {
@@ -361,29 +409,7 @@ __global__ void k_vt_pack_u8(const uint8_t* __restrict__ src, long long n, uint4
   if (i >= n * 32) return;
   const long long tl = i >> 5;
   const int t = (int)(i & 31);
-  const long long ti = first + tl;
-  const uint32_t* row = reinterpret_cast<const uint32_t*>(src + tl * 1024 + t * 32);
-  uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  uint32_t sum = 0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    const uint32_t v = row[w];
-#pragma unroll
-    for (int bb = 0; bb < 4; ++bb) {
-      const uint32_t px = (v >> (8 * bb)) & 0xffu;
-      sum += px;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) pl[k] |= ((px >> k) & 1u) << (w * 4 + bb);
-    }
-  }
-  uint4* grp = packed + (ti >> 5) * kGroupU4;
-  const int lane = (int)(ti & 31);
-  grp[(t * 2 + 0) * 32 + lane] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-  grp[(t * 2 + 1) * 32 + lane] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-  // row sums: 16-bit halves of word w = t/2 of this lane
-  uint16_t* rs = reinterpret_cast<uint16_t*>(grp + 32 * 2 * 32);
-  const int w = t >> 1;
-  rs[(((w >> 2) * 32 + lane) * 4 + (w & 3)) * 2 + (t & 1)] = (uint16_t)sum;
+  vt_pack_row(src + tl * 1024, packed, first + tl, t);
 }
 
 __global__ void k_vt_unpack_u8(const uint4* __restrict__ packed, long long ti, uint8_t* __restrict__ dst) {
@@ -1141,10 +1167,18 @@ extern "C" int prs_vt_sweep_packed_u8(const void* packed, long long n, const uin
   cudaStream_t st = (cudaStream_t)stream;
   PRS_CUDA(cudaMemsetAsync(key_out, 0xff, sizeof(unsigned long long), st));
   if (n == 0) return PRS_OK;
-  // query -> bit planes -> constant bank (stream ordered; one query in flight per device)
+  // query -> bit planes -> constant bank (stream ordered; sweeps on other streams of the device are ordered behind
+  // each other through VtqScope)
   k_vt_pack_query<<<1, 32, 0, st>>>(query, (uint32_t*)scratch);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
+  VtqScope scope;
+  if (cap == cudaStreamCaptureStatusNone)  // a caller capturing its own graph orders its launches itself
+    if (int rc = scope.begin(st)) return rc;
   PRS_CUDA(cudaMemcpyToSymbolAsync(c_vtq, scratch, (32 * 8 + 2) * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
-  return launch_packed_sweep((const uint4*)packed, n, n, mode, base_index, key_out, scores, nullptr, st);
+  int rc = launch_packed_sweep((const uint4*)packed, n, n, mode, base_index, key_out, scores, nullptr, st);
+  if (int rc2 = scope.end()) return rc != PRS_OK ? rc : rc2;
+  return rc;
 }
 
 // =============================================================================================
@@ -1173,27 +1207,7 @@ __global__ void k_vt_decide_append(const unsigned long long* __restrict__ key, c
   const unsigned score = (unsigned)(k >> 32);
   const bool create = (n == 0) || (k == ~0ull) || (score > threshold);  // strict '>' (view_templates.py:67)
   if (create) {
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(tpl + t * 32);
-    uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t sum = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const uint32_t v = row[w];
-#pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
-        const uint32_t px = (v >> (8 * bb)) & 0xffu;
-        sum += px;
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) pl[kk] |= ((px >> kk) & 1u) << (w * 4 + bb);
-      }
-    }
-    uint4* grp = packed + (size_t)(n >> 5) * kGroupU4;
-    const int lane = n & 31;
-    grp[(t * 2 + 0) * 32 + lane] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-    grp[(t * 2 + 1) * 32 + lane] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-    uint16_t* rs = reinterpret_cast<uint16_t*>(grp + 32 * 2 * 32);
-    const int w = t >> 1;
-    rs[(((w >> 2) * 32 + lane) * 4 + (w & 3)) * 2 + (t & 1)] = (uint16_t)sum;
+    vt_pack_row(tpl, packed, n, t);
   }
   if (t == 0) {
     if (write_pc) res->argmax = argmax ? argmax[0] : -1;  // else the pose-cell kernel writes both fields itself
@@ -1608,6 +1622,11 @@ extern "C" int prs_frame_launch(prs_frame_plan* f, int moved, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int v = moved ? 1 : 0;
   int rc = PRS_OK;
+  // the long chain sweeps through the per-device constant buffer: order the whole frame behind sweeps on other streams
+  const bool uses_vtq = !(f->odom_map && f->frame_map && f->result_map && f->mode == PRS_VT_MODE_REF && f->capacity <= kSmallLibrary);
+  VtqScope scope;
+  if (uses_vtq)
+    if (int rc0 = scope.begin(st)) return rc0;
   if (f->ready[v]) {
     PRS_CUDA(cudaGraphLaunch(f->exec[v], st));
   } else if (f->warm[v] < 1 || st == nullptr) {  // the legacy default stream cannot be captured
@@ -1629,7 +1648,7 @@ extern "C" int prs_frame_launch(prs_frame_plan* f, int moved, void* stream) {
     f->ready[v] = true;
     PRS_CUDA(cudaGraphLaunch(f->exec[v], st));
   }
-  return PRS_OK;
+  return scope.end();
 }
 
 extern "C" int prs_frame_run(prs_frame_plan* f, int moved, void* stream) {

@@ -340,13 +340,21 @@ class ViewTemplates:
 class ShardedViewTemplates:
     """A template library split by contiguous index ranges over the ranks of a process group.
 
-    Rank r holds templates ``[base_r, base_r + n_r)``.  ``match_key`` sweeps the local shard and MIN-reduces the
-    packed key over the group (NCCL on GPUs), which yields the global minimum score and, among equal scores, the
-    lowest global index -- ``numpy.argmin`` semantics (``view_templates.py:73``).  New templates are appended
-    to the last rank's shard so global indices stay contiguous.
+    Rank r holds templates ``[base_r, base_r + n_r)``.  A query sweeps the local shard and the ranks' packed keys
+    are MIN-reduced, which yields the global minimum score and, among equal scores, the lowest global index --
+    ``numpy.argmin`` semantics (``view_templates.py:73``).  New templates are appended to the last rank's shard so
+    global indices stay contiguous.
+
+    ``exchange`` selects how the keys meet: ``"fused"`` -- one small kernel per query that writes this rank's key
+    into every peer's CUDA-IPC-mapped buffer over NVLink, waits for the peers' keys, reduces them and (for
+    ``match``) takes the create-or-match decision and appends on the device, the 32-byte result landing in pinned
+    host memory (``csrc/sharded.cu``) -- or ``"nccl"``: a MIN all-reduce of the int64 key through
+    ``torch.distributed``.  ``"auto"`` uses the fused exchange and falls back to NCCL, with a warning, when the
+    peers' buffers cannot be mapped.  ``self.exchange`` names what is in use.
     """
 
-    def __init__(self, local_templates, base_index, match_threshold, mode="ref", group=None, device=None):
+    def __init__(self, local_templates, base_index, match_threshold, mode="ref", group=None, device=None,
+                 exchange="auto", capacity=None):
         import torch.distributed as dist
         nat.require_cuda()
         self._dist = dist
@@ -361,13 +369,27 @@ class ShardedViewTemplates:
             raise TypeError("templates must be uint8 or float32")
         self._n = int(t.shape[0])
         self._dtype = t.dtype
-        self._rows = t.to(self.device).contiguous()          # row-major copy (appends re-pack from it)
+        self._owner = self.rank == self.world - 1          # created templates go to the last rank's shard
+        self._cap = max(self._n + (64 if self._owner else 0), 32) if capacity is None else max(int(capacity), self._n, 32)
         self._scratch = torch.empty(4096, dtype=torch.uint8, device=self.device)
-        self._pack()
+        with torch.cuda.device(self.device):
+            self._lib = self._alloc(self._cap)
+            src = t.to(self.device).contiguous()
+            if self._n:
+                if self._dtype == torch.uint8:
+                    nat.check(nat.lib().prs_vt_pack_u8(src.data_ptr(), self._n, self._lib.data_ptr(), 0,
+                                                       nat.stream_ptr()), "prs_vt_pack_u8")
+                else:
+                    self._lib[: self._n].copy_(src)
+            torch.cuda.current_stream().synchronize()
+        del src
         self.base_index = int(base_index)
         self.match_threshold = match_threshold
         self.mode = {"ref": nat.VT_MODE_REF, "circular": nat.VT_MODE_CIRCULAR}[mode]
         self._key = torch.empty(1, dtype=torch.int64, device=self.device)
+        self._keys_pin = torch.zeros(64, dtype=torch.int64).pin_memory()
+        self._res_pin = torch.zeros(ctypes.sizeof(nat.ShardResult), dtype=torch.uint8).pin_memory()
+        self._res = nat.ShardResult.from_address(self._res_pin.data_ptr())
         if self._distributed:
             counts = torch.tensor([self._n], dtype=torch.int64, device=self.device)
             allc = [torch.zeros_like(counts) for _ in range(self.world)]
@@ -375,17 +397,105 @@ class ShardedViewTemplates:
             self.n_total = int(sum(int(c.item()) for c in allc))
         else:
             self.n_total = self._n
+        self._xchg = None
+        self.exchange = "nccl"
+        if exchange not in ("auto", "fused", "nccl"):
+            raise ValueError("exchange must be 'auto', 'fused' or 'nccl'")
+        if exchange != "nccl":
+            self._connect(strict=exchange == "fused")
 
-    def _pack(self):
+    # ------------------------------------------------------------------ set-up
+    def _alloc(self, capacity):
         if self._dtype == torch.uint8:
-            nbytes = int(nat.lib().prs_vt_packed_bytes(max(self._n, 1)))
-            self._lib = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-            with torch.cuda.device(self.device):
-                nat.check(nat.lib().prs_vt_pack_u8(self._rows.data_ptr() if self._n else None, self._n,
-                                                   self._lib.data_ptr(), 0, nat.stream_ptr()), "prs_vt_pack_u8")
-        else:
-            self._lib = self._rows
+            nbytes = int(nat.lib().prs_vt_packed_bytes(int(capacity)))
+            return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        return torch.empty((capacity, 32, 32), dtype=torch.float32, device=self.device)
 
+    def _connect(self, strict):
+        """Create this rank's exchange buffer and map the peers' (CUDA IPC handles all-gathered through the group)."""
+        dist = self._dist
+        L = nat.lib()
+        with torch.cuda.device(self.device):
+            h = ctypes.c_void_p()
+            nat.check(L.prs_xchg_create(self.world, self.rank, ctypes.byref(h)), "prs_xchg_create")
+            ok = 1
+            if self.world > 1:
+                mine = torch.zeros(nat.XCHG_HANDLE_BYTES, dtype=torch.uint8)
+                nat.check(L.prs_xchg_export(h, mine.data_ptr()), "prs_xchg_export")
+                on_gpu = dist.get_backend(self.group) == "nccl"
+                mine = mine.to(self.device) if on_gpu else mine
+                allh = [torch.zeros_like(mine) for _ in range(self.world)]
+                dist.all_gather(allh, mine, group=self.group)
+                handles = torch.stack([a.cpu() for a in allh]).contiguous()
+                rc = L.prs_xchg_connect(h, handles.data_ptr())
+                msg = L.prs_last_error().decode(errors="replace") if rc != 0 else ""
+                flag = torch.tensor([1 if rc == 0 else 0], dtype=torch.int64, device=self.device if on_gpu else "cpu")
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)   # all ranks take the same path
+                ok = int(flag.item())
+                if not ok:
+                    L.prs_xchg_destroy(h)
+                    if strict:
+                        raise nat.NativeError("fused exchange unavailable: %s" % (msg or "a peer could not map the buffers"))
+                    import warnings
+                    warnings.warn("ShardedViewTemplates: CUDA IPC mapping failed (%s); using the NCCL all-reduce" % msg)
+                    return
+            self._xchg = h
+            self.exchange = "fused"
+
+    def set_exchange(self, name):
+        """Switch between the fused device-side exchange and the NCCL all-reduce (every rank must do the same)."""
+        if name == "nccl":
+            if self._xchg is not None:
+                self._xchg_off, self._xchg = self._xchg, None
+            self.exchange = "nccl"
+        elif name == "fused":
+            if self._xchg is None:
+                if getattr(self, "_xchg_off", None) is None:
+                    raise nat.NativeError("the fused exchange was never connected")
+                self._xchg, self._xchg_off = self._xchg_off, None
+            self.exchange = "fused"
+        else:
+            raise ValueError("exchange must be 'fused' or 'nccl'")
+
+    def close(self):
+        if self._xchg is None and getattr(self, "_xchg_off", None) is not None:
+            self._xchg, self._xchg_off = self._xchg_off, None
+        if self._xchg is not None:
+            with torch.cuda.device(self.device):
+                nat.lib().prs_xchg_destroy(self._xchg)
+            self._xchg = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.n_total
+
+    def _grow(self, need):
+        if need <= self._cap:
+            return
+        cap = max(need, self._cap * 2)
+        new = self._alloc(cap)
+        if self._dtype == torch.uint8:
+            new[: self._lib.numel()].copy_(self._lib)        # whole 32-template groups, position independent
+        else:
+            new[: self._n].copy_(self._lib[: self._n])
+        self._lib, self._cap = new, cap
+
+    def _store_local(self, query_dev):
+        """Append the query to this rank's shard: ONE slot is written (``prs_vt_pack_u8(first=n)``)."""
+        self._grow(self._n + 1)
+        if self._dtype == torch.uint8:
+            nat.check(nat.lib().prs_vt_pack_u8(query_dev.data_ptr(), 1, self._lib.data_ptr(), self._n, nat.stream_ptr()),
+                      "prs_vt_pack_u8")
+        else:
+            self._lib[self._n].copy_(query_dev.reshape(32, 32))
+        self._n += 1
+
+    # ------------------------------------------------------------------ matching
     def local_sweep(self, query_dev, key=None):
         """Launch the local sweep; the packed key is left in ``key`` (a one-element int64 device tensor, default
         ``self._key``) on the device."""
@@ -401,35 +511,73 @@ class ShardedViewTemplates:
                                                  key.data_ptr(), None, nat.stream_ptr()), "prs_vt_sweep_f32")
         return key
 
+    def _check_status(self):
+        if self._res.status != 0:
+            raise nat.NativeError("sharded exchange %d timed out waiting for a peer rank" % self._res.seq)
+
     def match_keys(self, queries_dev):
-        """``match_key`` for a batch of queries ``[Q, 32, 32]``: Q local sweeps, ONE MIN all-reduce of the Q packed
-        keys and one read-back -- the exchange and the synchronisation are paid once per batch, not once per query.
+        """``match_key`` for a batch of queries ``[Q, 32, 32]``: Q local sweeps, ONE exchange of the Q packed keys
+        and one read-back -- the exchange and the synchronisation are paid once per batch, not once per query.
         Returns a list of ``(score, index)``, identical on every rank."""
         Q = int(queries_dev.shape[0])
         keys = torch.empty(Q, dtype=torch.int64, device=self.device)
+        is_float = self._dtype != torch.uint8
         with torch.cuda.device(self.device):
             for i in range(Q):
                 self.local_sweep(queries_dev[i], keys[i:i + 1])
-            host = reduce_packed_key(keys, self.group).cpu().numpy()
-        return [unpack_key(int(k), is_float=self._dtype != torch.uint8) for k in host]
+            if self._xchg is None:
+                host = reduce_packed_key(keys, self.group).cpu().numpy()
+                return [unpack_key(int(k), is_float=is_float) for k in host]
+            out = []
+            for q0 in range(0, Q, 64):                          # the exchange kernel carries up to 64 keys
+                nq = min(64, Q - q0)
+                nat.check(nat.lib().prs_vt_shard_exchange(self._xchg, keys[q0:].data_ptr(), nq, self._keys_pin.data_ptr(),
+                                                          self._res_pin.data_ptr(), nat.stream_ptr()),
+                          "prs_vt_shard_exchange")
+                torch.cuda.current_stream().synchronize()
+                self._check_status()
+                out += [unpack_key(int(k), is_float=is_float) for k in self._keys_pin[:nq].tolist()]
+        return out
 
     def match_key(self, query_dev):
         """Global ``(score, index)`` of the best match over all shards; identical on every rank."""
+        is_float = self._dtype != torch.uint8
         with torch.cuda.device(self.device):
-            key = reduce_packed_key(self.local_sweep(query_dev), self.group)
-            k = int(key.item())
-        return unpack_key(k, is_float=self._dtype != torch.uint8)
+            key = self.local_sweep(query_dev)
+            if self._xchg is None:
+                k = int(reduce_packed_key(key, self.group).item())
+                return unpack_key(k, is_float=is_float)
+            nat.check(nat.lib().prs_vt_shard_exchange(self._xchg, key.data_ptr(), 1, self._keys_pin.data_ptr(),
+                                                      self._res_pin.data_ptr(), nat.stream_ptr()), "prs_vt_shard_exchange")
+            torch.cuda.current_stream().synchronize()
+            self._check_status()
+            return unpack_key(int(self._keys_pin[0]), is_float=is_float)
 
     def match(self, query_dev):
         """``(index, created)`` with the reference's create-or-match rule applied identically on every rank."""
-        score, idx = self.match_key(query_dev)
-        index, created = decide(score, idx, self.n_total, self.match_threshold)
-        if created:
-            if self.rank == self.world - 1:
-                grown = torch.empty((self._n + 1, 32, 32), dtype=self._dtype, device=self.device)
-                grown[: self._n].copy_(self._rows)
-                grown[self._n].copy_(query_dev.reshape(32, 32))
-                self._rows, self._n = grown, self._n + 1
-                self._pack()
-            self.n_total += 1
-        return index, created
+        if self._xchg is None:
+            score, idx = self.match_key(query_dev)
+            index, created = decide(score, idx, self.n_total, self.match_threshold)
+            if created:
+                if self._owner:
+                    with torch.cuda.device(self.device):
+                        self._store_local(query_dev)
+                self.n_total += 1
+            return index, created
+        with torch.cuda.device(self.device):
+            if self._owner:
+                self._grow(self._n + 1)                        # room for the template the kernel may append
+            key = self.local_sweep(query_dev)
+            nat.check(nat.lib().prs_vt_shard_decide(
+                self._xchg, key.data_ptr(), float(self.match_threshold),
+                nat.PRS_U8 if self._dtype == torch.uint8 else nat.PRS_F32, query_dev.data_ptr(), self._lib.data_ptr(),
+                self._n, self.n_total, 1 if self._owner else 0, self._res_pin.data_ptr(), nat.stream_ptr()),
+                "prs_vt_shard_decide")
+            torch.cuda.current_stream().synchronize()
+            self._check_status()
+            created = bool(self._res.created)
+            if created:
+                if self._owner:
+                    self._n += 1
+                self.n_total += 1
+            return int(self._res.template_index), created
