@@ -298,6 +298,9 @@ PRS_API int prs_frame_create(prs_pc_handle pc, void* pc_state, const void* gi, v
                      int row_lo, int row_hi, int row_step, int col_lo, int col_hi, int col_step, void* scratch,
                      double* odom_host, uint8_t* frame_host, prs_frame_result* result_host, prs_frame_plan** out);
 PRS_API int prs_frame_destroy(prs_frame_plan* plan);
+/* Put the library size back into the plan's device-side counter after templates were appended outside the plan
+ * (ViewTemplates.match / create between fused frames); synchronises `stream`. */
+PRS_API int prs_frame_set_count(prs_frame_plan* plan, int n_templates, void* stream);
 PRS_API int prs_frame_run(prs_frame_plan* plan, int moved, void* stream);
 /* prs_frame_run without the final synchronisation: the caller waits on `stream` (or an event recorded on it) before
  * reading result_host.  Two plans that share pc / pc_work / scratch / vt_packed (hence the device-side template

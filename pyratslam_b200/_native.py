@@ -86,6 +86,7 @@ _SIGNATURES["prs_frame_create"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_
                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                            c_void_p, c_void_p, c_void_p, POINTER(c_void_p)])
 _SIGNATURES["prs_frame_destroy"] = (c_int, [c_void_p])
+_SIGNATURES["prs_frame_set_count"] = (c_int, [c_void_p, c_int, c_void_p])
 _SIGNATURES["prs_frame_run"] = (c_int, [c_void_p, c_int, c_void_p])
 _SIGNATURES["prs_frame_launch"] = (c_int, [c_void_p, c_int, c_void_p])
 _SIGNATURES["prs_replay_run"] = (c_int, [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p])

@@ -1614,6 +1614,15 @@ extern "C" int prs_frame_destroy(prs_frame_plan* f) {
   return PRS_OK;
 }
 
+// The library size the plan's kernels read lives in device memory (shared by the plans built on one scratch
+// buffer): a caller that appended templates outside the plan (ViewTemplates.match / create) puts the host's count back.
+extern "C" int prs_frame_set_count(prs_frame_plan* f, int n_templates, void* stream) {
+  PRS_REQUIRE(f && n_templates >= 0 && n_templates < f->capacity, "prs_frame_set_count: bad argument");
+  PRS_CUDA(cudaMemcpyAsync(f->d_n, &n_templates, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  PRS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return PRS_OK;
+}
+
 // One frame.  `moved` != 0: odom_host (given at creation) holds (vtrans, vrot) and the pose cells are updated first.
 // The first call of each kind runs eagerly (it also warms every lazily initialised kernel attribute), the second
 // captures the graph, later ones replay it.

@@ -118,6 +118,9 @@ class PoseCellEnsemble:
         self._res_pin_ptr = self._res_pin.data_ptr()
         self._update_host = nat.lib().prs_pc_update_host
         self.max_pc = np.zeros((B, 3), dtype=np.int64)
+        # bumped by every call that changes the device state; users that cache something derived from the state on
+        # the device (the frame plans of ros_simulate cache the arg-max) compare it with the value they last saw
+        self._state_gen = 0
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -174,6 +177,7 @@ class PoseCellEnsemble:
 
     @posecells.setter
     def posecells(self, value):
+        self._state_gen += 1
         v = np.asarray(value, dtype=self.np_dtype).reshape((self.n_networks,) + self.shape)
         with torch.cuda.device(self.device):
             src = torch.from_numpy(np.ascontiguousarray(v)).to(self.device)
@@ -183,6 +187,7 @@ class PoseCellEnsemble:
 
     def inject(self, energy, loc, network=None):
         """``posecells[loc] += energy`` on one network or on all of them (posecell_network.py:322-324)."""
+        self._state_gen += 1
         x, y, th = (int(v) for v in loc)  # py2 callers pass math.floor() floats; old numpy truncated them
         X, Y, Th = self.shape
         x, y, th = (v + n if -n <= v < 0 else v for v, n in ((x, X), (y, Y), (th, Th)))  # numpy negative indices
@@ -229,6 +234,7 @@ class PoseCellEnsemble:
 
         Results land in ``self._argmax`` (flat indices), ``self._total`` and ``self._err`` on the device.
         """
+        self._state_gen += 1
         od = self._odom if odom_dev is None else odom_dev
         with torch.cuda.device(self.device):
             nat.check(nat.lib().prs_pc_step(self._h, self._state.data_ptr(), od.data_ptr(), self._gi.data_ptr(),
@@ -241,6 +247,7 @@ class PoseCellEnsemble:
         Raises ``KeyError`` / ``ValueError`` if any network hit the conditions under which the reference
         raises or reads unwritten memory (see PRS_ERR_* in the header).
         """
+        self._state_gen += 1
         self._odom_np[...] = np.asarray(v, dtype=np.float64).reshape(self.n_networks, 2)
         with torch.cuda.device(self.device):
             nat.check(nat.lib().prs_pc_step_host_xyz(self._h, self._state.data_ptr(), self._odom_pin.data_ptr(),
@@ -256,6 +263,7 @@ class PoseCellEnsemble:
     # the current stream without waiting; ``update_result`` returns the oldest outstanding step's arg-max cells.  With
     # one step kept in flight the copies and the launch overhead of step t+1 hide behind the kernel of step t.
     def update_submit(self, v):
+        self._state_gen += 1
         if not hasattr(self, "_pipe"):
             B = self.n_networks
             self._pipe = [{"odom": torch.zeros((B, 2), dtype=torch.float64).pin_memory(),
@@ -299,6 +307,7 @@ class PoseCellEnsemble:
 
     def path_integration(self, v):
         """Path integration only (no DoG / inhibition / normalisation) with host odometry ``[B, 2]``."""
+        self._state_gen += 1
         vv = np.asarray(v, dtype=np.float64).reshape(self.n_networks, 2)
         self._odom.copy_(torch.from_numpy(vv))
         with torch.cuda.device(self.device):
@@ -309,6 +318,7 @@ class PoseCellEnsemble:
 
     def run(self, odom, return_totals=False):
         """``T`` consecutive updates from ``odom[T, B, 2]`` (host or device); returns ``int64[T, B, 3]``."""
+        self._state_gen += 1
         if isinstance(odom, torch.Tensor):
             od = odom.to(self.device, torch.float64).contiguous()
         else:
@@ -450,6 +460,7 @@ class PoseCellNetwork:
         if torch.cuda.current_device() != e._dev_index:
             with torch.cuda.device(e.device):
                 return self.update((vtrans, vrot))
+        e._state_gen += 1
         rc = e._update_host(e._h, e._state_ptr, vtrans, vrot, e._gi_ptr, e._odom_pin_ptr, e._res_pin_ptr,
                             _raw_stream(e._dev_index))
         if rc != 0:

@@ -99,7 +99,28 @@ class RatslamRos(object):
         self._f_stream = torch.cuda.Stream(device=dev)
         self._f_plan = ctypes.c_void_p()
         self._f_plan_key = None
+        self._f_gen = e._state_gen       # the pose-cell state the cached arg-max (_f_pcwork) was computed from
+        self._f_n_dev = None             # the template count the plans' device-side counter holds
+        torch.cuda.current_stream(dev).synchronize()
         self._fused_ready = True
+
+    def _fused_resync(self, plan):
+        """Bring the device-side caches of the frame plans back in step with what happened OUTSIDE them: a pose-cell
+        update / inject / assignment since the last fused frame invalidates the cached arg-max (it is recomputed on
+        the frame stream, behind whatever the current stream still has queued), templates appended by
+        ``vts.match`` / ``create`` invalidate the device-side library size."""
+        e, v = self.pcn._ens, self.vts
+        if e._state_gen != self._f_gen:
+            self._f_stream.wait_stream(torch.cuda.current_stream(e.device))
+            with torch.cuda.device(e.device):
+                nat.check(nat.lib().prs_pc_argmax(e._h, e._state.data_ptr(), self._f_pcwork.data_ptr(),
+                                                  ctypes.c_void_p(self._f_stream.cuda_stream)), "prs_pc_argmax")
+            self._f_gen = e._state_gen
+        if self._f_n_dev is not None and self._f_n_dev != v._n:
+            self._f_stream.wait_stream(torch.cuda.current_stream(e.device))
+            nat.check(nat.lib().prs_frame_set_count(plan, v._n, ctypes.c_void_p(self._f_stream.cuda_stream)),
+                      "prs_frame_set_count")
+        self._f_n_dev = v._n
 
     def _fused_plan(self):
         """(Re)create the CUDA-graph frame plan; needed again whenever the library buffer was reallocated."""
@@ -118,6 +139,7 @@ class RatslamRos(object):
             self._f_scratch.data_ptr(), self._f_odom.data_ptr(), self._f_frame.data_ptr(), self._f_res.data_ptr(),
             ctypes.byref(self._f_plan)), "prs_frame_create")
         self._f_plan_key = key
+        self._f_n_dev = v._n
 
     def __del__(self):
         plans = [getattr(self, "_f_plan", None)] + [sl["plan"] for sl in getattr(self, "_p_slots", [])]
@@ -144,6 +166,7 @@ class RatslamRos(object):
             o[0], o[1] = vtrans, vrot
         v._grow(v._n + 2)
         self._fused_plan()
+        self._fused_resync(self._f_plan)
         self._f_frame.numpy()[...] = im
         nat.check(nat.lib().prs_frame_run(self._f_plan, 1 if moved else 0, ctypes.c_void_p(self._f_stream.cuda_stream)),
                   "prs_frame_run")
@@ -159,7 +182,7 @@ class RatslamRos(object):
             self.published_pose.append(self.em.get_current_point())
         if r.created:
             v._loc[v._n] = pc_max
-        v._n = int(r.n_templates)
+        v._n = self._f_n_dev = int(r.n_templates)
         v.last_score = None if r.key == (1 << 64) - 1 else int(r.key >> 32)
         if self.inject_energy is not None:
             loc = tuple(int(c) for c in v._loc[int(r.template_index)])
@@ -169,6 +192,7 @@ class RatslamRos(object):
                     nat.check(nat.lib().prs_pc_argmax(e._h, e._state.data_ptr(), self._f_pcwork.data_ptr(),
                                                       nat.stream_ptr()), "prs_pc_argmax")
             self._f_stream.synchronize()
+        self._f_gen = e._state_gen       # the plan's own update and the injection above are reflected in _f_pcwork
         self.published_index.append(int(r.template_index))
         return int(r.template_index), bool(r.created)
 
@@ -209,6 +233,7 @@ class RatslamRos(object):
                 v.x_range[1], v.x_step, self._f_scratch.data_ptr(), sl["odom"].data_ptr(), sl["frame"].data_ptr(),
                 sl["res"].data_ptr(), ctypes.byref(sl["plan"])), "prs_frame_create")
         self._p_key = key
+        self._f_n_dev = v._n
 
     def pipe_submit(self, slot, twist, im):
         """Stage and launch one frame in ``slot`` (0 or 1) without waiting for it; ``pipe_finish(slot)`` returns its
@@ -224,6 +249,8 @@ class RatslamRos(object):
             vtrans, vrot = twist[0] / self.odom_freq, twist[1] / self.odom_freq          # :157-158
             sl["odom_np"][0], sl["odom_np"][1] = vtrans, vrot
         sl["frame_np"][...] = im
+        if self._p_inflight == 0:
+            self._fused_resync(sl["plan"])
         nat.check(nat.lib().prs_frame_launch(sl["plan"], 1 if moved else 0, ctypes.c_void_p(self._f_stream.cuda_stream)),
                   "prs_frame_launch")
         sl["event"].record(self._f_stream)
@@ -257,7 +284,8 @@ class RatslamRos(object):
             self.published_pose.append(self.em.get_current_point())
         if r.created:
             v._loc[int(r.n_templates) - 1] = pc_max
-        v._n = int(r.n_templates)
+        v._n = self._f_n_dev = int(r.n_templates)
+        self._f_gen = e._state_gen
         v.last_score = None if r.key == (1 << 64) - 1 else int(r.key >> 32)
         self.published_index.append(int(r.template_index))
         return int(r.template_index), bool(r.created)
@@ -285,6 +313,7 @@ class RatslamRos(object):
         assert self._p_inflight == 0
         v._grow(v._n + T + 2)
         self._pipe_plans()
+        self._fused_resync(self._p_slots[0]["plan"])
         moved = ((np.abs(odom[:, 0]) > 0.001) | (np.abs(odom[:, 1]) > 0.001)).astype(np.uint8)    # ros_simulate.py:128
         tw = np.ascontiguousarray(odom / float(self.odom_freq))                                    # :157-158
         res = np.zeros(T, dtype=self._RESULT_DTYPE)
@@ -308,7 +337,8 @@ class RatslamRos(object):
         self.published_index.extend(int(i) for i in res["template_index"][:stop])
         if T:
             last = T - 1
-            v._n = int(res["n_templates"][last])
+            v._n = self._f_n_dev = int(res["n_templates"][last])
+            self._f_gen = e._state_gen
             self.pcn.max_pc = tuple(int(c) for c in amax[last])
             self.pcn._max_valid = True
             k = int(res["key"][last])

@@ -418,3 +418,123 @@ def test_sharded_batch_matches_per_query():
     svf = ShardedViewTemplates(lib.astype(np.float32), 0, match_threshold=9000.0)
     gotf = svf.match_keys(torch.from_numpy(qs.astype(np.float32)).cuda())
     assert [i for _, i in gotf] == [int(np.argmin(ovt.library_scores(lib.astype(np.float64), q.astype(np.float64)))) for q in qs]
+
+
+def test_fused_frames_after_unfused_calls():
+    """the frame plans cache the arg-max and the library size on the device.  A pose-cell update, an inject
+    or a template append made OUTSIDE the plan (lone odometry message, vis_callback) between two fused frames must be
+    seen by the next fused frame -- also when that frame's own twist is below the 0.001 gate (no update of its own).
+    Reference for every step: the three reference-shaped calls on a second node."""
+    from pyratslam_b200 import ros_simulate
+    T = 14
+    frames = synth_frames(np.random.default_rng(5), T)
+    rng = np.random.default_rng(6)
+    odom = np.stack([rng.uniform(0.5, 3.0, T), rng.uniform(-1, 1, T)], axis=1)
+    a, b = ros_simulate.RatslamRos(), ros_simulate.RatslamRos()
+    still = (0.0, 0.0)
+
+    def plain(node, twist, im):
+        if twist is not None:
+            node.odom_callback(twist)
+            node.spin_once()
+        return node.vis_callback(im), tuple(int(c) for c in node.pcn.get_pc_max())
+
+    for t in range(T):
+        tw = (float(odom[t, 0]), float(odom[t, 1]))
+        kind = t % 4
+        if kind == 0:      # fused frame with its own update
+            got = a.fused_frame(tw, frames[t]), tuple(int(c) for c in a.pcn.max_pc)
+            want = plain(b, tw, frames[t])
+        elif kind == 1:    # odom(moving) alone, then odom(sub-threshold) + image as ONE fused frame: the stale-cache case
+            for node in (a, b):
+                node.odom_callback(tw)
+                node.spin_once()
+            got = a.fused_frame(still, frames[t]), tuple(int(c) for c in a.pcn.max_pc)
+            want = plain(b, None, frames[t])
+        elif kind == 2:    # a template appended outside the plan, then a fused frame that must not overwrite its slot
+            ra, rb_ = a.vis_callback(frames[t]), b.vis_callback(frames[t])
+            assert ra == rb_
+            got = a.fused_frame(tw, frames[(t + 5) % T]), tuple(int(c) for c in a.pcn.max_pc)
+            want = plain(b, tw, frames[(t + 5) % T])
+        else:              # inject outside the plan, then an image-only fused frame
+            for node in (a, b):
+                node.pcn.inject(0.5, (3, 4, 5))
+            got = a.fused_frame(None, frames[t]), tuple(int(c) for c in a.pcn.max_pc)
+            want = plain(b, None, frames[t])
+        assert got == want, (t, kind, got, want)
+    assert len(a.vts.templates) == len(b.vts.templates)
+    for i in range(len(b.vts.templates)):
+        assert np.array_equal(a.vts.templates[i].template, b.vts.templates[i].template), i
+        assert a.vts.templates[i].location() == b.vts.templates[i].location(), i
+
+
+def test_sharded_match_decides_on_device_single_rank():
+    """ShardedViewTemplates.match through the fused exchange kernel (csrc/sharded.cu) on one rank: create-or-match,
+    strict threshold, appends slot by slot (capacity growth included) -- against the oracle's ViewTemplates loop."""
+    from pyratslam_b200 import ShardedViewTemplates
+    rng = np.random.default_rng(33)
+    for dtype, thr in ((np.uint8, 45000), (np.float32, 30000.0)):
+        lib = rng.integers(0, 256, (40, 32, 32)).astype(dtype)
+        svt = ShardedViewTemplates(lib[:0], 0, match_threshold=thr, capacity=32)
+        assert svt.exchange == "fused"
+        ref_lib = []
+        for i in range(80):
+            if i % 3 == 2 and ref_lib:
+                src = ref_lib[int(rng.integers(0, len(ref_lib)))]
+                q = np.clip(src.astype(np.int16) - rng.integers(0, 3, src.shape), 0, 255).astype(dtype)
+            else:
+                q = rng.integers(0, 256, (32, 32)).astype(dtype)
+            if ref_lib:
+                sc = ovt.library_scores(np.stack(ref_lib), q)
+                j = int(np.argmin(sc))
+                want = (len(ref_lib), True) if sc[j] > thr else (j, False)
+            else:
+                want = (0, True)
+            if want[1]:
+                ref_lib.append(q)
+            assert svt.match(torch.from_numpy(q).cuda()) == want, (dtype, i)
+        assert svt.n_total == len(ref_lib) > 32
+        # threshold equality is a match (strict '>')
+        q = ref_lib[3]
+        s0 = int(ovt.library_scores(np.stack(ref_lib), q).min()) if dtype == np.uint8 else 0.0
+        svt.match_threshold = s0
+        assert svt.match(torch.from_numpy(q).cuda())[1] is False
+        svt.close()
+
+
+def test_two_streams_sweep_concurrently():
+    """The packed sweeps read the query planes from ONE constant buffer per device; sweeps issued on two streams must
+    not see each other's query (they are event-ordered on the device, csrc/view_templates.cu VtqScope)."""
+    from pyratslam_b200 import _native as nat
+    rng = np.random.default_rng(9)
+    n = 20000
+    lib = rng.integers(0, 256, (n, 32, 32), dtype=np.uint8)
+    L = nat.lib()
+    dlib = torch.from_numpy(lib).cuda()
+    packed = torch.zeros(int(L.prs_vt_packed_bytes(n)), dtype=torch.uint8, device="cuda")
+    nat.check(L.prs_vt_pack_u8(dlib.data_ptr(), n, packed.data_ptr(), 0, nat.stream_ptr()))
+    qa = np.clip(lib[111].astype(np.int16) - 1, 0, 255).astype(np.uint8)
+    qb = np.clip(lib[19000].astype(np.int16) - 1, 0, 255).astype(np.uint8)
+    want = {}
+    for name, q in (("a", qa), ("b", qb)):
+        sc = ovt.library_scores(lib, q)
+        want[name] = (int(sc.min()) << 32) | int(np.argmin(sc))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    qd = [torch.from_numpy(qa).cuda(), torch.from_numpy(qb).cuda()]
+    keys = [torch.zeros(64, dtype=torch.int64, device="cuda") for _ in range(2)]
+    scratch = [torch.zeros(4096, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    for it in range(64):
+        for s in range(2):
+            with torch.cuda.stream(streams[s]):
+                nat.check(L.prs_vt_sweep_packed_u8(packed.data_ptr(), n, qd[s].data_ptr(), 0, 0,
+                                                   keys[s][it:].data_ptr(), None, scratch[s].data_ptr(),
+                                                   ctypes_stream(streams[s])))
+    torch.cuda.synchronize()
+    assert set(keys[0].tolist()) == {want["a"]} and set(keys[1].tolist()) == {want["b"]}
+
+
+def ctypes_stream(s):
+    import ctypes
+    return ctypes.c_void_p(s.cuda_stream)
