@@ -96,6 +96,7 @@ PRS_API size_t prs_pc_state_bytes(prs_pc_handle h);
 #define PRS_PATH_RESIDENT 1
 #define PRS_PATH_TILED 2
 #define PRS_PATH_CLUSTER 3
+#define PRS_PATH_PAIR 4 /* fused SMEM-resident kernel, one network per 2-CTA cluster (float32 and float64) */
 PRS_API int prs_pc_path(prs_pc_handle h);
 /* force the generic path (1) or let the plan choose (0); for tests and profiling */
 PRS_API int prs_pc_force_generic(prs_pc_handle h, int on);
@@ -249,7 +250,8 @@ PRS_API int prs_xchg_connect(prs_xchg* x, const void* handles);
 PRS_API int prs_xchg_set_timeout(prs_xchg* x, double seconds);
 PRS_API int prs_xchg_destroy(prs_xchg* x);
 /* MIN over the ranks of n_keys (<= 64) packed keys: keys_local is this rank's (device), keys_out receives the global
- * minima (device memory or pinned host memory), result (optional, device or pinned host) the status record. */
+ * minima (device memory or pinned host memory; optional when result is given: result->key is the first key's minimum),
+ * result (optional, device or pinned host) the status record. */
 PRS_API int prs_vt_shard_exchange(prs_xchg* x, const unsigned long long* keys_local, int n_keys,
                           unsigned long long* keys_out, prs_shard_result* result, void* stream);
 /* ViewTemplates.match's decision for a sharded library (view_templates.py:67-73), taken on the device by every rank
@@ -261,6 +263,17 @@ PRS_API int prs_vt_shard_exchange(prs_xchg* x, const unsigned long long* keys_lo
 PRS_API int prs_vt_shard_decide(prs_xchg* x, const unsigned long long* key_local, double threshold, int dtype,
                         const void* tpl, void* lib, long long n_local, long long n_total, int owner,
                         prs_shard_result* result, void* stream);
+/* Host side of a polled exchange: with `result` in pinned host memory, spin until the LAST exchange issued on x has
+ * written its record (its sequence number goes out last) -- about 1 us after the kernel, where a stream
+ * synchronisation costs a thread wake-up.  PRS_E_CUDA after timeout_s seconds. */
+PRS_API int prs_xchg_wait(prs_xchg* x, const prs_shard_result* result_host, double timeout_s);
+/* One query of a sharded library in one call: local sweep (PRS_U8: bit-sliced library + scratch >= 2 KiB as for
+ * prs_vt_sweep_packed_u8; PRS_F32: row-major library), exchange (decide == 0: result->key is the MIN over the ranks;
+ * decide != 0: the create-or-match decision of prs_vt_shard_decide as well), wait for the pinned record.
+ * key_dev: device uint64 scratch for the local key. */
+PRS_API int prs_vt_shard_query(prs_xchg* x, int dtype, void* lib, long long n_local, const void* query_dev, int mode,
+                       long long base_index, unsigned long long* key_dev, void* scratch, int decide, double threshold,
+                       long long n_total, int owner, prs_shard_result* result_pinned, void* stream);
 
 /* ------------------------------------------------------------------- one frame */
 

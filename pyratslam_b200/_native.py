@@ -100,6 +100,9 @@ _SIGNATURES["prs_xchg_destroy"] = (c_int, [c_void_p])
 _SIGNATURES["prs_vt_shard_exchange"] = (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p])
 _SIGNATURES["prs_vt_shard_decide"] = (c_int, [c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p, c_longlong,
                                               c_longlong, c_int, c_void_p, c_void_p])
+_SIGNATURES["prs_xchg_wait"] = (c_int, [c_void_p, c_void_p, c_double])
+_SIGNATURES["prs_vt_shard_query"] = (c_int, [c_void_p, c_int, c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p,
+                                             c_void_p, c_int, c_double, c_longlong, c_int, c_void_p, c_void_p])
 XCHG_HANDLE_BYTES = 64
 PRS_U8 = 2
 

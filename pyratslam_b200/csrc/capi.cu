@@ -156,15 +156,17 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   ALLOC(p->tab_dev, sizeof(PcTables<float>));
   p->forced_path = PRS_PATH_AUTO;
   p->resident_ok = prs_pc_resident_supported(p);
+  p->pair_ok = prs_pc_pair_supported(p);
   p->tiled_ok = prs_pc_tiled_supported(p);
-  p->cluster_C = prs_pc_cluster_choose(p);
+  int one_wave = 0;
+  p->cluster_C = prs_pc_cluster_choose(p, &one_wave);
   p->cluster_ok = p->cluster_C >= 2;
-  // one network per cluster pays when one CTA per network (or four grid-wide launches of a few blocks) would leave
-  // most of the chip idle: a single 21x21x36 network takes 12.5 us against 18.5 us, a 50x50x10 one 16 against 19
-  p->cluster_pref = p->cluster_ok && (long long)p->B * p->cluster_C <= 148;
+  // One network per cluster pays when every cluster runs at once: a single 21x21x36 network takes 10 us against
+  // 16.4 us (pair kernel) / 18.5 us (one CTA per network), a 50x50x10 one 12.6 us against 19 us (tiled).
+  p->cluster_pref = p->cluster_ok && one_wave;
   // The multi-kernel paths need scratch of four state tensors; it is only allocated when such a path
   // can be taken for this plan (prs_pc_force_generic / path_integration allocate it lazily otherwise).
-  if (!p->resident_ok) {
+  if (!p->resident_ok && !p->pair_ok) {
     ALLOC(p->s1, 2 * sbytes);
     ALLOC(p->s3, 2 * sbytes);
     p->s2 = (char*)p->s1 + sbytes;
@@ -214,6 +216,15 @@ extern "C" int prs_pc_path(prs_pc_handle h) {
   if (!h || h->force_generic) return PRS_PATH_GENERIC;
   if (h->forced_path >= 0) return h->forced_path;
   if (h->cluster_pref) return PRS_PATH_CLUSTER;
+  // PRS_PC_PREFER (profiling): "resident" keeps round 1's one-CTA kernel as the automatic choice for float32
+  static const bool prefer_resident = [] {
+    const char* e = getenv("PRS_PC_PREFER");
+    return e && strcmp(e, "resident") == 0;
+  }();
+  // Fused kernels.  float64: the pair kernel is the only fused one.  float32: two CTAs per network finish a wave in
+  // 16.4 us against 18.5 us while every CTA has an SM of its own (B <= #SM / 2); beyond that the one-CTA kernel
+  // wins (0.344 ms against 0.463 ms for 4096 networks, profiles/r2_path_compare.txt).
+  if (h->pair_ok && !(prefer_resident && h->resident_ok) && (!h->resident_ok || h->B <= 74)) return PRS_PATH_PAIR;
   return h->resident_ok ? PRS_PATH_RESIDENT : (h->tiled_ok ? PRS_PATH_TILED : PRS_PATH_GENERIC);
 }
 
@@ -222,7 +233,8 @@ static void drop_graphs(prs_pc_handle h);
 extern "C" int prs_pc_set_path(prs_pc_handle h, int path) {
   PRS_REQUIRE(h, "prs_pc_set_path: null handle");
   const bool ok = path == PRS_PATH_AUTO || path == PRS_PATH_GENERIC || (path == PRS_PATH_RESIDENT && h->resident_ok) ||
-                  (path == PRS_PATH_TILED && h->tiled_ok) || (path == PRS_PATH_CLUSTER && h->cluster_ok);
+                  (path == PRS_PATH_TILED && h->tiled_ok) || (path == PRS_PATH_CLUSTER && h->cluster_ok) ||
+                  (path == PRS_PATH_PAIR && h->pair_ok);
   PRS_REQUIRE(ok, "prs_pc_set_path: path %d is not available for a %dx%dx%d %s plan", path, h->X, h->Y, h->Th,
               h->dtype == PRS_F32 ? "float32" : "float64");
   if (path == PRS_PATH_GENERIC || path == PRS_PATH_TILED) {
@@ -262,6 +274,7 @@ static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T
   const size_t es = h->dtype == PRS_F32 ? 4 : 8;
   const int path = prs_pc_path(h);
   if (path == PRS_PATH_RESIDENT) return prs_pc_resident_step(h, state, odom, T, gi, argmax, total, err, st);
+  if (path == PRS_PATH_PAIR) return prs_pc_pair_step(h, state, odom, T, gi, argmax, total, err, st);
   for (int t = 0; t < T; ++t) {
     int rc;
     if (path == PRS_PATH_CLUSTER)
@@ -295,7 +308,8 @@ extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, con
   if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
   // The fused kernels are one launch; a caller that is capturing its own graph gets plain launches as well.
   const int path_now = prs_pc_path(h);
-  if (path_now == PRS_PATH_RESIDENT || path_now == PRS_PATH_CLUSTER || cap != cudaStreamCaptureStatusNone)
+  if (path_now == PRS_PATH_RESIDENT || path_now == PRS_PATH_PAIR || path_now == PRS_PATH_CLUSTER ||
+      cap != cudaStreamCaptureStatusNone)
     return step_enqueue(h, state, odom, gi, argmax, total, err, st);
   // Multi-kernel paths: replay the launch sequence as a graph on a private stream, ordered after the caller's
   // stream on entry and before it on exit (no host synchronisation).

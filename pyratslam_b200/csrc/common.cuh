@@ -100,6 +100,7 @@ struct prs_pc_plan {
   int cluster_ok;       // = cluster_C >= 2
   int cluster_pref;     // ... and the network count is small enough for it to be the automatic choice
   int resident_ok;      // the fused SMEM-resident kernel supports this shape/dtype
+  int pair_ok;          // ... and so does the one-network-per-2-CTA-cluster kernel (posecell_pair.cu)
   void* tab_dev;        // device copy of PcTables<float> for the resident kernel
 };
 
@@ -118,7 +119,7 @@ int prs_pc_launch_unravel_pack(prs_pc_plan* p, const long long* argmax, const in
 int prs_pc_launch_plan(prs_pc_plan* p, const double* odom, int* err, cudaStream_t st);
 int prs_pc_launch_sum_final_f32(prs_pc_plan* p, int np, float* total, cudaStream_t st);
 int prs_pc_launch_argmax_final_f32(prs_pc_plan* p, int np, long long* argmax, cudaStream_t st);
-int prs_pc_cluster_choose(const prs_pc_plan* p);
+int prs_pc_cluster_choose(const prs_pc_plan* p, int* one_wave);
 // err_store != 0: err[b] is overwritten with the update's bits (needs no zeroed buffer); 0: OR-ed into it
 // argmax2 / err2: optional second destination of network b's arg-max and error bits (both or neither)
 int prs_pc_cluster_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax,
@@ -129,6 +130,9 @@ int prs_pc_cluster_step(prs_pc_plan* p, float* state, const double* odom, const 
 int prs_pc_step_mirror(prs_pc_plan* h, void* state, const double* odom, const void* gi, long long* argmax, void* total,
                        int* err, long long* argmax2, int* err2, int* mirrored, cudaStream_t st);
 int prs_pc_resident_supported(const prs_pc_plan* p);
+int prs_pc_pair_supported(const prs_pc_plan* p);
+int prs_pc_pair_step(prs_pc_plan* p, void* state, const double* odom, int T, const void* gi, long long* argmax,
+                     void* total, int* err, cudaStream_t st);
 int prs_pc_resident_step(prs_pc_plan* p, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st);
 

@@ -24,6 +24,8 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -498,17 +500,19 @@ cudaLaunchConfig_t make_config(const prs_pc_plan* p, int C, size_t smem, cudaStr
 // Can a cluster of C CTAs with this much shared memory be co-scheduled on the current device?  Sets the function
 // attributes the launch needs (shared-memory opt-in; non-portable cluster sizes above 8) as a side effect.
 template <int P>
-bool cluster_fits(const prs_pc_plan* p, int C) {
+int cluster_fits(const prs_pc_plan* p, int C) {  // the number of clusters of C CTAs the device runs at once (0: none)
   const ClLayout L(p->X, p->Y, P);
-  if (L.bytes > (size_t)227 * 1024) return false;
+  if (L.bytes > (size_t)227 * 1024) return 0;
   auto kern = k_pc_cluster<P>;
   static size_t smem_set[64] = {};  // the opt-in limit is only ever raised: other plans may need the larger value
-  if (p->device < 0 || p->device >= 64) return false;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (p->device < 0 || p->device >= 64) return 0;
   const size_t want = L.bytes > smem_set[p->device] ? L.bytes : smem_set[p->device];
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want) != cudaSuccess ||
       (C > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
     (void)cudaGetLastError();
-    return false;
+    return 0;
   }
   smem_set[p->device] = want;
   cudaLaunchAttribute attr[1];
@@ -517,9 +521,9 @@ bool cluster_fits(const prs_pc_plan* p, int C) {
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
     (void)cudaGetLastError();
-    return false;
+    return 0;
   }
-  return n >= 1;
+  return n;
 }
 
 template <int P>
@@ -531,7 +535,7 @@ int launch(prs_pc_plan* p, int C, const ClArgs& args, cudaStream_t st) {
   return PRS_OK;
 }
 
-bool fits_dispatch(const prs_pc_plan* p, int C, int P) {
+int fits_dispatch(const prs_pc_plan* p, int C, int P) {
   switch (P) {
     case 1: return cluster_fits<1>(p, C);
     case 2: return cluster_fits<2>(p, C);
@@ -543,17 +547,22 @@ bool fits_dispatch(const prs_pc_plan* p, int C, int P) {
     case 8: return cluster_fits<8>(p, C);
     case 9: return cluster_fits<9>(p, C);
   }
-  return false;
+  return 0;
 }
 
 }  // namespace
 
-// Plan-time choice of the cluster size: the largest divisor C of Th (up to 16; sizes above 8 are "non-portable" and
-// are only taken if the occupancy query confirms them on this device) whose CTAs hold P = Th / C <= 9 planes within
-// the shared-memory limit.  More CTAs mean less work on each one's critical path: measured 16.0 us (C = 10) against
-// 18.4 us (C = 5) for 50x50x10 and 12.5 us (C = 12) against 14.2 us (C = 6) for 21x21x36.  PRS_CLUSTER_MAX lowers
-// the limit (tuning knob).  Returns C, or 0 if the path does not apply to this plan.
-int prs_pc_cluster_choose(const prs_pc_plan* p) {
+// Plan-time choice of the cluster size C (a divisor of Th, up to 16; sizes above 8 are "non-portable" and are only
+// taken if the occupancy query confirms them on this device; a CTA holds P = Th / C <= 9 planes within the
+// shared-memory limit).  More CTAs mean less work on each one's critical path -- measured for ONE 21x21x36 network:
+// 9.9 us (C = 9), 10.3 (C = 12), 11.4 (C = 6), 13.6 (C = 4) -- but only while all B clusters run at once: the device
+// co-schedules about 12 clusters of 9, 16 of 6, 24 of 4 (cudaOccupancyMaxActiveClusters), and a second wave doubles the
+// time (profiles/r2_b_sweep.txt).  So: the largest C whose clusters all fit at once for this B; an even P (the packed
+// two-plane 7x7 stage) is preferred over a slightly larger C with an odd P.  *one_wave tells whether the chosen C runs
+// the B networks in a single wave.  PRS_CLUSTER_MAX lowers the limit (tuning knob).  Returns C, or 0 if the path does
+// not apply to this plan.
+int prs_pc_cluster_choose(const prs_pc_plan* p, int* one_wave) {
+  if (one_wave) *one_wave = 0;
   if (p->dtype != PRS_F32) return 0;
   if (p->X < 7 || p->Y < 7) return 0;  // a halo of 3 must be a single periodic image
   if ((long long)p->X * p->Y >= 65536) return 0;  // FastDiv range
@@ -562,13 +571,25 @@ int prs_pc_cluster_choose(const prs_pc_plan* p) {
     const int v = e ? atoi(e) : 16;
     return v < 2 ? 2 : (v > 16 ? 16 : v);
   }();
+  int cand[16], nact[16], nc = 0;
   for (int C = cmax; C >= 2; --C) {
     if (p->Th % C != 0) continue;
     const int P = p->Th / C;
     if (P > 9) break;
-    if (fits_dispatch(p, C, P)) return C;
+    const int n = fits_dispatch(p, C, P);
+    if (n >= 1) cand[nc] = C, nact[nc] = n, ++nc;
   }
-  return 0;
+  if (nc == 0) return 0;
+  int pick = -1;
+  for (int i = 0; i < nc && pick < 0; ++i)
+    if (p->B <= nact[i]) pick = i;
+  if (pick < 0) return cand[0];  // more networks than any cluster size runs at once: not the automatic choice anyway
+  if (one_wave) *one_wave = 1;
+  const int P = p->Th / cand[pick];
+  if ((P & 1) && pick + 1 < nc && p->B <= nact[pick + 1] && ((p->Th / cand[pick + 1]) & 1) == 0 &&
+      10 * cand[pick + 1] >= 7 * cand[pick])
+    ++pick;
+  return cand[pick];
 }
 
 int prs_pc_cluster_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax,

@@ -17,6 +17,7 @@
 // A bounded spin (default 10 s of %globaltimer) turns a missing peer into an error instead of a hung GPU.
 #include <new>
 #include <string.h>
+#include <time.h>
 
 #include "common.cuh"
 #include "vt_pack.cuh"
@@ -127,7 +128,6 @@ __global__ void __launch_bounds__(kXchgThreads)
       result->template_index = create ? (int)d.n_total : (int)(k & 0xffffffffu);
       result->n_total = (int)d.n_total + (create ? 1 : 0);
       result->status = timed_out ? 1 : 0;
-      result->seq = seq;
     }
   } else if (tid == 0 && result != nullptr) {
     result->key = s_key0;
@@ -135,9 +135,16 @@ __global__ void __launch_bounds__(kXchgThreads)
     result->template_index = -1;
     result->n_total = (int)d.n_total;
     result->status = timed_out ? 1 : 0;
-    result->seq = seq;
   }
-  if (tid == 0) *seq_dev = seq;
+  if (tid == 0) {
+    *seq_dev = seq;
+    // the sequence number is what a host that polls the (pinned) record waits for: it goes out last, behind a
+    // system-scope fence, so that the fields above and keys_out (written before the last barrier) are visible first
+    if (result != nullptr) {
+      __threadfence_system();
+      st_release_sys(&result->seq, seq);
+    }
+  }
 }
 
 // device-side alias of a pinned (mapped) host pointer; device pointers pass through
@@ -163,6 +170,7 @@ struct prs_xchg {
   unsigned long long* d_seq;
   unsigned long long timeout_ns;
   bool connected;
+  unsigned long long host_seq;  // exchanges issued so far (= the device-side sequence number once they have run)
 };
 
 extern "C" int prs_xchg_create(int world, int rank, prs_xchg** out) {
@@ -259,6 +267,7 @@ static int xchg_launch(prs_xchg* x, const unsigned long long* keys_local, int n_
   int dev = -1;
   PRS_CUDA(cudaGetDevice(&dev));
   PRS_REQUIRE(dev == x->device, "%s: the exchange was created on device %d but device %d is current", who, x->device, dev);
+  ++x->host_seq;
   k_vt_xchg_min<<<1, kXchgThreads, 0, st>>>(x->d_peers, x->world, x->rank, x->d_seq, keys_local, n_keys,
                                             (unsigned long long*)dev_alias(keys_out),
                                             (prs_shard_result*)dev_alias(result), x->timeout_ns, d);
@@ -268,7 +277,7 @@ static int xchg_launch(prs_xchg* x, const unsigned long long* keys_local, int n_
 
 extern "C" int prs_vt_shard_exchange(prs_xchg* x, const unsigned long long* keys_local, int n_keys,
                                      unsigned long long* keys_out, prs_shard_result* result, void* stream) {
-  PRS_REQUIRE(x && keys_local && keys_out, "prs_vt_shard_exchange: null argument");
+  PRS_REQUIRE(x && keys_local && (keys_out || result), "prs_vt_shard_exchange: null argument");
   PRS_REQUIRE(n_keys >= 1 && n_keys <= kMaxKeys, "prs_vt_shard_exchange: n_keys must be in [1, %d], got %d", kMaxKeys, n_keys);
   ShardDecide d;
   memset(&d, 0, sizeof(d));
@@ -292,4 +301,59 @@ extern "C" int prs_vt_shard_decide(prs_xchg* x, const unsigned long long* key_lo
   d.n_local = n_local;
   d.n_total = n_total;
   return xchg_launch(x, key_local, 1, nullptr, result, d, (cudaStream_t)stream, "prs_vt_shard_decide");
+}
+
+// Host side of a polled exchange: spin on the pinned record until the kernel of the LAST issued exchange has written
+// its sequence number (a stream synchronisation costs a wake-up of 5-10 us; the record arrives ~1 us after the kernel).
+extern "C" int prs_xchg_wait(prs_xchg* x, const prs_shard_result* result_host, double timeout_s) {
+  PRS_REQUIRE(x && result_host, "prs_xchg_wait: null argument");
+  const volatile unsigned long long* seq = &result_host->seq;
+  const unsigned long long want = x->host_seq;
+  unsigned long long spins = 0;
+  struct timespec t0;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  while (*seq < want) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0xffff) == 0) {
+      struct timespec t1;
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if ((double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec) > timeout_s) {
+        cudaError_t e = cudaGetLastError();
+        prs_set_error("prs_xchg_wait: exchange %llu did not complete within %.1f s (%s)", want, timeout_s,
+                      cudaGetErrorString(e));
+        return PRS_E_CUDA;
+      }
+    }
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  return PRS_OK;
+}
+
+// One query of a sharded library in ONE call: the local sweep (bit-sliced uint8 or float32), the exchange kernel
+// (MIN over the ranks, optionally the create-or-match decision and the append) and the wait for the pinned record.
+extern "C" int prs_vt_shard_query(prs_xchg* x, int dtype, void* lib, long long n_local, const void* query_dev, int mode,
+                                  long long base_index, unsigned long long* key_dev, void* scratch, int decide,
+                                  double threshold, long long n_total, int owner, prs_shard_result* result_pinned,
+                                  void* stream) {
+  PRS_REQUIRE(x && query_dev && key_dev && result_pinned, "prs_vt_shard_query: null argument");
+  int rc;
+  if (dtype == PRS_U8)
+    rc = prs_vt_sweep_packed_u8(n_local ? lib : nullptr, n_local, (const uint8_t*)query_dev, mode, base_index, key_dev,
+                                nullptr, scratch, stream);
+  else if (dtype == PRS_F32)
+    rc = prs_vt_sweep_f32(n_local ? (const float*)lib : nullptr, n_local, (const float*)query_dev, mode, base_index,
+                          key_dev, nullptr, stream);
+  else {
+    prs_set_error("prs_vt_shard_query: dtype must be PRS_U8 or PRS_F32");
+    return PRS_E_INVALID;
+  }
+  if (rc != PRS_OK) return rc;
+  if (decide)
+    rc = prs_vt_shard_decide(x, key_dev, threshold, dtype, query_dev, lib, n_local, n_total, owner, result_pinned, stream);
+  else
+    rc = prs_vt_shard_exchange(x, key_dev, 1, nullptr, result_pinned, stream);
+  if (rc != PRS_OK) return rc;
+  return prs_xchg_wait(x, result_pinned, 30.0);
 }

@@ -31,7 +31,7 @@ def _as_np_dtype(dtype):
     raise TypeError("Data type specified is not currently supported: %r" % (dtype,))  # convolution.py:25
 
 
-_PATHS = {0: "generic", 1: "resident", 2: "tiled", 3: "cluster"}
+_PATHS = {0: "generic", 1: "resident", 2: "tiled", 3: "cluster", 4: "pair"}
 
 
 
@@ -144,8 +144,9 @@ class PoseCellEnsemble:
 
     @property
     def path(self):
-        """``"resident"`` (fused SMEM-resident kernel, one CTA per network), ``"cluster"`` (one network per
-        thread-block cluster), ``"tiled"`` (large-grid kernels) or ``"generic"``."""
+        """``"pair"`` (fused SMEM-resident kernel, one network per 2-CTA cluster), ``"resident"`` (the same with one
+        CTA per network), ``"cluster"`` (one network spread over a large thread-block cluster: lowest latency),
+        ``"tiled"`` (large-grid kernels) or ``"generic"``."""
         return _PATHS[nat.lib().prs_pc_path(self._h)]
 
     def force_path(self, name):

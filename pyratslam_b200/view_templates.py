@@ -534,7 +534,7 @@ class ShardedViewTemplates:
                 nat.check(nat.lib().prs_vt_shard_exchange(self._xchg, keys[q0:].data_ptr(), nq, self._keys_pin.data_ptr(),
                                                           self._res_pin.data_ptr(), nat.stream_ptr()),
                           "prs_vt_shard_exchange")
-                torch.cuda.current_stream().synchronize()
+                nat.check(nat.lib().prs_xchg_wait(self._xchg, self._res_pin.data_ptr(), 30.0), "prs_xchg_wait")
                 self._check_status()
                 out += [unpack_key(int(k), is_float=is_float) for k in self._keys_pin[:nq].tolist()]
         return out
@@ -543,15 +543,20 @@ class ShardedViewTemplates:
         """Global ``(score, index)`` of the best match over all shards; identical on every rank."""
         is_float = self._dtype != torch.uint8
         with torch.cuda.device(self.device):
-            key = self.local_sweep(query_dev)
             if self._xchg is None:
-                k = int(reduce_packed_key(key, self.group).item())
+                k = int(reduce_packed_key(self.local_sweep(query_dev), self.group).item())
                 return unpack_key(k, is_float=is_float)
-            nat.check(nat.lib().prs_vt_shard_exchange(self._xchg, key.data_ptr(), 1, self._keys_pin.data_ptr(),
-                                                      self._res_pin.data_ptr(), nat.stream_ptr()), "prs_vt_shard_exchange")
-            torch.cuda.current_stream().synchronize()
-            self._check_status()
-            return unpack_key(int(self._keys_pin[0]), is_float=is_float)
+            return unpack_key(self._query(query_dev, 0).key, is_float=is_float)
+
+    def _query(self, query_dev, decide):
+        """Sweep + exchange (+ decision) + wait for the pinned record, one library call (``prs_vt_shard_query``)."""
+        nat.check(nat.lib().prs_vt_shard_query(
+            self._xchg, nat.PRS_U8 if self._dtype == torch.uint8 else nat.PRS_F32, self._lib.data_ptr(), self._n,
+            query_dev.data_ptr(), self.mode, self.base_index, self._key.data_ptr(), self._scratch.data_ptr(), decide,
+            float(self.match_threshold), self.n_total, 1 if self._owner else 0, self._res_pin.data_ptr(),
+            nat.stream_ptr()), "prs_vt_shard_query")
+        self._check_status()
+        return self._res
 
     def match(self, query_dev):
         """``(index, created)`` with the reference's create-or-match rule applied identically on every rank."""
@@ -567,14 +572,7 @@ class ShardedViewTemplates:
         with torch.cuda.device(self.device):
             if self._owner:
                 self._grow(self._n + 1)                        # room for the template the kernel may append
-            key = self.local_sweep(query_dev)
-            nat.check(nat.lib().prs_vt_shard_decide(
-                self._xchg, key.data_ptr(), float(self.match_threshold),
-                nat.PRS_U8 if self._dtype == torch.uint8 else nat.PRS_F32, query_dev.data_ptr(), self._lib.data_ptr(),
-                self._n, self.n_total, 1 if self._owner else 0, self._res_pin.data_ptr(), nat.stream_ptr()),
-                "prs_vt_shard_decide")
-            torch.cuda.current_stream().synchronize()
-            self._check_status()
+            self._query(query_dev, 1)
             created = bool(self._res.created)
             if created:
                 if self._owner:

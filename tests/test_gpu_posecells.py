@@ -16,7 +16,7 @@ from oracle import posecells as opc
 pytestmark = pytest.mark.gpu
 
 RTOL = {np.float32: 1e-5, np.float64: 1e-12}
-PATHS = ["auto", "generic", "resident", "tiled", "cluster"]
+PATHS = ["auto", "generic", "resident", "tiled", "cluster", "pair"]
 
 
 def _rel(a, b):
