@@ -13,7 +13,7 @@ import math
 
 import numpy as np
 
-from .experience_map import ExperienceMap
+from .experience_map import ExperienceMap, LinkedExperienceMap
 from .posecells import PoseCellNetwork
 from .view_templates import ViewTemplates
 
@@ -54,19 +54,23 @@ def simulate_run(data=None, shape=POSE_SIZE_SIM, keep_states=False):
     return amax, totals, (np.stack(states) if keep_states else pcn.posecells)
 
 
-def replay_run(frames, odom, shape=POSE_SIZE_ROS, match_threshold=MATCH_THRESHOLD, inject_energy=None):
+def replay_run(frames, odom, shape=POSE_SIZE_ROS, match_threshold=MATCH_THRESHOLD, inject_energy=None,
+               experience_links=False):
     """Offline replay of the ROS loop.
 
     ``frames``: uint8[T,256,256]; ``odom``: float64[T,2] = (linear.x, angular.z).
     ``inject_energy``: if set, the coupling the reference left commented out at ``ros_simulate.py:106-108`` is
     enabled: ``pcn.inject(energy, template_match.location())`` after every match.
+    ``experience_links``: use ``LinkedExperienceMap`` (the specification of the links / loop-closure extension), each
+    odometry update tagged with the most recent template match.
     Returns a dict of per-frame records.
     """
     pcn = PoseCellNetwork(shape)
     mid = (math.floor(shape[0] / 2), math.floor(shape[1] / 2), math.floor(shape[2] / 2))
     pcn.inject(1, mid)
     vts = ViewTemplates(X_RANGE, Y_RANGE, X_STEP, Y_STEP, IM_SIZE[0], IM_SIZE[1], match_threshold)
-    em = ExperienceMap()
+    em = LinkedExperienceMap(shape) if experience_links else ExperienceMap()
+    last_vt = None
     T = len(frames)
     rec = {
         "template": np.zeros(T, np.int64), "created": np.zeros(T, np.bool_),
@@ -78,18 +82,20 @@ def replay_run(frames, odom, shape=POSE_SIZE_ROS, match_threshold=MATCH_THRESHOL
         if abs(lin) > 0.001 or abs(ang) > 0.001:           # ros_simulate.py:128
             vtrans, vrot = lin / ODOM_FREQ, ang / ODOM_FREQ  # :157-158
             pcn.update((vtrans, vrot))                     # :135
-            em.update(vtrans, vrot, pcn.get_pc_max())      # :136-137
+            em.update(vtrans, vrot, pcn.get_pc_max(), last_vt if experience_links else None)      # :136-137
         pc_max = pcn.get_pc_max()                          # :103
         n_before = len(vts.templates)
         tm = vts.match(frames[t], pc_max[0], pc_max[1], pc_max[2])  # :104
         if inject_energy is not None:
             pcn.inject(inject_energy, tm.location())       # :106-108 (commented out in the reference)
+        last_vt = tm.get_index()
         rec["template"][t] = tm.get_index()
         rec["created"][t] = len(vts.templates) > n_before
         rec["argmax"][t] = pc_max
         rec["n_exp"][t] = len(em.experiences)
         if em.current_exp is not None:
             rec["em_xy"][t] = em.get_current_point()
+    rec["em"] = em
     rec["final_state"] = pcn.posecells
     rec["n_templates"] = len(vts.templates)
     return rec

@@ -39,7 +39,8 @@ ODOM_FREQ = 10
 class RatslamRos(object):
     """The node's state and callbacks, fed from arrays instead of ROS topics."""
 
-    def __init__(self, pose_size=POSE_SIZE, match_threshold=MATCH_THRESHOLD, inject_energy=None, **pcn_kwargs):
+    def __init__(self, pose_size=POSE_SIZE, match_threshold=MATCH_THRESHOLD, inject_energy=None,
+                 experience_links=False, **pcn_kwargs):
         # inject_energy: enable the view-template -> pose-cell coupling the reference left commented out
         # (ros_simulate.py:106-108): pcn.inject(energy, template_match.location()) after every match
         self.inject_energy = inject_energy
@@ -53,7 +54,9 @@ class RatslamRos(object):
         self.vts = ViewTemplates(x_range=X_RANGE, y_range=Y_RANGE, x_step=X_STEP, y_step=Y_STEP,
                                  im_x=IM_SIZE[0], im_y=IM_SIZE[1], match_threshold=match_threshold)
         self.vt_count = 0
-        self.em = ExperienceMap()
+        # experience_links: link the experiences and close loops on (view template, pose cell) revisits -- the
+        # reference's TODOs (experience_map.py:49,59); off by default = the reference's dead reckoning
+        self.em = ExperienceMap(linked=experience_links, pc_dims=pose_size)
         self.em_count = 0
         self.published_index = []
         self.published_pose = []
@@ -74,10 +77,19 @@ class RatslamRos(object):
         if abs(twist[0]) > 0.001 or abs(twist[1]) > 0.001:
             self.twist_data.append(twist)
 
+    _NO_VT = object()
+
+    def _em_update(self, vtrans, vrot, pc_max, vt=_NO_VT):
+        """``ExperienceMap.update`` (ros_simulate.py:136-137); with experience_links the most recent template match
+        rides along as the view the experience is tagged with."""
+        if vt is self._NO_VT:
+            vt = self.published_index[-1] if self.published_index else None
+        self.em.update(vtrans, vrot, pc_max, vt if self.em.linked else None)
+
     # ros_simulate.py:134-146
     def update_posecells(self, vtrans, vrot):
         pc_max = self.pcn.update((vtrans, vrot))
-        self.em.update(vtrans, vrot, pc_max)
+        self._em_update(vtrans, vrot, pc_max)
         self.published_pose.append(self.em.get_current_point())
 
     # ------------------------------------------------------------------ fused fast path
@@ -178,7 +190,7 @@ class RatslamRos(object):
         pc_max = (flat // (Y * Th), (flat // Th) % Y, flat % Th)
         self.pcn.max_pc, self.pcn._max_valid = pc_max, True
         if moved:
-            self.em.update(vtrans, vrot, pc_max)                                          # :136-137
+            self._em_update(vtrans, vrot, pc_max)                                          # :136-137
             self.published_pose.append(self.em.get_current_point())
         if r.created:
             v._loc[v._n] = pc_max
@@ -280,7 +292,7 @@ class RatslamRos(object):
         pc_max = (flat // (Y * Th), (flat // Th) % Y, flat % Th)
         self.pcn.max_pc, self.pcn._max_valid = pc_max, self._p_inflight == 0
         if moved:
-            self.em.update(vtrans, vrot, pc_max)                                          # :136-137
+            self._em_update(vtrans, vrot, pc_max)                                          # :136-137
             self.published_pose.append(self.em.get_current_point())
         if r.created:
             v._loc[int(r.n_templates) - 1] = pc_max
@@ -330,7 +342,8 @@ class RatslamRos(object):
         for t in range(stop):
             pc_max = (int(amax[t, 0]), int(amax[t, 1]), int(amax[t, 2]))
             if moved[t]:
-                self.em.update(float(tw[t, 0]), float(tw[t, 1]), pc_max)                           # :136-137
+                self._em_update(float(tw[t, 0]), float(tw[t, 1]), pc_max,
+                                int(res["template_index"][t - 1]) if t > 0 else None)                 # :136-137
                 self.published_pose.append(self.em.get_current_point())
             if res["created"][t]:
                 v._loc[int(res["n_templates"][t]) - 1] = pc_max

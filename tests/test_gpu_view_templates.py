@@ -538,3 +538,26 @@ def test_two_streams_sweep_concurrently():
 def ctypes_stream(s):
     import ctypes
     return ctypes.c_void_p(s.cuda_stream)
+
+
+def test_replay_with_experience_links():
+    """SURVEY 8f row 3 in the loop: every odometry update tagged with the latest template match, revisits close loops.
+    Plain, fused and native replays build the same graph as the oracle's replay with the specification map."""
+    from oracle import drivers as odrv
+    from pyratslam_b200 import ros_simulate
+    T = 72
+    frames = synth_frames(np.random.default_rng(7), T)
+    frames[36:] = frames[:36]                      # the second half revisits the first
+    odom = np.zeros((T, 2))                        # rotate on the spot by one theta cell per step (vrot = angular.z / 10):
+    odom[:, 1] = 2 * np.pi / 36 * 10 * 0.999       # after 36 steps the pose cells revisit as well
+    ref = odrv.replay_run(frames, odom, experience_links=True)
+    assert ref["em"].n_loop_closures > 20 and len(ref["em"].experiences) < T - 20
+    ref["em"].iterate(5)
+    for kw in ({}, {"fused": True}, {"native": True}):
+        rec = ros_simulate.replay(frames, odom, experience_links=True, **kw)
+        em = rec["node"].em
+        assert np.array_equal(rec["template"], ref["template"]), kw
+        assert em.n_loop_closures == ref["em"].n_loop_closures and len(em.experiences) == len(ref["em"].experiences), kw
+        assert em.links == [(l.exp_from, l.exp_to, l.d, l.heading_rad, l.facing_rad) for l in ref["em"].links], kw
+        em.iterate(5)
+        assert em.get_poses() == ref["em"].get_poses(), kw

@@ -97,3 +97,45 @@ def test_lower_order_kernels_normalised():
         assert f.shape == (7,) * order and abs(abs(f.sum()) - 1) < 1e-12
     assert K.diff_gaussian_separable().shape == (7,)
     assert abs(K.build_kernel(7, 1, order=2).sum() - 1) < 1e-12
+
+
+def test_linked_experience_map_against_specification():
+    """links, loop closure and relaxation (the reference's TODOs, experience_map.py:49,59) against
+    the specification in oracle/experience_map.py, on a looped trajectory with revisits; the default mode stays the
+    reference's class (one experience per update, no links)."""
+    import math
+    from oracle import experience_map as oem
+    from pyratslam_b200.experience_map import ExperienceMap
+    rng = np.random.default_rng(11)
+    ours, spec = ExperienceMap(linked=True, pc_dims=(21, 21, 36), delta_pc=1.5), oem.LinkedExperienceMap((21, 21, 36), 1.5)
+    plain_o, plain_s = ExperienceMap(), oem.ExperienceMap()
+    raw = ExperienceMap(linked=True, pc_dims=(21, 21, 36), delta_pc=1.5)      # never relaxed
+    T = 400
+    for t in range(T):
+        ph = 2 * math.pi * t / 100.0                      # four laps of a circle: lap k revisits lap 0
+        vtrans, vrot = 0.3 + 0.02 * rng.standard_normal(), 2 * math.pi / 100.0 + 0.003 * rng.standard_normal()
+        pc = (int(10 + 8 * math.cos(ph)) % 21, int(10 + 8 * math.sin(ph)) % 21, int(36 * (t % 100) / 100.0))
+        vt = (t % 100) // 2 if t % 7 else None            # a view template per two steps; some frames without one
+        for m in (ours, spec, raw):
+            m.update(vtrans, vrot, pc, vt)
+        for m in (plain_o, plain_s):
+            m.update(vtrans, vrot, pc, vt)
+        assert ours.get_current_point() == spec.get_current_point()
+        if t % 50 == 49:
+            ours.iterate(3)
+            spec.iterate(3)
+    assert len(ours.experiences) == len(spec.experiences) < T and ours.n_loop_closures == spec.n_loop_closures > 50
+    assert ours.links == [(l.exp_from, l.exp_to, l.d, l.heading_rad, l.facing_rad) for l in spec.links]
+    assert ours.get_poses() == spec.get_poses()
+    assert (ours.accum_delta_x, ours.accum_delta_y, ours.accum_delta_th) == \
+        (spec.accum_delta_x, spec.accum_delta_y, spec.accum_delta_th)
+    # relaxation spreads the loop-closure errors over the graph: the sum of squared link residuals shrinks
+    def residual(m):
+        r = 0.0
+        for a, b, d, h, _ in m.links:
+            ea, eb = m.experiences[a], m.experiences[b]
+            r += (eb.m_x - ea.m_x - d * math.cos(ea.th + h)) ** 2 + (eb.m_y - ea.m_y - d * math.sin(ea.th + h)) ** 2
+        return r
+    assert [l[:2] for l in raw.links] == [l[:2] for l in ours.links]   # relaxation moves poses (and with them the angles later links are measured from), never the graph
+    assert residual(ours) < 0.8 * residual(raw)
+    assert plain_o.get_points() == plain_s.get_points() and len(plain_o.experiences) == T
