@@ -103,6 +103,11 @@ PRS_API int prs_pc_force_generic(prs_pc_handle h, int on);
 /* choose the kernel family explicitly (PRS_PATH_*, PRS_PATH_AUTO = the plan's own choice); PRS_E_INVALID if the
  * plan's shape / dtype is not supported by that family; for tests and profiling */
 PRS_API int prs_pc_set_path(prs_pc_handle h, int path);
+/* Per-plan options.  PRS_OPT_TILED_TMA: the tiled (large-grid) family runs its 7x7 + theta stages as ONE kernel fed by
+ * TMA tensor copies from a padded, origin-aligned intermediate (value 1) or as two kernels (value 0, the default: the
+ * fused kernel is parity-equal but measured slower on B200). */
+#define PRS_OPT_TILED_TMA 0
+PRS_API int prs_pc_set_option(prs_pc_handle h, int option, int value);
 
 /* One PoseCellNetwork.update() for all B networks (posecell_network.py:326-353):
  *   state  : device, [B][Th][X][Y] of the plan's dtype, updated in place

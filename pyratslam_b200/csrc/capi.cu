@@ -50,7 +50,7 @@ static void fill_tables(PcTables<T>& t, const prs_pc_config* c) {
 static void free_plan(prs_pc_plan* p) {
   void* ptrs[] = {p->cos_th, p->sin_th, p->s1,       nullptr,      p->s3,     nullptr,     p->shift, p->fsel,
                   p->ogi,    p->part_val, p->part_idx, p->inv_total, p->d_odom, p->d_argmax, p->d_err, p->d_total,
-                  p->tab_dev, p->d_xyze, p->done_ctr};
+                  p->tab_dev, p->d_xyze, p->done_ctr, p->apad, p->lg_tmap_dev};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   if (p->sgraph) cudaGraphExecDestroy(p->sgraph);
@@ -243,6 +243,14 @@ extern "C" int prs_pc_set_path(prs_pc_handle h, int path) {
   }
   h->forced_path = path;
   h->force_generic = 0;
+  drop_graphs(h);
+  return PRS_OK;
+}
+
+extern "C" int prs_pc_set_option(prs_pc_handle h, int option, int value) {
+  PRS_REQUIRE(h, "prs_pc_set_option: null handle");
+  PRS_REQUIRE(option == PRS_OPT_TILED_TMA, "prs_pc_set_option: unknown option %d", option);
+  h->opt_tiled_tma = value ? 1 : -1;
   drop_graphs(h);
   return PRS_OK;
 }

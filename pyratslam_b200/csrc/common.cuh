@@ -64,6 +64,13 @@ struct prs_pc_plan {
   int nblk_plane;       // blocks per theta plane in the generic kernels
   int np_max;           // partial-result slots per network (covers the generic and the tiled kernels)
   int tiled_ok;         // the tiled large-grid kernels support this shape/dtype
+  // TMA path of the tiled kernels (posecell_tiled.cu, lg_prepare): padded A tensor [B*Th][XP][YP] and its tensor map
+  float* apad;
+  int XP, YP;
+  int lg_state;         // 0 = not prepared yet, 1 = ready, -1 = unavailable (small grid, legacy knob, no driver entry)
+  alignas(64) unsigned char lg_tmap[128];
+  int opt_tiled_tma;    // prs_pc_set_option(PRS_OPT_TILED_TMA): 1 = on, -1 = off, 0 = the PRS_TILED_TMA environment variable
+  void* lg_tmap_dev;    // device copy of the tensor map (the kernel takes the descriptor from global memory)
   void* part_val;       // [B][Th*nblk_plane] partial sums, later partial maxima
   long long* part_idx;  // [B][Th*nblk_plane]
   void* inv_total;      // [B]

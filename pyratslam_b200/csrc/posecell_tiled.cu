@@ -17,7 +17,10 @@
 // wrap back to zero, partials added in a fixed order).  Any X, Y, Th >= 3 (edge tiles are masked, halos
 // wrap by modulo); chosen by the plan for float32 grids of at least 1024 cells per plane that the fused
 // SMEM-resident kernel does not cover.
+#include <cuda.h>
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "common.cuh"
 
@@ -166,9 +169,21 @@ constexpr int kInStride = kYXcols + 1;   // 39: odd, so that lanes walking down 
 constexpr int kMidStride = kYXy + 1;     // 33
 constexpr int kTyx = 288;                // 9 warps: 4 x 70 = 280 y-pass items, 8 x 32 = 256 x-pass items
 
+// PAD: the output goes to the PADDED, ORIGIN-ALIGNED tensor Apad[plane][X + 6][YP] that the fused 7x7 + theta kernel
+// below fetches with TMA.  (i) Every plane is stored already displaced by its integer origin (convolution.py:329-331:
+// the 7x7 stage reads cell (x + ox, y + oy), so cell (x, y) is stored at (x - ox, y - oy) mod (X, Y)): the tile a CTA of
+// that kernel needs then starts at ITS OWN tile origin for every plane -- a multiple of four floats, which the tensor
+// copy demands of the innermost coordinate (an unaligned start is an illegal instruction; measured with
+// bench_tools/tma_probe.cu).  (ii) The 3-cell periodic halo is materialised -- a cell within 3 of a border is stored at
+// its periodic images as well -- so one wrap-free box is always enough.  Data cell (x, y) lives at [x + 3][y + 3].
+// And the last block of a network to retire adds up the tile sums (fixed order): that kernel needs 1/total from its start.
+constexpr int kHP = 3;
+template <bool PAD>
 __global__ void __launch_bounds__(kTyx) k_tl_yx(const float2* __restrict__ EI, float* __restrict__ A,
                                                 const float* __restrict__ gi, int X, int Y, int Th, TlPairs tp,
-                                                float* __restrict__ part) {
+                                                float* __restrict__ part, int YP, float* __restrict__ total,
+                                                float* __restrict__ inv_total, unsigned* __restrict__ done_ctr,
+                                                const int* __restrict__ shift) {
   constexpr int kT = kTyx;
   __shared__ float2 s_in[kYXrows * kInStride];
   __shared__ unsigned s_cnt;
@@ -263,12 +278,39 @@ __global__ void __launch_bounds__(kTyx) k_tl_yx(const float2* __restrict__ EI, f
     }
     // rows of this segment inside the grid (0 when the column is outside): one compare per element masks the edges
     const int nv = gy < Y ? X - gx0 : 0;
-    float* q = Ap + (unsigned)(gx0 * Y + gy);
+    if (PAD) {
+      float* Pp = A + (size_t)plane * (X + 2 * kHP) * YP;
+      // where this plane's cells go: displaced by the plane's origin (one wrap per thread / per row)
+      const int ox = modp(shift[2 * plane], X), oy = modp(shift[2 * plane + 1], Y);
+      int ys = gy - oy;
+      ys += ys < 0 ? Y : 0;
+      const int cy = ys + kHP;
+      const int cy2 = ys < kHP ? cy + Y : (ys >= Y - kHP ? cy - Y : -1);  // periodic image of the column, if in the halo
+      int xs = gx0 - ox;
+      xs += xs < 0 ? X : 0;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      if (jj < nv) {
-        q[(unsigned)(jj * Y)] = a[jj];
-        psum += a[jj];
+      for (int jj = 0; jj < 8; ++jj) {
+        if (jj < nv) {
+          const int rx = xs + kHP;
+          const int rx2 = xs < kHP ? rx + X : (xs >= X - kHP ? rx - X : -1);
+          Pp[rx * YP + cy] = a[jj];
+          if (cy2 >= 0) Pp[rx * YP + cy2] = a[jj];
+          if (rx2 >= 0) {
+            Pp[rx2 * YP + cy] = a[jj];
+            if (cy2 >= 0) Pp[rx2 * YP + cy2] = a[jj];
+          }
+          psum += a[jj];
+        }
+        xs = xs + 1 == X ? 0 : xs + 1;
+      }
+    } else {
+      float* q = Ap + (unsigned)(gx0 * Y + gy);
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        if (jj < nv) {
+          q[(unsigned)(jj * Y)] = a[jj];
+          psum += a[jj];
+        }
       }
     }
   }
@@ -285,6 +327,33 @@ __global__ void __launch_bounds__(kTyx) k_tl_yx(const float2* __restrict__ EI, f
     for (int w = 0; w < kT / 32; ++w) sum += s_red[w];
     const int ntiles = gridDim.x * gridDim.y, b = plane / Th, k = plane - b * Th;
     part[(size_t)b * Th * ntiles + (size_t)k * ntiles + blockIdx.y * gridDim.x + blockIdx.x] = sum;
+  }
+  if (PAD) {  // the last block of this network to retire forms the total (posecell_network.py:343-345)
+    const int np = Th * gridDim.x * gridDim.y, b = plane / Th;
+    int last = 0;
+    if (lane == 0) {
+      __threadfence();
+      last = (atomicInc(&done_ctr[b], (unsigned)(np - 1)) == (unsigned)(np - 1)) ? 1 : 0;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      const float* pp = part + (size_t)b * np;
+      float acc = 0.f;
+      for (int i0 = lane; i0 < np; i0 += 32 * 8) {  // eight independent L2 loads in flight per lane
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = i0 + 32 * u < np ? __ldcg(pp + i0 + 32 * u) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        total[b] = acc;
+        inv_total[b] = (acc != 0.f) ? 1.f / acc : 1.f;
+      }
+    }
   }
 }
 
@@ -704,6 +773,252 @@ __global__ void __launch_bounds__(kT, MINB) k_tl_theta_fin(const float* __restri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused 7x7 stage + shifted theta pass + arg-max for large grids (BASELINE config 3), fed by TMA.
+//
+// k_tl_2d_pair + k_tl_theta_fin stream the B tensor through L2 twice (18.9 MB written, 33 MB read back with the
+// theta halo) and are two dependent launches.  Here a CTA owns a 16x32 tile of (x, y) and walks a chunk of theta
+// planes; B never leaves shared memory:
+//   * seven warps work on seven consecutive planes at once.  Each warp fetches the 22x40 halo tile of ITS plane of
+//     the padded A tensor with one cp.async.bulk.tensor (3-D tensor map, box 40 x 22 x 1).  k_tl_yx<true> stored every
+//     plane displaced by its integer origin (convolution.py:329-331) and materialised the periodic wrap in the halo,
+//     so the box of every plane starts at the tile's own origin (aligned, wrap-free); two slots per warp, the copy of
+//     the warp's next plane is in flight while it computes (mbarrier complete_tx).
+//   * 7x7 correlate (posecell_network.py:273-274,300): a lane owns a 4x4 patch, ten window rows of three LDS.128
+//     (row stride 40 floats: the eight lanes of a quarter warp read eight consecutive 16-byte units, conflict-free)
+//     feed 784 FFMA; the clamped plane goes into a ring of 14 B planes in shared memory.
+//   * after each round of seven planes the CTA runs the theta pass (convolution.py:344-359) for the (up to) seven
+//     output planes whose +-3 neighbours are now in the ring, 1/total folded into the taps, clamp (:314), float4
+//     stores of whole 128-byte rows, running arg-max; the last block of a network to retire picks its arg-max.
+// A chunk of C output planes costs C + 6 planes of 7x7 work; two chunks of 36 for Th = 72 (overhead 1.17).
+constexpr int kSTX = 16, kSTY = 32;        // tile: x rows, y columns
+constexpr int kSBH = kSTX + 6;             // 22 box rows
+constexpr int kSBW = 40;                   // box columns: 38 used, a multiple of four floats
+constexpr int kSW = 7;                     // planes in flight per CTA, one warp each
+constexpr int kSNT = kSW * 32;
+constexpr int kSSlot = (kSBH * kSBW * 4 + 127) / 128 * 128;  // 3584 bytes
+constexpr int kSRing = 2 * kSW;            // B planes kept in shared memory
+constexpr size_t kSSmem = (size_t)kSW * 2 * kSSlot + (size_t)kSRing * kSTX * kSTY * 4 + kSW * 2 * 8 + 256;
+
+struct StArgs {
+  const float* Apad;
+  float* S;
+  const int* shift;
+  const unsigned char* fsel;
+  const int* ogi;
+  const float* inv_total;
+  float* part_val;
+  long long* part_idx;
+  unsigned* done_ctr;
+  long long* argmax;
+  int X, Y, Th, XP, YP, nchunks, tiles_y;
+};
+
+__device__ __forceinline__ unsigned st_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kSNT, 2)
+    k_tl_shift_theta(const CUtensorMap* __restrict__ tmap_g, StArgs a, PcTables<float> tab) {
+  extern __shared__ __align__(128) unsigned char st_smem_raw[];
+  float* a_slots = reinterpret_cast<float*>(st_smem_raw);                                 // [kSW][2][kSSlot / 4]
+  float* b_ring = reinterpret_cast<float*>(st_smem_raw + (size_t)kSW * 2 * kSSlot);       // [kSRing][kSTX * kSTY]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(st_smem_raw + (size_t)kSW * 2 * kSSlot +
+                                                                   (size_t)kSRing * kSTX * kSTY * 4);
+  float* s_v = reinterpret_cast<float*>(bars + kSW * 2);
+  long long* s_i = reinterpret_cast<long long*>(s_v + 8);  // 8-byte aligned: 14 barriers * 8 + 32
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int X = a.X, Y = a.Y, Th = a.Th;
+  const int tile = blockIdx.x, tx = tile / a.tiles_y, ty = tile - tx * a.tiles_y;
+  const int x0 = tx * kSTX, y0 = ty * kSTY;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const int k_begin = (int)((long long)chunk * Th / a.nchunks), k_end = (int)((long long)(chunk + 1) * Th / a.nchunks);
+  const int NB = k_end - k_begin + 6;              // B planes this chunk needs: rel j <-> plane k_begin - 3 + j
+  const int rounds = (NB + kSW - 1) / kSW;
+  const unsigned bar0 = st_smem(bars + wid * 2);
+  float* my_slots = a_slots + (size_t)wid * 2 * (kSSlot / 4);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  unsigned phase = 0;    // bit s: parity of the next completion of slot s's barrier
+
+  // fetch the halo tile of rel plane j into slot s: one tensor copy; the plane was stored displaced by its origin, so
+  // the box starts at the tile's own origin (padded coordinates: data cell (x, y) at [x + 3][y + 3], halo 3)
+  auto fetch = [&](int j, int s) {
+    if (j >= NB) return;
+    const int pl = b * Th + modp(k_begin - 3 + j, Th);
+    if (lane == 0) {
+      const unsigned bar = bar0 + 8 * s;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kSBH * kSBW * 4) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+              st_smem(my_slots + (size_t)s * (kSSlot / 4))),
+          "l"(tmap_g), "r"(y0), "r"(x0), "r"(pl), "r"(bar)
+          : "memory");
+    }
+  };
+  fetch(wid, 0);
+  fetch(kSW + wid, 1);
+
+  const float* f1 = tab.f1d[a.ogi[b]];
+  const float inv = a.inv_total[b];  // 1/total of the normalisation (posecell_network.py:344-345), folded into the taps
+  float fc[7];
+#pragma unroll
+  for (int t = 0; t < 7; ++t) fc[t] = f1[t] * inv;
+  float bestv = -1.f;
+  long long besti = 0x7fffffffffffffffLL;
+  const int li = lane >> 3, lj = lane & 7;  // patch rows 4 li .. 4 li + 3, columns 4 lj .. 4 lj + 3
+  const bool vec = (Y & 3) == 0;
+
+  for (int r = 0; r < rounds; ++r) {
+    const int j = r * kSW + wid;
+    const int s = r & 1;
+    float acc[4][4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[d][c] = 0.f;
+    if (j < NB) {
+      {
+        const unsigned bar = bar0 + 8 * s, parity = (phase >> s) & 1u;
+        phase ^= 1u << s;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@!p bra WAIT_%=;\n"
+            "}\n" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+      }
+      const int pl = b * Th + modp(k_begin - 3 + j, Th);
+      float F[49];
+      {
+        const float* f = tab.f2d[a.fsel[pl]];
+#pragma unroll
+        for (int i = 0; i < 49; ++i) F[i] = f[i];
+      }
+      const float* sp = my_slots + (size_t)s * (kSSlot / 4) + (4 * li) * kSBW + 4 * lj;
+#pragma unroll
+      for (int rr = 0; rr < 10; ++rr) {
+        const float4* rp = reinterpret_cast<const float4*>(sp + rr * kSBW);
+        const float4 v0 = rp[0], v1 = rp[1], v2 = rp[2];
+        const float in[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const int ta = rr - d;  // tap row of output row 4 li + d
+          if (ta >= 0 && ta <= 6) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int q = 0; q < 7; ++q) acc[d][c] = fmaf(in[c + q], F[ta * 7 + q], acc[d][c]);
+          }
+        }
+      }
+      __syncwarp();            // every lane has read its window: the slot may be refilled
+      fetch(j + 2 * kSW, s);   // the warp's plane of the round after next
+    }
+    __syncthreads();  // the theta pass of the previous round has finished reading the ring slots written now
+    if (j < NB) {
+      float* bp = b_ring + (size_t)(j % kSRing) * (kSTX * kSTY) + (4 * li) * kSTY + 4 * lj;
+#pragma unroll
+      for (int d = 0; d < 4; ++d)  // posecell_network.py:300 (1/total is applied by the taps of the theta pass)
+        *reinterpret_cast<float4*>(bp + d * kSTY) =
+            make_float4(fmaxf(acc[d][0], 0.f), fmaxf(acc[d][1], 0.f), fmaxf(acc[d][2], 0.f), fmaxf(acc[d][3], 0.f));
+    }
+    __syncthreads();
+    // theta pass: output rel planes whose neighbours j - 3 .. j + 3 are all in the ring now
+    const int hi_avail = (r * kSW + kSW - 1 < NB - 1 ? r * kSW + kSW - 1 : NB - 1) - 3;
+    const int o_lo = r == 0 ? 3 : r * kSW - 3;
+    const int n_out = hi_avail - o_lo + 1;
+    for (int it = tid; it < 128 * n_out; it += kSNT) {
+      const int q = it & 127, jo = o_lo + (it >> 7);
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        const float4 v = *reinterpret_cast<const float4*>(b_ring + (size_t)((jo + t - 3) % kSRing) * (kSTX * kSTY) + q * 4);
+        o.x = fmaf(fc[t], v.x, o.x);
+        o.y = fmaf(fc[t], v.y, o.y);
+        o.z = fmaf(fc[t], v.z, o.z);
+        o.w = fmaf(fc[t], v.w, o.w);
+      }
+      const int gx = x0 + (q >> 3), gy = y0 + (q & 7) * 4;
+      const int k = k_begin + jo - 3;
+      if (gx < X && gy < Y) {
+        const float c[4] = {fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f)};  // posecell_network.py:314
+        float* dst = a.S + ((size_t)b * Th + k) * ((size_t)X * Y) + (size_t)gx * Y + gy;
+        if (vec && gy + 3 < Y) {
+          *reinterpret_cast<float4*>(dst) = make_float4(c[0], c[1], c[2], c[3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (gy + u < Y) dst[u] = c[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (gy + u < Y) {
+            const long long flat = ((long long)gx * Y + gy + u) * Th + k;  // numpy.argmax order: [x][y][th]
+            if (c[u] > bestv || (c[u] == bestv && flat < besti)) bestv = c[u], besti = flat;
+          }
+        }
+      }
+    }
+  }
+  // block arg-max, then the network's in the last block to retire (as k_tl_theta_fin)
+  auto warp_best = [&](float& bv, long long& bi) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const long long i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (v2 > bv || (v2 == bv && i2 < bi)) bv = v2, bi = i2;
+    }
+  };
+  warp_best(bestv, besti);
+  if (lane == 0) s_v[wid] = bestv, s_i[wid] = besti;
+  __syncthreads();
+  if (wid != 0) return;
+  float bv = lane < kSW ? s_v[lane] : -1.f;
+  long long bi = lane < kSW ? s_i[lane] : 0x7fffffffffffffffLL;
+  warp_best(bv, bi);
+  const int nslots = gridDim.x * gridDim.y;
+  int last = 0;
+  if (lane == 0) {
+    const size_t slot = (size_t)b * nslots + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    a.part_val[slot] = bv;
+    a.part_idx[slot] = bi;
+    __threadfence();
+    last = (atomicInc(&a.done_ctr[b], (unsigned)(nslots - 1)) == (unsigned)(nslots - 1)) ? 1 : 0;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) {
+    __threadfence();
+    const float* pv = a.part_val + (size_t)b * nslots;
+    const long long* pi = a.part_idx + (size_t)b * nslots;
+    bv = -1.f;
+    bi = 0x7fffffffffffffffLL;
+    for (int i0 = lane; i0 < nslots; i0 += 32 * 8) {
+      float v[8];
+      long long ix[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + 32 * u;
+        v[u] = i < nslots ? __ldcg(pv + i) : -1.f;
+        ix[u] = i < nslots ? __ldcg(pi + i) : 0x7fffffffffffffffLL;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (v[u] > bv || (v[u] == bv && ix[u] < bi)) bv = v[u], bi = ix[u];
+    }
+    warp_best(bv, bi);
+    if (lane == 0) a.argmax[b] = bi;
+  }
+}
+
 }  // namespace
 
 int prs_pc_tiled_supported(const prs_pc_plan* p) {
@@ -712,12 +1027,76 @@ int prs_pc_tiled_supported(const prs_pc_plan* p) {
   return (p->X * p->Y >= 1024) ? 1 : 0;
 }
 
+// The TMA path (k_tl_theta -> k_tl_yx<true> -> k_tl_shift_theta: three launches, the B tensor never leaves shared
+// memory, 306 MB of L2 traffic per 256x256x72 update against 344 MB).  Parity-green, but measured SLOWER than the
+// four-kernel sequence on B200 (76 us against 60 us per update, profiles/r2_large_grid_kernels.txt): its 7x7 stage is
+// scalar FFMA (17.7 M warp instructions against 13.4 M for k_tl_2d_pair + k_tl_theta_fin, whose plane-pair interleave
+// gives FFMA2 but needs a SIMT fill), and the displaced, halo-replicating stores cost k_tl_yx 9 us.  It is therefore
+// opt-in: prs_pc_set_option(h, PRS_OPT_TILED_TMA, 1) or PRS_TILED_TMA=1.  Needs the padded A tensor and its 3-D tensor
+// map, made on first use (a driver without cuTensorMapEncodeTiled keeps the four-kernel sequence).
+static int lg_prepare(prs_pc_plan* p) {
+  if (p->lg_state != 0) return p->lg_state;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (p->lg_state != 0) return p->lg_state;
+  p->lg_state = -1;
+  if (p->X < 64 || p->Y < 64 || p->Th < 8) return -1;
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    (void)cudaGetLastError();
+    return -1;
+  }
+  p->XP = p->X + 2 * kHP;
+  p->YP = (p->Y + 2 * kHP + 2 + 3) / 4 * 4;  // + 2: the 40-column box overhangs the 38 columns a tile uses
+  const size_t bytes = (size_t)p->B * p->Th * p->XP * p->YP * sizeof(float);
+  if (cudaMalloc((void**)&p->apad, bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    p->apad = nullptr;
+    return -1;
+  }
+  cudaMemset(p->apad, 0, bytes);  // the columns beyond Y + 6 are never written; keep them finite
+  static_assert(sizeof(CUtensorMap) <= sizeof(p->lg_tmap), "tensor map slot");
+  const cuuint64_t dims[3] = {(cuuint64_t)p->YP, (cuuint64_t)p->XP, (cuuint64_t)p->B * p->Th};
+  const cuuint64_t strides[2] = {(cuuint64_t)p->YP * 4, (cuuint64_t)p->YP * p->XP * 4};
+  const cuuint32_t box[3] = {kSBW, kSBH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = ((encode_fn)fn)(reinterpret_cast<CUtensorMap*>(p->lg_tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->apad,
+                                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    cudaFree(p->apad);
+    p->apad = nullptr;
+    return -1;
+  }
+  // the kernel reads the descriptor from global memory (written once, here, before any launch that uses it)
+  if (cudaMalloc(&p->lg_tmap_dev, 128) != cudaSuccess ||
+      cudaMemcpy(p->lg_tmap_dev, p->lg_tmap, 128, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaFuncSetAttribute(k_tl_shift_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmem) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(p->apad);
+    p->apad = nullptr;
+    return -1;
+  }
+  p->lg_state = 1;
+  return 1;
+}
+
 int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const float* gi, long long* argmax, float* total,
                       int* err, cudaStream_t st) {
   const int X = p->X, Y = p->Y, Th = p->Th, B = p->B, XY = X * Y;
   float2* EI = (float2*)p->s1;  // s1|s2 are contiguous: 2*B*N floats
   float* A = (float*)p->s3;
   float* Bp = (float*)p->s4;
+  static const bool tma_env = [] {
+    const char* e = getenv("PRS_TILED_TMA");
+    return e && atoi(e) != 0;
+  }();
+  const bool tma_path = (p->opt_tiled_tma > 0 || (p->opt_tiled_tma == 0 && tma_env)) && lg_prepare(p) == 1;
   const int nchunk = (Th + kTK - 1) / kTK;
   const PlanArgs pa{odom, p->cos_th, p->sin_th, p->vtrans_scale, p->vrot_scale, p->shift, p->fsel, p->ogi, err,
                     X < Y ? X : Y};
@@ -739,7 +1118,33 @@ int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const fl
     }
   }
   const dim3 g2((X + kYXx - 1) / kYXx, (Y + kYXy - 1) / kYXy, B * Th);
-  k_tl_yx<<<g2, kTyx, 0, st>>>(EI, A, gi, X, Y, Th, p->tl, (float*)p->part_val);
+  if (tma_path) {
+    k_tl_yx<true><<<g2, kTyx, 0, st>>>(EI, p->apad, gi, X, Y, Th, p->tl, (float*)p->part_val, p->YP, total,
+                                        (float*)p->inv_total, p->done_ctr, p->shift);
+    StArgs sa;
+    sa.Apad = p->apad, sa.S = state, sa.shift = p->shift, sa.fsel = p->fsel, sa.ogi = p->ogi;
+    sa.inv_total = (const float*)p->inv_total, sa.part_val = (float*)p->part_val, sa.part_idx = p->part_idx;
+    sa.done_ctr = p->done_ctr + B, sa.argmax = argmax;
+    sa.X = X, sa.Y = Y, sa.Th = Th, sa.XP = p->XP, sa.YP = p->YP;
+    const int tiles_x = (X + kSTX - 1) / kSTX;
+    sa.tiles_y = (Y + kSTY - 1) / kSTY;
+    const long long tiles = (long long)tiles_x * sa.tiles_y * B;
+    // chunks of theta: every chunk recomputes six planes of 7x7 work, so as few as fill the chip (two CTAs per SM)
+    static const int force_chunks = [] {
+      const char* e = getenv("PRS_TILED_CHUNKS");
+      return e ? atoi(e) : 0;
+    }();
+    int nch = (int)((2 * 148 + tiles / 2) / tiles);
+    if (force_chunks > 0) nch = force_chunks;
+    if (nch < 1) nch = 1;
+    if (nch > Th / 8) nch = Th / 8 > 0 ? Th / 8 : 1;
+    sa.nchunks = nch;
+    k_tl_shift_theta<<<dim3((unsigned)(tiles_x * sa.tiles_y), nch, B), kSNT, kSSmem, st>>>(
+        reinterpret_cast<const CUtensorMap*>(p->lg_tmap_dev), sa, p->tf);
+    PRS_CUDA(cudaGetLastError());
+    return PRS_OK;
+  }
+  k_tl_yx<false><<<g2, kTyx, 0, st>>>(EI, A, gi, X, Y, Th, p->tl, (float*)p->part_val, 0, nullptr, nullptr, nullptr, nullptr);
   const int np = Th * (int)(g2.x * g2.y);
   const int NPh = (Th + 1) / 2;
   // PRS_TILED_PW (tuning knob): columns per thread patch in the plane-pair kernel, 4 (default) or 8

@@ -158,6 +158,12 @@ class PoseCellEnsemble:
         if nat.lib().prs_pc_set_path(self._h, code) != 0:
             raise ValueError(nat.lib().prs_last_error().decode())
 
+    def set_option(self, name, value):
+        """Per-plan options of the kernels; ``"tiled_tma"``: the large-grid family's TMA-fed fused 7x7 + theta kernel
+        (off by default)."""
+        code = {"tiled_tma": 0}[name]
+        nat.check(nat.lib().prs_pc_set_option(self._h, code, 1 if value else 0), "prs_pc_set_option")
+
     def force_generic(self, on=True):
         nat.check(nat.lib().prs_pc_force_generic(self._h, 1 if on else 0), "prs_pc_force_generic")
 

@@ -180,29 +180,42 @@ def test_large_grid_one_step_against_oracle():
     shape = (256, 256, 72)
     ref = opc.PoseCellNetwork(shape)
     net = _make(shape, np.float32, "auto")
-    for n in (ref, net):
+    tma = _make(shape, np.float32, "auto")          # the same grid through the TMA-fed fused kernel
+    tma._ens.set_option("tiled_tma", True)
+    for n in (ref, net, tma):
         n.inject(1.0, (128, 128, 36))
         n.inject(0.5, (3, 250, 70))      # a second packet across the periodic boundary
     for v in [(0.21, 0.03), (0.12, -0.04)]:
-        assert tuple(net.update(v)) == tuple(ref.update(v))
-    assert _rel(net.posecells, ref.posecells) <= 1e-5
+        want = tuple(ref.update(v))
+        assert tuple(net.update(v)) == want and tuple(tma.update(v)) == want
+    assert _rel(net.posecells, ref.posecells) <= 1e-5 and _rel(tma.posecells, ref.posecells) <= 1e-5
 
 
-@pytest.mark.parametrize("shape", [(33, 35, 9), (70, 40, 19), (128, 64, 8), (36, 36, 3)])
-@pytest.mark.parametrize("path", ["tiled", "cluster"])
+@pytest.mark.parametrize("shape", [(33, 35, 9), (70, 40, 19), (128, 64, 8), (36, 36, 3), (72, 100, 9), (65, 66, 20),
+                                   (96, 64, 23)])
+@pytest.mark.parametrize("path", ["tiled", "tiled_tma", "cluster"])
 def test_tiled_path_shapes_against_oracle(shape, path):
     """The large-grid kernels (and the cluster kernel, where it applies) on shapes that exercise their edges: X*Y
     not a multiple of 4 (scalar accesses), ragged tiles and segments in x and y, theta counts that are not a
     multiple of the chunk, tiles that wrap on every side.  Two packets (one across the periodic corner) and an
     exact tie for the maximum."""
     ref = opc.PoseCellNetwork(shape)
+    tma = path == "tiled_tma"           # the TMA-fed fused 7x7 + theta kernel of the tiled family (opt-in)
+    path = "tiled" if tma else path
+    if tma and (shape[0] < 64 or shape[1] < 64 or shape[2] < 8):
+        pytest.skip("the TMA path needs X, Y >= 64 and Th >= 8")
     net = _make(shape, np.float32, path)
     assert net.path == path
+    if tma:
+        net._ens.set_option("tiled_tma", True)
     X, Y, Th = shape
     for n in (ref, net):
         n.inject(1.0, (X // 2, Y // 2, Th // 2))
         n.inject(0.75, (X - 1, 0, Th - 1))
-    for v in [(0.21, 0.03), (0.12, -0.04), (0.0, 0.0), (0.33, 0.0)]:
+    # the last two steps move by 7 / 11 cells: origins beyond the padded halo of the TMA path (gather fallback)
+    for v in [(0.21, 0.03), (0.12, -0.04), (0.0, 0.0), (0.33, 0.0), (1.41, 0.02), (2.21, -0.03)]:
+        if 3 + np.ceil(abs(v[0]) / 0.2) > min(X, Y):
+            continue
         assert tuple(net.update(v)) == tuple(ref.update(v)), v
         assert _rel(net.posecells, ref.posecells) <= 1e-5
     # equal maxima: the lowest flat index must win; then an all-zero grid reports cell (0, 0, 0)
