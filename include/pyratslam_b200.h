@@ -107,6 +107,9 @@ PRS_API int prs_pc_set_path(prs_pc_handle h, int path);
  * TMA tensor copies from a padded, origin-aligned intermediate (value 1) or as two kernels (value 0, the default: the
  * fused kernel is parity-equal but measured slower on B200). */
 #define PRS_OPT_TILED_TMA 0
+/* PRS_OPT_TILED_DOG: the tiled family runs the theta, y and x passes of the DoG as ONE kernel (shared-memory ring fed by
+ * cp.async, no (E, I) intermediate in L2) instead of two; parity-equal, measured slower, off by default. */
+#define PRS_OPT_TILED_DOG 1
 PRS_API int prs_pc_set_option(prs_pc_handle h, int option, int value);
 
 /* One PoseCellNetwork.update() for all B networks (posecell_network.py:326-353):

@@ -249,8 +249,11 @@ extern "C" int prs_pc_set_path(prs_pc_handle h, int path) {
 
 extern "C" int prs_pc_set_option(prs_pc_handle h, int option, int value) {
   PRS_REQUIRE(h, "prs_pc_set_option: null handle");
-  PRS_REQUIRE(option == PRS_OPT_TILED_TMA, "prs_pc_set_option: unknown option %d", option);
-  h->opt_tiled_tma = value ? 1 : -1;
+  PRS_REQUIRE(option == PRS_OPT_TILED_TMA || option == PRS_OPT_TILED_DOG, "prs_pc_set_option: unknown option %d", option);
+  if (option == PRS_OPT_TILED_TMA)
+    h->opt_tiled_tma = value ? 1 : -1;
+  else
+    h->opt_tiled_dog = value ? 1 : -1;
   drop_graphs(h);
   return PRS_OK;
 }

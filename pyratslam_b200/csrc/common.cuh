@@ -69,6 +69,7 @@ struct prs_pc_plan {
   int XP, YP;
   int lg_state;         // 0 = not prepared yet, 1 = ready, -1 = unavailable (small grid, legacy knob, no driver entry)
   alignas(64) unsigned char lg_tmap[128];
+  int opt_tiled_dog;    // prs_pc_set_option(PRS_OPT_TILED_DOG), same convention
   int opt_tiled_tma;    // prs_pc_set_option(PRS_OPT_TILED_TMA): 1 = on, -1 = off, 0 = the PRS_TILED_TMA environment variable
   void* lg_tmap_dev;    // device copy of the tensor map (the kernel takes the descriptor from global memory)
   void* part_val;       // [B][Th*nblk_plane] partial sums, later partial maxima

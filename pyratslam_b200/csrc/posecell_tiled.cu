@@ -385,6 +385,183 @@ __device__ __forceinline__ void block_tile_total(const float* __restrict__ part,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused separable DoG: theta + y + x passes, inhibition and partial sums in ONE kernel (k_tl_theta + k_tl_yx fused).
+//
+// The (E, I) intermediate of the two-kernel sequence is the largest tensor of the update -- 37.7 MB written and 49 MB
+// read back (with the tile halo) per 256x256x72 update, 38 % of all L2 traffic of a path that is bound by L2 bandwidth
+// (profiles/r2_large_grid_kernels.txt).  Here a CTA owns a 32x32 tile of (x, y), walks a chunk of theta planes and
+// keeps everything between the input state and A in shared memory:
+//   * every thread owns (up to) six of the tile's 38x38 halo positions for the whole walk.  It streams its positions of
+//     the next planes into a shared-memory ring of nine planes with 4-byte cp.async copies (periodic wrap: the source
+//     offsets are computed once), two planes ahead of the one being processed; as a thread only ever reads ring entries
+//     it wrote itself, no barrier is needed between the copies and the theta pass (cp.async.wait_group is enough).
+//   * theta pass: seven ring reads per position, symmetric fold, (E, I) pair into s_ei            (11 op / halo cell)
+//   * y pass (8 outputs per item, 152 items) and x pass (128 items) as in k_tl_yx, FFMA2 on (E, I)
+//   * A = max(aE E - aI I - gi, 0) to global memory; the CTA keeps ONE partial sum for all its planes.
+// Two block barriers per plane.  The first block of a network also evaluates the update's decisions (prs_plan_cell).
+// MEASURED (B200, round 2): slower than the two kernels it replaces -- 39 us against 31.5 us for 256x256x72 with six
+// chunks (fewer chunks are slower still), 1.155 ms against 1.065 ms for 2600 networks of 50x50x10 -- although it moves
+// less than half of their bytes: three short dependent phases per plane with 24 warps per SM are latency bound, where
+// k_tl_yx keeps 45 warps per SM on independent tiles.  Kept as an opt-in (PRS_OPT_TILED_DOG), not the default.
+constexpr int kDgT = 32;                    // tile edge
+constexpr int kDgH = kDgT + 6;              // 38 halo positions per edge
+constexpr int kDgPos = kDgH * kDgH;         // 1444
+constexpr int kDgNT = 256;
+constexpr int kDgPP = (kDgPos + kDgNT - 1) / kDgNT;  // 6 positions per thread
+constexpr int kDgAhead = 2;                 // planes in flight beyond the one being processed
+constexpr int kDgRing = 7 + kDgAhead;
+constexpr int kDgEiStride = kDgH + 1;       // 39
+constexpr int kDgMidStride = kDgT + 1;      // 33
+constexpr size_t kDgSmem = (size_t)kDgRing * kDgPos * 4 + (size_t)kDgH * kDgEiStride * 8 + (size_t)kDgH * kDgMidStride * 8 + 64;
+
+__global__ void __launch_bounds__(kDgNT, 3)
+    k_tl_dog(const float* __restrict__ P, float* __restrict__ A, const float* __restrict__ gi, int X, int Y, int Th,
+             int nchunks, int tiles_y, PcTables<float> tab, TlPairs tp, PlanArgs pa, float* __restrict__ part,
+             float* __restrict__ total, float* __restrict__ inv_total, unsigned* __restrict__ done_ctr) {
+  extern __shared__ __align__(16) unsigned char dg_smem[];
+  float* ring = reinterpret_cast<float*>(dg_smem);                                              // [kDgRing][kDgPos]
+  float2* s_ei = reinterpret_cast<float2*>(dg_smem + (size_t)kDgRing * kDgPos * 4);             // [38][39]
+  float2* s_mid = s_ei + kDgH * kDgEiStride;                                                    // [38][33]
+  float* s_red = reinterpret_cast<float*>(s_mid + kDgH * kDgMidStride);                         // [8]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tile = blockIdx.x, txi = tile / tiles_y, tyi = tile - txi * tiles_y;
+  const int x0 = txi * kDgT, y0 = tyi * kDgT;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const int XY = X * Y;
+  if (tile == 0 && chunk == 0) {  // decisions of this update, needed by the kernels behind this one
+    for (int k = tid; k < Th; k += kDgNT)
+      prs_plan_cell(b, k, Th, pa.minXY, pa.odom, pa.cos_th, pa.sin_th, pa.vtrans_scale, pa.vrot_scale, pa.shift, pa.fsel,
+                    pa.ogi, pa.err);
+  }
+  const int k_begin = (int)((long long)chunk * Th / nchunks), k_end = (int)((long long)(chunk + 1) * Th / nchunks);
+  const int C = k_end - k_begin;
+  // my positions: source offset inside a plane (periodic wrap), and where the (E, I) pair goes
+  int goff[kDgPP], eoff[kDgPP];
+#pragma unroll
+  for (int i = 0; i < kDgPP; ++i) {
+    const int e = tid + i * kDgNT;
+    const int r = e / kDgH, c = e - r * kDgH;
+    goff[i] = e < kDgPos ? modp(x0 - 3 + r, X) * Y + modp(y0 - 3 + c, Y) : -1;
+    eoff[i] = r * kDgEiStride + c;
+  }
+  const float* Pb = P + (size_t)b * Th * XY;
+  const unsigned ring_a = (unsigned)__cvta_generic_to_shared(ring);
+  auto issue = [&](int j) {  // rel plane j <-> plane k_begin - 3 + j, into ring slot j % kDgRing
+    if (j < C + 6) {
+      const float* src = Pb + (size_t)modp(k_begin - 3 + j, Th) * XY;
+      const unsigned dst = ring_a + (unsigned)((j % kDgRing) * kDgPos + tid) * 4u;
+#pragma unroll
+      for (int i = 0; i < kDgPP; ++i)
+        if (goff[i] >= 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (unsigned)(i * kDgNT * 4)), "l"(src + goff[i])
+                       : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll 1
+  for (int j = 0; j < 6 + kDgAhead; ++j) issue(j);
+  const float e0 = pin(tab.ge[3]), e1 = pin(tab.ge[2]), e2 = pin(tab.ge[1]), e3 = pin(tab.ge[0]);
+  const float i0 = pin(tab.gi[3]), i1 = pin(tab.gi[2]), i2 = pin(tab.gi[1]), i3 = pin(tab.gi[0]);
+  const float g = gi[b];
+  float psum = 0.f;
+#pragma unroll 1
+  for (int kk = 0; kk < C; ++kk) {
+    issue(kk + 6 + kDgAhead);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kDgAhead) : "memory");  // rel planes kk .. kk + 6 have landed
+    // ---- theta pass on my positions
+#pragma unroll
+    for (int i = 0; i < kDgPP; ++i) {
+      if (goff[i] >= 0) {
+        float w[7];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) w[t] = ring[((kk + t) % kDgRing) * kDgPos + tid + i * kDgNT];
+        const float s1 = w[2] + w[4], s2 = w[1] + w[5], s3 = w[0] + w[6];
+        s_ei[eoff[i]] = make_float2(fmaf(e0, w[3], fmaf(e1, s1, fmaf(e2, s2, e3 * s3))),
+                                    fmaf(i0, w[3], fmaf(i1, s1, fmaf(i2, s2, i3 * s3))));
+      }
+    }
+    __syncthreads();
+    // ---- y pass: item = (halo row, segment of 8 outputs)
+    if (tid < 4 * kDgH) {
+      const int seg = tid / kDgH, r = tid - seg * kDgH;
+      const float2* sp = s_ei + r * kDgEiStride + seg * 8;
+      float2 in[14];
+#pragma unroll
+      for (int j = 0; j < 14; ++j) in[j] = sp[j];
+      float2* mp = s_mid + r * kDgMidStride + seg * 8;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 7; ++t) acc = __ffma2_rn(in[jj + t], tp.ty[t], acc);
+        mp[jj] = acc;
+      }
+    }
+    __syncthreads();
+    // ---- x pass + inhibition: item = (segment of 8 rows, column); lanes along y
+    if (tid < 4 * kDgT) {
+      const int seg = wid, y = lane;
+      const float2* sp = s_mid + seg * 8 * kDgMidStride + y;
+      float2 in[14];
+#pragma unroll
+      for (int j = 0; j < 14; ++j) in[j] = sp[j * kDgMidStride];
+      const int gy = y0 + y, gx0 = x0 + seg * 8;
+      const int nv = gy < Y ? X - gx0 : 0;
+      float* q = A + ((size_t)b * Th + k_begin + kk) * XY + (unsigned)(gx0 * Y + gy);
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 7; ++t) acc = __ffma2_rn(in[jj + t], tp.tx[t], acc);
+        const float a = fmaxf((acc.x - acc.y) - g, 0.f);  // posecell_network.py:339-340: (a < gi) ? 0 : a - gi
+        if (jj < nv) {
+          q[(unsigned)(jj * Y)] = a;
+          psum += a;
+        }
+      }
+    }
+    // no barrier here: the next theta pass writes s_ei (last read before the barrier above); the next y pass writes
+    // s_mid only behind the next barrier, which every thread passes after its x pass
+  }
+  // one partial sum per CTA; the last CTA of the network to retire forms the total (posecell_network.py:343-345)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+  if (lane == 0) s_red[wid] = psum;
+  __syncthreads();
+  if (wid != 0) return;
+  const int np = gridDim.x * gridDim.y;
+  int last = 0;
+  if (lane == 0) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) sum += s_red[w];  // only the four x-pass warps hold a sum
+    part[(size_t)b * np + (size_t)chunk * gridDim.x + tile] = sum;
+    __threadfence();
+    last = (atomicInc(&done_ctr[b], (unsigned)(np - 1)) == (unsigned)(np - 1)) ? 1 : 0;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) {
+    __threadfence();
+    const float* pp = part + (size_t)b * np;
+    float acc = 0.f;
+    for (int i0 = lane; i0 < np; i0 += 32 * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = i0 + 32 * u < np ? __ldcg(pp + i0 + 32 * u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      total[b] = acc;
+      inv_total[b] = (acc != 0.f) ? 1.f / acc : 1.f;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 constexpr int k2X = 64, k2Y = 32;          // outputs per tile
 constexpr int k2XH = k2X + 6, k2YH = k2Y + 6;
@@ -480,7 +657,7 @@ __global__ void __launch_bounds__(kT) k_tl_2d(const float* __restrict__ A, float
         if (gy + j < Y) dst[j] = o[j];
     }
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0 && plane % Th == 0)  // side job of one block per network
+  if (np > 0 && blockIdx.x == 0 && blockIdx.y == 0 && plane % Th == 0)  // side job of one block per network
     block_tile_total(part + (size_t)(plane / Th) * np, np, total + plane / Th, inv_total + plane / Th, s_a);
 }
 
@@ -644,7 +821,7 @@ __global__ void __launch_bounds__(kT, Pair2D<PW>::kMinBlocks)
       }
     }
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0 && kp == 0)  // side job of one block per network
+  if (np > 0 && blockIdx.x == 0 && blockIdx.y == 0 && kp == 0)  // side job of one block per network (np == 0: k_tl_dog did it)
     block_tile_total(part + (size_t)b * np, np, total + b, inv_total + b, reinterpret_cast<float*>(s_a));
 }
 
@@ -1100,7 +1277,39 @@ int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const fl
   const int nchunk = (Th + kTK - 1) / kTK;
   const PlanArgs pa{odom, p->cos_th, p->sin_th, p->vtrans_scale, p->vrot_scale, p->shift, p->fsel, p->ogi, err,
                     X < Y ? X : Y};
-  {
+  // The fused theta + y + x kernel (k_tl_dog) is parity-equal but measured slower than k_tl_theta + k_tl_yx (256x256x72:
+  // 39 us against 31.5 us; 2600 x 50x50x10: 1.155 ms against 1.065 ms per update): opt-in through
+  // prs_pc_set_option(h, PRS_OPT_TILED_DOG, 1) or PRS_TILED_DOG=1
+  static const int dog_env = [] {
+    const char* e = getenv("PRS_TILED_DOG");
+    return e ? atoi(e) : 0;
+  }();
+  const bool dog = (p->opt_tiled_dog > 0 || (p->opt_tiled_dog == 0 && dog_env != 0)) && !tma_path;
+  int np_2d = 0;  // partial sums the 7x7 kernel's side job still has to add up (0: k_tl_dog formed the total itself)
+  if (dog) {
+    static std::mutex mu;
+    static bool configured[64] = {};
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (p->device >= 0 && p->device < 64 && !configured[p->device]) {
+        PRS_CUDA(cudaFuncSetAttribute(k_tl_dog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
+        configured[p->device] = true;
+      }
+    }
+    const int tiles_x = (X + kDgT - 1) / kDgT, tiles_y = (Y + kDgT - 1) / kDgT;
+    const long long tiles = (long long)tiles_x * tiles_y * B;
+    // chunks of theta: a chunk of C planes loads and theta-filters C + 6, so as few chunks as fill the chip
+    static const int force_chunks = [] {
+      const char* e = getenv("PRS_DOG_CHUNKS");
+      return e ? atoi(e) : 0;
+    }();
+    int nch = (int)((2 * 148 + tiles - 1) / tiles);
+    if (nch > Th / 12) nch = Th / 12;
+    if (force_chunks > 0) nch = force_chunks < Th ? force_chunks : Th;
+    if (nch < 1) nch = 1;
+    k_tl_dog<<<dim3((unsigned)(tiles_x * tiles_y), nch, B), kDgNT, kDgSmem, st>>>(
+        state, A, gi, X, Y, Th, nch, tiles_y, p->tf, p->tl, pa, (float*)p->part_val, total, (float*)p->inv_total, p->done_ctr);
+  } else {
     const int V = (XY % 2 == 0) ? 2 : 1;
     const int nline = (XY / V + kT - 1) / kT;
     if (Th >= 36 && Th % 12 == 0) {  // longer chunks re-read fewer planes: (12 + 6) / 12 loads per cell
@@ -1144,8 +1353,11 @@ int prs_pc_tiled_step(prs_pc_plan* p, float* state, const double* odom, const fl
     PRS_CUDA(cudaGetLastError());
     return PRS_OK;
   }
-  k_tl_yx<false><<<g2, kTyx, 0, st>>>(EI, A, gi, X, Y, Th, p->tl, (float*)p->part_val, 0, nullptr, nullptr, nullptr, nullptr);
-  const int np = Th * (int)(g2.x * g2.y);
+  if (!dog) {
+    k_tl_yx<false><<<g2, kTyx, 0, st>>>(EI, A, gi, X, Y, Th, p->tl, (float*)p->part_val, 0, nullptr, nullptr, nullptr, nullptr);
+    np_2d = Th * (int)(g2.x * g2.y);
+  }
+  const int np = np_2d;
   const int NPh = (Th + 1) / 2;
   // PRS_TILED_PW (tuning knob): columns per thread patch in the plane-pair kernel, 4 (default) or 8
   static const int pw = [] {

@@ -159,9 +159,9 @@ class PoseCellEnsemble:
             raise ValueError(nat.lib().prs_last_error().decode())
 
     def set_option(self, name, value):
-        """Per-plan options of the kernels; ``"tiled_tma"``: the large-grid family's TMA-fed fused 7x7 + theta kernel
-        (off by default)."""
-        code = {"tiled_tma": 0}[name]
+        """Per-plan options of the kernels: ``"tiled_tma"`` -- the large-grid family's TMA-fed fused 7x7 + theta kernel,
+        ``"tiled_dog"`` -- its fused theta + y + x kernel (both parity-equal, measured slower, off by default)."""
+        code = {"tiled_tma": 0, "tiled_dog": 1}[name]
         nat.check(nat.lib().prs_pc_set_option(self._h, code, 1 if value else 0), "prs_pc_set_option")
 
     def force_generic(self, on=True):

@@ -193,7 +193,7 @@ def test_large_grid_one_step_against_oracle():
 
 @pytest.mark.parametrize("shape", [(33, 35, 9), (70, 40, 19), (128, 64, 8), (36, 36, 3), (72, 100, 9), (65, 66, 20),
                                    (96, 64, 23)])
-@pytest.mark.parametrize("path", ["tiled", "tiled_tma", "cluster"])
+@pytest.mark.parametrize("path", ["tiled", "tiled_tma", "tiled_dog", "cluster"])
 def test_tiled_path_shapes_against_oracle(shape, path):
     """The large-grid kernels (and the cluster kernel, where it applies) on shapes that exercise their edges: X*Y
     not a multiple of 4 (scalar accesses), ragged tiles and segments in x and y, theta counts that are not a
@@ -201,13 +201,16 @@ def test_tiled_path_shapes_against_oracle(shape, path):
     exact tie for the maximum."""
     ref = opc.PoseCellNetwork(shape)
     tma = path == "tiled_tma"           # the TMA-fed fused 7x7 + theta kernel of the tiled family (opt-in)
-    path = "tiled" if tma else path
+    dog = path == "tiled_dog"           # the fused theta + y + x kernel of the tiled family (opt-in)
+    path = "tiled" if tma or dog else path
     if tma and (shape[0] < 64 or shape[1] < 64 or shape[2] < 8):
         pytest.skip("the TMA path needs X, Y >= 64 and Th >= 8")
     net = _make(shape, np.float32, path)
     assert net.path == path
     if tma:
         net._ens.set_option("tiled_tma", True)
+    if dog:
+        net._ens.set_option("tiled_dog", True)
     X, Y, Th = shape
     for n in (ref, net):
         n.inject(1.0, (X // 2, Y // 2, Th // 2))
