@@ -106,7 +106,7 @@ def kernel_source_sha():
     """sha256 over the sources of the headline kernel (what a committed ncu capture must have been taken from)."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("posecell_resident.cu", "common.cuh"):
+    for f in ("posecell_resident.cu",):
         h.update(open(os.path.join(ROOT, "pyratslam_b200", "csrc", f), "rb").read())
     return h.hexdigest()
 
