@@ -569,6 +569,447 @@ int pair_launch(prs_pc_plan* p, R* state, const double* odom, int n_steps, const
   return PRS_OK;
 }
 
+
+// =============================================================================================
+// The same fused update for grids whose lines do not fit a thread's registers (simulate.py's 50x50x10,
+// ratslam/simulate.py:9): k_pc_pair_seg.  One network per 2-CTA cluster as above, but
+//   * the y and x passes and the 7x7 stage work on SEGMENTS of a line (25 / 25 / 17 outputs plus a 6-cell halo);
+//   * the y pass goes from one (E, I) buffer to a second one (segments of a line are owned by different threads, so it
+//     cannot run in place), the x pass from there into A2, which has a periodic halo in x AND y (no index wraps in the
+//     7x7 stage); the two buffers (2 x 100 KB for 50x50x10) and A2 | B2 share the CTA's shared memory;
+//   * a half may hold an ODD number of planes (Th = 10: five): the window is then centre +- LC with no edge plane and
+//     pair 0 is the centre plane alone;
+//   * one CTA per SM (205 KB of shared memory), the decisions of an update are evaluated at its start.
+template <int X, int Y, int T>
+struct SegLayout {
+  static constexpr int XY = X * Y;
+  static constexpr int H = T / 2;
+  static constexpr bool kEdge = (H % 2 == 0);
+  static constexpr int LC = kEdge ? H / 2 : (H - 1) / 2;
+  static constexpr int NM = kEdge ? LC - 1 : LC;   // mirror pairs (LC + q, LC - q), q = 1..NM
+  static constexpr int NQ = NM + 1;                // + pair 0 = (centre, edge or nothing)
+  static constexpr int YS = Y + 6;                 // A2 row stride: 3 periodic halo columns each side
+  static constexpr int PS = (X + 6) * YS;          // A2 plane stride: 3 periodic halo rows each side
+  static constexpr int kElems = 2 * H * XY;        // float2: two (E, I) buffers; A2 | B2 alias them
+  static_assert(NQ * PS <= H * XY, "A2 must not reach into the second (E, I) buffer the x pass reads");
+  static_assert(NQ * PS + NQ * XY <= kElems, "A2 | B2 must fit the two (E, I) buffers");
+  static constexpr int kPlanInts = 4 * T + 4;
+  static constexpr size_t kTabOff = (size_t)8 * kElems;
+  static constexpr size_t kPairOff = (kTabOff + sizeof(PcTables<float>) + 15) / 16 * 16;
+  static constexpr size_t kCfOff = kPairOff + 4 * 7 * 8 * 8;
+  static constexpr size_t kPlanOff = kCfOff + 14 * 8;
+  static constexpr size_t kRedOff = (kPlanOff + kPlanInts * 4 + 15) / 16 * 16;
+  static constexpr size_t kBytes = kRedOff + 32 * 8 + 32 * 4 + 2 * 4 + 8 + 4 + 4 + 16;
+};
+
+template <int X, int Y, int T, int NT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
+    k_pc_pair_seg(float* state, const double* __restrict__ odom, int n_steps, const float* __restrict__ gi,
+                  long long* __restrict__ argmax, float* __restrict__ total, int* __restrict__ err,
+                  const double* __restrict__ cos_th, const double* __restrict__ sin_th, double vtrans_scale,
+                  double vrot_scale, int B, const __grid_constant__ PcTables<float> tabp) {
+  using L = SegLayout<X, Y, T>;
+  constexpr int XY = L::XY, H = L::H, LC = L::LC, NM = L::NM, NQ = L::NQ, YS = L::YS, PS = L::PS, MID = T / 2;
+  constexpr bool kEdge = L::kEdge;
+  constexpr int NW = NT / 32;
+  constexpr int NSY = (Y + 24) / 25, SY = (Y + NSY - 1) / NSY;    // y-pass segments (<= 25 outputs)
+  constexpr int NSX = (X + 24) / 25, SX = (X + NSX - 1) / NSX;    // x-pass segments
+  constexpr int NS4 = (Y + 16) / 17, S4 = (Y + NS4 - 1) / NS4;    // 7x7 row segments (<= 17 outputs)
+  static_assert(X >= 7 && Y >= 7 && T % 2 == 0 && H >= 5 && T <= NT, "shape not supported by the segmented pair kernel");
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = (int)(blockIdx.x >> 1), ncl = (int)(gridDim.x >> 1);
+  const int CC = rank == 0 ? MID : 0;
+  const int P0 = (CC - LC + T) % T;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2* bufA = reinterpret_cast<float2*>(smem);     // (E, I) after the theta pass, [H][X][Y]
+  float2* bufB = bufA + H * XY;                       // ... after the y pass
+  float2* A2 = bufA;                                  // [NQ][X + 6][Y + 6]
+  float2* B2 = bufA + NQ * PS;                        // [NQ][X][Y]
+  const PcTables<float>* tab = reinterpret_cast<const PcTables<float>*>(smem + L::kTabOff);
+  float2* s_f2p = reinterpret_cast<float2*>(smem + L::kPairOff);
+  float2* s_cf_ty = reinterpret_cast<float2*>(smem + L::kCfOff);
+  float2* s_cf_x = s_cf_ty + 7;
+  int* s_plan = reinterpret_cast<int*>(smem + L::kPlanOff);
+  unsigned long long* s_wmax = reinterpret_cast<unsigned long long*>(smem + L::kRedOff);
+  float* s_wsum = reinterpret_cast<float*>(smem + L::kRedOff + 32 * 8);
+  float* s_part = s_wsum + 32;
+  unsigned long long* s_peer_val = reinterpret_cast<unsigned long long*>(smem + L::kRedOff + 32 * 8 + 34 * 4);
+  int* s_peer_flat = reinterpret_cast<int*>(s_peer_val + 1);
+  int* s_best_flat = s_peer_flat + 1;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const float2* peerB2 = cluster.map_shared_rank(B2, rank ^ 1);
+  float* peer_part = cluster.map_shared_rank(s_part, rank ^ 1);
+  unsigned long long* peer_peer_val = cluster.map_shared_rank(s_peer_val, rank ^ 1);
+  int* peer_peer_flat = cluster.map_shared_rank(s_peer_flat, rank ^ 1);
+  int* err_dst = rank == 0 ? err : nullptr;
+
+  for (int i = tid; i < (int)(sizeof(PcTables<float>) / 4); i += NT)
+    reinterpret_cast<float*>(smem + L::kTabOff)[i] = reinterpret_cast<const float*>(&tabp)[i];
+  if (tid < 7) {
+    s_cf_ty[tid] = make_float2(tabp.ge[tid], tabp.gi[tid]);
+    s_cf_x[tid] = make_float2(tabp.gex[tid], tabp.gix[tid]);
+  }
+  for (int i = tid; i < 4 * 7 * 8; i += NT) {
+    const int q = i & 7, a = (i >> 3) % 7, combo = i / 56;
+    s_f2p[i] = q < 7 ? make_float2(tabp.f2d[combo >> 1][a * 7 + q], tabp.f2d[combo & 1][a * 7 + q]) : make_float2(0.f, 0.f);
+  }
+  if (tid == 0) *s_best_flat = 0x7fffffff;
+  cluster.sync();
+  const int4* plan4 = reinterpret_cast<const int4*>(s_plan);
+  // global plane of local plane l, and the local planes of pair q
+  auto gplane = [&](int l) {
+    int k = P0 + l;
+    return k >= T ? k - T : k;
+  };
+
+  for (int b = cid; b < B; b += ncl) {
+    float* gst = state + (size_t)b * (XY * T);
+    const float g_inh = gi[b];
+    for (int step = 0; step < n_steps; ++step) {
+      // ---- 0. the decisions of this update (posecell_network.py:252-267,249,304), float64 as numpy computes them
+      if (tid < T)
+        pair_plan_plane<X, Y, T>(tid, odom + ((size_t)step * B + b) * 2, cos_th, sin_th, vtrans_scale, vrot_scale, s_plan,
+                                 err_dst ? err_dst + b : nullptr);
+      __syncthreads();
+
+      // ---- 1. theta pass: global -> (E, I) pairs of my H planes
+      {
+        const float e0 = tab->ge[3], e1 = tab->ge[2], e2 = tab->ge[1], e3 = tab->ge[0];
+        const float i0 = tab->gi[3], i1 = tab->gi[2], i2 = tab->gi[1], i3 = tab->gi[0];
+        const int rot = kEdge ? (plan4[P0].x - plan4[CC].x) * Y : 0;  // the edge plane is stored rotated (see above)
+#pragma unroll 1
+        for (int p = tid; p < XY; p += NT) {
+          float in[H + 6];
+          int k = P0 - 3 + T;
+          k -= k >= T ? T : 0;
+#pragma unroll
+          for (int l = 0; l < H + 6; ++l) {
+            in[l] = __ldcg(gst + k * XY + p);
+            k = k + 1 == T ? 0 : k + 1;
+          }
+          int pe = p - rot;
+          pe += pe < 0 ? XY : 0;
+          pe -= pe >= XY ? XY : 0;
+#pragma unroll
+          for (int l = 0; l < H; ++l) {
+            const float c = in[l + 3];
+            const float s1 = in[l + 4] + in[l + 2], s2 = in[l + 5] + in[l + 1], s3 = in[l + 6] + in[l];
+            bufA[(kEdge && l == 0) ? pe : l * XY + p] =
+                make_float2(fmaf(e0, c, fmaf(e1, s1, fmaf(e2, s2, e3 * s3))), fmaf(i0, c, fmaf(i1, s1, fmaf(i2, s2, i3 * s3))));
+          }
+        }
+      }
+      __syncthreads();
+
+      // ---- 2. y pass, bufA -> bufB; item = (line, segment)
+      {
+        float2 cf[7];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) cf[t] = s_cf_ty[t];
+#pragma unroll 1
+        for (int it = tid; it < H * X * NSY; it += NT) {
+          const int ln = it / NSY, sg = it - ln * NSY;
+          const int y0 = sg * SY;
+          const float2* line = bufA + ln * Y;
+          float2 in[SY + 6];
+#pragma unroll
+          for (int t = 0; t < SY + 6; ++t) {
+            int y = y0 - 3 + t;
+            y += y < 0 ? Y : 0;
+            y -= y >= Y ? Y : 0;
+            in[t] = line[y];
+          }
+          float2* o = bufB + ln * Y + y0;
+#pragma unroll
+          for (int j = 0; j < SY; ++j) {
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 7; ++t) acc = __ffma2_rn(in[j + t], cf[t], acc);
+            if (y0 + j < Y) o[j] = acc;
+          }
+        }
+      }
+      __syncthreads();
+
+      // ---- 3. x pass + inhibition + sum, bufB -> A2 (periodic halo in x and y); item = (pair, y, segment)
+      float psum = 0.f;
+      {
+        float2 cf[7];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) cf[t] = s_cf_x[t];
+#pragma unroll 1
+        for (int it = tid; it < NQ * Y * NSX; it += NT) {
+          const int sg = it % NSX, qy = it / NSX;
+          const int q = qy / Y, y = qy - q * Y;
+          const int x0 = sg * SX;
+          float2 keep[SX];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && q == 0 && !kEdge) {
+#pragma unroll
+              for (int j = 0; j < SX; ++j) keep[j].y = 0.f;
+              continue;
+            }
+            const int l = h == 0 ? LC + q : (q == 0 ? 0 : LC - q);
+            int ys = y + plan4[gplane(l)].y;   // the y part of the plane's origin: the column that is READ
+            ys -= ys >= Y ? Y : 0;
+            const float2* col = bufB + l * XY + ys;
+            float2 in[SX + 6];
+#pragma unroll
+            for (int t = 0; t < SX + 6; ++t) {
+              int x = x0 - 3 + t;
+              x += x < 0 ? X : 0;
+              x -= x >= X ? X : 0;
+              in[t] = col[x * Y];
+            }
+#pragma unroll
+            for (int j = 0; j < SX; ++j) {
+              float2 acc = make_float2(-g_inh, 0.f);
+#pragma unroll
+              for (int t = 0; t < 7; ++t) acc = __ffma2_rn(in[j + t], cf[t], acc);
+              const float a = fmaxf(acc.x - acc.y, 0.f);  // posecell_network.py:339-340
+              if (h == 0)
+                keep[j].x = a;
+              else
+                keep[j].y = a;
+            }
+          }
+          // A2[q][x + 3][y + 3] and its periodic images
+          const int cy = y + 3;
+          const int cy2 = y < 3 ? cy + Y : (y >= Y - 3 ? cy - Y : -1);
+          float2* dst = A2 + q * PS;
+#pragma unroll
+          for (int j = 0; j < SX; ++j) {
+            const int x = x0 + j;
+            if (x < X) {
+              psum += keep[j].x + keep[j].y;
+              const int rx = x + 3;
+              const int rx2 = x < 3 ? rx + X : (x >= X - 3 ? rx - X : -1);
+              dst[rx * YS + cy] = keep[j];
+              if (cy2 >= 0) dst[rx * YS + cy2] = keep[j];
+              if (rx2 >= 0) {
+                dst[rx2 * YS + cy] = keep[j];
+                if (cy2 >= 0) dst[rx2 * YS + cy2] = keep[j];
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      if (lane == 0) s_wsum[wid] = psum;
+      __syncthreads();
+      if (wid == 0) {
+        float sacc = lane < NW ? s_wsum[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) {
+          s_part[rank] = sacc;
+          peer_part[rank] = sacc;
+        }
+      }
+
+      // ---- 4. 7x7 correlate of both planes of a pair (posecell_network.py:273-274,300); item = (pair, x, segment)
+#pragma unroll 1
+      for (int it = tid; it < NQ * X * NS4; it += NT) {
+        const int sg = it % NS4, qx = it / NS4;
+        const int q = qx / X, x = qx - q * X;
+        const int y0 = sg * S4;
+        const int kA = gplane(LC + q), kB = gplane(q == 0 ? 0 : LC - q);
+        const int fsA = plan4[kA].w, fsB = (q == 0 && !kEdge) ? 0 : plan4[kB].w;
+        const float2* ctab = s_f2p + (fsA * 2 + fsB) * 56;
+        const float2* rows = A2 + q * PS + x * YS + y0;  // halo layout: tap (a, c) of output (x, y0 + j) is [x + a][y0 + j + c]
+        float2 acc[S4];
+#pragma unroll
+        for (int j = 0; j < S4; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+          float2 row[S4 + 6];
+#pragma unroll
+          for (int j = 0; j < S4 + 6; ++j) row[j] = (y0 + j < Y + 6) ? rows[a * YS + j] : make_float2(0.f, 0.f);
+          float2 cf[7];
+#pragma unroll
+          for (int c = 0; c < 7; ++c) cf[c] = ctab[a * 8 + c];
+#pragma unroll
+          for (int j = 0; j < S4; ++j)
+#pragma unroll
+            for (int c = 0; c < 7; ++c) acc[j] = __ffma2_rn(row[j + c], cf[c], acc[j]);
+        }
+        int xs = x - plan4[kA].x;  // the x part of the pair's origin, applied to the row that is stored
+        xs += xs < 0 ? X : 0;
+        float2* o = B2 + q * XY + xs * Y + y0;
+#pragma unroll
+        for (int j = 0; j < S4; ++j)
+          if (y0 + j < Y) o[j] = make_float2(fmaxf(acc[j].x, 0.f), fmaxf(acc[j].y, 0.f));
+      }
+      cluster.sync();  // B2 and the partial sums of both halves are complete and visible to both CTAs
+
+      // ---- 5. theta pass (convolution.py:344-359), clamp (:314), -> global, maximum.  V(j) = (local LC + j, local LC - j).
+      const float tot = s_part[0] + s_part[1];
+      const float inv = (tot != 0.f) ? 1.f / tot : 1.f;
+      float best_v = -1.f;
+      int best_flat = 0x7fffffff;
+      {
+        float fc[7];
+        const float* f1 = tab->f1d[s_plan[4 * T]];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) fc[t] = f1[t] * inv;
+        float2 cf2[7];
+#pragma unroll
+        for (int u = -3; u <= 3; ++u) cf2[u + 3] = make_float2(fc[3 + u], fc[3 - u]);
+#pragma unroll 1
+        for (int p = tid; p < XY; p += NT) {
+          float2 pin[NQ];
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) pin[q] = B2[q * XY + p];
+          // the peer's planes next to my window: lo[t] = my local t - 3 = its local H - 3 + t, hi[t] = my local H + t =
+          // its local t.  Its local l is pair |l - LC|: first half (.x) above its centre, second half (.y) below,
+          // and its edge plane (local 0 when H is even) is pair 0's second half.
+          auto peer_val = [&](int l) -> float {            // the peer's local plane l (compile-time l)
+            if (l == LC) return peerB2[p].x;
+            if (kEdge && l == 0) return peerB2[p].y;
+            return l > LC ? peerB2[(l - LC) * XY + p].x : peerB2[(LC - l) * XY + p].y;
+          };
+          float lo[3], hi[3];
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            lo[t] = peer_val(H - 3 + t);
+            hi[t] = peer_val(t);
+          }
+          // value of my local plane l (may lie outside 0..H-1 by up to 3)
+          auto plane_val = [&](int l) -> float {
+            if (l < 0) return lo[3 + l];
+            if (l >= H) return hi[l - H];
+            if (l == LC) return pin[0].x;
+            if (kEdge && l == 0) return pin[0].y;
+            return l > LC ? pin[l - LC].x : pin[LC - l].y;
+          };
+          float2 out[NQ];
+#pragma unroll
+          for (int m = 1; m <= NM; ++m) {
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = -3; u <= 3; ++u)
+              acc = __ffma2_rn(make_float2(plane_val(LC + m + u), plane_val(LC - m - u)), cf2[u + 3], acc);
+            out[m] = make_float2(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f));
+          }
+          {
+            float a = 0.f, c = 0.f;
+#pragma unroll
+            for (int u = -3; u <= 3; ++u) {
+              a = fmaf(fc[3 + u], plane_val(LC + u), a);
+              if (kEdge) c = fmaf(fc[3 + u], plane_val(u), c);
+            }
+            out[0] = make_float2(fmaxf(a, 0.f), fmaxf(c, 0.f));
+          }
+          float vmax = out[0].x;
+          int kb = T;
+#pragma unroll
+          for (int m = 0; m < NQ; ++m) {
+            const int kx = gplane(LC + m);
+            gst[kx * XY + p] = out[m].x;
+            vmax = out[m].x > vmax ? out[m].x : vmax;
+            if (m > 0 || kEdge) {
+              const int ky = gplane(m == 0 ? 0 : LC - m);
+              gst[ky * XY + p] = out[m].y;
+              vmax = out[m].y > vmax ? out[m].y : vmax;
+            }
+          }
+          if (vmax > best_v) {  // numpy.argmax: first maximum in [x][y][th] order; p grows along the loop
+#pragma unroll
+            for (int m = 0; m < NQ; ++m) {
+              const int kx = gplane(LC + m);
+              if (out[m].x == vmax && kx < kb) kb = kx;
+              if (m > 0 || kEdge) {
+                const int ky = gplane(m == 0 ? 0 : LC - m);
+                if (out[m].y == vmax && ky < kb) kb = ky;
+              }
+            }
+            best_v = vmax;
+            best_flat = p * T + kb;
+          }
+        }
+      }
+      const unsigned long long vb = best_v >= 0.f ? val_bits(best_v) : 0ull;
+      unsigned long long wm = vb;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, wm, o);
+        wm = other > wm ? other : wm;
+      }
+      if (lane == 0) s_wmax[wid] = wm;
+      __syncthreads();
+      unsigned long long gm = lane < NW ? s_wmax[lane] : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, gm, o);
+        gm = other > gm ? other : gm;
+      }
+      if (best_flat != 0x7fffffff && vb == gm) atomicMin(s_best_flat, best_flat);
+      __syncthreads();
+      if (tid == 0 && rank == 1) {
+        *peer_peer_val = gm;
+        *peer_peer_flat = *s_best_flat;
+      }
+      cluster.sync();  // the peer has read my B2; candidates exchanged; the state in global memory is consistent
+      if (tid == 0) {
+        if (rank == 0) {
+          const unsigned long long pv = *s_peer_val;
+          const int pf = *s_peer_flat, mf = *s_best_flat;
+          const int flat = pv > gm ? pf : (pv < gm ? mf : (pf < mf ? pf : mf));
+          argmax[(size_t)step * B + b] = (long long)flat;
+          total[(size_t)step * B + b] = tot;
+        }
+        *s_best_flat = 0x7fffffff;
+      }
+    }
+  }
+  cluster.sync();
+}
+
+template <int X, int Y, int T, int NT>
+int pair_seg_launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const float* gi, long long* argmax,
+                    float* total, int* err, cudaStream_t st) {
+  using L = SegLayout<X, Y, T>;
+  auto kern = k_pc_pair_seg<X, Y, T, NT>;
+  static PairState S;
+  const int dev = p->device;
+  PRS_REQUIRE(dev >= 0 && dev < 64, "pair path: device index %d out of range", dev);
+  {
+    std::lock_guard<std::mutex> lk(S.mu);
+    if (!S.configured[dev]) {
+      PRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
+      int nsm = 0;
+      PRS_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * 148, 1, 1);
+      cfg.blockDim = dim3(NT, 1, 1);
+      cfg.dynamicSmemBytes = L::kBytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = nsm / 2 > 0 ? nsm / 2 : 1;
+      }
+      S.clusters[dev] = n;
+      S.configured[dev] = true;
+    }
+  }
+  int ncl = S.clusters[dev];
+  if (p->B < ncl) ncl = p->B;
+  kern<<<2 * ncl, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale,
+                                       p->vrot_scale, p->B, p->tf);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+
 }  // namespace
 
 #ifdef PRS_PAIR_TIMING
@@ -586,7 +1027,9 @@ extern "C" __attribute__((visibility("default"))) int prs_debug_pair_cycles(unsi
 // The kernel applies ONE x origin per mirror pair: around(vt * cos) must be the same for both planes, which holds
 // when the host's cosine table is bitwise even about MID and about plane 0 (numpy's cos is).
 int prs_pc_pair_supported(const prs_pc_plan* p) {
-  if (!(p->X == 21 && p->Y == 21 && p->Th == 36)) return 0;
+  const bool ros = p->X == 21 && p->Y == 21 && p->Th == 36;                       // ros_simulate.py:31
+  const bool sim = p->X == 50 && p->Y == 50 && p->Th == 10 && p->dtype == PRS_F32;  // simulate.py:9 (segmented kernel)
+  if (!ros && !sim) return 0;
   const int T = p->Th, mid = T / 2;
   for (int m = 1; m < mid; ++m)
     if (p->h_cos[mid + m] != p->h_cos[mid - m]) return 0;   // covers both windows: plane T - m is plane mid + (mid - m)
@@ -601,6 +1044,19 @@ int prs_pc_pair_step(prs_pc_plan* p, void* state, const double* odom, int T, con
                                                  p->tf, st);
     return pair_launch<21, 21, 36, 256, double>(p, (double*)state, odom, T, (const double*)gi, argmax, (double*)total,
                                                 err, p->td, st);
+  }
+  if (p->X == 50 && p->Y == 50 && p->Th == 10 && p->dtype == PRS_F32) {
+    // PRS_PAIRSEG_NT (tuning knob): CTA size of the segmented kernel; measured for 2600 networks: 0.855 ms (256
+    // threads, 178 registers), 0.791 ms (384), 0.768 ms (512, 120 registers) -- one CTA per SM, so more warps win
+    static const int nt = [] {
+      const char* e = getenv("PRS_PAIRSEG_NT");
+      return e ? atoi(e) : 512;
+    }();
+    if (nt == 512)
+      return pair_seg_launch<50, 50, 10, 512>(p, (float*)state, odom, T, (const float*)gi, argmax, (float*)total, err, st);
+    if (nt == 384)
+      return pair_seg_launch<50, 50, 10, 384>(p, (float*)state, odom, T, (const float*)gi, argmax, (float*)total, err, st);
+    return pair_seg_launch<50, 50, 10, 256>(p, (float*)state, odom, T, (const float*)gi, argmax, (float*)total, err, st);
   }
   prs_set_error("pair path not available for this plan");
   return PRS_E_INVALID;

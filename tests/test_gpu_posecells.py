@@ -342,3 +342,33 @@ def test_single_call_update_checks_match_numpy():
             net.update((float(v), 0.0))
     assert n_key >= 3
     assert net.get_pc_max() == net.max_pc
+
+
+def test_segmented_pair_kernel_50x50x10_ensemble():
+    """simulate.py's grid (50, 50, 10) as an ensemble on the fused, segmented pair kernel (k_pc_pair_seg): per-network
+    inhibition and odometry, a network that dies, theta shifts in both directions, single steps and a multi-step run."""
+    from pyratslam_b200 import PoseCellEnsemble
+    shape, B, T = (50, 50, 10), 7, 14
+    rng = np.random.default_rng(50)
+    gis = np.linspace(0.05, 0.27, B)              # the last one is above max(kernel_3d): that network dies
+    odom = np.stack([rng.uniform(0, 0.6, (T, B)), rng.uniform(-0.7, 0.7, (T, B))], axis=-1)
+    odom[5] = 0.0
+    ref_amax, ref_states = opc.run_ensemble(shape, gis, odom)
+    ens = PoseCellEnsemble(shape, B, global_inhibition=gis)
+    _force(ens, "pair")
+    assert ens.path == "pair"
+    ens.inject(1.0, (25, 25, 5))
+    ens.inject(0.6, (49, 0, 9))                   # a second packet across the periodic corner
+    ref2 = []
+    for b in range(B):                            # the oracle ensemble starts from one packet: redo it with two
+        n = opc.PoseCellNetwork(shape, global_inhibition=float(gis[b]))
+        n.inject(1.0, (25, 25, 5))
+        n.inject(0.6, (49, 0, 9))
+        ref2.append(n)
+    got = [ens.update(odom[t]) for t in range(6)]
+    got = np.concatenate([np.stack(got), ens.run(odom[6:])])
+    want = np.stack([[n.update(odom[t, b]) for b, n in enumerate(ref2)] for t in range(T)])
+    assert np.array_equal(got, want)
+    states = np.stack([n.posecells for n in ref2])
+    assert _rel(ens.posecells, states) <= 1e-5
+    assert states[-1].max() == 0 and ens.posecells[-1].max() == 0
