@@ -144,6 +144,11 @@ int prs_pc_pair_step(prs_pc_plan* p, void* state, const double* odom, int T, con
 int prs_pc_resident_step(prs_pc_plan* p, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st);
 
+// ordering of the packed sweeps through their per-device constant buffer (view_templates.cu, VtqScope): a caller that
+// launches a GRAPH containing such a sweep brackets the launch with these (begin locks a host mutex, end releases it)
+int prs_vtq_begin(cudaStream_t st);
+int prs_vtq_end(cudaStream_t st);
+
 // ---- small device helpers -------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ int prs_modp_dev(int v, int n) {

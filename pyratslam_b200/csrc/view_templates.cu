@@ -1137,6 +1137,29 @@ static int launch_packed_sweep(const uint4* packed, long long n, long long n_gri
   return PRS_OK;
 }
 
+// VtqScope for callers outside this file (sharded.cu replays a graph that contains a packed sweep): the scope object
+// lives from begin to end; one at a time per host thread is all the mutex allows anyway.
+static thread_local VtqScope* t_ext_scope = nullptr;
+int prs_vtq_begin(cudaStream_t st) {
+  VtqScope* sc = new (std::nothrow) VtqScope();
+  PRS_REQUIRE(sc, "out of host memory");
+  int rc = sc->begin(st);
+  if (rc != PRS_OK) {
+    delete sc;
+    return rc;
+  }
+  t_ext_scope = sc;
+  return PRS_OK;
+}
+int prs_vtq_end(cudaStream_t) {
+  VtqScope* sc = t_ext_scope;
+  t_ext_scope = nullptr;
+  if (!sc) return PRS_OK;
+  int rc = sc->end();
+  delete sc;
+  return rc;
+}
+
 extern "C" size_t prs_vt_packed_bytes(long long n) {
   return (size_t)((n + 31) / 32) * kGroupU4 * sizeof(uint4);
 }

@@ -339,6 +339,8 @@ class RatslamRos(object):
         amax = np.stack([flat // (Y * Th), (flat // Th) % Y, flat % Th], axis=1)
         bad = np.nonzero((res["pc_err"] != 0) & (moved != 0))[0]
         stop = int(bad[0]) if len(bad) else T
+        self._native_n_exp = np.zeros(T, np.int64)       # per-frame experience count / current point, for replay()
+        self._native_em_xy = np.zeros((T, 2))
         for t in range(stop):
             pc_max = (int(amax[t, 0]), int(amax[t, 1]), int(amax[t, 2]))
             if moved[t]:
@@ -347,6 +349,9 @@ class RatslamRos(object):
                 self.published_pose.append(self.em.get_current_point())
             if res["created"][t]:
                 v._loc[int(res["n_templates"][t]) - 1] = pc_max
+            self._native_n_exp[t] = len(self.em.experiences)
+            if self.em.current_exp is not None:
+                self._native_em_xy[t] = self.em.get_current_point()
         self.published_index.extend(int(i) for i in res["template_index"][:stop])
         if T:
             last = T - 1
@@ -389,11 +394,7 @@ def replay(frames, odom, fused=False, pipelined=False, native=False, **kwargs):
         rec["argmax"] = np.stack([flat // (Y * Th), (flat // Th) % Y, flat % Th], axis=1).astype(np.int64)
         rec["template"] = res["template_index"].astype(np.int64)
         rec["created"] = res["created"] != 0
-        moved = (np.abs(odom[:, 0]) > 0.001) | (np.abs(odom[:, 1]) > 0.001)
-        rec["n_exp"] = np.cumsum(moved).astype(np.int64)          # one experience per pose-cell update
-        pts = np.asarray(node.em.get_points(), dtype=np.float64).reshape(-1, 2)
-        has = rec["n_exp"] > 0
-        rec["em_xy"][has] = pts[rec["n_exp"][has] - 1]
+        rec["n_exp"], rec["em_xy"] = node._native_n_exp, node._native_em_xy
         rec["n_templates"] = len(node.vts.templates)
         rec["node"] = node
         return rec

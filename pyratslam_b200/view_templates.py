@@ -123,7 +123,9 @@ class ViewTemplates:
             raise ValueError("cannot reshape array of size %d into shape %r"
                              % (self._n_rows * self._n_cols, self.shape))
         # 32x32 (the reference configuration) takes the tuned kernels; any other shape the general one
-        self._fast = tuple(self.shape) == (32, 32) and self._n_rows == 32 and self._n_cols == 32
+        # (a non-square image takes the mask path: the reference builds its mask with row = base / im_x but reshapes it
+        # to (im_x, im_y), view_templates.py:48-57, and only the mask itself reproduces that)
+        self._fast = tuple(self.shape) == (32, 32) and self._n_rows == 32 and self._n_cols == 32 and self.im_x == self.im_y
         if not self._fast and mode != "ref":
             raise NotImplementedError("circular mode is implemented for 32x32 templates")
         self._mask = None
@@ -249,10 +251,23 @@ class ViewTemplates:
             fr = input
         else:
             fr = np.asarray(input)
-        if tuple(fr.shape) != (self.im_x, self.im_y):
-            raise IndexError("boolean index did not match indexed array: frame %r, mask %r"
-                             % (tuple(fr.shape), (self.im_x, self.im_y)))
         is_u8 = (fr.dtype == torch.uint8) if isinstance(fr, torch.Tensor) else (fr.dtype == np.uint8)
+        if tuple(fr.shape) != (self.im_x, self.im_y):
+            # The reference's numpy accepted a frame smaller than the mask as long as every selected pixel was inside it
+            # (ros_scenario.py publishes 128x128 frames against the 256x256 mask): the fast uint8 path takes such frames
+            # with their own row stride; anything else is the IndexError numpy raises.
+            covers = (fr.ndim == 2 and self._fast and is_u8 and fr.shape[0] >= self.y_range[1]
+                      and fr.shape[1] >= self.x_range[1])
+            if not covers:
+                raise IndexError("boolean index did not match indexed array: frame %r, mask %r"
+                                 % (tuple(fr.shape), (self.im_x, self.im_y)))
+            t = fr if isinstance(fr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(fr))
+            t = t.to(self.device).contiguous()
+            nat.check(nat.lib().prs_vt_extract_u8(
+                t.data_ptr(), int(t.shape[0]), int(t.shape[1]), self.y_range[0], self.y_range[1], self.y_step,
+                self.x_range[0], self.x_range[1], self.x_step, self._tpl_u8.data_ptr(), self._n_rows, self._n_cols,
+                nat.stream_ptr()), "prs_vt_extract_u8")
+            return self._tpl_u8, torch.uint8
         if not self._fast:
             if self._mask_dev is None:
                 self._mask_dev = torch.from_numpy(self.mask).to(self.device)
@@ -334,7 +349,9 @@ class ViewTemplates:
         with torch.cuda.device(self.device):
             tpl, td = self._subsample(input)
             self._ensure_lib(td)
-            return self._append(tpl, pc_x, pc_y, pc_th)
+            t = self._append(tpl, pc_x, pc_y, pc_th)
+            torch.cuda.current_stream().synchronize()   # the pinned staging frame may be rewritten by the next call
+            return t
 
 
 class ShardedViewTemplates:

@@ -561,3 +561,25 @@ def test_replay_with_experience_links():
         assert em.links == [(l.exp_from, l.exp_to, l.d, l.heading_rad, l.facing_rad) for l in ref["em"].links], kw
         em.iterate(5)
         assert em.get_poses() == ref["em"].get_poses(), kw
+
+
+def test_smaller_frames_that_cover_the_mask():
+    """the reference scenario publishes 128x128 frames against the 256x256 mask; every selected pixel (rows /
+    columns 33..95) lies inside such a frame, and the reference's numpy accepted it.  Same templates and decisions as the
+    padded 256x256 frame; a frame that does not cover the selection is numpy's IndexError."""
+    rng = np.random.default_rng(4)
+    a, b = _vts(), _vts()
+    for i in range(6):
+        small = rng.integers(0, 256, (128, 128), dtype=np.uint8)
+        if i == 4:
+            small = np.clip(first.astype(np.int16) - 1, 0, 255).astype(np.uint8)     # a revisit
+        if i == 0:
+            first = small
+        big = np.zeros((256, 256), np.uint8)
+        big[:128, :128] = small
+        ta, tb = a.match(small, 1, 2, 3), b.match(big, 1, 2, 3)
+        assert ta.get_index() == tb.get_index() and a.last_score == b.last_score
+    assert len(a.templates) == len(b.templates) == 5
+    assert np.array_equal(a.templates[2].template, b.templates[2].template)
+    with pytest.raises(IndexError):
+        a.match(np.zeros((90, 128), np.uint8), 0, 0, 0)
