@@ -110,7 +110,19 @@ PRS_API int prs_pc_set_path(prs_pc_handle h, int path);
 /* PRS_OPT_TILED_DOG: the tiled family runs the theta, y and x passes of the DoG as ONE kernel (shared-memory ring fed by
  * cp.async, no (E, I) intermediate in L2) instead of two; parity-equal, measured slower, off by default. */
 #define PRS_OPT_TILED_DOG 1
+/* PRS_OPT_ACTIVE_SET: sparsity-aware update (csrc/posecell_active.cu).  The attractor dynamics of
+ * posecell_network.py:326-353 keep the activity in a compact packet (tens of non-zero cells out of thousands); with this
+ * option an update does the reference's arithmetic only where the result can be non-zero and writes the state in place,
+ * instead of the dense kernels whose cost does not depend on the state.  Exact for any state: a network whose non-zero
+ * cells do not fit the kernel's lists / shared memory, or whose global inhibition is negative, is updated by the dense
+ * kernels in the same call.  0 = off (default), 1 = the state is scanned for its non-zero cells every update,
+ * 2 = the list of non-zero cells an update leaves behind is the next update's input (no pass over the state at all);
+ * every library call that writes the state invalidates the lists, a caller that writes the state by other means must
+ * call prs_pc_invalidate_active.  Dimensions up to 256 per axis. */
+#define PRS_OPT_ACTIVE_SET 2
 PRS_API int prs_pc_set_option(prs_pc_handle h, int option, int value);
+/* the state was written by something other than this library's calls: forget the active lists (PRS_OPT_ACTIVE_SET = 2) */
+PRS_API int prs_pc_invalidate_active(prs_pc_handle h, void* stream);
 
 /* One PoseCellNetwork.update() for all B networks (posecell_network.py:326-353):
  *   state  : device, [B][Th][X][Y] of the plan's dtype, updated in place

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "prs_pc_force_generic": (c_int, [c_void_p, c_int]),
     "prs_pc_set_path": (c_int, [c_void_p, c_int]),
     "prs_pc_set_option": (c_int, [c_void_p, c_int, c_int]),
+    "prs_pc_invalidate_active": (c_int, [c_void_p, c_void_p]),
     "prs_pc_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_run": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "prs_pc_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

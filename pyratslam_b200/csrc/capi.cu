@@ -69,6 +69,9 @@ static void free_plan(prs_pc_plan* p) {
   }
   if (p->cs_in) cudaStreamDestroy(p->cs_in);
   if (p->cs_out) cudaStreamDestroy(p->cs_out);
+  void* act[6] = {p->al_cnt, p->al_idx, p->al_valid, p->dense_flag, p->dense_list, p->dense_cnt};
+  for (void* q : act)
+    if (q) cudaFree(q);
   free(p->h_cos);
   delete p;
 }
@@ -249,13 +252,32 @@ extern "C" int prs_pc_set_path(prs_pc_handle h, int path) {
 
 extern "C" int prs_pc_set_option(prs_pc_handle h, int option, int value) {
   PRS_REQUIRE(h, "prs_pc_set_option: null handle");
-  PRS_REQUIRE(option == PRS_OPT_TILED_TMA || option == PRS_OPT_TILED_DOG, "prs_pc_set_option: unknown option %d", option);
+  PRS_REQUIRE(option == PRS_OPT_TILED_TMA || option == PRS_OPT_TILED_DOG || option == PRS_OPT_ACTIVE_SET,
+              "prs_pc_set_option: unknown option %d", option);
   if (option == PRS_OPT_TILED_TMA)
     h->opt_tiled_tma = value ? 1 : -1;
-  else
+  else if (option == PRS_OPT_TILED_DOG)
     h->opt_tiled_dog = value ? 1 : -1;
+  else {
+    PRS_REQUIRE(value >= 0 && value <= 2, "prs_pc_set_option: PRS_OPT_ACTIVE_SET takes 0, 1 or 2, got %d", value);
+    if (value) {
+      if (int rc_ = prs_pc_check_device(h, "prs_pc_set_option")) return rc_;
+      int rc = prs_pc_active_prepare(h);
+      if (rc == PRS_OK && !h->resident_ok) rc = ensure_scratch(h);  // the dense fallback is then the generic path
+      if (rc != PRS_OK) return rc;
+      rc = prs_pc_active_invalidate(h, nullptr);
+      if (rc != PRS_OK) return rc;
+      PRS_CUDA(cudaStreamSynchronize(nullptr));
+    }
+    h->opt_active = value;
+  }
   drop_graphs(h);
   return PRS_OK;
+}
+
+extern "C" int prs_pc_invalidate_active(prs_pc_handle h, void* stream) {
+  PRS_REQUIRE(h, "prs_pc_invalidate_active: null handle");
+  return prs_pc_active_invalidate(h, (cudaStream_t)stream);
 }
 
 extern "C" int prs_pc_force_generic(prs_pc_handle h, int on) {
@@ -283,6 +305,26 @@ static void drop_graphs(prs_pc_handle h) {
 static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st, int err_store = 0) {
   const size_t es = h->dtype == PRS_F32 ? 4 : 8;
+  if (h->opt_active) {
+    // Active-set update (posecell_active.cu): scan + one CTA per network; the networks it flags (dense state, negative
+    // inhibition, ...) are then updated by a dense family that processes the flagged networks only: the fused
+    // one-CTA-per-network kernel where the plan has it, else the generic kernels.
+    for (int t = 0; t < T; ++t) {
+      const double* od = odom + (size_t)t * h->B * 2;
+      long long* am = argmax + (size_t)t * h->B;
+      void* tt = (char*)total + (size_t)t * h->B * es;
+      int rc = prs_pc_active_step(h, state, od, gi, am, tt, err, st);
+      if (rc != PRS_OK) return rc;
+      h->only_flag = h->dense_flag, h->only_list = h->dense_list, h->only_cnt = h->dense_cnt;
+      if (h->resident_ok)
+        rc = prs_pc_resident_step(h, state, od, 1, gi, am, tt, err, st);
+      else
+        rc = prs_pc_generic_step(h, state, od, gi, am, tt, err, st);
+      h->only_flag = h->only_list = h->only_cnt = nullptr;
+      if (rc != PRS_OK) return rc;
+    }
+    return PRS_OK;
+  }
   const int path = prs_pc_path(h);
   if (path == PRS_PATH_RESIDENT) return prs_pc_resident_step(h, state, odom, T, gi, argmax, total, err, st);
   if (path == PRS_PATH_PAIR) return prs_pc_pair_step(h, state, odom, T, gi, argmax, total, err, st);
@@ -305,7 +347,7 @@ static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T
 static int step_enqueue(prs_pc_handle h, void* state, const double* odom, const void* gi, long long* argmax, void* total,
                         int* err, cudaStream_t st) {
   // the cluster kernel gathers its error bits and stores them: one node less on a 12 us update
-  if (prs_pc_path(h) == PRS_PATH_CLUSTER) return step_dispatch(h, state, odom, 1, gi, argmax, total, err, st, 1);
+  if (prs_pc_path(h) == PRS_PATH_CLUSTER && !h->opt_active) return step_dispatch(h, state, odom, 1, gi, argmax, total, err, st, 1);
   PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
   return step_dispatch(h, state, odom, 1, gi, argmax, total, err, st);
 }
@@ -319,7 +361,7 @@ extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, con
   if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
   // The fused kernels are one launch; a caller that is capturing its own graph gets plain launches as well.
   const int path_now = prs_pc_path(h);
-  if (path_now == PRS_PATH_RESIDENT || path_now == PRS_PATH_PAIR || path_now == PRS_PATH_CLUSTER ||
+  if (((path_now == PRS_PATH_RESIDENT || path_now == PRS_PATH_PAIR || path_now == PRS_PATH_CLUSTER) && !h->opt_active) ||
       cap != cudaStreamCaptureStatusNone)
     return step_enqueue(h, state, odom, gi, argmax, total, err, st);
   // Multi-kernel paths: replay the launch sequence as a graph on a private stream, ordered after the caller's
@@ -369,7 +411,7 @@ extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, con
 int prs_pc_step_mirror(prs_pc_plan* h, void* state, const double* odom, const void* gi, long long* argmax, void* total,
                        int* err, long long* argmax2, int* err2, int* mirrored, cudaStream_t st) {
   *mirrored = 0;
-  if (h && argmax2 && err2 && prs_pc_path(h) == PRS_PATH_CLUSTER) {
+  if (h && argmax2 && err2 && prs_pc_path(h) == PRS_PATH_CLUSTER && !h->opt_active) {
     PRS_REQUIRE(state && odom && gi && argmax && total && err, "prs_pc_step: null argument");
     if (int rc_ = prs_pc_check_device(h, "prs_pc_step")) return rc_;
     *mirrored = 1;
@@ -385,6 +427,7 @@ extern "C" int prs_pc_path_integration(prs_pc_handle h, void* state, const doubl
   int rc = ensure_scratch(h);
   if (rc != PRS_OK) return rc;
   PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
+  if (int rc_ = prs_pc_active_invalidate(h, st)) return rc_;
   return prs_pc_generic_path_integration(h, state, odom, err, st);
 }
 

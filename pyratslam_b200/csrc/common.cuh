@@ -110,6 +110,21 @@ struct prs_pc_plan {
   int resident_ok;      // the fused SMEM-resident kernel supports this shape/dtype
   int pair_ok;          // ... and so does the one-network-per-2-CTA-cluster kernel (posecell_pair.cu)
   void* tab_dev;        // device copy of PcTables<float> for the resident kernel
+  // active-set path (posecell_active.cu), prs_pc_set_option(PRS_OPT_ACTIVE_SET)
+  int opt_active;       // 0 = off, 1 = scan the state for its non-zero cells every update, 2 = keep the list across updates
+  int* al_cnt;          // [B] entries in a network's active list (may exceed al_cap: overflow)
+  int* al_idx;          // [B][al_cap] flat state indices of the non-zero cells
+  int* al_valid;        // [B] the list describes the state as it is (mode 2)
+  int al_cap;
+  int* dense_flag;      // [B] 1 = the active-set kernel left this network to the dense kernels
+  int* dense_list;      // [B] the flagged networks, dense_cnt of them
+  int* dense_cnt;
+  int act_threads, act_arena;
+  // non-null while a dense launcher runs as the active-set fallback: the kernels process network b only if only_flag[b]
+  // (generic kernels), the resident kernel walks only_list[0 .. *only_cnt)
+  const int* only_flag;
+  const int* only_list;
+  const int* only_cnt;
 };
 
 int prs_pc_check_device(const prs_pc_plan* p, const char* who);
@@ -143,6 +158,14 @@ int prs_pc_pair_step(prs_pc_plan* p, void* state, const double* odom, int T, con
                      void* total, int* err, cudaStream_t st);
 int prs_pc_resident_step(prs_pc_plan* p, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st);
+int prs_pc_active_supported(const prs_pc_plan* p);
+int prs_pc_active_prepare(prs_pc_plan* p);
+// scan + active-set update of every network (one update); networks it could not handle are flagged in p->dense_flag /
+// p->dense_list for the caller's dense kernels
+int prs_pc_active_step(prs_pc_plan* p, void* state, const double* odom, const void* gi, long long* argmax, void* total,
+                       int* err, cudaStream_t st);
+// the active lists no longer describe the state (something else wrote it)
+int prs_pc_active_invalidate(prs_pc_plan* p, cudaStream_t st);
 
 // ordering of the packed sweeps through their per-device constant buffer (view_templates.cu, VtqScope): a caller that
 // launches a GRAPH containing such a sweep brackets the launch with these (begin locks a host mutex, end releases it)

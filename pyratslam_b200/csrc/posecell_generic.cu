@@ -45,7 +45,8 @@ __global__ void k_plan(const double* __restrict__ odom, const double* __restrict
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_dog_theta(const T* __restrict__ P, T* __restrict__ E, T* __restrict__ I,
-                                                        int XY, int Th, PcTables<T> tab) {
+                                                        int XY, int Th, PcTables<T> tab, const int* __restrict__ only) {
+  if (only != nullptr && !only[blockIdx.z]) return;  // active-set fallback: only the flagged networks (posecell_active.cu)
   int p = blockIdx.x * kThreads + threadIdx.x;
   if (p >= XY) return;
   int k = blockIdx.y;
@@ -65,7 +66,9 @@ __global__ void __launch_bounds__(kThreads) k_dog_theta(const T* __restrict__ P,
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_dog_y(const T* __restrict__ Ei, const T* __restrict__ Ii, T* __restrict__ E,
-                                                    T* __restrict__ I, int X, int Y, int Th, PcTables<T> tab) {
+                                                    T* __restrict__ I, int X, int Y, int Th, PcTables<T> tab,
+                                                    const int* __restrict__ only) {
+  if (only != nullptr && !only[blockIdx.z]) return;
   int XY = X * Y;
   int p = blockIdx.x * kThreads + threadIdx.x;
   if (p >= XY) return;
@@ -100,8 +103,9 @@ __device__ __forceinline__ T block_sum(T v, T* sm) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
     k_dog_x_inhib(const T* __restrict__ Ei, const T* __restrict__ Ii, T* __restrict__ A, const T* __restrict__ gi, int X,
-                  int Y, int Th, PcTables<T> tab, T* __restrict__ part) {
+                  int Y, int Th, PcTables<T> tab, T* __restrict__ part, const int* __restrict__ only) {
   __shared__ T sm[kThreads / 32];
+  if (only != nullptr && !only[blockIdx.z]) return;
   int XY = X * Y;
   int p = blockIdx.x * kThreads + threadIdx.x;
   T a = 0;
@@ -126,8 +130,9 @@ __global__ void __launch_bounds__(kThreads)
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_sum_final(const T* __restrict__ part, int np, T* __restrict__ total,
-                                                        T* __restrict__ inv_total) {
+                                                        T* __restrict__ inv_total, const int* __restrict__ only) {
   __shared__ T sm[kThreads / 32];
+  if (only != nullptr && !only[blockIdx.x]) return;
   const T* p = part + (size_t)blockIdx.x * np;
   T s = 0;
   for (int i = threadIdx.x; i < np; i += kThreads) s += p[i];
@@ -142,7 +147,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
     k_shift2d(const T* __restrict__ A, T* __restrict__ Bp, const int* __restrict__ shift,
               const unsigned char* __restrict__ fsel, const T* __restrict__ inv_total, int X, int Y, int Th,
-              PcTables<T> tab) {
+              PcTables<T> tab, const int* __restrict__ only) {
+  if (only != nullptr && !only[blockIdx.z]) return;
   int XY = X * Y;
   int p = blockIdx.x * kThreads + threadIdx.x;
   if (p >= XY) return;
@@ -213,9 +219,11 @@ __device__ __forceinline__ void block_argmax(T& v, long long& idx, T* smv, long 
 template <typename T, bool FINAL>
 __global__ void __launch_bounds__(kThreads)
     k_theta_final(const T* __restrict__ Bp, T* __restrict__ S, const int* __restrict__ ogi, int X, int Y, int Th,
-                  PcTables<T> tab, T* __restrict__ part_val, long long* __restrict__ part_idx) {
+                  PcTables<T> tab, T* __restrict__ part_val, long long* __restrict__ part_idx,
+                  const int* __restrict__ only) {
   __shared__ T smv[kThreads / 32];
   __shared__ long long smi[kThreads / 32];
+  if (only != nullptr && !only[blockIdx.z]) return;
   int XY = X * Y;
   int p = blockIdx.x * kThreads + threadIdx.x;
   int k = blockIdx.y;
@@ -246,9 +254,10 @@ __global__ void __launch_bounds__(kThreads)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_argmax_final(const T* __restrict__ part_val,
                                                            const long long* __restrict__ part_idx, int np,
-                                                           long long* __restrict__ argmax) {
+                                                           long long* __restrict__ argmax, const int* __restrict__ only) {
   __shared__ T smv[kThreads / 32];
   __shared__ long long smi[kThreads / 32];
+  if (only != nullptr && !only[blockIdx.x]) return;
   const T* pv = part_val + (size_t)blockIdx.x * np;
   const long long* pi = part_idx + (size_t)blockIdx.x * np;
   T v = -INFINITY;
@@ -291,15 +300,16 @@ int generic_step_t(prs_pc_plan* p, const PcTables<T>& tab, T* state, const doubl
   const int np = Th * p->nblk_plane;
   T *s1 = (T*)p->s1, *s2 = (T*)p->s2, *s3 = (T*)p->s3, *s4 = (T*)p->s4;
   int nbt = B * Th;
+  const int* only = p->only_flag;  // non-null while prs_pc_step runs this path as the active-set fallback
   k_plan<<<(nbt + 127) / 128, 128, 0, st>>>(odom, p->cos_th, p->sin_th, B, Th, X < Y ? X : Y, p->vtrans_scale,
                                             p->vrot_scale, p->shift, p->fsel, p->ogi, err);
-  k_dog_theta<T><<<grid, kThreads, 0, st>>>(state, s1, s2, XY, Th, tab);
-  k_dog_y<T><<<grid, kThreads, 0, st>>>(s1, s2, s3, s4, X, Y, Th, tab);
-  k_dog_x_inhib<T><<<grid, kThreads, 0, st>>>(s3, s4, s1, gi, X, Y, Th, tab, (T*)p->part_val);
-  k_sum_final<T><<<B, kThreads, 0, st>>>((const T*)p->part_val, np, total, (T*)p->inv_total);
-  k_shift2d<T><<<grid, kThreads, 0, st>>>(s1, s2, p->shift, p->fsel, (const T*)p->inv_total, X, Y, Th, tab);
-  k_theta_final<T, true><<<grid, kThreads, 0, st>>>(s2, state, p->ogi, X, Y, Th, tab, (T*)p->part_val, p->part_idx);
-  k_argmax_final<T><<<B, kThreads, 0, st>>>((const T*)p->part_val, p->part_idx, np, argmax);
+  k_dog_theta<T><<<grid, kThreads, 0, st>>>(state, s1, s2, XY, Th, tab, only);
+  k_dog_y<T><<<grid, kThreads, 0, st>>>(s1, s2, s3, s4, X, Y, Th, tab, only);
+  k_dog_x_inhib<T><<<grid, kThreads, 0, st>>>(s3, s4, s1, gi, X, Y, Th, tab, (T*)p->part_val, only);
+  k_sum_final<T><<<B, kThreads, 0, st>>>((const T*)p->part_val, np, total, (T*)p->inv_total, only);
+  k_shift2d<T><<<grid, kThreads, 0, st>>>(s1, s2, p->shift, p->fsel, (const T*)p->inv_total, X, Y, Th, tab, only);
+  k_theta_final<T, true><<<grid, kThreads, 0, st>>>(s2, state, p->ogi, X, Y, Th, tab, (T*)p->part_val, p->part_idx, only);
+  k_argmax_final<T><<<B, kThreads, 0, st>>>((const T*)p->part_val, p->part_idx, np, argmax, only);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
@@ -313,9 +323,9 @@ int generic_path_integration_t(prs_pc_plan* p, const PcTables<T>& tab, T* state,
   k_plan<<<(nbt + 127) / 128, 128, 0, st>>>(odom, p->cos_th, p->sin_th, B, Th, X < Y ? X : Y, p->vtrans_scale,
                                             p->vrot_scale, p->shift, p->fsel, p->ogi, err);
   k_fill<T><<<(B + 127) / 128, 128, 0, st>>>((T*)p->inv_total, B, T(1));
-  k_shift2d<T><<<grid, kThreads, 0, st>>>(state, (T*)p->s2, p->shift, p->fsel, (const T*)p->inv_total, X, Y, Th, tab);
+  k_shift2d<T><<<grid, kThreads, 0, st>>>(state, (T*)p->s2, p->shift, p->fsel, (const T*)p->inv_total, X, Y, Th, tab, nullptr);
   k_theta_final<T, true><<<grid, kThreads, 0, st>>>((const T*)p->s2, state, p->ogi, X, Y, Th, tab, (T*)p->part_val,
-                                                    p->part_idx);
+                                                    p->part_idx, nullptr);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
@@ -331,13 +341,13 @@ int prs_pc_launch_plan(prs_pc_plan* p, const double* odom, int* err, cudaStream_
 }
 
 int prs_pc_launch_sum_final_f32(prs_pc_plan* p, int np, float* total, cudaStream_t st) {
-  k_sum_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, np, total, (float*)p->inv_total);
+  k_sum_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, np, total, (float*)p->inv_total, nullptr);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
 
 int prs_pc_launch_argmax_final_f32(prs_pc_plan* p, int np, long long* argmax, cudaStream_t st) {
-  k_argmax_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, p->part_idx, np, argmax);
+  k_argmax_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, p->part_idx, np, argmax, nullptr);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
@@ -359,12 +369,12 @@ int prs_pc_generic_argmax(prs_pc_plan* p, const void* state, long long* argmax, 
   const int np = p->Th * p->nblk_plane;
   if (p->dtype == PRS_F32) {
     k_theta_final<float, false><<<grid, kThreads, 0, st>>>((const float*)state, nullptr, nullptr, p->X, p->Y, p->Th, p->tf,
-                                                           (float*)p->part_val, p->part_idx);
-    k_argmax_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, p->part_idx, np, argmax);
+                                                           (float*)p->part_val, p->part_idx, nullptr);
+    k_argmax_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, p->part_idx, np, argmax, nullptr);
   } else {
     k_theta_final<double, false><<<grid, kThreads, 0, st>>>((const double*)state, nullptr, nullptr, p->X, p->Y, p->Th,
-                                                            p->td, (double*)p->part_val, p->part_idx);
-    k_argmax_final<double><<<p->B, kThreads, 0, st>>>((const double*)p->part_val, p->part_idx, np, argmax);
+                                                            p->td, (double*)p->part_val, p->part_idx, nullptr);
+    k_argmax_final<double><<<p->B, kThreads, 0, st>>>((const double*)p->part_val, p->part_idx, np, argmax, nullptr);
   }
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
@@ -379,6 +389,7 @@ extern "C" int prs_pc_inject(prs_pc_handle h, void* state, int b, int x, int y, 
   const int first = b < 0 ? 0 : b, count = b < 0 ? h->B : 1;
   size_t off = ((size_t)first * h->Th + th) * h->X * h->Y + (size_t)x * h->Y + y;
   cudaStream_t st = (cudaStream_t)stream;
+  if (int rc_ = prs_pc_active_invalidate(h, st)) return rc_;
   if (h->dtype == PRS_F32)
     k_inject<float><<<(count + 127) / 128, 128, 0, st>>>((float*)state, off, (size_t)h->N, count, (float)energy);
   else
@@ -522,6 +533,7 @@ static int transpose(prs_pc_handle h, void* state, void* xyt, bool import, cudaS
 
 extern "C" int prs_pc_import_xyt(prs_pc_handle h, void* state, const void* xyt, void* stream) {
   PRS_REQUIRE(h && state && xyt, "prs_pc_import_xyt: null argument");
+  if (int rc_ = prs_pc_active_invalidate(h, (cudaStream_t)stream)) return rc_;
   return transpose(h, state, const_cast<void*>(xyt), true, (cudaStream_t)stream);
 }
 

@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(NT, 1)
     k_pc_resident(float* state, const double* __restrict__ odom, int n_steps, const float* __restrict__ gi,
                   long long* __restrict__ argmax, float* __restrict__ total, int* __restrict__ err,
                   const double* __restrict__ cos_th, const double* __restrict__ sin_th, double vtrans_scale,
-                  double vrot_scale, int B, const PcTables<float>* __restrict__ tab_g, int ablate) {
+                  double vrot_scale, int B, const PcTables<float>* __restrict__ tab_g, int ablate,
+                  const int* __restrict__ wl, const int* __restrict__ wl_cnt) {
   using L = ResLayout<X, Y, T>;
   constexpr int XY = L::XY, N = L::N, NP = L::NP, PS = L::PS;
   constexpr int kPlanT0 = NT - 64;  // the threads that prepare the next update's plan during stage 4
@@ -176,6 +177,11 @@ __global__ void __launch_bounds__(NT, 1)
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + L::kBarOff);
   const int tid = threadIdx.x;
   const int wid = tid >> 5, lane = tid & 31;
+  // Work items: the B networks, or -- as the dense fallback of the active-set path (posecell_active.cu) -- the *wl_cnt
+  // networks listed in wl.
+  const int nW = wl_cnt != nullptr ? *wl_cnt : B;
+  if ((int)blockIdx.x >= nW) return;
+  auto net = [&](int wi) { return wl != nullptr ? wl[wi] : wi; };
 
   // ---- one-time set-up: tables, coefficient pairs, mbarrier, first prefetch, first plan
   for (int i = tid; i < (int)(sizeof(PcTables<float>) / 4); i += NT)
@@ -192,14 +198,12 @@ __global__ void __launch_bounds__(NT, 1)
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_proxy_async();
-    if ((int)blockIdx.x < B) {
-      mbar_expect_tx(bar, N * 4);
-      bulk_g2s(stage, state + (size_t)blockIdx.x * N, N * 4, bar);
-    }
+    mbar_expect_tx(bar, N * 4);
+    bulk_g2s(stage, state + (size_t)net(blockIdx.x) * N, N * 4, bar);
   }
-  if (tid >= kPlanT0 && tid < kPlanT0 + T && (int)blockIdx.x < B && n_steps > 0)
-    plan_plane<X, Y, T>(tid - kPlanT0, odom + (size_t)blockIdx.x * 2, cos_th, sin_th, vtrans_scale, vrot_scale, s_plan,
-                        err + blockIdx.x);
+  if (tid >= kPlanT0 && tid < kPlanT0 + T && n_steps > 0)
+    plan_plane<X, Y, T>(tid - kPlanT0, odom + (size_t)net(blockIdx.x) * 2, cos_th, sin_th, vtrans_scale, vrot_scale, s_plan,
+                        err + net(blockIdx.x));
   __syncthreads();
   uint32_t parity = 0;
   int slot = 0;
@@ -218,7 +222,8 @@ __global__ void __launch_bounds__(NT, 1)
   long long stamp_ = 0;
 #endif
 
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  for (int wi = blockIdx.x; wi < nW; wi += gridDim.x) {
+    const int b = net(wi);
     float* gst = state + (size_t)b * N;
     const float g_inh = gi[b];
     for (int step = 0; step < n_steps; ++step) {
@@ -278,11 +283,11 @@ __global__ void __launch_bounds__(NT, 1)
       pend_valid = false;
       // the staging buffer is free again: fetch the next network while this one is computed
       if (tid == 0 && step == 0) {
-        const int nb = b + gridDim.x;
-        if (nb < B) {
+        const int nwi = wi + gridDim.x;
+        if (nwi < nW) {
           fence_proxy_async();
           mbar_expect_tx(bar, N * 4);
-          bulk_g2s(stage, state + (size_t)nb * N, N * 4, bar);
+          bulk_g2s(stage, state + (size_t)net(nwi) * N, N * 4, bar);
         }
       }
 
@@ -407,10 +412,11 @@ __global__ void __launch_bounds__(NT, 1)
       // ---- 4. 7x7 periodic correlate of both planes of a pair at once (posecell_network.py:273-274,300);
       //      meanwhile two otherwise idle warps prepare the plan of the next update.
       const bool last_step = (step + 1 == n_steps);
-      const int nb = last_step ? b + (int)gridDim.x : b;
+      const int nwi = last_step ? wi + (int)gridDim.x : wi;
+      const int nb = nwi < nW ? net(nwi) : 0;
       const int nstep = last_step ? 0 : step + 1;
       if (tid >= kPlanT0) {
-        if (tid < kPlanT0 + T && nb < B)
+        if (tid < kPlanT0 + T && nwi < nW)
           plan_plane<X, Y, T>(tid - kPlanT0, odom + ((size_t)nstep * B + nb) * 2, cos_th, sin_th, vtrans_scale,
                               vrot_scale, s_plan + (slot ^ 1) * L::kPlanInts, err + nb);
       } else if (!(ablate & 16) && tid < NP * X) {
@@ -574,6 +580,7 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
     configured[dev] = true;
   }
   const int nsm = nsm_of[dev];
+  // (as the active-set fallback the work-list length is only known on the device: CTAs without work return at once)
   const int grid = p->B < nsm ? p->B : nsm;
   // PRS_RESIDENT_ABLATE (profiling only): bit i skips stage i+1 to attribute time; results are then meaningless
   static int ablate = [] {
@@ -581,7 +588,8 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
     return e ? atoi(e) : 0;
   }();
   kern<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale,
-                                    p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate);
+                                    p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate, p->only_list,
+                                    p->only_cnt);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }

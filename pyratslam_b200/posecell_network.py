@@ -63,7 +63,8 @@ def _raw_stream(dev_index):
 class PoseCellEnsemble:
     """B independent pose-cell networks of one shape, resident on one GPU."""
 
-    def __init__(self, shape, n_networks=1, global_inhibition=K.PC_GLOBAL_INHIB, dtype=np.float32, device=None):
+    def __init__(self, shape, n_networks=1, global_inhibition=K.PC_GLOBAL_INHIB, dtype=np.float32, device=None,
+                 active_set=0):
         nat.require_cuda()
         if len(shape) != 3:
             raise ValueError("shape must be (X, Y, Th)")
@@ -121,6 +122,8 @@ class PoseCellEnsemble:
         # bumped by every call that changes the device state; users that cache something derived from the state on
         # the device (the frame plans of ros_simulate cache the arg-max) compare it with the value they last saw
         self._state_gen = 0
+        if active_set:
+            self.set_option("active_set", active_set)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -160,9 +163,20 @@ class PoseCellEnsemble:
 
     def set_option(self, name, value):
         """Per-plan options of the kernels: ``"tiled_tma"`` -- the large-grid family's TMA-fed fused 7x7 + theta kernel,
-        ``"tiled_dog"`` -- its fused theta + y + x kernel (both parity-equal, measured slower, off by default)."""
-        code = {"tiled_tma": 0, "tiled_dog": 1}[name]
-        nat.check(nat.lib().prs_pc_set_option(self._h, code, 1 if value else 0), "prs_pc_set_option")
+        ``"tiled_dog"`` -- its fused theta + y + x kernel (both parity-equal, measured slower, off by default; DESIGN.md);
+        ``"active_set"`` -- 0 / 1 / 2: the sparsity-aware update of csrc/posecell_active.cu (off / the state is scanned for its
+        non-zero cells every update / the list of non-zero cells is carried from update to update), same results, a cost
+        that follows the size of the activity packet instead of the grid."""
+        code = {"tiled_tma": 0, "tiled_dog": 1, "active_set": 2}[name]
+        v = int(value) if name == "active_set" else (1 if value else 0)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().prs_pc_set_option(self._h, code, v), "prs_pc_set_option")
+
+    def invalidate_active(self):
+        """``active_set=2`` keeps the list of non-zero cells from one update to the next; whoever writes ``state`` other
+        than through this class (a torch operation on the tensor) calls this afterwards."""
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().prs_pc_invalidate_active(self._h, nat.stream_ptr()), "prs_pc_invalidate_active")
 
     def force_generic(self, on=True):
         nat.check(nat.lib().prs_pc_force_generic(self._h, 1 if on else 0), "prs_pc_force_generic")
@@ -366,8 +380,8 @@ class PoseCellNetwork:
     the reference's ``**kwargs`` (posecell_network.py:24).
     """
 
-    def __init__(self, shape, dtype=np.float32, device=None, **kwargs):
-        self._ens = PoseCellEnsemble(shape, 1, dtype=dtype, device=device)
+    def __init__(self, shape, dtype=np.float32, device=None, active_set=0, **kwargs):
+        self._ens = PoseCellEnsemble(shape, 1, dtype=dtype, device=device, active_set=active_set)
         self.shape = self._ens.shape
         e = self._ens
         self.kernel_3d = e.kernel_3d

@@ -372,3 +372,113 @@ def test_segmented_pair_kernel_50x50x10_ensemble():
     states = np.stack([n.posecells for n in ref2])
     assert _rel(ens.posecells, states) <= 1e-5
     assert states[-1].max() == 0 and ens.posecells[-1].max() == 0
+
+
+# ------------------------------------------------------------------ active-set (sparsity-aware) path, posecell_active.cu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name,shape,inject", [
+    ("simulate_50x50x10.npz", (50, 50, 10), None),
+    ("ros_21x21x36.npz", (21, 21, 36), None),
+    ("ros_21x21x36_dies.npz", (21, 21, 36), None),
+    ("odd_9x8x7.npz", (9, 8, 7), (4, 3, 2)),
+    ("odd_17x23x11.npz", (17, 23, 11), (16, 0, 10)),
+])
+def test_active_set_golden_trajectories(golden, name, shape, inject, dtype, mode):
+    """The reference's own trajectories through the active-set kernels (scan every update / list carried over)."""
+    g = golden(name)
+    net = _make(shape, dtype, "auto", active_set=mode)
+    net.inject(1, tuple(s // 2 for s in shape) if inject is None else inject)
+    worst = 0.0
+    for s, v in enumerate(g["odom"]):
+        got = net.update(v)
+        assert tuple(got) == tuple(g["argmax"][s]), (name, s, got, g["argmax"][s])
+        key = "state_%03d" % s
+        if key in g.files:
+            ref = g[key]
+            if ref.max() == 0:
+                assert net.posecells.max() == 0
+            else:
+                worst = max(worst, _rel(net.posecells, ref))
+    assert worst <= RTOL[dtype], worst
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_active_set_ensemble_against_oracle(dtype, mode):
+    """An ensemble whose networks are in every regime at once: compact packets (active-set kernel), a dense random state
+    and a negative global inhibition (flagged, updated by the dense kernels in the same call), a dead network, two packets
+    across the periodic border, an injection between updates (invalidates the carried list)."""
+    from pyratslam_b200 import PoseCellEnsemble
+    shape, B, T = (21, 21, 36), 9, 14
+    rng = np.random.default_rng(11)
+    gis = np.linspace(0.05, 0.25, B)
+    gis[5] = -0.01                                   # zero cells do not stay zero: dense from the first update on
+    odom = np.stack([rng.uniform(0, 0.3, (T, B)), rng.uniform(-0.1, 0.1, (T, B))], axis=-1)
+    init = np.zeros((B,) + shape)
+    init[:, 10, 10, 18] = 1.0
+    init[2] = rng.uniform(0, 1, shape)               # dense state: falls back for one update, compact afterwards
+    init[3] = 0.0                                    # dead from the start
+    init[4, 0, 20, 35] = 0.7                         # second packet, wraps in all three axes
+    refs = [opc.PoseCellNetwork(shape, global_inhibition=float(g)) for g in gis]
+    for r, s in zip(refs, init):
+        r.posecells = s.copy()
+    ens = PoseCellEnsemble(shape, B, global_inhibition=gis, dtype=dtype, active_set=mode)
+    ens.posecells = init
+    for t in range(T):
+        if t == 6:                                   # view-template style injection in the middle of a run
+            for r in refs:
+                r.inject(0.3, (3, 17, 5))
+            ens.inject(0.3, (3, 17, 5))
+        want = np.array([r.update(tuple(odom[t, b])) for b, r in enumerate(refs)])
+        got = ens.update(odom[t])
+        assert np.array_equal(got, want), t
+        assert _rel(ens.posecells, np.stack([r.posecells for r in refs])) <= RTOL[dtype], t
+    got = ens.run(odom[:5])                          # multi-step entry
+    want = np.array([[r.update(tuple(odom[t, b])) for b, r in enumerate(refs)] for t in range(5)])
+    assert np.array_equal(got, want)
+    assert _rel(ens.posecells, np.stack([r.posecells for r in refs])) <= RTOL[dtype]
+
+
+def test_active_set_matches_dense_kernels_on_a_large_ensemble():
+    """600 networks of the ROS grid, 30 updates: same arg-max trace as the fused dense kernel; with mode 2 a torch write to
+    the state followed by invalidate_active() is picked up.  The states of two float32 implementations are compared at 1e-4
+    of the peak: a few parameter regimes amplify any rounding difference by ~1.3x per update (bench_tools/error_growth.py:
+    the float64 build drifts from 1e-16 to 1e-13 against the oracle over these 30 updates, the fused dense kernel reaches
+    2.7e-5 and the active-set kernels 4e-6 on network 373), everywhere else they agree to 1e-6."""
+    from pyratslam_b200 import PoseCellEnsemble
+    shape, B, T = (21, 21, 36), 600, 30
+    rng = np.random.default_rng(12)
+    gis = np.linspace(0.05, 0.25, B)
+    odom = np.stack([rng.uniform(0, 0.3, (T, B)), rng.uniform(-0.1, 0.1, (T, B))], axis=-1)
+    dense = PoseCellEnsemble(shape, B, global_inhibition=gis)
+    act = {m: PoseCellEnsemble(shape, B, global_inhibition=gis, active_set=m) for m in (1, 2)}
+    for e in [dense] + list(act.values()):
+        e.inject(1.0, (10, 10, 18))
+    want = dense.run(odom)
+    for m, e in act.items():
+        assert np.array_equal(e.run(odom), want), m
+        assert _rel(e.posecells, dense.posecells) <= 1e-4, m
+    for e in [dense] + list(act.values()):
+        e.state[:, 7, 3, 4] += 0.25                  # behind the library's back
+    act[2].invalidate_active()
+    want = dense.run(odom[:4])
+    for m, e in act.items():
+        assert np.array_equal(e.run(odom[:4]), want), m
+        assert _rel(e.posecells, dense.posecells) <= 1e-4, m
+
+
+def test_active_set_large_grid_against_oracle():
+    """BASELINE config 3 (256x256x72) through the active-set kernels: two packets, one across the periodic border."""
+    shape = (256, 256, 72)
+    ref = opc.PoseCellNetwork(shape)
+    nets = [_make(shape, np.float32, "auto", active_set=m) for m in (1, 2)]
+    for n in [ref] + nets:
+        n.inject(1.0, (128, 128, 36))
+        n.inject(0.5, (3, 250, 70))
+    for v in [(0.21, 0.03), (0.12, -0.04), (2.93, 0.3)]:
+        want = tuple(ref.update(v))
+        for n in nets:
+            assert tuple(n.update(v)) == want
+    for n in nets:
+        assert _rel(n.posecells, ref.posecells) <= 1e-5
