@@ -318,6 +318,46 @@ def extra_single_gpu(torch, peak, steps):
                                                "frac": tf / fma_peak,
                                                "pipe": "FP32 (128 FMA/clk/SM)" if nbytes == 4 else "FP64 (64 DFMA/clk/SM, measured)"}}}
         del e, od
+    # ---- the sparsity-aware update (csrc/posecell_active.cu, opt-in).  SURVEY.md 8(d): the headline must not exploit
+    #      the sparsity of the attractor state; a variant that does is reported separately -- here.  Same ensemble, same
+    #      odometry as the headline; the dense result of the same steps is the check.
+    B = B_TOTAL
+    cells = N_CELLS
+    gis, odom = ensemble_inputs(B, 64, 3)
+    od = torch.from_numpy(odom).cuda()
+    act = {}
+    ref_state = ref_amax = None
+    for mode in (0, 1, 2):
+        e = PoseCellEnsemble(SHAPE, B, global_inhibition=gis, active_set=mode)
+        e.inject(1.0, tuple(v // 2 for v in SHAPE))
+        fn = lambda t: e.update_async(od[t % 64])  # noqa: E731
+        timed(torch, None, 1, fn, 8)
+        k = max(5, min(steps, 20))
+        ms = timed(torch, None, 1, fn, k) / k
+        st = e.state.clone()
+        am = e._argmax.clone()
+        if mode == 0:
+            ref_state, ref_amax = st, am
+            nnz = int((st != 0).sum().item())
+            dense_ms = ms
+            del e
+            continue
+        same = bool(torch.equal(am, ref_amax))
+        rel = float((st - ref_state).abs().max().item() / ref_state.abs().max().item())
+        # what this variant moves: mode 1 reads every cell once (the scan), writes only the cells that change
+        alg = (4 * B * cells if mode == 1 else 0) + 8 * nnz
+        act["scan_every_update" if mode == 1 else "list_carried_over"] = {
+            "metric": METRIC, "value": B * cells / (ms * 1e-3), "ms_per_step": ms, "speedup_over_dense": dense_ms / ms,
+            "argmax_identical_to_dense": same, "state_rel_diff_to_dense": rel,
+            "bytes_moved_per_update": alg, "gbs": alg / (ms * 1e-3) / 1e9,
+            "hbm_frac_of_bytes_moved": alg / (ms * 1e-3) / 1e9 / peak}
+        assert same and rel <= 1e-4, (mode, same, rel)
+        del e
+    out["active_set_4096x21x21x36"] = dict(act, networks=B, non_zero_cells_per_network=nnz / B, dense_ms_per_step=dense_ms,
+                                           note="reported separately from the headline (SURVEY 8d): an update costs what "
+                                                "the activity packet costs, not what the grid costs; exact for any state "
+                                                "(flagged networks are updated by the dense kernels in the same call)")
+    del od, ref_state, ref_amax
     # ---- BASELINE config 1: simulate.py's own scenario (50x50x10, 40 steps), every step through update()
     from pyratslam_b200 import simulate
     from oracle import drivers as odrv
@@ -423,13 +463,22 @@ def extra_sharded_library(torch, dist, world, rank, peak, steps, n_total, label)
         fns = lambda t: svt.local_sweep(qs[t % 8])  # noqa: E731      the shard's sweep alone, no exchange, no read-back
         timed(torch, dist, world, fns, 3)
         ms_s = timed(torch, dist, world, fns, k) / k
+        def fnl(t):  # what a blocking query costs with NO exchange: the shard's sweep, then the host waits for it
+            svt.local_sweep(qs[t % 8])
+            torch.cuda.current_stream().synchronize()
+        timed(torch, dist, world, fnl, 3)
+        ms_l = timed(torch, dist, world, fnl, k) / k
         rec = {"metric": "VT shift-compares/s", "value": n_total * offs / (ms * 1e-3), "ms_per_query": ms,
                "local_sweep_only_ms": ms_s, "exchange_and_readback_ms": ms - ms_s,
+               "blocking_local_query_ms": ms_l, "exchange_over_blocking_local_query_ms": ms - ms_l,
                "batched_8_queries": {"value": n_total * offs / (ms_b * 1e-3), "ms_per_query": ms_b},
                "roofline": {"bound": "hbm", "achieved": n * 1024 / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                             "frac": n * 1024 / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_template": 1024},
                "note": "value: ONE query per call (match_key): local sweep + device-side MIN over the ranks + 8-byte "
-                       "result in pinned host memory + stream sync, every query; batched: 8 sweeps, one exchange"}
+                       "result in pinned host memory + stream sync, every query; batched: 8 sweeps, one exchange; "
+                       "local_sweep_only: back-to-back sweeps, no host wait (device time per sweep); blocking_local_query: "
+                       "the same sweep with the host waiting for it and NO exchange -- what the sharding adds to a blocking "
+                       "query is exchange_over_blocking_local_query_ms"}
         if world > 1 and svt.exchange == "fused":
             svt.set_exchange("nccl")
             assert svt.match_key(qs[0]) == (want0, j0)

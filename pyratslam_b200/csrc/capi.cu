@@ -69,7 +69,7 @@ static void free_plan(prs_pc_plan* p) {
   }
   if (p->cs_in) cudaStreamDestroy(p->cs_in);
   if (p->cs_out) cudaStreamDestroy(p->cs_out);
-  void* act[6] = {p->al_cnt, p->al_idx, p->al_valid, p->dense_flag, p->dense_list, p->dense_cnt};
+  void* act[7] = {p->al_cnt, p->al_idx, p->al_valid, p->dense_flag, p->dense_list, p->dense_cnt, p->big_list};
   for (void* q : act)
     if (q) cudaFree(q);
   free(p->h_cos);

@@ -119,7 +119,8 @@ struct prs_pc_plan {
   int* dense_flag;      // [B] 1 = the active-set kernel left this network to the dense kernels
   int* dense_list;      // [B] the flagged networks, dense_cnt of them
   int* dense_cnt;
-  int act_threads, act_arena;
+  int* big_list;        // [B] networks whose compressed grids need the second tier's arena, dense_cnt[1] of them
+  int act_threads, act_arena, act_arena1;  // arena bytes of the (second) tier; first tier's, 0 = one tier only
   // non-null while a dense launcher runs as the active-set fallback: the kernels process network b only if only_flag[b]
   // (generic kernels), the resident kernel walks only_list[0 .. *only_cnt)
   const int* only_flag;

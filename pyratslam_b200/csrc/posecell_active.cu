@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kScanT) k_pc_scan(const T* __restrict__ state,
                                                     int* __restrict__ al_cnt, int* __restrict__ al_idx, int cap,
                                                     const int* __restrict__ al_valid, int* __restrict__ dense_cnt) {
   const int b = blockIdx.y;
-  if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) *dense_cnt = 0;  // k_pc_active, next on the stream, counts from 0
+  if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) dense_cnt[0] = dense_cnt[1] = 0;  // k_pc_active counts from 0
   if (al_valid[b]) return;  // the list k_pc_active left is current
   const T* src = state + (size_t)b * N;
   int* cnt = al_cnt + b;
@@ -203,7 +203,12 @@ struct ActArgs {
   int *al_cnt, *al_idx, *al_valid;
   int cap, track;
   int *dense_flag, *dense_list, *dense_cnt;
-  int half;  // elements of T in each half of the dynamic shared-memory arena
+  // work items: every network (wl == nullptr) or the *wl_cnt networks listed in wl (second tier)
+  const int *wl, *wl_cnt;
+  // where a network whose compressed grids do not fit this launch's arena goes: the second tier's list (first tier of
+  // two), else the dense list
+  int *over_list, *over_cnt;
+  int cap0, cap1;  // elements of T in the two regions of the dynamic shared-memory arena
   PcTables<T> tab;
 };
 
@@ -236,12 +241,13 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
   __shared__ T s_total;
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-  const int b = blockIdx.x;
+  if (a.wl_cnt != nullptr && (int)blockIdx.x >= *a.wl_cnt) return;
+  const int b = a.wl != nullptr ? a.wl[blockIdx.x] : (int)blockIdx.x;
   const int X = a.X, Y = a.Y, Th = a.Th, XY = X * Y;
   T* st = a.state + (size_t)b * ((size_t)XY * Th);
   T* R0 = reinterpret_cast<T*>(arena_raw);
-  T* R1 = R0 + a.half;
-  const int half = a.half;
+  T* R1 = R0 + a.cap0;
+  const int cap0 = a.cap0, cap1 = a.cap1;
   const int n_act = a.al_cnt[b];
   const int* lidx = a.al_idx + (size_t)b * a.cap;
   const T g_inh = a.gi[b];
@@ -264,6 +270,12 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
       a.al_cnt[b] = 0;
       a.al_valid[b] = 0;
     }
+  };
+  auto overflow = [&]() {  // the compressed grids do not fit this launch's arena
+    if (a.over_list == nullptr)
+      go_dense();
+    else if (tid == 0)
+      a.over_list[atomicAdd(a.over_cnt, 1)] = b;  // the list and its count stay as they are for the second tier
   };
   if (n_act > a.cap || !(g_inh >= T(0))) {
     go_dense();
@@ -301,8 +313,8 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
       for (int g = tid; g < s_n[3 + ax]; g += nt) s_spos[ax][g] = s_set[ax].pos[s_set[3 + ax].list[g]];
     const long long nXc = (long long)nSx * nSy * nSk, nP1 = (long long)nSx * nSy * nGk, nP2 = (long long)nSx * nGy * nGk,
                     nA = (long long)nGx * nGy * nGk;
-    if (nXc > half || 2 * nP1 > half || 2 * nP2 > half || nA > half) {
-      go_dense();
+    if (nXc > cap0 || 2 * nP2 > cap0 || 2 * nP1 > cap1 || nA > cap1) {
+      overflow();
       return;
     }
     // ---- compact input Xc[i][j][s] (R0), positions in S_x, S_y, S_th
@@ -443,8 +455,8 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
       }
       __syncthreads();
       nBX = s_n[12], nBY = s_n[13];
-      if ((long long)nDAx * nDAy * nSAk > half) {
-        go_dense();
+      if ((long long)nDAx * nDAy * nSAk > cap0) {
+        overflow();
         return;
       }
       // From here on the update is carried out: the old active cells go to zero now, the theta stage below -- behind the
@@ -597,13 +609,26 @@ int active_launch(prs_pc_plan* p, T* state, const double* odom, const T* gi, lon
   a.al_cnt = p->al_cnt, a.al_idx = p->al_idx, a.al_valid = p->al_valid, a.cap = p->al_cap;
   a.track = p->opt_active == 2 ? 1 : 0;
   a.dense_flag = p->dense_flag, a.dense_list = p->dense_list, a.dense_cnt = p->dense_cnt;
-  a.half = p->act_arena / (int)sizeof(T) / 2;
   a.tab = tab;
   const int maxd = p->X > p->Y ? (p->X > p->Th ? p->X : p->Th) : (p->Y > p->Th ? p->Y : p->Th);
-  if (maxd <= 64)
-    k_pc_active<T, 64><<<p->B, p->act_threads, p->act_arena, st>>>(a);
-  else
-    k_pc_active<T, kMaxDim><<<p->B, p->act_threads, p->act_arena, st>>>(a);
+  // Optionally two tiers (PRS_ACTIVE_ARENA1_KB): a first launch with a small arena -- more CTAs per SM; the kernel is
+  // bound by the latency of a CTA's dependent phases, so networks in flight are what counts -- then the networks whose
+  // compressed grids did not fit, with the big arena.  Off by default: measured slower for the ensembles tried (the
+  // second tier repeats the set-up of every network it takes).  Regions: 40 % for {Xc, P2, B'}, 60 % for {P1, A}.
+  for (int tier = p->act_arena1 > 0 ? 0 : 1; tier < 2; ++tier) {
+    const int arena = tier == 0 ? p->act_arena1 : p->act_arena;
+    const int elems = arena / (int)sizeof(T);
+    a.cap0 = (elems * 2 / 5) & ~3, a.cap1 = elems - a.cap0;
+    const bool first_of_two = tier == 0;
+    a.wl = tier == 1 && p->act_arena1 > 0 ? p->big_list : nullptr;
+    a.wl_cnt = a.wl != nullptr ? p->dense_cnt + 1 : nullptr;
+    a.over_list = first_of_two ? p->big_list : nullptr;
+    a.over_cnt = first_of_two ? p->dense_cnt + 1 : nullptr;
+    if (maxd <= 64)
+      k_pc_active<T, 64><<<p->B, p->act_threads, arena, st>>>(a);
+    else
+      k_pc_active<T, kMaxDim><<<p->B, p->act_threads, arena, st>>>(a);
+  }
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
@@ -620,13 +645,16 @@ int prs_pc_active_prepare(prs_pc_plan* p) {
   PRS_REQUIRE(prs_pc_active_supported(p), "active-set path: every grid dimension must be in [3, %d]", kMaxDim);
   // a few large networks: one big CTA each with most of an SM's shared memory; many networks: several CTAs per SM
   const bool few = p->B <= 2 * 148;
-  int threads = few ? 256 : 128, arena = few ? 160 * 1024 : 20 * 1024, cap = few ? 8192 : 512;
+  // (measured, 4096 networks of 21x21x36: one tier of 20 KB 0.158 ms per update; 12 KB + 48 KB tiers 0.192 ms)
+  int threads = few ? 256 : 128, arena = few ? 160 * 1024 : 20 * 1024, arena1 = 0, cap = few ? 8192 : 512;
   if (const char* e = getenv("PRS_ACTIVE_THREADS")) threads = atoi(e);
   if (const char* e = getenv("PRS_ACTIVE_ARENA_KB")) arena = atoi(e) * 1024;
+  if (const char* e = getenv("PRS_ACTIVE_ARENA1_KB")) arena1 = atoi(e) * 1024;  // 0: one tier
   if (const char* e = getenv("PRS_ACTIVE_CAP")) cap = atoi(e);
   PRS_REQUIRE(threads >= 32 && threads <= kActMaxT && threads % 32 == 0, "PRS_ACTIVE_THREADS must be in [32, %d]", kActMaxT);
   PRS_REQUIRE(arena >= 4096 && arena <= 200 * 1024 && cap >= 16, "PRS_ACTIVE_ARENA_KB / PRS_ACTIVE_CAP out of range");
-  p->act_threads = threads, p->act_arena = arena, p->al_cap = cap;
+  PRS_REQUIRE(arena1 == 0 || (arena1 >= 4096 && arena1 < arena), "PRS_ACTIVE_ARENA1_KB must be 0 or in [4, arena)");
+  p->act_threads = threads, p->act_arena = arena, p->act_arena1 = arena1, p->al_cap = cap;
   PRS_CUDA(cudaFuncSetAttribute(k_pc_active<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   PRS_CUDA(cudaFuncSetAttribute(k_pc_active<double, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   PRS_CUDA(cudaFuncSetAttribute(k_pc_active<float, kMaxDim>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -636,12 +664,13 @@ int prs_pc_active_prepare(prs_pc_plan* p) {
   PRS_CUDA(cudaMalloc(&p->al_valid, B * sizeof(int)));
   PRS_CUDA(cudaMalloc(&p->dense_flag, B * sizeof(int)));
   PRS_CUDA(cudaMalloc(&p->dense_list, B * sizeof(int)));
-  PRS_CUDA(cudaMalloc(&p->dense_cnt, sizeof(int)));
+  PRS_CUDA(cudaMalloc(&p->big_list, B * sizeof(int)));
+  PRS_CUDA(cudaMalloc(&p->dense_cnt, 2 * sizeof(int)));  // [0] dense networks, [1] second-tier networks
   PRS_CUDA(cudaMalloc(&p->al_cnt, B * sizeof(int)));
   PRS_CUDA(cudaMemset(p->al_cnt, 0, B * sizeof(int)));
   PRS_CUDA(cudaMemset(p->al_valid, 0, B * sizeof(int)));
   PRS_CUDA(cudaMemset(p->dense_flag, 0, B * sizeof(int)));
-  PRS_CUDA(cudaMemset(p->dense_cnt, 0, sizeof(int)));
+  PRS_CUDA(cudaMemset(p->dense_cnt, 0, 2 * sizeof(int)));
   return PRS_OK;
 }
 

@@ -33,6 +33,8 @@
 // lets the shared-memory loads issue alongside.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 #ifndef PRS_RESIDENT_S3FOLD
@@ -574,10 +576,14 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
   static int nsm_of[64] = {};
   const int dev = p->device;
   PRS_REQUIRE(dev >= 0 && dev < 64, "resident path: device index %d out of range", dev);
-  if (!configured[dev]) {
-    PRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
-    PRS_CUDA(cudaDeviceGetAttribute(&nsm_of[dev], cudaDevAttrMultiProcessorCount, dev));
-    configured[dev] = true;
+  {
+    static std::mutex mu;  // two host threads may make their first call at the same time
+    std::lock_guard<std::mutex> lk(mu);
+    if (!configured[dev]) {
+      PRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
+      PRS_CUDA(cudaDeviceGetAttribute(&nsm_of[dev], cudaDevAttrMultiProcessorCount, dev));
+      configured[dev] = true;
+    }
   }
   const int nsm = nsm_of[dev];
   // (as the active-set fallback the work-list length is only known on the device: CTAs without work return at once)

@@ -30,6 +30,7 @@
 #include <new>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -258,7 +259,7 @@ int sweep_grid(long long units_per_warp_total) {
 // with one 640-thread CTA per SM), [1] CTAs per SM its grid is sized for, [2] ring depth of the float32 reference-mode
 // sweep (0 = the register kernel, 1..4 = one template per warp, 11..13 = the column-pair kernel with depth - 10 slots),
 // [3] CTAs per SM of that ring sweep.
-static int g_vt_knob[4] = {34, 5, 13, 2};  // measured best on B200 (bench_tools/vt_tune.py)
+static std::atomic<int> g_vt_knob[4] = {{34}, {5}, {13}, {2}};  // measured best on B200 (bench_tools/vt_tune.py)
 static int launch_f32_ring(int depth, int ctas_per_sm, const float* lib, long long n, const float* query,
                            long long base_index, unsigned long long* key_out, float* scores, cudaStream_t st);
 
@@ -1111,7 +1112,7 @@ static int launch_packed_sweep(const uint4* packed, long long n, long long n_gri
   if (blocks < 1) blocks = 1;
   if (mode == PRS_VT_MODE_REF) {
     const int depth = g_vt_knob[0];
-    const long long cap = 148LL * (depth ? g_vt_knob[1] : 16);
+    const long long cap = 148LL * (depth ? (int)g_vt_knob[1] : 16);
     if (blocks > cap) blocks = cap;
     int rc = PRS_OK;
     const int cps = g_vt_knob[1];
