@@ -33,7 +33,6 @@
 namespace {
 
 constexpr int kMaxDim = 256;        // per-axis bitmasks
-constexpr int kMW = kMaxDim / 32;   // words per mask
 constexpr int kScanT = 256;
 
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
@@ -127,8 +126,9 @@ __device__ __forceinline__ bool test_bit(const unsigned* m, int c) { return (m[c
 
 // One warp turns a finished mask (bits >= n are clear) into the sorted list and the position table; returns the size.
 template <int MAXD>
-__device__ __forceinline__ int set_from_mask(const unsigned* mask, int n, AxisSet<MAXD>* s, int lane) {
+__device__ __noinline__ int set_from_mask(const unsigned* mask, int n, AxisSet<MAXD>* s, int lane) {
   int off = 0;
+#pragma unroll 1
   for (int w = 0; w * 32 < n; ++w) {
     const unsigned m = mask[w];
     const int c = w * 32 + lane;
@@ -144,6 +144,7 @@ __device__ __forceinline__ int set_from_mask(const unsigned* mask, int n, AxisSe
 // The whole block derives a mask: bit c = pred(c) for c < n (the caller separates this from its readers by a barrier).
 template <typename P>
 __device__ __forceinline__ void derive_mask(int n, unsigned* mask, P pred) {
+#pragma unroll 1
   for (int c0 = 0; c0 < n; c0 += blockDim.x) {
     const int c = c0 + threadIdx.x;
     const unsigned w = __ballot_sync(0xffffffffu, c < n && pred(c));
@@ -151,11 +152,18 @@ __device__ __forceinline__ void derive_mask(int n, unsigned* mask, P pred) {
   }
 }
 
-__device__ __forceinline__ bool dilated(const unsigned* m, int c, int n) {  // any member within 3 cells (periodic), n >= 3
-  bool b = false;
+// any member within 3 cells (periodic), n >= 3.  Seven independent bit tests (no short-circuit: the kernel is bound by the
+// latency of dependent steps), one copy of the code.
+__device__ __noinline__ bool dilated(const unsigned* m, int c, int n) {
+  unsigned b = 0;
+  int q = c - 3;
+  q += q < 0 ? n : 0;
 #pragma unroll
-  for (int d = -3; d <= 3; ++d) b = b || test_bit(m, wrap1(c + d, n));
-  return b;
+  for (int d = 0; d < 7; ++d) {
+    b |= (m[q >> 5] >> (q & 31));
+    q = q + 1 == n ? 0 : q + 1;
+  }
+  return b & 1u;
 }
 
 // One periodic line of a 7-tap correlate on a compressed axis.  Outputs live at the n positions of the DILATED set G of
@@ -163,25 +171,31 @@ __device__ __forceinline__ bool dilated(const unsigned* m, int c, int n) {  // a
 // The neighbours of G-position g are the G-positions g-3 .. g+3 taken cyclically: inside a run of consecutive coordinates
 // that is literally true, and a step across the end of a run lands on the first / last three members of the neighbouring
 // run, which are not in S (a run of G begins exactly three cells before a member of S) -- the input there is the same
-// zero the true neighbour (outside G, or such a fringe cell itself) holds.  So a thread walks its line in chunks of CH
-// outputs with a register window of CH + 6 inputs: no coordinate arithmetic and no table look-up per tap.
+// zero the true neighbour (outside G, or such a fringe cell itself) holds.  So a chunk of CH consecutive outputs of a line
+// is a register window of CH + 6 inputs: no coordinate arithmetic and no table look-up per tap.  A work item is one
+// (line, chunk): the kernel is bound by the latency of a CTA's dependent steps, so the chunks of a line go to different
+// threads rather than one after the other.
 template <typename W, int CH, typename LD, typename EM>
-__device__ __forceinline__ void line_windows(const short* __restrict__ spos, int n, W zero, LD ld, EM emit) {
-  for (int g0 = 0; g0 < n; g0 += CH) {
-    W win[CH + 6];
-    int q = g0 - 3;
-    while (q < 0) q += n;  // at most three rounds (n >= 1): no integer division in the hot loops
+__device__ __forceinline__ void window_chunk(const short* __restrict__ spos, int n, int g0, W zero, LD ld, EM emit) {
+  W win[CH + 6];
+  int q = g0 - 3;
+  while (q < 0) q += n;  // at most three rounds (n >= 1): no integer division in the hot loops
 #pragma unroll
-    for (int j = 0; j < CH + 6; ++j) {
-      const int s = spos[q];
-      win[j] = zero;
-      if (s >= 0) win[j] = ld(s);
-      q = q + 1 == n ? 0 : q + 1;
-    }
-#pragma unroll
-    for (int jj = 0; jj < CH; ++jj)
-      if (g0 + jj < n) emit(g0 + jj, &win[jj]);
+  for (int j = 0; j < CH + 6; ++j) {
+    const int s = spos[q];
+    win[j] = zero;
+    if (s >= 0) win[j] = ld(s);
+    q = q + 1 == n ? 0 : q + 1;
   }
+#pragma unroll
+  for (int jj = 0; jj < CH; ++jj)
+    if (g0 + jj < n) emit(g0 + jj, &win[jj]);
+}
+
+__device__ __noinline__ void plan_cell_noinline(int k, int Th, int minXY, const double* odom, const double* cos_th,
+                                                const double* sin_th, double vts, double vrs, int* shift,
+                                                unsigned char* fsel, int* ogi, int* err) {
+  prs_plan_cell(0, k, Th, minXY, odom, cos_th, sin_th, vts, vrs, shift, fsel, ogi, err);
 }
 
 template <typename T>
@@ -213,12 +227,32 @@ struct ActArgs {
 };
 
 constexpr int kActMaxT = 256;
+// Optional in-kernel phase timing (profiling builds only: -DPRS_ACTIVE_TIMING): thread 0 of CTA 0 accumulates the cycles
+// between consecutive stamps into g_act_cycles[i].
+#ifdef PRS_ACTIVE_TIMING
+__device__ unsigned long long g_act_cycles[32];
+#define ACT_STAMP(i)                                        \
+  do {                                                      \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {              \
+      const long long now_ = clock64();                     \
+      g_act_cycles[i] += (unsigned long long)(now_ - stamp_); \
+      stamp_ = now_;                                        \
+    }                                                       \
+  } while (0)
+#else
+#define ACT_STAMP(i) \
+  do {               \
+  } while (0)
+#endif
+#ifndef PRS_ACTIVE_CH
+#define PRS_ACTIVE_CH 4
+#endif
 
 // MAXD: upper bound of the three grid dimensions (64 for ensembles of small grids: 4 KB of static shared memory per CTA
 // instead of 15 KB, so that more networks are in flight per SM)
 template <typename T, int MAXD>
 __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ ActArgs<T> a) {
-  constexpr int CH = sizeof(T) == 4 ? 8 : 4;  // outputs per register window
+  constexpr int CH = PRS_ACTIVE_CH;  // outputs per register window
   constexpr int MW = MAXD / 32;
   using Set = AxisSet<MAXD>;
   extern __shared__ __align__(16) unsigned char arena_raw[];
@@ -241,6 +275,9 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
   __shared__ T s_total;
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+#ifdef PRS_ACTIVE_TIMING
+  long long stamp_ = clock64();
+#endif
   if (a.wl_cnt != nullptr && (int)blockIdx.x >= *a.wl_cnt) return;
   const int b = a.wl != nullptr ? a.wl[blockIdx.x] : (int)blockIdx.x;
   const int X = a.X, Y = a.Y, Th = a.Th, XY = X * Y;
@@ -253,15 +290,20 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
   const T g_inh = a.gi[b];
 
   // the update's decisions (posecell_network.py:252-267,304), the arithmetic of every other path
+#pragma unroll 1
   for (int k = tid; k < Th; k += nt)
-    prs_plan_cell(0, k, Th, X < Y ? X : Y, a.odom + 2 * (size_t)b, a.cos_th, a.sin_th, a.vtrans_scale, a.vrot_scale,
-                  s_shift, s_fsel, &s_ogi, a.err + b);
+    plan_cell_noinline(k, Th, X < Y ? X : Y, a.odom + 2 * (size_t)b, a.cos_th, a.sin_th, a.vtrans_scale, a.vrot_scale,
+                       s_shift, s_fsel, &s_ogi, a.err + b);
+#pragma unroll 1
   for (int i = tid; i < 3 * MW; i += nt)
     (&s_mS[0][0])[i] = 0u, (&s_mG[0][0])[i] = 0u, (&s_mA[0][0])[i] = 0u, (&s_mD[0][0])[i] = 0u;
+#pragma unroll 1
   for (int i = tid; i < 2 * MW; i += nt) (&s_mB[0][0])[i] = 0u;
+#pragma unroll 1
   for (int i = tid; i < 98; i += nt) (&s_F[0][0])[i] = a.tab.f2d[i / 49][i % 49];
   if (tid == 0) s_newcnt = 0;
   __syncthreads();
+  ACT_STAMP(0);
 
   auto go_dense = [&]() {
     if (tid == 0) {
@@ -290,6 +332,7 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
       *DAx = &s_set[6], *DAy = &s_set[7], *BXs = &s_set[8], *BYs = &s_set[9], *DK = &s_set[10];
   if (n_act > 0) {
     // ---- occupancy of the three axes, their dilations, the sets
+#pragma unroll 1
     for (int e = tid; e < n_act; e += nt) {
       const int f = lidx[e];
       const int k = f / XY, r = f - k * XY, x = r / Y, y = r - x * Y;
@@ -298,18 +341,24 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
       atomicOr(&s_mS[2][k >> 5], 1u << (k & 31));
     }
     __syncthreads();
+    ACT_STAMP(1);
     derive_mask(X, s_mG[0], [&](int c) { return dilated(s_mS[0], c, X); });
     derive_mask(Y, s_mG[1], [&](int c) { return dilated(s_mS[1], c, Y); });
     derive_mask(Th, s_mG[2], [&](int c) { return dilated(s_mS[2], c, Th); });
     __syncthreads();
+    ACT_STAMP(2);
+#pragma unroll 1
     for (int q = wid; q < 6; q += nw) {
       const int ax = q % 3, n = ax == 0 ? X : (ax == 1 ? Y : Th);
       const int c = set_from_mask(q < 3 ? s_mS[ax] : s_mG[ax], n, &s_set[q], lane);
       if (lane == 0) s_n[q] = c;
     }
     __syncthreads();
+    ACT_STAMP(3);
     const int nSx = s_n[0], nSy = s_n[1], nSk = s_n[2], nGx = s_n[3], nGy = s_n[4], nGk = s_n[5];
+#pragma unroll 1
     for (int ax = 0; ax < 3; ++ax)
+#pragma unroll 1
       for (int g = tid; g < s_n[3 + ax]; g += nt) s_spos[ax][g] = s_set[ax].pos[s_set[3 + ax].list[g]];
     const long long nXc = (long long)nSx * nSy * nSk, nP1 = (long long)nSx * nSy * nGk, nP2 = (long long)nSx * nGy * nGk,
                     nA = (long long)nGx * nGy * nGk;
@@ -319,21 +368,28 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
     }
     // ---- compact input Xc[i][j][s] (R0), positions in S_x, S_y, S_th
     T* Xc = R0;
+#pragma unroll 1
     for (int c = tid; c < (int)nXc; c += nt) Xc[c] = T(0);
     __syncthreads();
+    ACT_STAMP(4);
+#pragma unroll 1
     for (int e = tid; e < n_act; e += nt) {
       const int f = lidx[e];
       const int k = f / XY, r = f - k * XY, x = r / Y, y = r - x * Y;
       Xc[(s_set[0].pos[x] * nSy + s_set[1].pos[y]) * nSk + s_set[2].pos[k]] = st[f];
     }
     __syncthreads();
+    ACT_STAMP(5);
     // ---- theta pass (k_dog_theta), one thread per (i, j) line: P1[i][j][g] pairs (R1)
     Pr<T>* P1 = reinterpret_cast<Pr<T>*>(R1);
-    for (int l = tid; l < nSx * nSy; l += nt) {
+    const int chK = (nGk + CH - 1) / CH, chY = (nGy + CH - 1) / CH, chX = (nGx + CH - 1) / CH;
+#pragma unroll 1
+    for (int it = tid; it < nSx * nSy * chK; it += nt) {
+      const int l = it / chK, g0 = (it - l * chK) * CH;
       const T* in = Xc + l * nSk;
       Pr<T>* out = P1 + l * nGk;
-      line_windows<T, CH>(
-          s_spos[2], nGk, T(0), [&](int s) { return in[s]; },
+      window_chunk<T, CH>(
+          s_spos[2], nGk, g0, T(0), [&](int s) { return in[s]; },
           [&](int g, const T* w) {
             T e = 0, i = 0;
 #pragma unroll
@@ -342,14 +398,17 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
           });
     }
     __syncthreads();
+    ACT_STAMP(6);
     // ---- y pass (k_dog_y), one thread per (i, g) line: P2[i][gy][g] pairs (R0)
     Pr<T>* P2 = reinterpret_cast<Pr<T>*>(R0);
-    for (int l = tid; l < nSx * nGk; l += nt) {
+#pragma unroll 1
+    for (int it = tid; it < nSx * nGk * chY; it += nt) {
+      const int c = it / (nSx * nGk), l = it - c * (nSx * nGk), g0 = c * CH;  // neighbouring threads: neighbouring lines
       const int i0 = l / nGk, g = l - i0 * nGk;
       const Pr<T>* in = P1 + i0 * nSy * nGk + g;
       Pr<T>* out = P2 + i0 * nGy * nGk + g;
-      line_windows<Pr<T>, CH>(
-          s_spos[1], nGy, Pr<T>{T(0), T(0)}, [&](int s) { return in[s * nGk]; },
+      window_chunk<Pr<T>, CH>(
+          s_spos[1], nGy, g0, Pr<T>{T(0), T(0)}, [&](int s) { return in[s * nGk]; },
           [&](int gy, const Pr<T>* w) {
             T e = 0, i = 0;
 #pragma unroll
@@ -358,18 +417,21 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
           });
     }
     __syncthreads();
+    ACT_STAMP(7);
     // ---- x pass, inhibition (posecell_network.py:339-340), sum (:343) (k_dog_x_inhib), one thread per (gy, g) line:
     //      A[gx][gy][g] (R1); the axes' occupancy of the result
     T* A = R1;
     T psum = T(0);
     const int lineA = nGy * nGk;
-    for (int l = tid; l < lineA; l += nt) {
+#pragma unroll 1
+    for (int it = tid; it < lineA * chX; it += nt) {
+      const int c = it / lineA, l = it - c * lineA, g0 = c * CH;
       const Pr<T>* in = P2 + l;
       T* out = A + l;
       const int gy = l / nGk, g = l - gy * nGk;
       bool any = false;
-      line_windows<Pr<T>, CH>(
-          s_spos[0], nGx, Pr<T>{T(0), T(0)}, [&](int s) { return in[s * lineA]; },
+      window_chunk<Pr<T>, CH>(
+          s_spos[0], nGx, g0, Pr<T>{T(0), T(0)}, [&](int s) { return in[s * lineA]; },
           [&](int gx, const Pr<T>* w) {
             T e = 0, i = 0;
 #pragma unroll
@@ -394,8 +456,10 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
     for (int o = 16; o > 0; o >>= 1) psum += __shfl_down_sync(0xffffffffu, psum, o);
     if (lane == 0) s_red[wid] = psum;
     __syncthreads();
+    ACT_STAMP(8);
     if (tid == 0) {
       T s = T(0);
+#pragma unroll 1
       for (int w = 0; w < nw; ++w) s += s_red[w];  // fixed order
       s_total = s;
     }
@@ -404,10 +468,12 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
     derive_mask(Y, s_mD[1], [&](int c) { return dilated(s_mA[1], c, Y); });
     derive_mask(Th, s_mD[2], [&](int c) { return dilated(s_mA[2], c, Th); });
     __syncthreads();
+    ACT_STAMP(9);
     tot = s_total;
     alive = tot != T(0);
     if (alive) {
       const T inv = T(1) / tot;  // posecell_network.py:344-345
+#pragma unroll 1
       for (int q = wid; q < 6; q += nw) {  // SA_x, SA_y, SA_th (slots 0..2), DA_x, DA_y (6, 7), D_th (10)
         const int ax = q % 3, n = ax == 0 ? X : (ax == 1 ? Y : Th);
         const int slot = q < 3 ? q : (q < 5 ? q + 3 : 10);
@@ -415,23 +481,32 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
         if (lane == 0) s_n[6 + q] = c;
       }
       __syncthreads();
+      ACT_STAMP(10);
       const int nSAx = s_n[6], nSAy = s_n[7], nSAk = s_n[8], nDAx = s_n[9], nDAy = s_n[10];
       nDK = s_n[11];
+#pragma unroll 1
       for (int s = tid; s < nSAk; s += nt) {
         const int k = SAk->list[s];
         s_om[0][s] = modp(s_shift[2 * k], X);
         s_om[1][s] = modp(s_shift[2 * k + 1], Y);
       }
+#pragma unroll 1
       for (int g = tid; g < nDAx; g += nt) s_spos[3][g] = SAx->pos[DAx->list[g]];
+#pragma unroll 1
       for (int g = tid; g < nDAy; g += nt) s_spos[4][g] = SAy->pos[DAy->list[g]];
+#pragma unroll 1
       for (int g = tid; g < nDK; g += nt) s_spos[5][g] = SAk->pos[DK->list[g]];
+#pragma unroll 1
       for (int g = tid; g < nSAx; g += nt) s_a2g[0][g] = Gx->pos[SAx->list[g]];
+#pragma unroll 1
       for (int g = tid; g < nSAy; g += nt) s_a2g[1][g] = Gy->pos[SAy->list[g]];
       __syncthreads();
+      ACT_STAMP(11);
       // where the result of the 7x7 stage can be non-zero: cell x of plane k reads rows x + ox_k - 3 .. + 3
       // (convolution.py:329-331), i.e. x + ox_k must be in DA_x for one of the active planes
       derive_mask(X, s_mB[0], [&](int c) {
         bool in = false;
+#pragma unroll 1
         for (int s = 0; s < nSAk; ++s) {
           int q = c + s_om[0][s];
           q -= q >= X ? X : 0;
@@ -441,6 +516,7 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
       });
       derive_mask(Y, s_mB[1], [&](int c) {
         bool in = false;
+#pragma unroll 1
         for (int s = 0; s < nSAk; ++s) {
           int q = c + s_om[1][s];
           q -= q >= Y ? Y : 0;
@@ -449,11 +525,14 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
         return in;
       });
       __syncthreads();
+      ACT_STAMP(12);
+#pragma unroll 1
       for (int q = wid; q < 2; q += nw) {
         const int c = set_from_mask(s_mB[q], q == 0 ? X : Y, &s_set[8 + q], lane);
         if (lane == 0) s_n[12 + q] = c;
       }
       __syncthreads();
+      ACT_STAMP(13);
       nBX = s_n[12], nBY = s_n[13];
       if ((long long)nDAx * nDAy * nSAk > cap0) {
         overflow();
@@ -461,6 +540,7 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
       }
       // From here on the update is carried out: the old active cells go to zero now, the theta stage below -- behind the
       // barrier that follows the 7x7 stage -- writes the new non-zero cells into the state as it produces them.
+#pragma unroll 1
       for (int e = tid; e < n_act; e += nt) st[lidx[e]] = T(0);
       zeroed = true;
       // ---- 7x7 stage (k_shift2d) in each active plane's own frame -- B'[jx][jy][s] (R0) holds the value of the cell whose
@@ -468,13 +548,16 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
       //      gather.  One thread per (jx, s) line along y: the seven source rows and the window's columns are looked up
       //      once, then it is register windows and FMAs (rows and columns outside SA hold zeros: skipped / zero).
       T* Bc = R0;
-      for (int l = tid; l < nDAx * nSAk; l += nt) {
+      const int chB = (nDAy + CH - 1) / CH, nLB = nDAx * nSAk;
+#pragma unroll 1
+      for (int it = tid; it < nLB * chB; it += nt) {
+        const int cb = it / nLB, l = it - cb * nLB, g0 = cb * CH;
         const int s = l % nSAk, jx = l / nSAk, k = SAk->list[s];
         const T* F = s_F[s_fsel[k]];
         const int gk = Gk->pos[k];
         int q0 = jx - 3;
         while (q0 < 0) q0 += nDAx;
-        for (int g0 = 0; g0 < nDAy; g0 += CH) {
+        {
           int col[CH + 6];
           int q = g0 - 3;
           while (q < 0) q += nDAy;
@@ -488,8 +571,8 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
 #pragma unroll
           for (int jj = 0; jj < CH; ++jj) acc[jj] = T(0);
           int qx = q0;
-#pragma unroll 1
-          for (int u = 0; u < 7; ++u) {  // rolled: the unrolled body is 1 500 instructions of a kernel that is instruction-fetch bound
+#pragma unroll
+          for (int u = 0; u < 7; ++u) {
             const int sa = s_spos[3][qx];
             qx = qx + 1 == nDAx ? 0 : qx + 1;
             if (sa < 0) continue;
@@ -517,17 +600,21 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
         }
       }
       __syncthreads();
+      ACT_STAMP(14);
       // ---- theta stage (k_theta_final), clamp (:314), arg-max candidates, one thread per (x, y) line, written straight into the state
       T ft[7];
 #pragma unroll
       for (int t = 0; t < 7; ++t) ft[t] = a.tab.f1d[s_ogi][t];
       int* nidx = a.al_idx + (size_t)b * a.cap;
-      for (int l = tid; l < nBX * nBY; l += nt) {
+      const int chD = (nDK + CH - 1) / CH, nLD = nBX * nBY;
+#pragma unroll 1
+      for (int it = tid; it < nLD * chD; it += nt) {
+        const int cd = it / nLD, l = it - cd * nLD, g0 = cd * CH;
         const int jy = l % nBY, jx = l / nBY, x = BXs->list[jx], y = BYs->list[jy];
         const int ref0 = (x * Y + y) * Th;  // numpy.argmax order (:317-319)
         T* out = st + x * Y + y;
-        line_windows<T, CH>(
-            s_spos[5], nDK, T(0),
+        window_chunk<T, CH>(
+            s_spos[5], nDK, g0, T(0),
             [&](int s) {  // plane SA_th[s] at (x, y): the 7x7 result whose window is centred on (x + ox, y + oy)
               int cx = x + s_om[0][s], cy = y + s_om[1][s];
               cx -= cx >= X ? X : 0;
@@ -561,13 +648,17 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
     if (v2 > best_v || (v2 == best_v && i2 < best_i)) best_v = v2, best_i = i2;
   }
   __syncthreads();
+  ACT_STAMP(15);
   if (lane == 0) s_red[wid] = best_v, s_redi[wid] = best_i;
   if (!zeroed)  // a network that died in this update (nothing survived the inhibition): its old cells go to zero
+#pragma unroll 1
     for (int e = tid; e < n_act; e += nt) st[lidx[e]] = T(0);
   __syncthreads();
+  ACT_STAMP(16);
   if (tid == 0) {
     T v = s_red[0];
     int i = s_redi[0];
+#pragma unroll 1
     for (int w = 1; w < nw; ++w)
       if (s_red[w] > v || (s_red[w] == v && s_redi[w] < i)) v = s_red[w], i = s_redi[w];
     a.argmax[b] = v > T(0) ? (long long)i : 0;
@@ -577,6 +668,7 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
     a.al_cnt[b] = keep ? s_newcnt : 0;
     a.al_valid[b] = keep ? 1 : 0;
   }
+  ACT_STAMP(17);
 }
 
 template <typename T>
@@ -634,6 +726,18 @@ int active_launch(prs_pc_plan* p, T* state, const double* odom, const T* gi, lon
 }
 
 }  // namespace
+
+#ifdef PRS_ACTIVE_TIMING
+extern "C" __attribute__((visibility("default"))) int prs_debug_active_cycles(unsigned long long* out32, int reset) {
+  PRS_CUDA(cudaDeviceSynchronize());
+  PRS_CUDA(cudaMemcpyFromSymbol(out32, g_act_cycles, 32 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[32] = {};
+    PRS_CUDA(cudaMemcpyToSymbol(g_act_cycles, z, sizeof(z)));
+  }
+  return PRS_OK;
+}
+#endif
 
 int prs_pc_active_supported(const prs_pc_plan* p) {
   return p->X <= kMaxDim && p->Y <= kMaxDim && p->Th <= kMaxDim && p->X >= 3 && p->Y >= 3 && p->Th >= 3;
