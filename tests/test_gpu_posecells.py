@@ -482,3 +482,47 @@ def test_active_set_large_grid_against_oracle():
             assert tuple(n.update(v)) == want
     for n in nets:
         assert _rel(n.posecells, ref.posecells) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,B", [((5, 6, 4), 3), ((3, 3, 3), 2), ((7, 9, 5), 4), ((21, 21, 36), 7), ((50, 50, 10), 3),
+                                     ((64, 33, 17), 2), ((70, 40, 19), 2), ((130, 65, 9), 1), ((256, 12, 72), 1)])
+def test_active_set_random_states_match_the_generic_kernels(shape, B, dtype):
+    """Random sparse states -- several packets, packets across the periodic border, single cells, negative cells, shifts of
+    many cells -- on shapes that exercise every corner of the set arithmetic (axes shorter than the 7-tap reach, axes longer
+    than 64 cells, odd strides): the active-set kernels run the taps in the generic kernels' order, so the two agree to
+    rounding of the one sum whose order differs (the total)."""
+    from pyratslam_b200 import PoseCellEnsemble
+    X, Y, Th = shape
+    rng = np.random.default_rng(X * 1000 + Y * 10 + Th)
+    T = 6
+    init = np.zeros((B,) + shape)
+    for b in range(B):
+        for _ in range(int(rng.integers(1, 4))):          # packets
+            c = [int(rng.integers(0, n)) for n in shape]
+            for _ in range(int(rng.integers(1, 12))):
+                d = [int(rng.integers(-1, 2)) for _ in range(3)]
+                init[b, (c[0] + d[0]) % X, (c[1] + d[1]) % Y, (c[2] + d[2]) % Th] += rng.uniform(0.05, 1.0)
+        if b % 3 == 2:
+            init[b, int(rng.integers(0, X)), int(rng.integers(0, Y)), int(rng.integers(0, Th))] = -0.3
+    vmax = 0.2 * (min(X, Y) - 3) * 0.999                  # 3 + ceil(|vtrans| / 0.2) <= min(X, Y)
+    odom = np.stack([rng.uniform(-vmax, vmax, (T, B)), rng.uniform(-0.5, 0.5, (T, B))], axis=-1)
+    gis = rng.uniform(0.0, 0.05, B)                        # low inhibition: the packets survive and grow
+    want = PoseCellEnsemble(shape, B, global_inhibition=gis, dtype=dtype)
+    want.force_path("generic")
+    got = {m: PoseCellEnsemble(shape, B, global_inhibition=gis, dtype=dtype, active_set=m) for m in (1, 2)}
+    for e in [want] + list(got.values()):
+        e.posecells = init
+    tol = 2e-6 if dtype == np.float32 else 1e-13
+    for t in range(T):
+        try:
+            ref = want.update(odom[t])
+        except KeyError:                                   # the LUT hole of the reference: the same for every path
+            for e in got.values():
+                with pytest.raises(KeyError):
+                    e.update(odom[t])
+            continue
+        ws = want.posecells
+        for m, e in got.items():
+            assert np.array_equal(e.update(odom[t]), ref), (m, t)
+            assert _rel(e.posecells, ws) <= tol, (m, t, _rel(e.posecells, ws))
