@@ -67,6 +67,7 @@ static void free_plan(prs_pc_plan* p) {
     if (p->d_odom2[i]) cudaFree(p->d_odom2[i]);
     if (p->d_xyze2[i]) cudaFree(p->d_xyze2[i]);
   }
+  if (p->ss2) cudaStreamDestroy(p->ss2);
   if (p->cs_in) cudaStreamDestroy(p->cs_in);
   if (p->cs_out) cudaStreamDestroy(p->cs_out);
   void* act[7] = {p->al_cnt, p->al_idx, p->al_valid, p->dense_flag, p->dense_list, p->dense_cnt, p->big_list};
@@ -302,6 +303,77 @@ static void drop_graphs(prs_pc_handle h) {
   }
 }
 
+// what follows the first active-set launch: its second tier, then the dense kernels for the flagged networks
+static int active_fallback(prs_pc_handle h, void* state, const double* od, const void* gi, long long* am, void* tt, int* err,
+                           cudaStream_t st) {
+  int rc = prs_pc_active_step(h, state, od, gi, am, tt, err, 1, st);  // second tier, if the plan has one
+  if (rc != PRS_OK) return rc;
+  h->only_flag = h->dense_flag, h->only_list = h->dense_list, h->only_cnt = h->dense_cnt;
+  if (h->resident_ok)
+    rc = prs_pc_resident_step(h, state, od, 1, gi, am, tt, err, st);
+  else
+    rc = prs_pc_generic_step(h, state, od, gi, am, tt, err, st);
+  h->only_flag = h->only_list = h->only_cnt = nullptr;
+  return rc;
+}
+
+// One update of the active-set path as a graph whose dense fall-back sits behind a CONDITIONAL node: the active-set kernel
+// raises the condition (cudaGraphSetConditional) when it flags a network, otherwise the fall-back's launches -- eight of
+// them for plans without the fused kernel, each a grid of early exits -- do not exist on the device's timeline at all.
+// Any failure (an older driver) returns PRS_E_CUDA with *out = nullptr and the caller captures the plain sequence.
+static int capture_active_graph(prs_pc_handle h, void* state, const void* gi, long long* argmax, void* total, int* err,
+                                cudaGraph_t* out) {
+  *out = nullptr;
+  cudaStream_t ss = h->ss;
+  if (!h->ss2 && cudaStreamCreateWithFlags(&h->ss2, cudaStreamNonBlocking) != cudaSuccess) return PRS_E_CUDA;
+  if (cudaStreamBeginCapture(ss, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return PRS_E_CUDA;
+  cudaGraph_t g = nullptr, body = nullptr, done = nullptr;
+  cudaStreamCaptureStatus cs;
+  cudaGraphConditionalHandle hd = 0;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t nd = 0;
+  cudaGraphNode_t cn;
+  cudaGraphNodeParams cp = {};
+  bool ok = cudaStreamGetCaptureInfo_v2(ss, &cs, nullptr, &g, nullptr, nullptr) == cudaSuccess && g != nullptr &&
+            cudaGraphConditionalHandleCreate(&hd, g, 0, cudaGraphCondAssignDefault) == cudaSuccess;
+  if (ok) {
+    h->act_cond = (unsigned long long)hd;
+    ok = cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), ss) == cudaSuccess &&
+         prs_pc_active_step(h, state, h->d_odom, gi, argmax, total, err, 0, ss) == PRS_OK;
+    h->act_cond = 0;
+  }
+  ok = ok && cudaStreamGetCaptureInfo_v2(ss, &cs, nullptr, &g, &deps, &nd) == cudaSuccess;
+  if (ok) {
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = hd;
+    cp.conditional.type = cudaGraphCondTypeIf;
+    cp.conditional.size = 1;
+    ok = cudaGraphAddNode(&cn, g, deps, nd, &cp) == cudaSuccess && cp.conditional.phGraph_out != nullptr;
+  }
+  if (ok) {
+    body = cp.conditional.phGraph_out[0];
+    ok = cudaStreamUpdateCaptureDependencies(ss, &cn, 1, cudaStreamSetCaptureDependencies) == cudaSuccess;
+  }
+  const cudaError_t e_end = cudaStreamEndCapture(ss, &done);
+  ok = ok && e_end == cudaSuccess && done != nullptr;
+  if (ok) {  // the body: the dense kernels for the flagged networks
+    ok = cudaStreamBeginCaptureToGraph(h->ss2, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const int rc = active_fallback(h, state, h->d_odom, gi, argmax, total, err, h->ss2);
+      cudaGraph_t b2 = nullptr;
+      const cudaError_t e2 = cudaStreamEndCapture(h->ss2, &b2);
+      ok = rc == PRS_OK && e2 == cudaSuccess;
+    }
+  }
+  if (!ok) {
+    (void)cudaGetLastError();
+    if (done) cudaGraphDestroy(done);
+    return PRS_E_CUDA;
+  }
+  *out = done;
+  return PRS_OK;
+}
+
 static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T, const void* gi, long long* argmax,
                          void* total, int* err, cudaStream_t st, int err_store = 0) {
   const size_t es = h->dtype == PRS_F32 ? 4 : 8;
@@ -313,14 +385,8 @@ static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T
       const double* od = odom + (size_t)t * h->B * 2;
       long long* am = argmax + (size_t)t * h->B;
       void* tt = (char*)total + (size_t)t * h->B * es;
-      int rc = prs_pc_active_step(h, state, od, gi, am, tt, err, st);
-      if (rc != PRS_OK) return rc;
-      h->only_flag = h->dense_flag, h->only_list = h->dense_list, h->only_cnt = h->dense_cnt;
-      if (h->resident_ok)
-        rc = prs_pc_resident_step(h, state, od, 1, gi, am, tt, err, st);
-      else
-        rc = prs_pc_generic_step(h, state, od, gi, am, tt, err, st);
-      h->only_flag = h->only_list = h->only_cnt = nullptr;
+      int rc = prs_pc_active_step(h, state, od, gi, am, tt, err, 0, st);
+      if (rc == PRS_OK) rc = active_fallback(h, state, od, gi, am, tt, err, st);
       if (rc != PRS_OK) return rc;
     }
     return PRS_OK;
@@ -390,16 +456,31 @@ extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, con
       h->sgraph = nullptr;
     }
     cudaGraph_t g = nullptr;
-    PRS_CUDA(cudaStreamBeginCapture(h->ss, cudaStreamCaptureModeThreadLocal));
-    int rc = step_enqueue(h, state, h->d_odom, gi, argmax, total, err, h->ss);
-    cudaError_t e = cudaStreamEndCapture(h->ss, &g);
-    if (rc != PRS_OK || e != cudaSuccess) {
+    static const bool no_cond = [] {  // PRS_ACTIVE_NO_COND (tuning knob): the fall-back's launches unconditionally
+      const char* e = getenv("PRS_ACTIVE_NO_COND");
+      return e && atoi(e) != 0;
+    }();
+    if (h->opt_active && !no_cond) {
+      if (capture_active_graph(h, state, gi, argmax, total, err, &g) == PRS_OK &&
+          cudaGraphInstantiate(&h->sgraph, g, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        h->sgraph = nullptr;
+      }
       if (g) cudaGraphDestroy(g);
-      if (rc == PRS_OK) prs_set_error("prs_pc_step: graph capture failed: %s", cudaGetErrorString(e));
-      return rc != PRS_OK ? rc : PRS_E_CUDA;
+      g = nullptr;
     }
-    PRS_CUDA(cudaGraphInstantiate(&h->sgraph, g, 0));
-    cudaGraphDestroy(g);
+    if (!h->sgraph) {
+      PRS_CUDA(cudaStreamBeginCapture(h->ss, cudaStreamCaptureModeThreadLocal));
+      int rc = step_enqueue(h, state, h->d_odom, gi, argmax, total, err, h->ss);
+      cudaError_t e = cudaStreamEndCapture(h->ss, &g);
+      if (rc != PRS_OK || e != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        if (rc == PRS_OK) prs_set_error("prs_pc_step: graph capture failed: %s", cudaGetErrorString(e));
+        return rc != PRS_OK ? rc : PRS_E_CUDA;
+      }
+      PRS_CUDA(cudaGraphInstantiate(&h->sgraph, g, 0));
+      cudaGraphDestroy(g);
+    }
     for (int i = 0; i < 6; ++i) h->skey[i] = key[i];
   }
   PRS_CUDA(cudaGraphLaunch(h->sgraph, h->ss));

@@ -119,6 +119,8 @@ struct prs_pc_plan {
   int* dense_flag;      // [B] 1 = the active-set kernel left this network to the dense kernels
   int* dense_list;      // [B] the flagged networks, dense_cnt of them
   int* dense_cnt;
+  unsigned long long act_cond;  // conditional-graph handle the active-set kernel raises when it flags a network (0: none)
+  cudaStream_t ss2;     // the stream the conditional node's body is captured on
   int* big_list;        // [B] networks whose compressed grids need the second tier's arena, dense_cnt[1] of them
   int act_threads, act_arena, act_arena1;  // arena bytes of the (second) tier; first tier's, 0 = one tier only
   // non-null while a dense launcher runs as the active-set fallback: the kernels process network b only if only_flag[b]
@@ -163,8 +165,10 @@ int prs_pc_active_supported(const prs_pc_plan* p);
 int prs_pc_active_prepare(prs_pc_plan* p);
 // scan + active-set update of every network (one update); networks it could not handle are flagged in p->dense_flag /
 // p->dense_list for the caller's dense kernels
+// part 0: the scan and the (first-tier) active-set kernel over all networks; part 1: the second tier over the networks
+// the first one could not hold (a no-op for one-tier plans)
 int prs_pc_active_step(prs_pc_plan* p, void* state, const double* odom, const void* gi, long long* argmax, void* total,
-                       int* err, cudaStream_t st);
+                       int* err, int part, cudaStream_t st);
 // the active lists no longer describe the state (something else wrote it)
 int prs_pc_active_invalidate(prs_pc_plan* p, cudaStream_t st);
 

@@ -222,6 +222,7 @@ struct ActArgs {
   // where a network whose compressed grids do not fit this launch's arena goes: the second tier's list (first tier of
   // two), else the dense list
   int *over_list, *over_cnt;
+  unsigned long long cond;  // conditional handle of the graph this launch is a node of (0: none): raised with the first flag
   int cap0, cap1;  // elements of T in the two regions of the dynamic shared-memory arena
   PcTables<T> tab;
 };
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
     if (tid == 0) {
       a.dense_flag[b] = 1;
       a.dense_list[atomicAdd(a.dense_cnt, 1)] = b;
+      if (a.cond != 0ull) cudaGraphSetConditional((cudaGraphConditionalHandle)a.cond, 1u);  // the dense fall-back runs
       a.al_cnt[b] = 0;
       a.al_valid[b] = 0;
     }
@@ -316,8 +318,10 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
   auto overflow = [&]() {  // the compressed grids do not fit this launch's arena
     if (a.over_list == nullptr)
       go_dense();
-    else if (tid == 0)
+    else if (tid == 0) {
       a.over_list[atomicAdd(a.over_cnt, 1)] = b;  // the list and its count stay as they are for the second tier
+      if (a.cond != 0ull) cudaGraphSetConditional((cudaGraphConditionalHandle)a.cond, 1u);  // ... which is in the body
+    }
   };
   if (n_act > a.cap || !(g_inh >= T(0))) {
     go_dense();
@@ -673,8 +677,9 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
 
 template <typename T>
 int active_launch(prs_pc_plan* p, T* state, const double* odom, const T* gi, long long* argmax, T* total, int* err,
-                  const PcTables<T>& tab, cudaStream_t st) {
+                  const PcTables<T>& tab, int part, cudaStream_t st) {
   const long long N = p->N;
+  if (part == 0) {
   const bool vec = (N * (long long)sizeof(T)) % 16 == 0 && ((uintptr_t)state % 16) == 0;
   // scan: chunks of a network so that the grid fills the machine; a chunk is a multiple of what one pass of a CTA covers
   const long long units = vec ? N / V16<T>::n : N;
@@ -694,6 +699,7 @@ int active_launch(prs_pc_plan* p, T* state, const double* odom, const T* gi, lon
   else
     k_pc_scan<T, false><<<sgrid, kScanT, 0, st>>>(state, N, (int)per, p->al_cnt, p->al_idx, p->al_cap, p->al_valid,
                                                   p->dense_cnt);
+  }
   ActArgs<T> a;
   a.state = state, a.odom = odom, a.gi = gi, a.argmax = argmax, a.total = total, a.err = err;
   a.cos_th = p->cos_th, a.sin_th = p->sin_th, a.vtrans_scale = p->vtrans_scale, a.vrot_scale = p->vrot_scale;
@@ -702,17 +708,21 @@ int active_launch(prs_pc_plan* p, T* state, const double* odom, const T* gi, lon
   a.track = p->opt_active == 2 ? 1 : 0;
   a.dense_flag = p->dense_flag, a.dense_list = p->dense_list, a.dense_cnt = p->dense_cnt;
   a.tab = tab;
+  a.cond = p->act_cond;
   const int maxd = p->X > p->Y ? (p->X > p->Th ? p->X : p->Th) : (p->Y > p->Th ? p->Y : p->Th);
-  // Optionally two tiers (PRS_ACTIVE_ARENA1_KB): a first launch with a small arena -- more CTAs per SM; the kernel is
-  // bound by the latency of a CTA's dependent phases, so networks in flight are what counts -- then the networks whose
-  // compressed grids did not fit, with the big arena.  Off by default: measured slower for the ensembles tried (the
-  // second tier repeats the set-up of every network it takes).  Regions: 40 % for {Xc, P2, B'}, 60 % for {P1, A}.
-  for (int tier = p->act_arena1 > 0 ? 0 : 1; tier < 2; ++tier) {
+  // Two tiers for plans of many networks: part 0 launches every network with a small arena (the typical packet; the kernel
+  // is bound by the latency of a CTA's dependent phases, so networks in flight per SM are what counts), part 1 the
+  // networks whose compressed grids did not fit, with a big arena, before anything is left to the dense kernels.  Plans
+  // of a few networks have one tier (part 0, big arena).  Regions: 40 % for {Xc, P2, B'}, 60 % for {P1, A}.
+  const bool two = p->act_arena1 > 0;
+  if (part == 1 && !two) return PRS_OK;
+  {
+    const int tier = two ? part : 1;
     const int arena = tier == 0 ? p->act_arena1 : p->act_arena;
     const int elems = arena / (int)sizeof(T);
     a.cap0 = (elems * 2 / 5) & ~3, a.cap1 = elems - a.cap0;
     const bool first_of_two = tier == 0;
-    a.wl = tier == 1 && p->act_arena1 > 0 ? p->big_list : nullptr;
+    a.wl = tier == 1 && two ? p->big_list : nullptr;
     a.wl_cnt = a.wl != nullptr ? p->dense_cnt + 1 : nullptr;
     a.over_list = first_of_two ? p->big_list : nullptr;
     a.over_cnt = first_of_two ? p->dense_cnt + 1 : nullptr;
@@ -749,8 +759,9 @@ int prs_pc_active_prepare(prs_pc_plan* p) {
   PRS_REQUIRE(prs_pc_active_supported(p), "active-set path: every grid dimension must be in [3, %d]", kMaxDim);
   // a few large networks: one big CTA each with most of an SM's shared memory; many networks: several CTAs per SM
   const bool few = p->B <= 2 * 148;
-  // (measured, 4096 networks of 21x21x36: one tier of 20 KB 0.158 ms per update; 12 KB + 48 KB tiers 0.192 ms)
-  int threads = few ? 256 : 128, arena = few ? 160 * 1024 : 20 * 1024, arena1 = 0, cap = few ? 8192 : 512;
+  // (measured, 4096 networks of 21x21x36: first tier of 20 KB 0.158 ms per update; of 12 KB 0.192 ms: too many networks
+  // run twice; of 48 KB 0.20 ms: too few in flight)
+  int threads = few ? 256 : 128, arena = few ? 160 * 1024 : 72 * 1024, arena1 = few ? 0 : 20 * 1024, cap = few ? 8192 : 512;
   if (const char* e = getenv("PRS_ACTIVE_THREADS")) threads = atoi(e);
   if (const char* e = getenv("PRS_ACTIVE_ARENA_KB")) arena = atoi(e) * 1024;
   if (const char* e = getenv("PRS_ACTIVE_ARENA1_KB")) arena1 = atoi(e) * 1024;  // 0: one tier
@@ -787,8 +798,8 @@ int prs_pc_active_invalidate(prs_pc_plan* p, cudaStream_t st) {
 
 // scan + active-set update of every network; the flagged ones are left to the caller's dense kernels
 int prs_pc_active_step(prs_pc_plan* p, void* state, const double* odom, const void* gi, long long* argmax, void* total,
-                       int* err, cudaStream_t st) {
+                       int* err, int part, cudaStream_t st) {
   if (p->dtype == PRS_F32)
-    return active_launch<float>(p, (float*)state, odom, (const float*)gi, argmax, (float*)total, err, p->tf, st);
-  return active_launch<double>(p, (double*)state, odom, (const double*)gi, argmax, (double*)total, err, p->td, st);
+    return active_launch<float>(p, (float*)state, odom, (const float*)gi, argmax, (float*)total, err, p->tf, part, st);
+  return active_launch<double>(p, (double*)state, odom, (const double*)gi, argmax, (double*)total, err, p->td, part, st);
 }

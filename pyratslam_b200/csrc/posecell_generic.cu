@@ -23,6 +23,16 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// Which network a block works on.  Normally blockIdx.z (or .x) itself.  As the dense fall-back of the active-set path
+// (posecell_active.cu) the grid has only kFallbackSlots entries in that dimension and walks the device-side list of flagged
+// networks: a grid sized for all B networks costs 0.5 ns per block that merely finds out it has nothing to do -- 0.7 ms per
+// update for 2600 networks of 50x50x10.
+constexpr int kFallbackSlots = 32;
+#define PRS_NET_LOOP(bz, dim)                                                                \
+  const int n_work_ = only_cnt != nullptr ? *only_cnt : (int)gridDim.dim;                    \
+  for (int slot_ = blockIdx.dim; slot_ < n_work_; slot_ += gridDim.dim)                      \
+    if (const int bz = only_list != nullptr ? only_list[slot_] : slot_; true)
+
 template <typename T>
 __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <>
@@ -45,44 +55,48 @@ __global__ void k_plan(const double* __restrict__ odom, const double* __restrict
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_dog_theta(const T* __restrict__ P, T* __restrict__ E, T* __restrict__ I,
-                                                        int XY, int Th, PcTables<T> tab, const int* __restrict__ only) {
-  if (only != nullptr && !only[blockIdx.z]) return;  // active-set fallback: only the flagged networks (posecell_active.cu)
+                                                        int XY, int Th, PcTables<T> tab,
+                                                        const int* __restrict__ only_list, const int* __restrict__ only_cnt) {
   int p = blockIdx.x * kThreads + threadIdx.x;
   if (p >= XY) return;
   int k = blockIdx.y;
-  size_t base = (size_t)blockIdx.z * Th * XY;
-  T e = 0, i = 0;
+  PRS_NET_LOOP(bz, z) {
+    size_t base = (size_t)bz * Th * XY;
+    T e = 0, i = 0;
 #pragma unroll
-  for (int t = 0; t < 7; ++t) {
-    int kk = wrap1(k + t - 3, Th);
-    T v = P[base + (size_t)kk * XY + p];
-    e = fma_t(tab.ge[t], v, e);
-    i = fma_t(tab.gi[t], v, i);
+    for (int t = 0; t < 7; ++t) {
+      int kk = wrap1(k + t - 3, Th);
+      T v = P[base + (size_t)kk * XY + p];
+      e = fma_t(tab.ge[t], v, e);
+      i = fma_t(tab.gi[t], v, i);
+    }
+    size_t o = base + (size_t)k * XY + p;
+    E[o] = e;
+    I[o] = i;
   }
-  size_t o = base + (size_t)k * XY + p;
-  E[o] = e;
-  I[o] = i;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_dog_y(const T* __restrict__ Ei, const T* __restrict__ Ii, T* __restrict__ E,
                                                     T* __restrict__ I, int X, int Y, int Th, PcTables<T> tab,
-                                                    const int* __restrict__ only) {
-  if (only != nullptr && !only[blockIdx.z]) return;
+                                                    const int* __restrict__ only_list,
+                                                    const int* __restrict__ only_cnt) {
   int XY = X * Y;
   int p = blockIdx.x * kThreads + threadIdx.x;
   if (p >= XY) return;
   int x = p / Y, y = p - x * Y;
-  size_t row = ((size_t)blockIdx.z * Th + blockIdx.y) * XY + (size_t)x * Y;
-  T e = 0, i = 0;
+  PRS_NET_LOOP(bz, z) {
+    size_t row = ((size_t)bz * Th + blockIdx.y) * XY + (size_t)x * Y;
+    T e = 0, i = 0;
 #pragma unroll
-  for (int t = 0; t < 7; ++t) {
-    int yy = wrap1(y + t - 3, Y);
-    e = fma_t(tab.ge[t], Ei[row + yy], e);
-    i = fma_t(tab.gi[t], Ii[row + yy], i);
+    for (int t = 0; t < 7; ++t) {
+      int yy = wrap1(y + t - 3, Y);
+      e = fma_t(tab.ge[t], Ei[row + yy], e);
+      i = fma_t(tab.gi[t], Ii[row + yy], i);
+    }
+    E[row + y] = e;
+    I[row + y] = i;
   }
-  E[row + y] = e;
-  I[row + y] = i;
 }
 
 template <typename T>
@@ -103,43 +117,49 @@ __device__ __forceinline__ T block_sum(T v, T* sm) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
     k_dog_x_inhib(const T* __restrict__ Ei, const T* __restrict__ Ii, T* __restrict__ A, const T* __restrict__ gi, int X,
-                  int Y, int Th, PcTables<T> tab, T* __restrict__ part, const int* __restrict__ only) {
+                  int Y, int Th, PcTables<T> tab, T* __restrict__ part, const int* __restrict__ only_list,
+                  const int* __restrict__ only_cnt) {
   __shared__ T sm[kThreads / 32];
-  if (only != nullptr && !only[blockIdx.z]) return;
   int XY = X * Y;
   int p = blockIdx.x * kThreads + threadIdx.x;
-  T a = 0;
-  if (p < XY) {
-    int x = p / Y, y = p - x * Y;
-    size_t plane = ((size_t)blockIdx.z * Th + blockIdx.y) * XY;
-    T e = 0, i = 0;
+  PRS_NET_LOOP(bz, z) {
+    T a = 0;
+    if (p < XY) {
+      int x = p / Y, y = p - x * Y;
+      size_t plane = ((size_t)bz * Th + blockIdx.y) * XY;
+      T e = 0, i = 0;
 #pragma unroll
-    for (int t = 0; t < 7; ++t) {
-      int xx = wrap1(x + t - 3, X);
-      e = fma_t(tab.gex[t], Ei[plane + (size_t)xx * Y + y], e);
-      i = fma_t(tab.gix[t], Ii[plane + (size_t)xx * Y + y], i);
+      for (int t = 0; t < 7; ++t) {
+        int xx = wrap1(x + t - 3, X);
+        e = fma_t(tab.gex[t], Ei[plane + (size_t)xx * Y + y], e);
+        i = fma_t(tab.gix[t], Ii[plane + (size_t)xx * Y + y], i);
+      }
+      a = e - i;
+      T g = gi[bz];
+      a = (a < g) ? T(0) : a - g;  // posecell_network.py:339-340
+      A[plane + p] = a;
     }
-    a = e - i;
-    T g = gi[blockIdx.z];
-    a = (a < g) ? T(0) : a - g;  // posecell_network.py:339-340
-    A[plane + p] = a;
+    T s = block_sum(a, sm);
+    if (threadIdx.x == 0) part[((size_t)bz * Th + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+    __syncthreads();  // sm is reused by the next network of the list
   }
-  T s = block_sum(a, sm);
-  if (threadIdx.x == 0) part[((size_t)blockIdx.z * Th + blockIdx.y) * gridDim.x + blockIdx.x] = s;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_sum_final(const T* __restrict__ part, int np, T* __restrict__ total,
-                                                        T* __restrict__ inv_total, const int* __restrict__ only) {
+                                                        T* __restrict__ inv_total, const int* __restrict__ only_list,
+                                                        const int* __restrict__ only_cnt) {
   __shared__ T sm[kThreads / 32];
-  if (only != nullptr && !only[blockIdx.x]) return;
-  const T* p = part + (size_t)blockIdx.x * np;
-  T s = 0;
-  for (int i = threadIdx.x; i < np; i += kThreads) s += p[i];
-  s = block_sum(s, sm);
-  if (threadIdx.x == 0) {
-    total[blockIdx.x] = s;
-    inv_total[blockIdx.x] = (s != T(0)) ? T(1) / s : T(1);  // posecell_network.py:344-345
+  PRS_NET_LOOP(bz, x) {
+    const T* p = part + (size_t)bz * np;
+    T s = 0;
+    for (int i = threadIdx.x; i < np; i += kThreads) s += p[i];
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) {
+      total[bz] = s;
+      inv_total[bz] = (s != T(0)) ? T(1) / s : T(1);  // posecell_network.py:344-345
+    }
+    __syncthreads();
   }
 }
 
@@ -147,32 +167,33 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
     k_shift2d(const T* __restrict__ A, T* __restrict__ Bp, const int* __restrict__ shift,
               const unsigned char* __restrict__ fsel, const T* __restrict__ inv_total, int X, int Y, int Th,
-              PcTables<T> tab, const int* __restrict__ only) {
-  if (only != nullptr && !only[blockIdx.z]) return;
+              PcTables<T> tab, const int* __restrict__ only_list, const int* __restrict__ only_cnt) {
   int XY = X * Y;
   int p = blockIdx.x * kThreads + threadIdx.x;
   if (p >= XY) return;
   int x = p / Y, y = p - x * Y;
-  int bk = blockIdx.z * Th + blockIdx.y;
-  size_t plane = (size_t)bk * XY;
-  int ox = shift[2 * bk], oy = shift[2 * bk + 1];
-  const T* F = tab.f2d[fsel[bk]];
-  int xs[7], ys[7];
-  int sx = modp(x + ox - 3, X), sy = modp(y + oy - 3, Y);
+  PRS_NET_LOOP(bz, z) {
+    int bk = bz * Th + blockIdx.y;
+    size_t plane = (size_t)bk * XY;
+    int ox = shift[2 * bk], oy = shift[2 * bk + 1];
+    const T* F = tab.f2d[fsel[bk]];
+    int xs[7], ys[7];
+    int sx = modp(x + ox - 3, X), sy = modp(y + oy - 3, Y);
 #pragma unroll
-  for (int t = 0; t < 7; ++t) {
-    xs[t] = (sx + t) % X;
-    ys[t] = (sy + t) % Y;
+    for (int t = 0; t < 7; ++t) {
+      xs[t] = (sx + t) % X;
+      ys[t] = (sy + t) % Y;
+    }
+    T acc = 0;
+#pragma unroll
+    for (int a = 0; a < 7; ++a) {
+      const T* row = A + plane + (size_t)xs[a] * Y;
+#pragma unroll
+      for (int b = 0; b < 7; ++b) acc = fma_t(F[a * 7 + b], row[ys[b]], acc);
+    }
+    acc *= inv_total[bz];
+    Bp[plane + p] = (acc < T(0)) ? T(0) : acc;  // posecell_network.py:300
   }
-  T acc = 0;
-#pragma unroll
-  for (int a = 0; a < 7; ++a) {
-    const T* row = A + plane + (size_t)xs[a] * Y;
-#pragma unroll
-    for (int b = 0; b < 7; ++b) acc = fma_t(F[a * 7 + b], row[ys[b]], acc);
-  }
-  acc *= inv_total[blockIdx.z];
-  Bp[plane + p] = (acc < T(0)) ? T(0) : acc;  // posecell_network.py:300
 }
 
 template <typename T>
@@ -220,51 +241,57 @@ template <typename T, bool FINAL>
 __global__ void __launch_bounds__(kThreads)
     k_theta_final(const T* __restrict__ Bp, T* __restrict__ S, const int* __restrict__ ogi, int X, int Y, int Th,
                   PcTables<T> tab, T* __restrict__ part_val, long long* __restrict__ part_idx,
-                  const int* __restrict__ only) {
+                  const int* __restrict__ only_list, const int* __restrict__ only_cnt) {
   __shared__ T smv[kThreads / 32];
   __shared__ long long smi[kThreads / 32];
-  if (only != nullptr && !only[blockIdx.z]) return;
   int XY = X * Y;
   int p = blockIdx.x * kThreads + threadIdx.x;
   int k = blockIdx.y;
-  size_t base = (size_t)blockIdx.z * Th * XY;
-  T c = -INFINITY;
-  long long idx = 0x7fffffffffffffffLL;
-  if (p < XY) {
-    if (FINAL) {
-      const T* f = tab.f1d[ogi[blockIdx.z]];
-      c = 0;
+  PRS_NET_LOOP(bz, z) {
+    size_t base = (size_t)bz * Th * XY;
+    T c = -INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    if (p < XY) {
+      if (FINAL) {
+        const T* f = tab.f1d[ogi[bz]];
+        c = 0;
 #pragma unroll
-      for (int t = 0; t < 7; ++t) c = fma_t(f[t], Bp[base + (size_t)wrap1(k + t - 3, Th) * XY + p], c);
-      c = (c < T(0)) ? T(0) : c;  // posecell_network.py:314
-      S[base + (size_t)k * XY + p] = c;
-    } else {
-      c = Bp[base + (size_t)k * XY + p];
+        for (int t = 0; t < 7; ++t) c = fma_t(f[t], Bp[base + (size_t)wrap1(k + t - 3, Th) * XY + p], c);
+        c = (c < T(0)) ? T(0) : c;  // posecell_network.py:314
+        S[base + (size_t)k * XY + p] = c;
+      } else {
+        c = Bp[base + (size_t)k * XY + p];
+      }
+      idx = (long long)p * Th + k;  // reference flat index (x*Y + y)*Th + th
     }
-    idx = (long long)p * Th + k;  // reference flat index (x*Y + y)*Th + th
-  }
-  block_argmax(c, idx, smv, smi);
-  if (threadIdx.x == 0) {
-    size_t o = ((size_t)blockIdx.z * Th + blockIdx.y) * gridDim.x + blockIdx.x;
-    part_val[o] = c;
-    part_idx[o] = idx;
+    block_argmax(c, idx, smv, smi);
+    if (threadIdx.x == 0) {
+      size_t o = ((size_t)bz * Th + blockIdx.y) * gridDim.x + blockIdx.x;
+      part_val[o] = c;
+      part_idx[o] = idx;
+    }
+    __syncthreads();  // smv / smi are reused by the next network of the list
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_argmax_final(const T* __restrict__ part_val,
                                                            const long long* __restrict__ part_idx, int np,
-                                                           long long* __restrict__ argmax, const int* __restrict__ only) {
+                                                           long long* __restrict__ argmax,
+                                                           const int* __restrict__ only_list,
+                                                           const int* __restrict__ only_cnt) {
   __shared__ T smv[kThreads / 32];
   __shared__ long long smi[kThreads / 32];
-  if (only != nullptr && !only[blockIdx.x]) return;
-  const T* pv = part_val + (size_t)blockIdx.x * np;
-  const long long* pi = part_idx + (size_t)blockIdx.x * np;
-  T v = -INFINITY;
-  long long idx = 0x7fffffffffffffffLL;
-  for (int i = threadIdx.x; i < np; i += kThreads) amax_combine(v, idx, pv[i], pi[i]);
-  block_argmax(v, idx, smv, smi);
-  if (threadIdx.x == 0) argmax[blockIdx.x] = idx;
+  PRS_NET_LOOP(bz, x) {
+    const T* pv = part_val + (size_t)bz * np;
+    const long long* pi = part_idx + (size_t)bz * np;
+    T v = -INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    for (int i = threadIdx.x; i < np; i += kThreads) amax_combine(v, idx, pv[i], pi[i]);
+    block_argmax(v, idx, smv, smi);
+    if (threadIdx.x == 0) argmax[bz] = idx;
+    __syncthreads();
+  }
 }
 
 template <typename T>
@@ -300,16 +327,19 @@ int generic_step_t(prs_pc_plan* p, const PcTables<T>& tab, T* state, const doubl
   const int np = Th * p->nblk_plane;
   T *s1 = (T*)p->s1, *s2 = (T*)p->s2, *s3 = (T*)p->s3, *s4 = (T*)p->s4;
   int nbt = B * Th;
-  const int* only = p->only_flag;  // non-null while prs_pc_step runs this path as the active-set fallback
+  // non-null while prs_pc_step runs this path as the active-set fall-back: a small grid walks the list of flagged networks
+  const int *ol = p->only_list, *oc = p->only_cnt;
+  if (ol != nullptr) grid.z = B < kFallbackSlots ? B : kFallbackSlots;
+  const int nb1 = ol != nullptr ? (int)grid.z : B;
   k_plan<<<(nbt + 127) / 128, 128, 0, st>>>(odom, p->cos_th, p->sin_th, B, Th, X < Y ? X : Y, p->vtrans_scale,
                                             p->vrot_scale, p->shift, p->fsel, p->ogi, err);
-  k_dog_theta<T><<<grid, kThreads, 0, st>>>(state, s1, s2, XY, Th, tab, only);
-  k_dog_y<T><<<grid, kThreads, 0, st>>>(s1, s2, s3, s4, X, Y, Th, tab, only);
-  k_dog_x_inhib<T><<<grid, kThreads, 0, st>>>(s3, s4, s1, gi, X, Y, Th, tab, (T*)p->part_val, only);
-  k_sum_final<T><<<B, kThreads, 0, st>>>((const T*)p->part_val, np, total, (T*)p->inv_total, only);
-  k_shift2d<T><<<grid, kThreads, 0, st>>>(s1, s2, p->shift, p->fsel, (const T*)p->inv_total, X, Y, Th, tab, only);
-  k_theta_final<T, true><<<grid, kThreads, 0, st>>>(s2, state, p->ogi, X, Y, Th, tab, (T*)p->part_val, p->part_idx, only);
-  k_argmax_final<T><<<B, kThreads, 0, st>>>((const T*)p->part_val, p->part_idx, np, argmax, only);
+  k_dog_theta<T><<<grid, kThreads, 0, st>>>(state, s1, s2, XY, Th, tab, ol, oc);
+  k_dog_y<T><<<grid, kThreads, 0, st>>>(s1, s2, s3, s4, X, Y, Th, tab, ol, oc);
+  k_dog_x_inhib<T><<<grid, kThreads, 0, st>>>(s3, s4, s1, gi, X, Y, Th, tab, (T*)p->part_val, ol, oc);
+  k_sum_final<T><<<nb1, kThreads, 0, st>>>((const T*)p->part_val, np, total, (T*)p->inv_total, ol, oc);
+  k_shift2d<T><<<grid, kThreads, 0, st>>>(s1, s2, p->shift, p->fsel, (const T*)p->inv_total, X, Y, Th, tab, ol, oc);
+  k_theta_final<T, true><<<grid, kThreads, 0, st>>>(s2, state, p->ogi, X, Y, Th, tab, (T*)p->part_val, p->part_idx, ol, oc);
+  k_argmax_final<T><<<nb1, kThreads, 0, st>>>((const T*)p->part_val, p->part_idx, np, argmax, ol, oc);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
@@ -323,9 +353,9 @@ int generic_path_integration_t(prs_pc_plan* p, const PcTables<T>& tab, T* state,
   k_plan<<<(nbt + 127) / 128, 128, 0, st>>>(odom, p->cos_th, p->sin_th, B, Th, X < Y ? X : Y, p->vtrans_scale,
                                             p->vrot_scale, p->shift, p->fsel, p->ogi, err);
   k_fill<T><<<(B + 127) / 128, 128, 0, st>>>((T*)p->inv_total, B, T(1));
-  k_shift2d<T><<<grid, kThreads, 0, st>>>(state, (T*)p->s2, p->shift, p->fsel, (const T*)p->inv_total, X, Y, Th, tab, nullptr);
+  k_shift2d<T><<<grid, kThreads, 0, st>>>(state, (T*)p->s2, p->shift, p->fsel, (const T*)p->inv_total, X, Y, Th, tab, nullptr, nullptr);
   k_theta_final<T, true><<<grid, kThreads, 0, st>>>((const T*)p->s2, state, p->ogi, X, Y, Th, tab, (T*)p->part_val,
-                                                    p->part_idx, nullptr);
+                                                    p->part_idx, nullptr, nullptr);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
@@ -341,13 +371,13 @@ int prs_pc_launch_plan(prs_pc_plan* p, const double* odom, int* err, cudaStream_
 }
 
 int prs_pc_launch_sum_final_f32(prs_pc_plan* p, int np, float* total, cudaStream_t st) {
-  k_sum_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, np, total, (float*)p->inv_total, nullptr);
+  k_sum_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, np, total, (float*)p->inv_total, nullptr, nullptr);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
 
 int prs_pc_launch_argmax_final_f32(prs_pc_plan* p, int np, long long* argmax, cudaStream_t st) {
-  k_argmax_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, p->part_idx, np, argmax, nullptr);
+  k_argmax_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, p->part_idx, np, argmax, nullptr, nullptr);
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
@@ -369,12 +399,12 @@ int prs_pc_generic_argmax(prs_pc_plan* p, const void* state, long long* argmax, 
   const int np = p->Th * p->nblk_plane;
   if (p->dtype == PRS_F32) {
     k_theta_final<float, false><<<grid, kThreads, 0, st>>>((const float*)state, nullptr, nullptr, p->X, p->Y, p->Th, p->tf,
-                                                           (float*)p->part_val, p->part_idx, nullptr);
-    k_argmax_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, p->part_idx, np, argmax, nullptr);
+                                                           (float*)p->part_val, p->part_idx, nullptr, nullptr);
+    k_argmax_final<float><<<p->B, kThreads, 0, st>>>((const float*)p->part_val, p->part_idx, np, argmax, nullptr, nullptr);
   } else {
     k_theta_final<double, false><<<grid, kThreads, 0, st>>>((const double*)state, nullptr, nullptr, p->X, p->Y, p->Th,
-                                                            p->td, (double*)p->part_val, p->part_idx, nullptr);
-    k_argmax_final<double><<<p->B, kThreads, 0, st>>>((const double*)p->part_val, p->part_idx, np, argmax, nullptr);
+                                                            p->td, (double*)p->part_val, p->part_idx, nullptr, nullptr);
+    k_argmax_final<double><<<p->B, kThreads, 0, st>>>((const double*)p->part_val, p->part_idx, np, argmax, nullptr, nullptr);
   }
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;

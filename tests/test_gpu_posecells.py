@@ -526,3 +526,29 @@ def test_active_set_random_states_match_the_generic_kernels(shape, B, dtype):
         for m, e in got.items():
             assert np.array_equal(e.update(odom[t]), ref), (m, t)
             assert _rel(e.posecells, ws) <= tol, (m, t, _rel(e.posecells, ws))
+
+
+@pytest.mark.parametrize("shape,B", [((21, 21, 36), 5), ((50, 50, 10), 3)])
+def test_active_set_fallback_behind_a_conditional_graph_node(shape, B):
+    """prs_pc_step replays the active-set update as a graph whose dense fall-back is the body of a conditional node that the
+    kernel raises when it flags a network.  Network 1 has a negative inhibition (dense on every update: the body runs),
+    in a second ensemble nothing is ever flagged (the body never runs); both against the dense kernels, update by update."""
+    from pyratslam_b200 import PoseCellEnsemble
+    rng = np.random.default_rng(21)
+    T = 7
+    odom = torch.from_numpy(np.stack([rng.uniform(0, 0.3, (T, B)), rng.uniform(-0.1, 0.1, (T, B))], axis=-1)).cuda()
+    for neg in (True, False):
+        gis = np.linspace(0.05, 0.2, B)
+        if neg:
+            gis[1] = -0.02
+        want = PoseCellEnsemble(shape, B, global_inhibition=gis)
+        got = PoseCellEnsemble(shape, B, global_inhibition=gis, active_set=2)
+        for e in (want, got):
+            e.inject(1.0, tuple(s // 2 for s in shape))
+        for t in range(T):                               # the third call on captures the graph
+            want.update_async(odom[t])
+            got.update_async(odom[t])
+            torch.cuda.synchronize()
+            assert torch.equal(got._argmax, want._argmax), (neg, t)
+            assert _rel(got.posecells, want.posecells) <= 1e-5, (neg, t)
+            assert int(got._err.abs().sum().item()) == 0
