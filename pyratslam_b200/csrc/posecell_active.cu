@@ -246,14 +246,23 @@ __device__ unsigned long long g_act_cycles[32];
   } while (0)
 #endif
 #ifndef PRS_ACTIVE_CH
-#define PRS_ACTIVE_CH 4
+#define PRS_ACTIVE_CH 12
 #endif
+#ifndef PRS_ACTIVE_CH2
+#define PRS_ACTIVE_CH2 8
+#endif
+
+// l / n for 0 <= l < 2^21, n > 0, inv = 1.0f / n: (l + 0.5) / n is never within float rounding of an integer there
+__device__ __forceinline__ int fdiv(int l, float inv) { return __float2int_rz((__int2float_rn(l) + 0.5f) * inv); }
 
 // MAXD: upper bound of the three grid dimensions (64 for ensembles of small grids: 4 KB of static shared memory per CTA
 // instead of 15 KB, so that more networks are in flight per SM)
 template <typename T, int MAXD>
-__global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ ActArgs<T> a) {
-  constexpr int CH = PRS_ACTIVE_CH;  // outputs per register window
+__global__ void __launch_bounds__(kActMaxT, 4) k_pc_active(const __grid_constant__ ActArgs<T> a) {
+  // Outputs per register window.  A work item costs ~100 instructions before its first FMA (window positions, predicated
+  // loads, line decode), so a window covers the whole line of a typical packet (11 outputs) where the registers allow it.
+  constexpr int CH = sizeof(T) == 4 ? PRS_ACTIVE_CH : PRS_ACTIVE_CH / 2;        // 1-D passes
+  constexpr int CH2 = sizeof(T) == 4 ? PRS_ACTIVE_CH2 : PRS_ACTIVE_CH2 / 2;     // 7x7 stage (CH2 accumulators + two windows)
   constexpr int MW = MAXD / 32;
   using Set = AxisSet<MAXD>;
   extern __shared__ __align__(16) unsigned char arena_raw[];
@@ -387,9 +396,10 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
     // ---- theta pass (k_dog_theta), one thread per (i, j) line: P1[i][j][g] pairs (R1)
     Pr<T>* P1 = reinterpret_cast<Pr<T>*>(R1);
     const int chK = (nGk + CH - 1) / CH, chY = (nGy + CH - 1) / CH, chX = (nGx + CH - 1) / CH;
+    const float inv_nGk = 1.0f / (float)nGk;
 #pragma unroll 1
     for (int it = tid; it < nSx * nSy * chK; it += nt) {
-      const int l = it / chK, g0 = (it - l * chK) * CH;
+      const int c = chK == 1 ? 0 : it / (nSx * nSy), l = it - c * (nSx * nSy), g0 = c * CH;
       const T* in = Xc + l * nSk;
       Pr<T>* out = P1 + l * nGk;
       window_chunk<T, CH>(
@@ -407,8 +417,8 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
     Pr<T>* P2 = reinterpret_cast<Pr<T>*>(R0);
 #pragma unroll 1
     for (int it = tid; it < nSx * nGk * chY; it += nt) {
-      const int c = it / (nSx * nGk), l = it - c * (nSx * nGk), g0 = c * CH;  // neighbouring threads: neighbouring lines
-      const int i0 = l / nGk, g = l - i0 * nGk;
+      const int c = chY == 1 ? 0 : it / (nSx * nGk), l = it - c * (nSx * nGk), g0 = c * CH;
+      const int i0 = fdiv(l, inv_nGk), g = l - i0 * nGk;
       const Pr<T>* in = P1 + i0 * nSy * nGk + g;
       Pr<T>* out = P2 + i0 * nGy * nGk + g;
       window_chunk<Pr<T>, CH>(
@@ -429,10 +439,9 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
     const int lineA = nGy * nGk;
 #pragma unroll 1
     for (int it = tid; it < lineA * chX; it += nt) {
-      const int c = it / lineA, l = it - c * lineA, g0 = c * CH;
+      const int c = chX == 1 ? 0 : it / lineA, l = it - c * lineA, g0 = c * CH;
       const Pr<T>* in = P2 + l;
       T* out = A + l;
-      const int gy = l / nGk, g = l - gy * nGk;
       bool any = false;
       window_chunk<Pr<T>, CH>(
           s_spos[0], nGx, g0, Pr<T>{T(0), T(0)}, [&](int s) { return in[s * lineA]; },
@@ -451,6 +460,7 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
             }
           });
       if (any) {
+        const int gy = fdiv(l, inv_nGk), g = l - gy * nGk;
         const int y = Gy->list[gy], k = Gk->list[g];
         atomicOr(&s_mA[1][y >> 5], 1u << (y & 31));
         atomicOr(&s_mA[2][k >> 5], 1u << (k & 31));
@@ -552,28 +562,29 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
       //      gather.  One thread per (jx, s) line along y: the seven source rows and the window's columns are looked up
       //      once, then it is register windows and FMAs (rows and columns outside SA hold zeros: skipped / zero).
       T* Bc = R0;
-      const int chB = (nDAy + CH - 1) / CH, nLB = nDAx * nSAk;
+      const int chB = (nDAy + CH2 - 1) / CH2, nLB = nDAx * nSAk;
+      const float inv_nSAk = 1.0f / (float)nSAk, inv_nBY = 1.0f / (float)s_n[13];
 #pragma unroll 1
       for (int it = tid; it < nLB * chB; it += nt) {
-        const int cb = it / nLB, l = it - cb * nLB, g0 = cb * CH;
-        const int s = l % nSAk, jx = l / nSAk, k = SAk->list[s];
+        const int cb = chB == 1 ? 0 : it / nLB, l = it - cb * nLB, g0 = cb * CH2;
+        const int jx = fdiv(l, inv_nSAk), s = l - jx * nSAk, k = SAk->list[s];
         const T* F = s_F[s_fsel[k]];
         const int gk = Gk->pos[k];
         int q0 = jx - 3;
         while (q0 < 0) q0 += nDAx;
         {
-          int col[CH + 6];
+          int col[CH2 + 6];
           int q = g0 - 3;
           while (q < 0) q += nDAy;
 #pragma unroll
-          for (int j = 0; j < CH + 6; ++j) {
+          for (int j = 0; j < CH2 + 6; ++j) {
             const int sa = s_spos[4][q];
             col[j] = sa >= 0 ? s_a2g[1][sa] * nGk : -1;
             q = q + 1 == nDAy ? 0 : q + 1;
           }
-          T acc[CH];
+          T acc[CH2];
 #pragma unroll
-          for (int jj = 0; jj < CH; ++jj) acc[jj] = T(0);
+          for (int jj = 0; jj < CH2; ++jj) acc[jj] = T(0);
           int qx = q0;
 #pragma unroll
           for (int u = 0; u < 7; ++u) {
@@ -584,19 +595,19 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
             T fr[7];
 #pragma unroll
             for (int t = 0; t < 7; ++t) fr[t] = F[u * 7 + t];
-            T w[CH + 6];
+            T w[CH2 + 6];
 #pragma unroll
-            for (int j = 0; j < CH + 6; ++j) {
+            for (int j = 0; j < CH2 + 6; ++j) {
               w[j] = T(0);
               if (col[j] >= 0) w[j] = row[col[j]];
             }
 #pragma unroll
-            for (int jj = 0; jj < CH; ++jj)
+            for (int jj = 0; jj < CH2; ++jj)
 #pragma unroll
               for (int t = 0; t < 7; ++t) acc[jj] = fma_t(fr[t], w[jj + t], acc[jj]);
           }
 #pragma unroll
-          for (int jj = 0; jj < CH; ++jj)
+          for (int jj = 0; jj < CH2; ++jj)
             if (g0 + jj < nDAy) {
               const T v = acc[jj] * inv;
               Bc[(jx * nDAy + g0 + jj) * nSAk + s] = (v < T(0)) ? T(0) : v;  // posecell_network.py:300
@@ -613,8 +624,8 @@ __global__ void __launch_bounds__(kActMaxT) k_pc_active(const __grid_constant__ 
       const int chD = (nDK + CH - 1) / CH, nLD = nBX * nBY;
 #pragma unroll 1
       for (int it = tid; it < nLD * chD; it += nt) {
-        const int cd = it / nLD, l = it - cd * nLD, g0 = cd * CH;
-        const int jy = l % nBY, jx = l / nBY, x = BXs->list[jx], y = BYs->list[jy];
+        const int cd = chD == 1 ? 0 : it / nLD, l = it - cd * nLD, g0 = cd * CH;
+        const int jx = fdiv(l, inv_nBY), jy = l - jx * nBY, x = BXs->list[jx], y = BYs->list[jy];
         const int ref0 = (x * Y + y) * Th;  // numpy.argmax order (:317-319)
         T* out = st + x * Y + y;
         window_chunk<T, CH>(
