@@ -303,6 +303,15 @@ static void drop_graphs(prs_pc_handle h) {
   }
 }
 
+// The carried lists (PRS_OPT_ACTIVE_SET = 2) describe the state tensor of the previous call: another tensor starts afresh.
+static int active_same_state(prs_pc_handle h, const void* state, cudaStream_t st) {
+  if (h->act_state != state) {
+    h->act_state = state;
+    return prs_pc_active_invalidate(h, st);
+  }
+  return PRS_OK;
+}
+
 // what follows the first active-set launch: its second tier, then the dense kernels for the flagged networks
 static int active_fallback(prs_pc_handle h, void* state, const double* od, const void* gi, long long* am, void* tt, int* err,
                            cudaStream_t st) {
@@ -381,6 +390,7 @@ static int step_dispatch(prs_pc_handle h, void* state, const double* odom, int T
     // Active-set update (posecell_active.cu): scan + one CTA per network; the networks it flags (dense state, negative
     // inhibition, ...) are then updated by a dense family that processes the flagged networks only: the fused
     // one-CTA-per-network kernel where the plan has it, else the generic kernels.
+    if (int rc_ = active_same_state(h, state, st)) return rc_;
     for (int t = 0; t < T; ++t) {
       const double* od = odom + (size_t)t * h->B * 2;
       long long* am = argmax + (size_t)t * h->B;
@@ -450,6 +460,8 @@ extern "C" int prs_pc_step(prs_pc_handle h, void* state, const double* odom, con
   PRS_CUDA(cudaStreamWaitEvent(h->ss, h->sev_in, 0));
   if (odom != h->d_odom)
     PRS_CUDA(cudaMemcpyAsync(h->d_odom, odom, (size_t)h->B * 2 * sizeof(double), cudaMemcpyDefault, h->ss));
+  if (h->opt_active)  // outside the graph: a capture must not record the invalidation of another tensor's lists
+    if (int rc_ = active_same_state(h, state, h->ss)) return rc_;
   if (!same) {
     if (h->sgraph) {
       cudaGraphExecDestroy(h->sgraph);

@@ -119,6 +119,7 @@ struct prs_pc_plan {
   int* dense_flag;      // [B] 1 = the active-set kernel left this network to the dense kernels
   int* dense_list;      // [B] the flagged networks, dense_cnt of them
   int* dense_cnt;
+  const void* act_state;        // the state tensor the carried lists describe
   unsigned long long act_cond;  // conditional-graph handle the active-set kernel raises when it flags a network (0: none)
   cudaStream_t ss2;     // the stream the conditional node's body is captured on
   int* big_list;        // [B] networks whose compressed grids need the second tier's arena, dense_cnt[1] of them

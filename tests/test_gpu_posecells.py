@@ -552,3 +552,29 @@ def test_active_set_fallback_behind_a_conditional_graph_node(shape, B):
             assert torch.equal(got._argmax, want._argmax), (neg, t)
             assert _rel(got.posecells, want.posecells) <= 1e-5, (neg, t)
             assert int(got._err.abs().sum().item()) == 0
+
+
+def test_active_set_lists_follow_the_state_tensor():
+    """One plan, two state tensors through the C ABI (prs_pc_step): the carried list of non-zero cells (mode 2) describes
+    the tensor of the previous call; a call with another tensor must start from a scan of that tensor."""
+    from pyratslam_b200 import PoseCellEnsemble, _native as nat
+    shape, B = (21, 21, 36), 3
+    gis = np.array([0.05, 0.1, 0.2])
+    act = PoseCellEnsemble(shape, B, global_inhibition=gis, active_set=2)
+    ref = [PoseCellEnsemble(shape, B, global_inhibition=gis) for _ in range(2)]
+    states = [act.state, torch.zeros_like(act.state)]
+    for st, r, loc in ((states[0], ref[0], (10, 10, 18)), (states[1], ref[1], (3, 17, 30))):
+        r.inject(1.0, loc)
+        st.copy_(r.state)
+    act.invalidate_active()
+    rng = np.random.default_rng(8)
+    L = nat.lib()
+    for t in range(8):
+        od = torch.from_numpy(np.stack([rng.uniform(0, 0.3, B), rng.uniform(-0.1, 0.1, B)], axis=-1)).cuda()
+        w = t % 2 if t < 6 else 1                     # alternate the tensors, then stay on one
+        nat.check(L.prs_pc_step(act._h, states[w].data_ptr(), od.data_ptr(), act._gi.data_ptr(), act._argmax.data_ptr(),
+                                act._total.data_ptr(), act._err.data_ptr(), nat.stream_ptr()), "prs_pc_step")
+        ref[w].update_async(od)
+        torch.cuda.synchronize()
+        assert torch.equal(act._argmax, ref[w]._argmax), t
+        assert float((states[w] - ref[w].state).abs().max() / ref[w].state.abs().max()) <= 1e-5, t
