@@ -175,6 +175,9 @@ int prs_pc_active_invalidate(prs_pc_plan* p, cudaStream_t st);
 
 // ordering of the packed sweeps through their per-device constant buffer (view_templates.cu, VtqScope): a caller that
 // launches a GRAPH containing such a sweep brackets the launch with these (begin locks a host mutex, end releases it)
+int prs_vt_pack_query_launch(const uint8_t* query, void* scratch, unsigned long long* key, cudaStream_t st);
+int prs_vt_sweep_packed_planes(const void* packed, long long n, const void* planes, int mode, long long base_index,
+                               unsigned long long* key_out, cudaStream_t st);
 int prs_vtq_begin(cudaStream_t st);
 int prs_vtq_end(cudaStream_t st);
 

@@ -76,14 +76,15 @@ __global__ void __launch_bounds__(kXchgThreads)
   const unsigned long long seq = *seq_dev + 1;  // thread 0 stores it back after the last barrier
   const int par = (int)(seq & 1);
   if (tid == 0) s_timeout = 0;
-  // 1. publish: my keys into my slot of every rank's buffer (mine included), then the sequence number
-  for (int i = tid; i < W * Q; i += kXchgThreads) {
-    const int p = i / Q, q = i - p * Q;
-    st_relaxed_sys(&peers[p]->keys[par][rank][q], keys_local[q]);
+  // 1. publish: my keys into my slot of every rank's buffer (mine included), then the sequence number.  Thread p does
+  //    both for peer p: its release store orders its own key stores before the flag, so no block-wide system fence
+  //    (MEMBAR.SC.SYS, microseconds when writes to peers are in flight) is needed in front of it.
+  if (tid < W) {
+    XchgBuf* pb = peers[tid];
+    for (int q = 0; q < Q; ++q) st_relaxed_sys(&pb->keys[par][rank][q], keys_local[q]);
+    st_release_sys(&pb->flag[par][rank], seq);
   }
-  __threadfence_system();
-  __syncthreads();
-  if (tid < W) st_release_sys(&peers[tid]->flag[par][rank], seq);
+  __syncthreads();  // s_timeout is initialised for the waiters below
   // 2. wait for the W publishes of this query in my own buffer
   XchgBuf* mine = peers[rank];
   if (tid < W) {
@@ -139,12 +140,9 @@ __global__ void __launch_bounds__(kXchgThreads)
   }
   if (tid == 0) {
     *seq_dev = seq;
-    // the sequence number is what a host that polls the (pinned) record waits for: it goes out last, behind a
-    // system-scope fence, so that the fields above and keys_out (written before the last barrier) are visible first
-    if (result != nullptr) {
-      __threadfence_system();
-      st_release_sys(&result->seq, seq);
-    }
+    // the sequence number is what a host that polls the (pinned) record waits for: it goes out last, as a system-scope
+    // release, so that the fields above and keys_out (written before the last barrier) are visible first
+    if (result != nullptr) st_release_sys(&result->seq, seq);  // a release at system scope: cumulative over the barrier above
   }
 }
 
@@ -352,9 +350,11 @@ extern "C" int prs_xchg_wait(prs_xchg* x, const prs_shard_result* result_host, d
 static int shard_query_enqueue(prs_xchg* x, int dtype, void* lib, long long n_local, const void* query_dev, int mode,
                                long long base_index, unsigned long long* key_dev, void* scratch, int decide,
                                double threshold, long long n_total, int owner, prs_shard_result* result_pinned,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool planes_ready = false) {
   int rc;
-  if (dtype == PRS_U8)
+  if (dtype == PRS_U8 && planes_ready)  // the query's bit planes are in `scratch` and the key is reset already
+    rc = prs_vt_sweep_packed_planes(n_local ? lib : nullptr, n_local, scratch, mode, base_index, key_dev, st);
+  else if (dtype == PRS_U8)
     rc = prs_vt_sweep_packed_u8(n_local ? lib : nullptr, n_local, (const uint8_t*)query_dev, mode, base_index, key_dev,
                                 nullptr, scratch, st);
   else
@@ -414,7 +414,7 @@ extern "C" int prs_vt_shard_query(prs_xchg* x, int dtype, void* lib, long long n
     PRS_CUDA(cudaStreamBeginCapture(x->gs, cudaStreamCaptureModeThreadLocal));
     x->capturing = true;
     int rc = shard_query_enqueue(x, dtype, lib, n_local, x->q_stage, mode, base_index, key_dev, scratch, decide, threshold,
-                                 n_total, owner, result_pinned, x->gs);
+                                 n_total, owner, result_pinned, x->gs, true);
     x->capturing = false;
     cudaError_t e = cudaStreamEndCapture(x->gs, &g);
     if (rc != PRS_OK || e != cudaSuccess) {
@@ -428,7 +428,16 @@ extern "C" int prs_vt_shard_query(prs_xchg* x, int dtype, void* lib, long long n
   }
   // replay: the query goes into the staging buffer on the caller's stream (behind whatever produced it), the graph
   // runs behind that copy and behind sweeps of other streams
-  PRS_CUDA(cudaMemcpyAsync(x->q_stage, query_dev, dtype == PRS_U8 ? 1024 : 4096, cudaMemcpyDeviceToDevice, st));
+  // uint8: the query's bit planes go into `scratch` and the key is reset by one small kernel on the caller's stream (the
+  // chain is then constant upload, sweep, exchange); the decision kernel still reads the raw query from the staging buffer
+  // when it may append, and such chains are never replayed.  float32: the raw query is staged.
+  if (dtype == PRS_U8 && n_local > 0) {
+    if (int rc = prs_vt_pack_query_launch((const uint8_t*)query_dev, scratch, key_dev, st)) return rc;
+    if (decide) PRS_CUDA(cudaMemcpyAsync(x->q_stage, query_dev, 1024, cudaMemcpyDeviceToDevice, st));
+  } else {
+    if (dtype == PRS_U8) PRS_CUDA(cudaMemsetAsync(key_dev, 0xff, sizeof(unsigned long long), st));
+    PRS_CUDA(cudaMemcpyAsync(x->q_stage, query_dev, dtype == PRS_U8 ? 1024 : 4096, cudaMemcpyDeviceToDevice, st));
+  }
   PRS_CUDA(cudaEventRecord(x->gev, st));
   PRS_CUDA(cudaStreamWaitEvent(x->gs, x->gev, 0));
   if (int rc = prs_vtq_begin(x->gs)) return rc;

@@ -426,9 +426,12 @@ __global__ void k_vt_unpack_u8(const uint4* __restrict__ packed, long long ti, u
   dst[t * 32 + c] = (uint8_t)px;
 }
 
-__global__ void k_vt_pack_query(const uint8_t* __restrict__ q, uint32_t* __restrict__ out) {
-  // 32 threads: thread t packs row t; then the two sums
+__global__ void k_vt_pack_query(const uint8_t* __restrict__ q, uint32_t* __restrict__ out,
+                                unsigned long long* __restrict__ key_init = nullptr) {
+  // 32 threads: thread t packs row t; then the two sums.  key_init: the sweep's packed key starts at "nothing found"
+  // (one graph node less than a memset of its own on the sharded query chain)
   const int t = threadIdx.x;
+  if (t == 0 && key_init != nullptr) *key_init = ~0ull;
   uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint32_t sum = 0;
   for (int c = 0; c < 32; ++c) {
@@ -1189,11 +1192,13 @@ extern "C" int prs_vt_sweep_packed_u8(const void* packed, long long n, const uin
   PRS_REQUIRE(base_index >= 0 && base_index + n <= 0xffffffffLL,
               "prs_vt_sweep_packed_u8: template index does not fit 32 bits");
   cudaStream_t st = (cudaStream_t)stream;
-  PRS_CUDA(cudaMemsetAsync(key_out, 0xff, sizeof(unsigned long long), st));
-  if (n == 0) return PRS_OK;
+  if (n == 0) {
+    PRS_CUDA(cudaMemsetAsync(key_out, 0xff, sizeof(unsigned long long), st));
+    return PRS_OK;
+  }
   // query -> bit planes -> constant bank (stream ordered; sweeps on other streams of the device are ordered behind
   // each other through VtqScope)
-  k_vt_pack_query<<<1, 32, 0, st>>>(query, (uint32_t*)scratch);
+  k_vt_pack_query<<<1, 32, 0, st>>>(query, (uint32_t*)scratch, key_out);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
   VtqScope scope;
@@ -1201,6 +1206,27 @@ extern "C" int prs_vt_sweep_packed_u8(const void* packed, long long n, const uin
     if (int rc = scope.begin(st)) return rc;
   PRS_CUDA(cudaMemcpyToSymbolAsync(c_vtq, scratch, (32 * 8 + 2) * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
   int rc = launch_packed_sweep((const uint4*)packed, n, n, mode, base_index, key_out, scores, nullptr, st);
+  if (int rc2 = scope.end()) return rc != PRS_OK ? rc : rc2;
+  return rc;
+}
+
+// The two halves of prs_vt_sweep_packed_u8 for a caller that replays the second one as a graph (sharded.cu): the query's
+// bit planes (and the reset of the key) on the caller's stream, then constant upload + sweep from those planes.
+int prs_vt_pack_query_launch(const uint8_t* query, void* scratch, unsigned long long* key, cudaStream_t st) {
+  k_vt_pack_query<<<1, 32, 0, st>>>(query, (uint32_t*)scratch, key);
+  PRS_CUDA(cudaGetLastError());
+  return PRS_OK;
+}
+int prs_vt_sweep_packed_planes(const void* packed, long long n, const void* planes, int mode, long long base_index,
+                               unsigned long long* key_out, cudaStream_t st) {
+  if (n == 0) return PRS_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
+  VtqScope scope;
+  if (cap == cudaStreamCaptureStatusNone)
+    if (int rc = scope.begin(st)) return rc;
+  PRS_CUDA(cudaMemcpyToSymbolAsync(c_vtq, planes, (32 * 8 + 2) * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
+  int rc = launch_packed_sweep((const uint4*)packed, n, n, mode, base_index, key_out, nullptr, nullptr, st);
   if (int rc2 = scope.end()) return rc != PRS_OK ? rc : rc2;
   return rc;
 }
