@@ -438,12 +438,12 @@ extern "C" int prs_vt_shard_query(prs_xchg* x, int dtype, void* lib, long long n
     if (dtype == PRS_U8) PRS_CUDA(cudaMemsetAsync(key_dev, 0xff, sizeof(unsigned long long), st));
     PRS_CUDA(cudaMemcpyAsync(x->q_stage, query_dev, dtype == PRS_U8 ? 1024 : 4096, cudaMemcpyDeviceToDevice, st));
   }
-  PRS_CUDA(cudaEventRecord(x->gev, st));
-  PRS_CUDA(cudaStreamWaitEvent(x->gs, x->gev, 0));
-  if (int rc = prs_vtq_begin(x->gs)) return rc;
-  cudaError_t le = cudaGraphLaunch(x->gexec, x->gs);
+  // the recorded chain runs on the caller's own stream, right behind the staging (the private stream is only what the
+  // chain was captured on): no event, no cross-stream dependency on the way to a 25 us answer
+  if (int rc = prs_vtq_begin(st)) return rc;
+  cudaError_t le = cudaGraphLaunch(x->gexec, st);
   ++x->host_seq;
-  int rc2 = prs_vtq_end(x->gs);
+  int rc2 = prs_vtq_end(st);
   PRS_CUDA(le);
   if (rc2 != PRS_OK) return rc2;
   return prs_xchg_wait(x, result_pinned, 30.0);
