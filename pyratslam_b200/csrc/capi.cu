@@ -70,6 +70,7 @@ static void free_plan(prs_pc_plan* p) {
   if (p->ss2) cudaStreamDestroy(p->ss2);
   if (p->cs_in) cudaStreamDestroy(p->cs_in);
   if (p->cs_out) cudaStreamDestroy(p->cs_out);
+  if (p->net_seq) cudaFree(p->net_seq);
   void* act[7] = {p->al_cnt, p->al_idx, p->al_valid, p->dense_flag, p->dense_list, p->dense_cnt, p->big_list};
   for (void* q : act)
     if (q) cudaFree(q);
@@ -158,6 +159,8 @@ extern "C" int prs_pc_create(const prs_pc_config* cfg, prs_pc_handle* out) {
   ALLOC(p->done_ctr, (size_t)p->B * 2 * sizeof(unsigned));
   cudaMemset(p->done_ctr, 0, (size_t)p->B * 2 * sizeof(unsigned));
   ALLOC(p->tab_dev, sizeof(PcTables<float>));
+  ALLOC(p->net_seq, (size_t)p->B * sizeof(unsigned));
+  cudaMemset(p->net_seq, 0, (size_t)p->B * sizeof(unsigned));
   p->forced_path = PRS_PATH_AUTO;
   p->resident_ok = prs_pc_resident_supported(p);
   p->pair_ok = prs_pc_pair_supported(p);
@@ -424,7 +427,10 @@ static int step_enqueue(prs_pc_handle h, void* state, const double* odom, const 
                         int* err, cudaStream_t st) {
   // the cluster kernel gathers its error bits and stores them: one node less on a 12 us update
   if (prs_pc_path(h) == PRS_PATH_CLUSTER && !h->opt_active) return step_dispatch(h, state, odom, 1, gi, argmax, total, err, st, 1);
-  PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
+  // the fused one-CTA kernel zeroes err[b] itself: a memset between two of its launches would keep the second from
+  // starting while the first one's last wave runs (posecell_resident.cu, programmatic dependent launch)
+  if (!(prs_pc_path(h) == PRS_PATH_RESIDENT && !h->opt_active))
+    PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
   return step_dispatch(h, state, odom, 1, gi, argmax, total, err, st);
 }
 
@@ -530,7 +536,8 @@ extern "C" int prs_pc_run(prs_pc_handle h, void* state, const double* odom, int 
   if (int rc_ = prs_pc_check_device(h, "prs_pc_run")) return rc_;
   PRS_REQUIRE(T >= 0, "prs_pc_run: negative step count");
   cudaStream_t st = (cudaStream_t)stream;
-  PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
+  if (T == 0 || !(prs_pc_path(h) == PRS_PATH_RESIDENT && !h->opt_active))
+    PRS_CUDA(cudaMemsetAsync(err, 0, (size_t)h->B * sizeof(int), st));
   if (T == 0) return PRS_OK;
   return step_dispatch(h, state, odom, T, gi, argmax, total, err, st);
 }

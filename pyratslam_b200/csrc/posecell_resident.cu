@@ -100,6 +100,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- update n+1 of an ensemble may start while update n still runs (programmatic dependent launch): what orders them is
+//      one sequence number per network, released when the network's state of launch n is in global memory and acquired
+//      before launch n+1 fetches it.
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_network(const unsigned* net_seq, int b, unsigned seq) {
+  if (seq == 0u) return;
+  const unsigned want = seq - 1u;
+  if (ld_acquire_gpu_u32(net_seq + b) < want) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_gpu_u32(net_seq + b) < want) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) __trap();  // two seconds: a broken launch order, not a slow predecessor
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copy that follows reads what another CTA's stores wrote
+}
+
 // Decisions of one update for theta plane k, float64 exactly as numpy computes them on the host
 // (posecell_network.py:252-267,249,304).  plan[k] = (ox mod X, oy mod Y, ox*Y + oy, LUT filter).
 template <int X, int Y, int T>
@@ -149,7 +174,7 @@ __global__ void __launch_bounds__(NT, 1)
                   long long* __restrict__ argmax, float* __restrict__ total, int* __restrict__ err,
                   const double* __restrict__ cos_th, const double* __restrict__ sin_th, double vtrans_scale,
                   double vrot_scale, int B, const PcTables<float>* __restrict__ tab_g, int ablate,
-                  const int* __restrict__ wl, const int* __restrict__ wl_cnt) {
+                  const int* __restrict__ wl, const int* __restrict__ wl_cnt, unsigned* __restrict__ net_seq, unsigned seq) {
   using L = ResLayout<X, Y, T>;
   constexpr int XY = L::XY, N = L::N, NP = L::NP, PS = L::PS;
   constexpr int kPlanT0 = NT - 64;  // the threads that prepare the next update's plan during stage 4
@@ -184,6 +209,10 @@ __global__ void __launch_bounds__(NT, 1)
   const int nW = wl_cnt != nullptr ? *wl_cnt : B;
   if ((int)blockIdx.x >= nW) return;
   auto net = [&](int wi) { return wl != nullptr ? wl[wi] : wi; };
+  // seq != 0: this launch is number `seq` of the plan's chain of overlappable launches.  The next one may be scheduled as
+  // soon as SMs are free (the CTAs of a ragged last wave leave 80 of 148 SMs idle for a whole network otherwise); it
+  // waits per network, not per grid.
+  if (seq != 0u) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // ---- one-time set-up: tables, coefficient pairs, mbarrier, first prefetch, first plan
   for (int i = tid; i < (int)(sizeof(PcTables<float>) / 4); i += NT)
@@ -200,9 +229,12 @@ __global__ void __launch_bounds__(NT, 1)
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_proxy_async();
+    wait_network(net_seq, net(blockIdx.x), seq);
     mbar_expect_tx(bar, N * 4);
     bulk_g2s(stage, state + (size_t)net(blockIdx.x) * N, N * 4, bar);
+    err[net(blockIdx.x)] = 0;  // the kernel owns err[b]: zeroed before the network's first plan ORs its bits in
   }
+  __syncthreads();
   if (tid >= kPlanT0 && tid < kPlanT0 + T && n_steps > 0)
     plan_plane<X, Y, T>(tid - kPlanT0, odom + (size_t)net(blockIdx.x) * 2, cos_th, sin_th, vtrans_scale, vrot_scale, s_plan,
                         err + net(blockIdx.x));
@@ -220,6 +252,7 @@ __global__ void __launch_bounds__(NT, 1)
   int pend_slot = 0;
   size_t pend_off = 0;
   float pend_tot = 0.f;
+  int rel_b = -1;  // the network whose final state is still on its way to global memory (deferred stores)
 #ifdef PRS_RESIDENT_TIMING
   long long stamp_ = 0;
 #endif
@@ -288,8 +321,10 @@ __global__ void __launch_bounds__(NT, 1)
         const int nwi = wi + gridDim.x;
         if (nwi < nW) {
           fence_proxy_async();
+          wait_network(net_seq, net(nwi), seq);
           mbar_expect_tx(bar, N * 4);
           bulk_g2s(stage, state + (size_t)net(nwi) * N, N * 4, bar);
+          err[net(nwi)] = 0;  // long before that network's plan is made (stage 4 of this network's last update)
         }
       }
 
@@ -329,6 +364,13 @@ __global__ void __launch_bounds__(NT, 1)
       }
       __syncthreads();
       PRS_STAMP(2);
+      if (rel_b >= 0) {  // the previous network's deferred stores are behind the barrier above: its state is complete
+        if (tid == 0 && seq != 0u) {
+          __threadfence();
+          st_release_gpu_u32(net_seq + rel_b, seq);
+        }
+        rel_b = -1;
+      }
 
       // ---- 3. x pass + global inhibition (posecell_network.py:339-340) + sum (:343).
       //      A thread takes the same (y) column of BOTH planes of a mirror pair, so that the result is
@@ -520,6 +562,7 @@ __global__ void __launch_bounds__(NT, 1)
           }
         } else {
           st_gst = gst;  // deferred into the next network's stage 1 (or the kernel's epilogue)
+          rel_b = b;
         }
       }
       // arg-max (numpy.argmax: first maximum in [x][y][th] order).  Values are >= 0, so their bit patterns order
@@ -565,6 +608,10 @@ __global__ void __launch_bounds__(NT, 1)
     argmax[pend_off] = (long long)red_i[30 + pend_slot];
     total[pend_off] = pend_tot;
   }
+  if (tid == 0 && seq != 0u && rel_b >= 0) {
+    __threadfence();
+    st_release_gpu_u32(net_seq + rel_b, seq);
+  }
 }
 
 template <int X, int Y, int T, int NT>
@@ -593,9 +640,32 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
     const char* e = getenv("PRS_RESIDENT_ABLATE");
     return e ? atoi(e) : 0;
   }();
-  kern<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale,
-                                    p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate, p->only_list,
-                                    p->only_cnt);
+  // Overlappable launches (programmatic dependent launch + per-network sequence numbers): whole-ensemble launches on a
+  // stream that is not being captured.  PRS_RESIDENT_PDL=0 switches it off (profiling).
+  static const bool pdl_on = [] {
+    const char* e = getenv("PRS_RESIDENT_PDL");
+    return !(e && atoi(e) == 0);
+  }();
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
+  const bool pdl = pdl_on && p->only_list == nullptr && cap == cudaStreamCaptureStatusNone && p->net_seq != nullptr;
+  if (pdl) {
+    const unsigned seq = ++p->res_seq;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NT), cfg.dynamicSmemBytes = L::kBytes, cfg.stream = st;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at, cfg.numAttrs = 1;
+    PRS_CUDA(cudaLaunchKernelEx(&cfg, kern, state, odom, n_steps, gi, argmax, total, err, (const double*)p->cos_th,
+                                (const double*)p->sin_th, p->vtrans_scale, p->vrot_scale, p->B,
+                                (const PcTables<float>*)p->tab_dev, ablate, (const int*)nullptr, (const int*)nullptr,
+                                p->net_seq, seq));
+  } else {
+    kern<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale,
+                                      p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate, p->only_list,
+                                      p->only_cnt, nullptr, 0u);
+  }
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
 }
