@@ -252,7 +252,6 @@ __global__ void __launch_bounds__(NT, 1)
   int pend_slot = 0;
   size_t pend_off = 0;
   float pend_tot = 0.f;
-  int rel_b = -1;  // the network whose final state is still on its way to global memory (deferred stores)
 #ifdef PRS_RESIDENT_TIMING
   long long stamp_ = 0;
 #endif
@@ -316,17 +315,8 @@ __global__ void __launch_bounds__(NT, 1)
         total[pend_off] = pend_tot;
       }
       pend_valid = false;
-      // the staging buffer is free again: fetch the next network while this one is computed
-      if (tid == 0 && step == 0) {
-        const int nwi = wi + gridDim.x;
-        if (nwi < nW) {
-          fence_proxy_async();
-          wait_network(net_seq, net(nwi), seq);
-          mbar_expect_tx(bar, N * 4);
-          bulk_g2s(stage, state + (size_t)net(nwi) * N, N * 4, bar);
-          err[net(nwi)] = 0;  // long before that network's plan is made (stage 4 of this network's last update)
-        }
-      }
+      // (the staging buffer is free again from here on; the next network is fetched by an idle thread of stage 4: code
+      // at this spot -- even code that does not run -- costs the y pass 3 % of the update, measured)
 
       // ---- 2. y pass, in place on each (theta, x) line; the remaining deferred result planes leave here
       if (kDefer1 < T && st_gst != nullptr) {
@@ -364,12 +354,11 @@ __global__ void __launch_bounds__(NT, 1)
       }
       __syncthreads();
       PRS_STAMP(2);
-      if (rel_b >= 0) {  // the previous network's deferred stores are behind the barrier above: its state is complete
-        if (tid == 0 && seq != 0u) {
-          __threadfence();
-          st_release_gpu_u32(net_seq + rel_b, seq);
-        }
-        rel_b = -1;
+      // the previous network's deferred stores are behind the barrier above: its state is complete (no variable of its
+      // own for this -- the kernel's hot stages use every register they can get)
+      if (tid == 0 && seq != 0u && step == 0 && wi != (int)blockIdx.x) {
+        __threadfence();
+        st_release_gpu_u32(net_seq + net(wi - (int)gridDim.x), seq);
       }
 
       // ---- 3. x pass + global inhibition (posecell_network.py:339-340) + sum (:343).
@@ -446,6 +435,8 @@ __global__ void __launch_bounds__(NT, 1)
         for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
         if (lane == 0) s_val[0] = sacc;
       }
+      // err[] of the next network is zeroed a barrier ahead of stage 4, where its plan may OR bits in
+      if (tid == NT - 1 && step == 0 && wi + (int)gridDim.x < nW) err[net(wi + (int)gridDim.x)] = 0;
       __syncthreads();  // publishes A2 and the total
       PRS_STAMP(4);
       // posecell_network.py:344-345.  The normalisation is a positive scale: max(s*v, 0) = s*max(v, 0) and the
@@ -463,6 +454,15 @@ __global__ void __launch_bounds__(NT, 1)
         if (tid < kPlanT0 + T && nwi < nW)
           plan_plane<X, Y, T>(tid - kPlanT0, odom + ((size_t)nstep * B + nb) * 2, cos_th, sin_th, vtrans_scale,
                               vrot_scale, s_plan + (slot ^ 1) * L::kPlanInts, err + nb);
+        // The staging buffer has been free since stage 1: an otherwise idle thread fetches the next network while this
+        // one is computed -- after it has seen that network's state of the previous launch complete.
+        if (tid == NT - 1 && step == 0 && wi + (int)gridDim.x < nW) {
+          const int fb = net(wi + (int)gridDim.x);
+          fence_proxy_async();
+          wait_network(net_seq, fb, seq);
+          mbar_expect_tx(bar, N * 4);
+          bulk_g2s(stage, state + (size_t)fb * N, N * 4, bar);
+        }
       } else if (!(ablate & 16) && tid < NP * X) {
         const int kp = tid / X, x = tid - kp * X;
         const int fsA = plan4[MID + kp].w, fsB = plan4[kp == 0 ? 0 : MID - kp].w;
@@ -562,7 +562,6 @@ __global__ void __launch_bounds__(NT, 1)
           }
         } else {
           st_gst = gst;  // deferred into the next network's stage 1 (or the kernel's epilogue)
-          rel_b = b;
         }
       }
       // arg-max (numpy.argmax: first maximum in [x][y][th] order).  Values are >= 0, so their bit patterns order
@@ -608,9 +607,10 @@ __global__ void __launch_bounds__(NT, 1)
     argmax[pend_off] = (long long)red_i[30 + pend_slot];
     total[pend_off] = pend_tot;
   }
-  if (tid == 0 && seq != 0u && rel_b >= 0) {
+  if (tid == 0 && seq != 0u && n_steps > 0) {  // the last network of this CTA
+    const int last_wi = (int)blockIdx.x + ((nW - 1 - (int)blockIdx.x) / (int)gridDim.x) * (int)gridDim.x;
     __threadfence();
-    st_release_gpu_u32(net_seq + rel_b, seq);
+    st_release_gpu_u32(net_seq + net(last_wi), seq);
   }
 }
 
