@@ -168,7 +168,9 @@ __device__ unsigned long long g_stage_cycles[8];
   } while (0)
 #endif
 
-template <int X, int Y, int T, int NT>
+// LIST: the work items are the *wl_cnt networks listed in wl (the dense fall-back of the active-set path) instead of all B
+// networks; a separate instantiation, so that the plain kernel pays nothing for the indirection.
+template <int X, int Y, int T, int NT, bool LIST>
 __global__ void __launch_bounds__(NT, 1)
     k_pc_resident(float* state, const double* __restrict__ odom, int n_steps, const float* __restrict__ gi,
                   long long* __restrict__ argmax, float* __restrict__ total, int* __restrict__ err,
@@ -206,9 +208,9 @@ __global__ void __launch_bounds__(NT, 1)
   const int wid = tid >> 5, lane = tid & 31;
   // Work items: the B networks, or -- as the dense fallback of the active-set path (posecell_active.cu) -- the *wl_cnt
   // networks listed in wl.
-  const int nW = wl_cnt != nullptr ? *wl_cnt : B;
+  const int nW = LIST ? *wl_cnt : B;
   if ((int)blockIdx.x >= nW) return;
-  auto net = [&](int wi) { return wl != nullptr ? wl[wi] : wi; };
+  auto net = [&](int wi) { return LIST ? wl[wi] : wi; };
   // seq != 0: this launch is number `seq` of the plan's chain of overlappable launches.  The next one may be scheduled as
   // soon as SMs are free (the CTAs of a ragged last wave leave 80 of 148 SMs idle for a whole network otherwise); it
   // waits per network, not per grid.
@@ -618,7 +620,8 @@ template <int X, int Y, int T, int NT>
 int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const float* gi, long long* argmax,
            float* total, int* err, cudaStream_t st) {
   using L = ResLayout<X, Y, T>;
-  auto kern = k_pc_resident<X, Y, T, NT>;
+  auto kern = k_pc_resident<X, Y, T, NT, false>;
+  auto kern_list = k_pc_resident<X, Y, T, NT, true>;
   static bool configured[64] = {};  // function attributes are per device
   static int nsm_of[64] = {};
   const int dev = p->device;
@@ -628,6 +631,7 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
     std::lock_guard<std::mutex> lk(mu);
     if (!configured[dev]) {
       PRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
+      PRS_CUDA(cudaFuncSetAttribute(kern_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
       PRS_CUDA(cudaDeviceGetAttribute(&nsm_of[dev], cudaDevAttrMultiProcessorCount, dev));
       configured[dev] = true;
     }
@@ -661,10 +665,14 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
                                 (const double*)p->sin_th, p->vtrans_scale, p->vrot_scale, p->B,
                                 (const PcTables<float>*)p->tab_dev, ablate, (const int*)nullptr, (const int*)nullptr,
                                 p->net_seq, seq));
+  } else if (p->only_list != nullptr) {
+    kern_list<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th,
+                                           p->vtrans_scale, p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate,
+                                           p->only_list, p->only_cnt, nullptr, 0u);
   } else {
     kern<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale,
-                                      p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate, p->only_list,
-                                      p->only_cnt, nullptr, 0u);
+                                      p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate, nullptr, nullptr,
+                                      nullptr, 0u);
   }
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
