@@ -566,6 +566,18 @@ static void* mapped_alias(const void* p) {
   return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
+// prs_pc_step followed by the (x, y, th, err) packing of its result into `xyze` (device or mapped host memory): the fused
+// one-CTA kernel writes the packed record itself (one kernel less between two updates -- which is also what lets two
+// updates of the overlapped host API overlap), every other path launches the small packing kernel.
+static int step_and_pack(prs_pc_handle h, void* state, const double* odom, const void* gi, int* xyze, cudaStream_t st) {
+  const bool fused = prs_pc_path(h) == PRS_PATH_RESIDENT && !h->opt_active;
+  h->res_xyze = fused ? xyze : nullptr;
+  int rc = prs_pc_step(h, state, odom, gi, h->d_argmax, h->d_total, h->d_err, st);
+  h->res_xyze = nullptr;
+  if (rc != PRS_OK || fused) return rc;
+  return prs_pc_launch_unravel_pack(h, h->d_argmax, h->d_err, xyze, st);
+}
+
 static int step_host_xyz_enqueue(prs_pc_handle h, void* state, const double* odom_host, const void* gi, int* result_host,
                                  cudaStream_t st) {
   // A handful of networks: with pinned host buffers the kernels read the odometry and write the packed result in
@@ -573,16 +585,10 @@ static int step_host_xyz_enqueue(prs_pc_handle h, void* state, const double* odo
   if (h->B <= 64) {
     const double* od = (const double*)mapped_alias(odom_host);
     int* res = (int*)mapped_alias(result_host);
-    if (od && res) {
-      int rc = prs_pc_step(h, state, od, gi, h->d_argmax, h->d_total, h->d_err, st);
-      if (rc != PRS_OK) return rc;
-      return prs_pc_launch_unravel_pack(h, h->d_argmax, h->d_err, res, st);
-    }
+    if (od && res) return step_and_pack(h, state, od, gi, res, st);
   }
   PRS_CUDA(cudaMemcpyAsync(h->d_odom, odom_host, (size_t)h->B * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-  int rc = prs_pc_step(h, state, h->d_odom, gi, h->d_argmax, h->d_total, h->d_err, st);
-  if (rc != PRS_OK) return rc;
-  rc = prs_pc_launch_unravel_pack(h, h->d_argmax, h->d_err, h->d_xyze, st);
+  int rc = step_and_pack(h, state, h->d_odom, gi, h->d_xyze, st);
   if (rc != PRS_OK) return rc;
   PRS_CUDA(cudaMemcpyAsync(result_host, h->d_xyze, (size_t)h->B * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   return PRS_OK;
@@ -613,11 +619,9 @@ extern "C" int prs_pc_step_host_xyz_async(prs_pc_handle h, void* state, const do
   PRS_CUDA(cudaEventRecord(h->ev_h2d[s], h->cs_in));
   PRS_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[s], 0));
   if (h->pipe_used[s]) PRS_CUDA(cudaStreamWaitEvent(st, h->ev_d2h[s], 0));  // this slot's result buffer is free again
-  int rc = prs_pc_step(h, state, h->d_odom2[s], gi, h->d_argmax, h->d_total, h->d_err, st);
+  int rc = step_and_pack(h, state, h->d_odom2[s], gi, h->d_xyze2[s], st);
   if (rc != PRS_OK) return rc;
   PRS_CUDA(cudaEventRecord(h->ev_k[s], st));
-  rc = prs_pc_launch_unravel_pack(h, h->d_argmax, h->d_err, h->d_xyze2[s], st);
-  if (rc != PRS_OK) return rc;
   PRS_CUDA(cudaEventRecord(h->ev_done[s], st));
   // result out, on the copy-out stream
   PRS_CUDA(cudaStreamWaitEvent(h->cs_out, h->ev_done[s], 0));

@@ -112,6 +112,7 @@ struct prs_pc_plan {
   void* tab_dev;        // device copy of PcTables<float> for the resident kernel
   unsigned* net_seq;    // [B] per-network sequence numbers of the resident kernel's overlappable launches
   unsigned res_seq;     // launches of that chain so far
+  int* res_xyze;        // set around a launch by the host API: the kernel also writes (x, y, th, err) per network there
   // active-set path (posecell_active.cu), prs_pc_set_option(PRS_OPT_ACTIVE_SET)
   int opt_active;       // 0 = off, 1 = scan the state for its non-zero cells every update, 2 = keep the list across updates
   int* al_cnt;          // [B] entries in a network's active list (may exceed al_cap: overflow)

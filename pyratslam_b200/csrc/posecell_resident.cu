@@ -130,7 +130,7 @@ __device__ __forceinline__ void wait_network(const unsigned* net_seq, int b, uns
 template <int X, int Y, int T>
 __device__ __forceinline__ void plan_plane(int k, const double* __restrict__ od, const double* __restrict__ cos_th,
                                            const double* __restrict__ sin_th, double vtrans_scale, double vrot_scale,
-                                           int* plan, int* err_b) {
+                                           int* plan, int* err_b, int* err_s) {
   const double vt = __ddiv_rn(od[0], vtrans_scale);
   const double ex = __dmul_rn(vt, cos_th[k]);
   const double ey = __dmul_rn(vt, sin_th[k]);
@@ -146,7 +146,10 @@ __device__ __forceinline__ void plan_plane(int k, const double* __restrict__ od,
     const int ogc = og < -(double)PRS_OG_RANGE ? -PRS_OG_RANGE : (og > (double)PRS_OG_RANGE ? PRS_OG_RANGE : (int)og);
     plan[4 * T] = ogc + PRS_OG_RANGE;
   }
-  if (e) atomicOr(err_b, e);
+  if (e) {
+    atomicOr(err_b, e);
+    atomicOr(err_s, e);  // the CTA's own copy: what the packed result reports (err_b may be re-zeroed by the next launch)
+  }
 }
 
 // Optional in-kernel stage timing (profiling builds of this file only: -DPRS_RESIDENT_TIMING).  Thread 0 of
@@ -176,7 +179,8 @@ __global__ void __launch_bounds__(NT, 1)
                   long long* __restrict__ argmax, float* __restrict__ total, int* __restrict__ err,
                   const double* __restrict__ cos_th, const double* __restrict__ sin_th, double vtrans_scale,
                   double vrot_scale, int B, const PcTables<float>* __restrict__ tab_g, int ablate,
-                  const int* __restrict__ wl, const int* __restrict__ wl_cnt, unsigned* __restrict__ net_seq, unsigned seq) {
+                  const int* __restrict__ wl, const int* __restrict__ wl_cnt, unsigned* __restrict__ net_seq, unsigned seq,
+                  int4* __restrict__ xyze) {
   using L = ResLayout<X, Y, T>;
   constexpr int XY = L::XY, N = L::N, NP = L::NP, PS = L::PS;
   constexpr int kPlanT0 = NT - 64;  // the threads that prepare the next update's plan during stage 4
@@ -215,6 +219,17 @@ __global__ void __launch_bounds__(NT, 1)
   // soon as SMs are free (the CTAs of a ragged last wave leave 80 of 148 SMs idle for a whole network otherwise); it
   // waits per network, not per grid.
   if (seq != 0u) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // xyze != nullptr (single-update launches of the host API): the result also leaves as (x, y, th, err) per network --
+  // get_pc_max's unravelling (posecell_network.py:318) -- which saves the host API a kernel between two updates
+  auto publish = [&](size_t off, int pslot, float tot_) {
+    const int flat = red_i[30 + pslot];
+    argmax[off] = (long long)flat;
+    total[off] = tot_;
+    if (xyze != nullptr) {
+      const int xy = flat / T, th = flat - xy * T, x = xy / Y;
+      xyze[off] = make_int4(x, xy - x * Y, th, red_i[28 + pslot]);
+    }
+  };
 
   // ---- one-time set-up: tables, coefficient pairs, mbarrier, first prefetch, first plan
   for (int i = tid; i < (int)(sizeof(PcTables<float>) / 4); i += NT)
@@ -235,11 +250,12 @@ __global__ void __launch_bounds__(NT, 1)
     mbar_expect_tx(bar, N * 4);
     bulk_g2s(stage, state + (size_t)net(blockIdx.x) * N, N * 4, bar);
     err[net(blockIdx.x)] = 0;  // the kernel owns err[b]: zeroed before the network's first plan ORs its bits in
+    red_i[28] = red_i[29] = 0;  // error bits of the two plan slots, as the packed result reports them
   }
   __syncthreads();
   if (tid >= kPlanT0 && tid < kPlanT0 + T && n_steps > 0)
     plan_plane<X, Y, T>(tid - kPlanT0, odom + (size_t)net(blockIdx.x) * 2, cos_th, sin_th, vtrans_scale, vrot_scale, s_plan,
-                        err + net(blockIdx.x));
+                        err + net(blockIdx.x), red_i + 28);
   __syncthreads();
   uint32_t parity = 0;
   int slot = 0;
@@ -312,10 +328,8 @@ __global__ void __launch_bounds__(NT, 1)
       }
       __syncthreads();
       PRS_STAMP(1);
-      if (tid == 0 && pend_valid) {  // every winner of the previous update has done its atomicMin by now
-        argmax[pend_off] = (long long)red_i[30 + pend_slot];
-        total[pend_off] = pend_tot;
-      }
+      if (tid == 0 && pend_valid)  // every winner of the previous update has done its atomicMin by now
+        publish(pend_off, pend_slot, pend_tot);
       pend_valid = false;
       // (the staging buffer is free again from here on; the next network is fetched by an idle thread of stage 4: code
       // at this spot -- even code that does not run -- costs the y pass 3 % of the update, measured)
@@ -437,8 +451,13 @@ __global__ void __launch_bounds__(NT, 1)
         for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
         if (lane == 0) s_val[0] = sacc;
       }
-      // err[] of the next network is zeroed a barrier ahead of stage 4, where its plan may OR bits in
-      if (tid == NT - 1 && step == 0 && wi + (int)gridDim.x < nW) err[net(wi + (int)gridDim.x)] = 0;
+      // the error bits of the next plan start from zero, a barrier ahead of stage 4 where it is made: the shared-memory
+      // copy of its slot, and err[] of the next network when that plan is its first (the previous launch ORed its own bits
+      // into err[] before it finished the network this CTA is working on, so this store comes after them)
+      if (tid == NT - 1) {
+        red_i[28 + (slot ^ 1)] = 0;
+        if (step == 0 && wi + (int)gridDim.x < nW) err[net(wi + (int)gridDim.x)] = 0;
+      }
       __syncthreads();  // publishes A2 and the total
       PRS_STAMP(4);
       // posecell_network.py:344-345.  The normalisation is a positive scale: max(s*v, 0) = s*max(v, 0) and the
@@ -455,7 +474,7 @@ __global__ void __launch_bounds__(NT, 1)
       if (tid >= kPlanT0) {
         if (tid < kPlanT0 + T && nwi < nW)
           plan_plane<X, Y, T>(tid - kPlanT0, odom + ((size_t)nstep * B + nb) * 2, cos_th, sin_th, vtrans_scale,
-                              vrot_scale, s_plan + (slot ^ 1) * L::kPlanInts, err + nb);
+                              vrot_scale, s_plan + (slot ^ 1) * L::kPlanInts, err + nb, red_i + 28 + (slot ^ 1));
         // The staging buffer has been free since stage 1: an otherwise idle thread fetches the next network while this
         // one is computed -- after it has seen that network's state of the previous launch complete.
         if (tid == NT - 1 && step == 0 && wi + (int)gridDim.x < nW) {
@@ -605,10 +624,7 @@ __global__ void __launch_bounds__(NT, 1)
     }
   }
   __syncthreads();
-  if (tid == 0 && pend_valid) {
-    argmax[pend_off] = (long long)red_i[30 + pend_slot];
-    total[pend_off] = pend_tot;
-  }
+  if (tid == 0 && pend_valid) publish(pend_off, pend_slot, pend_tot);
   if (tid == 0 && seq != 0u && n_steps > 0) {  // the last network of this CTA
     const int last_wi = (int)blockIdx.x + ((nW - 1 - (int)blockIdx.x) / (int)gridDim.x) * (int)gridDim.x;
     __threadfence();
@@ -664,15 +680,15 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
     PRS_CUDA(cudaLaunchKernelEx(&cfg, kern, state, odom, n_steps, gi, argmax, total, err, (const double*)p->cos_th,
                                 (const double*)p->sin_th, p->vtrans_scale, p->vrot_scale, p->B,
                                 (const PcTables<float>*)p->tab_dev, ablate, (const int*)nullptr, (const int*)nullptr,
-                                p->net_seq, seq));
+                                p->net_seq, seq, (int4*)(n_steps == 1 ? p->res_xyze : nullptr)));
   } else if (p->only_list != nullptr) {
     kern_list<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th,
                                            p->vtrans_scale, p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate,
-                                           p->only_list, p->only_cnt, nullptr, 0u);
+                                           p->only_list, p->only_cnt, nullptr, 0u, nullptr);
   } else {
     kern<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale,
                                       p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate, nullptr, nullptr,
-                                      nullptr, 0u);
+                                      nullptr, 0u, (int4*)(n_steps == 1 ? p->res_xyze : nullptr));
   }
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
