@@ -646,11 +646,16 @@ def run_ours(args):
                        "parallelism": "networks sharded by rank, no collective"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * 16,
                     "d2h_bytes_per_step": B * 16,
-                    "api": "PoseCellEnsemble.update_submit / update_result (prs_pc_step_host_xyz_async): pinned odometry "
-                           "H2D + step + packed (x, y, th, err) D2H every step, one step in flight; the blocking call "
+                    "api": "PoseCellEnsemble.update_submit / update_result (prs_pc_step_host_xyz_async): host odometry in "
+                           "pinned memory -> step -> packed (x, y, th, err) per network in pinned host memory, every step, "
+                           "one step in flight.  On the fused path the transfers are the kernel's own: it reads the "
+                           "16 B of odometry per network from the pinned buffer over PCIe and writes the 16 B record "
+                           "back (h2d / d2h_bytes_per_step), completion is a pinned word the host polls -- no copy "
+                           "engine, no event between two updates, so that consecutive updates overlap "
+                           "(PRS_HOST_ZERO_COPY=0 restores cudaMemcpyAsync on two copy streams).  The blocking call "
                            "(PoseCellEnsemble.update, host waits for every step) is blocking_call",
                     "blocking_call": {"value": e2e_blk, "ms_per_step": ms_blk / K,
-                                      "api": "PoseCellEnsemble.update (prs_pc_step_host_xyz): same copies, host waits "
+                                      "api": "PoseCellEnsemble.update (prs_pc_step_host_xyz): same transfers, host waits "
                                              "for every step"}},
             "gpu_launches": K * launches_per_step,
             "clocks": clocks,

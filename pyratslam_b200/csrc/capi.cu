@@ -68,6 +68,8 @@ static void free_plan(prs_pc_plan* p) {
     if (p->d_xyze2[i]) cudaFree(p->d_xyze2[i]);
   }
   if (p->ss2) cudaStreamDestroy(p->ss2);
+  if (p->zc_ctr) cudaFree(p->zc_ctr);
+  if (p->zc_done) cudaFreeHost(p->zc_done);
   if (p->cs_in) cudaStreamDestroy(p->cs_in);
   if (p->cs_out) cudaStreamDestroy(p->cs_out);
   if (p->net_seq) cudaFree(p->net_seq);
@@ -594,11 +596,80 @@ static int step_host_xyz_enqueue(prs_pc_handle h, void* state, const double* odo
   return PRS_OK;
 }
 
+// Fused path with mapped pinned buffers: the kernel reads the odometry from host memory (two doubles per network, read a
+// whole stage ahead of their use), writes the packed records into host memory and signals completion through a pinned
+// word (slot 0 / 1: the overlapped API's two steps in flight; slot 2: the blocking call).  The stream then carries nothing
+// but the update kernels, and consecutive updates overlap (posecell_resident.cu).  *launched = 0: not applicable.
+static int zero_copy_submit(prs_pc_handle h, void* state, const double* odom_host, const void* gi, int* result_host,
+                            cudaStream_t st, int s, int* launched) {
+  *launched = 0;
+  static const bool zc_on = [] {
+    const char* e = getenv("PRS_HOST_ZERO_COPY");
+    return !(e && atoi(e) == 0);
+  }();
+  if (!zc_on || prs_pc_path(h) != PRS_PATH_RESIDENT || h->opt_active) return PRS_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (cap != cudaStreamCaptureStatusNone) return PRS_OK;
+  const double* od = (const double*)mapped_alias(odom_host);
+  int* res = (int*)mapped_alias(result_host);
+  if (!od || !res) return PRS_OK;
+  if (!h->zc_ctr) {
+    PRS_CUDA(cudaMalloc((void**)&h->zc_ctr, 3 * sizeof(unsigned)));
+    PRS_CUDA(cudaMemset(h->zc_ctr, 0, 3 * sizeof(unsigned)));
+    PRS_CUDA(cudaHostAlloc((void**)&h->zc_done, 3 * sizeof(unsigned), cudaHostAllocMapped));
+    h->zc_done[0] = h->zc_done[1] = h->zc_done[2] = 0;
+  }
+  unsigned* done_dev = nullptr;
+  PRS_CUDA(cudaHostGetDevicePointer((void**)&done_dev, h->zc_done + s, 0));
+  h->zc_seq[s] = ++h->zc_launch;
+  h->res_xyze = res, h->res_done_ctr = h->zc_ctr + s, h->res_done_host = done_dev, h->res_done_val = h->zc_seq[s];
+  int rc = prs_pc_step(h, state, od, gi, h->d_argmax, h->d_total, h->d_err, st);
+  h->res_xyze = nullptr, h->res_done_ctr = nullptr, h->res_done_host = nullptr;
+  if (rc == PRS_OK) *launched = 1;
+  return rc;
+}
+
+static int zero_copy_wait(prs_pc_handle h, int slot) {
+  const volatile unsigned* w = h->zc_done + slot;
+  const unsigned want = h->zc_seq[slot];
+  struct timespec t0;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  unsigned long long spins = 0;
+  while ((int)(*w - want) < 0) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0xfffff) == 0) {
+      struct timespec t1;
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if ((double)(t1.tv_sec - t0.tv_sec) > 30.0) {
+        cudaError_t e = cudaGetLastError();
+        prs_set_error("zero-copy update %u did not complete within 30 s (%s)", want, cudaGetErrorString(e));
+        return PRS_E_CUDA;
+      }
+    }
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  return PRS_OK;
+}
+
 extern "C" int prs_pc_step_host_xyz_async(prs_pc_handle h, void* state, const double* odom_host, const void* gi,
                                           int* result_host, void* stream, int* slot_out) {
   PRS_REQUIRE(h && state && odom_host && gi && result_host && slot_out, "prs_pc_step_host_xyz_async: null argument");
   if (int rc_ = prs_pc_check_device(h, "prs_pc_step_host_xyz_async")) return rc_;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    int launched = 0;
+    const int s = h->pipe_slot;
+    if (int rc = zero_copy_submit(h, state, odom_host, gi, result_host, st, s, &launched)) return rc;
+    if (launched) {
+      h->pipe_slot ^= 1;
+      h->pipe_used[s] = 2;
+      *slot_out = s;
+      return PRS_OK;
+    }
+  }
   if (!h->cs_in) {
     PRS_CUDA(cudaStreamCreateWithFlags(&h->cs_in, cudaStreamNonBlocking));
     PRS_CUDA(cudaStreamCreateWithFlags(&h->cs_out, cudaStreamNonBlocking));
@@ -634,6 +705,7 @@ extern "C" int prs_pc_step_host_xyz_async(prs_pc_handle h, void* state, const do
 
 extern "C" int prs_pc_host_result_wait(prs_pc_handle h, int slot) {
   PRS_REQUIRE(h && (slot == 0 || slot == 1) && h->pipe_used[slot], "prs_pc_host_result_wait: no step was submitted in slot %d", slot);
+  if (h->pipe_used[slot] == 2) return zero_copy_wait(h, slot);  // the kernel's last CTA stores the launch number
   PRS_CUDA(cudaEventSynchronize(h->ev_d2h[slot]));
   return PRS_OK;
 }
@@ -643,6 +715,11 @@ extern "C" int prs_pc_step_host_xyz(prs_pc_handle h, void* state, const double* 
   PRS_REQUIRE(h && state && odom_host && gi && result_host, "prs_pc_step_host_xyz: null argument");
   if (int rc_ = prs_pc_check_device(h, "prs_pc_step_host_xyz")) return rc_;
   cudaStream_t caller = (cudaStream_t)stream;
+  if (h->B > 64) {  // (a handful of networks keep their graph: zero-copy there already, one launch either way)
+    int launched = 0;
+    if (int rc = zero_copy_submit(h, state, odom_host, gi, result_host, caller, 2, &launched)) return rc;
+    if (launched) return zero_copy_wait(h, 2);
+  }
   if (!h->hs) {
     PRS_CUDA(cudaStreamCreateWithFlags(&h->hs, cudaStreamNonBlocking));
     PRS_CUDA(cudaEventCreateWithFlags(&h->hev, cudaEventDisableTiming));

@@ -113,6 +113,14 @@ struct prs_pc_plan {
   unsigned* net_seq;    // [B] per-network sequence numbers of the resident kernel's overlappable launches
   unsigned res_seq;     // launches of that chain so far
   int* res_xyze;        // set around a launch by the host API: the kernel also writes (x, y, th, err) per network there
+  // zero-copy host stepping (prs_pc_step_host_xyz_async with mapped pinned buffers on the fused path): no copies, no
+  // events; the launch's last CTA stores the launch number into a pinned word that prs_pc_host_result_wait polls
+  unsigned* res_done_ctr;   // set around a launch: device counter of finished CTAs
+  unsigned* res_done_host;  // ... device alias of the pinned completion word
+  unsigned res_done_val;
+  unsigned* zc_ctr;         // [3] device counters, one per slot (2: the blocking call)
+  unsigned* zc_done;        // [3] pinned completion words
+  unsigned zc_seq[3], zc_launch;
   // active-set path (posecell_active.cu), prs_pc_set_option(PRS_OPT_ACTIVE_SET)
   int opt_active;       // 0 = off, 1 = scan the state for its non-zero cells every update, 2 = keep the list across updates
   int* al_cnt;          // [B] entries in a network's active list (may exceed al_cap: overflow)

@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(NT, 1)
                   const double* __restrict__ cos_th, const double* __restrict__ sin_th, double vtrans_scale,
                   double vrot_scale, int B, const PcTables<float>* __restrict__ tab_g, int ablate,
                   const int* __restrict__ wl, const int* __restrict__ wl_cnt, unsigned* __restrict__ net_seq, unsigned seq,
-                  int4* __restrict__ xyze) {
+                  int4* __restrict__ xyze, unsigned* __restrict__ done_ctr, unsigned* __restrict__ done_host,
+                  unsigned done_val) {
   using L = ResLayout<X, Y, T>;
   constexpr int XY = L::XY, N = L::N, NP = L::NP, PS = L::PS;
   constexpr int kPlanT0 = NT - 64;  // the threads that prepare the next update's plan during stage 4
@@ -630,6 +631,16 @@ __global__ void __launch_bounds__(NT, 1)
     __threadfence();
     st_release_gpu_u32(net_seq + net(last_wi), seq);
   }
+  // The zero-copy host API polls one word of pinned memory instead of an event (an event between two launches would
+  // keep them from overlapping): the last CTA of the launch to get here stores the launch's number, behind the records.
+  if (tid == 0 && done_host != nullptr) {
+    __threadfence_system();
+    if (atomicAdd(done_ctr, 1u) == gridDim.x - 1u) {
+      atomicExch(done_ctr, 0u);
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(done_host), "r"(done_val) : "memory");
+    }
+  }
 }
 
 template <int X, int Y, int T, int NT>
@@ -680,15 +691,17 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
     PRS_CUDA(cudaLaunchKernelEx(&cfg, kern, state, odom, n_steps, gi, argmax, total, err, (const double*)p->cos_th,
                                 (const double*)p->sin_th, p->vtrans_scale, p->vrot_scale, p->B,
                                 (const PcTables<float>*)p->tab_dev, ablate, (const int*)nullptr, (const int*)nullptr,
-                                p->net_seq, seq, (int4*)(n_steps == 1 ? p->res_xyze : nullptr)));
+                                p->net_seq, seq, (int4*)(n_steps == 1 ? p->res_xyze : nullptr), p->res_done_ctr,
+                                p->res_done_host, p->res_done_val));
   } else if (p->only_list != nullptr) {
     kern_list<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th,
                                            p->vtrans_scale, p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate,
-                                           p->only_list, p->only_cnt, nullptr, 0u, nullptr);
+                                           p->only_list, p->only_cnt, nullptr, 0u, nullptr, nullptr, nullptr, 0u);
   } else {
     kern<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th, p->vtrans_scale,
                                       p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate, nullptr, nullptr,
-                                      nullptr, 0u, (int4*)(n_steps == 1 ? p->res_xyze : nullptr));
+                                      nullptr, 0u, (int4*)(n_steps == 1 ? p->res_xyze : nullptr), p->res_done_ctr,
+                                      p->res_done_host, p->res_done_val);
   }
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
