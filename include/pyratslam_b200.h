@@ -132,6 +132,10 @@ PRS_API int prs_pc_invalidate_active(prs_pc_handle h, void* stream);
  *            (numpy.argmax order, posecell_network.py:317-319)
  *   total  : device, [B] of the plan's dtype, the sum before normalisation (posecell_network.py:343)
  *   err    : device, int32 [B], PRS_ERR_* bits (0 = fine)
+ * Calls on one plan must be ordered by the stream(s) they are enqueued on (as for any in-place update of `state`).  On the
+ * fused one-CTA-per-network path consecutive calls on a stream overlap on the device -- update n+1 of a network starts as
+ * soon as its update n is complete, not when the whole launch n is (per-network sequence numbers, posecell_resident.cu);
+ * a launch that was NOT ordered behind its predecessor would wait for it in vain and traps after two seconds.
  */
 PRS_API int prs_pc_step(prs_pc_handle h, void* state, const double* odom, const void* gi, long long* argmax,
                 void* total, int* err, void* stream);
