@@ -578,3 +578,41 @@ def test_active_set_lists_follow_the_state_tensor():
         torch.cuda.synchronize()
         assert torch.equal(act._argmax, ref[w]._argmax), t
         assert float((states[w] - ref[w].state).abs().max() / ref[w].state.abs().max()) <= 1e-5, t
+
+
+@pytest.mark.parametrize("B", [160, 300, 512])
+def test_overlapping_launches_equal_serialised_launches(B):
+    """Consecutive updates of an ensemble overlap on the device (programmatic dependent launch + one sequence number per
+    network, posecell_resident.cu): 120 back-to-back updates of one ensemble -- and of two ensembles interleaved on one
+    stream -- give bit for bit the states and arg-max cells of the same updates with a device synchronisation between
+    them; so does the zero-copy host API (update_stream) against blocking update() calls."""
+    from pyratslam_b200 import PoseCellEnsemble
+    shape, T = (21, 21, 36), 120
+    rng = np.random.default_rng(B)
+    gis = np.linspace(0.05, 0.25, B)
+    odom = np.stack([rng.uniform(0, 0.3, (T, B)), rng.uniform(-0.1, 0.1, (T, B))], axis=-1)
+    od = torch.from_numpy(odom).cuda()
+    ens = [PoseCellEnsemble(shape, B, global_inhibition=gis) for _ in range(5)]
+    for e in ens:
+        assert e.path == "resident"
+        e.inject(1.0, (10, 10, 18))
+    a, b1, b2, c, d = ens
+    amax_a, amax_b = [], []
+    for t in range(T):                                   # serialised
+        a.update_async(od[t])
+        torch.cuda.synchronize()
+        amax_a.append(a._argmax.clone())
+    for t in range(T):                                   # overlapping, two ensembles interleaved
+        b1.update_async(od[t])
+        b2.update_async(od[t])
+        if t % 7 == 0:
+            amax_b.append((t, b1._argmax.clone()))       # a stream-ordered read between two launches
+    torch.cuda.synchronize()
+    assert torch.equal(b1.state, a.state) and torch.equal(b2.state, a.state)
+    assert torch.equal(b1._argmax, a._argmax) and torch.equal(b2._argmax, a._argmax)
+    for t, am in amax_b:
+        assert torch.equal(am, amax_a[t]), t
+    want = np.stack([c.update(odom[t]) for t in range(T)])               # blocking host calls
+    got = np.stack(list(d.update_stream(odom[t] for t in range(T))))     # one step in flight
+    assert np.array_equal(got, want) and torch.equal(c.state, d.state) and torch.equal(c.state, a.state)
+    assert np.array_equal(want[-1], a._unravel(a._argmax.cpu().numpy()))
