@@ -219,15 +219,27 @@ __global__ void __launch_bounds__(kTyx) k_tl_yx(const float2* __restrict__ EI, f
       int gx = xnear ? wrap_near(x0 - 3 + wid, X) : modp(x0 - 3 + wid, X);
       const float2* pa = src + gya;
       const float2* pb = src + gyb;
+      if (xnear) {  // (block-uniform; as a select inside one loop the integer division ran for every row, taken or not)
 #pragma unroll
-      for (int i = 0; i < NR; ++i) {
-        if (wid + i * NW < kYXrows) {
-          const unsigned rb = (unsigned)(gx * Y);
-          va[i] = pa[rb];
-          if (lane + 32 < kYXcols) vb[i] = pb[rb];
+        for (int i = 0; i < NR; ++i) {
+          if (wid + i * NW < kYXrows) {
+            const unsigned rb = (unsigned)(gx * Y);
+            va[i] = pa[rb];
+            if (lane + 32 < kYXcols) vb[i] = pb[rb];
+          }
+          gx += NW;
+          gx -= gx >= X ? X : 0;
         }
-        gx += NW;
-        gx = xnear ? (gx >= X ? gx - X : gx) : gx % X;
+      } else {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          if (wid + i * NW < kYXrows) {
+            const unsigned rb = (unsigned)(gx * Y);
+            va[i] = pa[rb];
+            if (lane + 32 < kYXcols) vb[i] = pb[rb];
+          }
+          gx = (gx + NW) % X;
+        }
       }
     }
     float2* d = s_in + wid * kInStride + lane;
