@@ -232,7 +232,23 @@ __global__ void __launch_bounds__(NT, 1)
     }
   };
 
-  // ---- one-time set-up: tables, coefficient pairs, mbarrier, first prefetch, first plan
+  // ---- one-time set-up: first prefetch and the first plan's odometry (possibly a read over PCIe) are under way while the
+  //      tables and coefficient pairs are copied; then the first plan
+  if (tid == NT - 1) {
+    mbar_init(bar, 1);
+    fence_proxy_async();
+    wait_network(net_seq, net(blockIdx.x), seq);
+    mbar_expect_tx(bar, N * 4);
+    bulk_g2s(stage, state + (size_t)net(blockIdx.x) * N, N * 4, bar);
+    err[net(blockIdx.x)] = 0;  // the kernel owns err[b]: zeroed before the network's first plan ORs its bits in
+    red_i[28] = red_i[29] = 0;  // error bits of the two plan slots, as the packed result reports them
+  }
+  double od0[2] = {0.0, 0.0};
+  const bool planner = tid >= kPlanT0 && tid < kPlanT0 + T && n_steps > 0;
+  if (planner) {
+    const double* od = odom + (size_t)net(blockIdx.x) * 2;
+    od0[0] = od[0], od0[1] = od[1];
+  }
   for (int i = tid; i < (int)(sizeof(PcTables<float>) / 4); i += NT)
     reinterpret_cast<float*>(smem + L::kTabOff)[i] = reinterpret_cast<const float*>(tab_g)[i];
   if (tid < 7) {
@@ -244,19 +260,10 @@ __global__ void __launch_bounds__(NT, 1)
     s_f2p[i] = q < 7 ? make_float2(tab_g->f2d[combo >> 1][a * 7 + q], tab_g->f2d[combo & 1][a * 7 + q])
                      : make_float2(0.f, 0.f);
   }
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_proxy_async();
-    wait_network(net_seq, net(blockIdx.x), seq);
-    mbar_expect_tx(bar, N * 4);
-    bulk_g2s(stage, state + (size_t)net(blockIdx.x) * N, N * 4, bar);
-    err[net(blockIdx.x)] = 0;  // the kernel owns err[b]: zeroed before the network's first plan ORs its bits in
-    red_i[28] = red_i[29] = 0;  // error bits of the two plan slots, as the packed result reports them
-  }
   __syncthreads();
-  if (tid >= kPlanT0 && tid < kPlanT0 + T && n_steps > 0)
-    plan_plane<X, Y, T>(tid - kPlanT0, odom + (size_t)net(blockIdx.x) * 2, cos_th, sin_th, vtrans_scale, vrot_scale, s_plan,
-                        err + net(blockIdx.x), red_i + 28);
+  if (planner)
+    plan_plane<X, Y, T>(tid - kPlanT0, od0, cos_th, sin_th, vtrans_scale, vrot_scale, s_plan, err + net(blockIdx.x),
+                        red_i + 28);
   __syncthreads();
   uint32_t parity = 0;
   int slot = 0;
@@ -680,19 +687,31 @@ int launch(prs_pc_plan* p, float* state, const double* odom, int n_steps, const 
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (st != nullptr) PRS_CUDA(cudaStreamIsCapturing(st, &cap));
   const bool pdl = pdl_on && p->only_list == nullptr && cap == cudaStreamCaptureStatusNone && p->net_seq != nullptr;
+  bool launched = false;
   if (pdl) {
-    const unsigned seq = ++p->res_seq;
+    const unsigned seq = p->res_seq + 1u;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NT), cfg.dynamicSmemBytes = L::kBytes, cfg.stream = st;
     cudaLaunchAttribute at;
     at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &at, cfg.numAttrs = 1;
-    PRS_CUDA(cudaLaunchKernelEx(&cfg, kern, state, odom, n_steps, gi, argmax, total, err, (const double*)p->cos_th,
-                                (const double*)p->sin_th, p->vtrans_scale, p->vrot_scale, p->B,
-                                (const PcTables<float>*)p->tab_dev, ablate, (const int*)nullptr, (const int*)nullptr,
-                                p->net_seq, seq, (int4*)(n_steps == 1 ? p->res_xyze : nullptr), p->res_done_ctr,
-                                p->res_done_host, p->res_done_val));
+    const cudaError_t le = cudaLaunchKernelEx(
+        &cfg, kern, state, odom, n_steps, gi, argmax, total, err, (const double*)p->cos_th, (const double*)p->sin_th,
+        p->vtrans_scale, p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate, (const int*)nullptr,
+        (const int*)nullptr, p->net_seq, seq, (int4*)(n_steps == 1 ? p->res_xyze : nullptr), p->res_done_ctr,
+        p->res_done_host, p->res_done_val);
+    if (le == cudaSuccess) {
+      p->res_seq = seq;
+      launched = true;
+    } else {  // a driver that refuses the attribute: plain launches from now on (the chain of sequence numbers ends here)
+      (void)cudaGetLastError();
+      cudaFree(p->net_seq);
+      p->net_seq = nullptr;
+    }
+  }
+  if (launched) {
+    // (launched above, overlappable)
   } else if (p->only_list != nullptr) {
     kern_list<<<grid, NT, L::kBytes, st>>>(state, odom, n_steps, gi, argmax, total, err, p->cos_th, p->sin_th,
                                            p->vtrans_scale, p->vrot_scale, p->B, (const PcTables<float>*)p->tab_dev, ablate,
