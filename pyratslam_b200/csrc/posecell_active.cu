@@ -264,12 +264,14 @@ __device__ __forceinline__ int fdiv(int l, float inv) { return __float2int_rz((_
 
 // MAXD: upper bound of the three grid dimensions (64 for ensembles of small grids: 4 KB of static shared memory per CTA
 // instead of 15 KB, so that more networks are in flight per SM)
-template <typename T, int MAXD>
+// WIDE: register windows that cover a whole line of a typical packet (fewer work items: fewer instructions, the choice for
+// thousands of networks) or windows of four outputs (more items in flight: lower latency, the choice for a few networks).
+template <typename T, int MAXD, bool WIDE>
 __global__ void __launch_bounds__(kActMaxT, 4) k_pc_active(const __grid_constant__ ActArgs<T> a) {
   // Outputs per register window.  A work item costs ~100 instructions before its first FMA (window positions, predicated
   // loads, line decode), so a window covers the whole line of a typical packet (11 outputs) where the registers allow it.
-  constexpr int CH = sizeof(T) == 4 ? PRS_ACTIVE_CH : PRS_ACTIVE_CH / 2;        // 1-D passes
-  constexpr int CH2 = sizeof(T) == 4 ? PRS_ACTIVE_CH2 : PRS_ACTIVE_CH2 / 2;     // 7x7 stage (CH2 accumulators + two windows)
+  constexpr int CH = !WIDE ? 4 : (sizeof(T) == 4 ? PRS_ACTIVE_CH : PRS_ACTIVE_CH / 2);      // 1-D passes
+  constexpr int CH2 = !WIDE ? 4 : (sizeof(T) == 4 ? PRS_ACTIVE_CH2 : PRS_ACTIVE_CH2 / 2);   // 7x7 stage (accumulators + two windows)
   constexpr int MW = MAXD / 32;
   using Set = AxisSet<MAXD>;
   extern __shared__ __align__(16) unsigned char arena_raw[];
@@ -744,10 +746,15 @@ int active_launch(prs_pc_plan* p, T* state, const double* odom, const T* gi, lon
     a.wl_cnt = a.wl != nullptr ? p->dense_cnt + 1 : nullptr;
     a.over_list = first_of_two ? p->big_list : nullptr;
     a.over_cnt = first_of_two ? p->dense_cnt + 1 : nullptr;
-    if (maxd <= 64)
-      k_pc_active<T, 64><<<p->B, p->act_threads, arena, st>>>(a);
+    const bool wide = p->B > 2 * 148;  // (a few hundred small networks: all CTAs resident at once, latency is what counts)
+    if (maxd <= 64 && wide)
+      k_pc_active<T, 64, true><<<p->B, p->act_threads, arena, st>>>(a);
+    else if (maxd <= 64)
+      k_pc_active<T, 64, false><<<p->B, p->act_threads, arena, st>>>(a);
+    else if (wide)
+      k_pc_active<T, kMaxDim, true><<<p->B, p->act_threads, arena, st>>>(a);
     else
-      k_pc_active<T, kMaxDim><<<p->B, p->act_threads, arena, st>>>(a);
+      k_pc_active<T, kMaxDim, false><<<p->B, p->act_threads, arena, st>>>(a);
   }
   PRS_CUDA(cudaGetLastError());
   return PRS_OK;
@@ -776,7 +783,8 @@ int prs_pc_active_prepare(prs_pc_plan* p) {
   if (p->al_cnt) return PRS_OK;
   PRS_REQUIRE(prs_pc_active_supported(p), "active-set path: every grid dimension must be in [3, %d]", kMaxDim);
   // a few large networks: one big CTA each with most of an SM's shared memory; many networks: several CTAs per SM
-  const bool few = p->B <= 2 * 148;
+  const int maxd0 = p->X > p->Y ? (p->X > p->Th ? p->X : p->Th) : (p->Y > p->Th ? p->Y : p->Th);
+  const bool few = p->B <= 16 || (maxd0 > 64 && p->B <= 2 * 148);  // big CTAs only where a network can need the room
   // (measured, 4096 networks of 21x21x36: first tier of 20 KB 0.158 ms per update; of 12 KB 0.192 ms: too many networks
   // run twice; of 48 KB 0.20 ms: too few in flight)
   int threads = few ? 256 : 128, arena = few ? 160 * 1024 : 72 * 1024, arena1 = few ? 0 : 20 * 1024, cap = few ? 8192 : 512;
@@ -788,10 +796,14 @@ int prs_pc_active_prepare(prs_pc_plan* p) {
   PRS_REQUIRE(arena >= 4096 && arena <= 200 * 1024 && cap >= 16, "PRS_ACTIVE_ARENA_KB / PRS_ACTIVE_CAP out of range");
   PRS_REQUIRE(arena1 == 0 || (arena1 >= 4096 && arena1 < arena), "PRS_ACTIVE_ARENA1_KB must be 0 or in [4, arena)");
   p->act_threads = threads, p->act_arena = arena, p->act_arena1 = arena1, p->al_cap = cap;
-  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<double, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<float, kMaxDim>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<double, kMaxDim>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<float, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<double, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<float, kMaxDim, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<double, kMaxDim, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<float, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<double, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<float, kMaxDim, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PRS_CUDA(cudaFuncSetAttribute(k_pc_active<double, kMaxDim, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const size_t B = (size_t)p->B;
   PRS_CUDA(cudaMalloc(&p->al_idx, B * cap * sizeof(int)));
   PRS_CUDA(cudaMalloc(&p->al_valid, B * sizeof(int)));
