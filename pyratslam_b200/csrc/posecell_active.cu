@@ -25,8 +25,8 @@
 //                launch and the dense kernels are the body of a conditional node that this kernel raises
 //                (cudaGraphSetConditional) only when it defers or flags a network.
 //
-// Measured (B200): 1.7-2.3x the dense kernels on 4096 x 21x21x36 float32, 3.5-4.8x on the float64 and 50x50x10 ensembles,
-// 1.6-1.9x on one 256x256x72 network; the scan runs at the HBM roof, k_pc_active at 61 % issue utilisation
+// Measured (B200): 1.6-2.1x the dense kernels on 4096 x 21x21x36 float32, 3.4-4.7x on the float64 and 50x50x10 ensembles,
+// 1.7-1.8x on one 256x256x72 network; the scan runs at the HBM roof, k_pc_active at 61 % issue utilisation
 // with 19 k warp instructions per network.
 //
 // PRS_OPT_ACTIVE_SET = 2 additionally keeps the list k_pc_active wrote (the new non-zero cells) as the next update's
